@@ -1,0 +1,226 @@
+/*
+ * tigar_b200.h -- C-ABI of the B200-native tIGAr hot path
+ * (extraction -> Gauss-point assembly -> M^T A M / M^T b -> BCs -> CG).
+ *
+ * The reference (david-kamensky/tIGAr) has no FFI of its own: its hot path is
+ * Python calling DOLFIN/PETSc.  Each entry point below names the reference
+ * interface it replaces (file:line into the reference tree).  The Python
+ * classes in tigar_b200/ (same names as the reference's) are the only callers;
+ * INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - plain C, no torch types.  All pointers are DEVICE pointers unless the
+ *    parameter name starts with h_ (host).  Memory is caller-owned.
+ *  - every call enqueues on the caller's CUDA stream (void* = cudaStream_t,
+ *    NULL = default stream) and returns without synchronising unless stated.
+ *  - return 0 on success, non-zero on error; tg_last_error() gives the text.
+ *  - FP64 values, int32 column indices, int64 row pointers.
+ *  - tensor-product index convention of the reference: first parametric
+ *    direction fastest (BSplines.py:354-358).
+ */
+#ifndef TIGAR_B200_H
+#define TIGAR_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TG_MAXDIM 3
+#define TG_MAXJET 16   /* max distinct derivative multi-indices per form side */
+
+/* Tensor-product basis tabulated at the Gauss points of every element of the
+ * one-cell-per-knot-span mesh (BSplines.py:505-569).  Used both for the
+ * extracted spline basis N = M_e^T phi and for the Lagrange FE basis phi.   */
+typedef struct {
+  int32_t dim;
+  int32_t n[TG_MAXDIM];     /* global basis functions per direction          */
+  int32_t nel[TG_MAXDIM];   /* elements (non-degenerate spans) per direction */
+  int32_t nloc[TG_MAXDIM];  /* local functions per element per direction     */
+  int32_t nq[TG_MAXDIM];    /* Gauss points per direction                    */
+  int32_t nder;             /* derivative orders 0..nder are tabulated       */
+  const double*  tab[TG_MAXDIM]; /* [nel][nq][nloc][nder+1]                  */
+  const int32_t* idx[TG_MAXDIM]; /* [nel][nloc] global 1-D index             */
+  const double*  wq[TG_MAXDIM];  /* [nel][nq]  Gauss weight * span length    */
+  const double*  xq[TG_MAXDIM];  /* [nel][nq]  parametric coordinate         */
+} tg_basis;
+
+/* CSR matrix whose row patterns are tensor-product windows: row (r1,r2,r3)
+ * holds the columns  lo[d][r_d] <= c_d <= hi[d][r_d], stored c1 fastest.   */
+typedef struct {
+  int32_t dim;
+  int32_t nr[TG_MAXDIM];
+  int32_t nc[TG_MAXDIM];
+  const int32_t* lo[TG_MAXDIM];
+  const int32_t* hi[TG_MAXDIM];
+  const int64_t* rowptr;     /* [nrows+1]                                    */
+} tg_win;
+
+const char* tg_last_error(void);
+int tg_version(void);
+/* number of SMs of the current device (grid sizing) */
+int tg_device_sm_count(void);
+
+/* ---- (i) extraction ---------------------------------------------------- */
+
+/* Batched span search + Cox-de Boor: BSpline1.getKnotSpan / getNodes /
+ * basisFuncs -> basisFuncsInner (BSplines.py:285-351, 73-120).  Bit-exact
+ * with the reference recurrence (no FMA contraction).
+ * out: span[n], nodes[n*(p+1)] (= (span-p+i) mod ncp), vals[n*(p+1)].      */
+int tg_bspline_eval_batch(const double* knots, int32_t nk,
+                          const double* ghostKnots, int32_t nGhost,
+                          int32_t p, int32_t ncp, int32_t mult0, int32_t multLast,
+                          const double* u, int64_t n,
+                          int32_t* span, int32_t* nodes, double* vals,
+                          void* stream);
+
+/* FE node coordinates of the CG Q_pf mesh in one direction
+ * (DOLFIN tabulate_dof_coordinates, common.py:1471-1472): node e*pf+a.     */
+int tg_fe_nodes_1d(const double* uniqueKnots, int32_t nel, int32_t pf,
+                   double* x, void* stream);
+
+/* Per-element 1-D tables in one direction:
+ *   Me[e][a][i]   = N_{first(e)+i}(x_{e,a})   1-D element extraction block
+ *   tabN[e][q][i][k] = d^k N_i/dxi^k (xi_q) = sum_a Me[e][a][i] lag[q][a][k]/h^k
+ *   tabL[e][q][a][k] = lag[q][a][k]/h^k       (Lagrange FE basis)
+ *   idxN[e][i] = (espan[e]-p+i) mod ncp ; idxL[e][a] = e*pf+a
+ *   wq[e][q] = h_wq[q]*h ; xq[e][q] = uk[e]+tq[q]*h
+ * lag/tq/gw are reference-element constants computed by the host.
+ * Replaces the per-node Python loop of common.py:1497-1509 for tensor-
+ * product B-splines (together with tg_m_fill).                              */
+int tg_tabulate_1d(const double* ghostKnots, int32_t nGhost, int32_t p, int32_t ncp,
+                   const double* uniqueKnots, const int32_t* espan, int32_t nel,
+                   int32_t pf, int32_t nq, int32_t nder,
+                   const double* lag, const double* tq, const double* gw,
+                   double* Me, double* tabN, int32_t* idxN,
+                   double* tabL, int32_t* idxL, double* wq, double* xq,
+                   void* stream);
+
+/* windowed-CSR pattern helpers */
+int tg_win_rowlen(const tg_win* h_w, int64_t* rowlen, void* stream);
+int tg_win_fill_cols(const tg_win* h_w, int32_t* cols, void* stream);
+
+/* Global extraction operator values, M = M_w (x) M_v (x) M_u on its window
+ * (AbstractCoordinateChartSpline.generateM, common.py:1516-1578).
+ * mfirst[d][I_d] = first 1-D column of node I_d (span-p), mvals[d][I_d*(p_d+1)+i]. */
+int tg_m_fill(const tg_win* h_wM, const int32_t* const* h_mfirst,
+              const double* const* h_mvals, const int32_t* h_p,
+              double* vals, void* stream);
+
+/* y = A x for a general CSR matrix (M*U of common.py:379,1259; C*p in CG)  */
+int tg_spmv(const int64_t* rowptr, const int32_t* cols, const double* vals,
+            const double* x, double* y, int64_t nrows, void* stream);
+
+/* out = M^T b without forming M^T (multTranspose, common.py:97-109):
+ * gather over the support box of each IGA function; h_wT holds the
+ * transposed ranges (rows = IGA functions, cols = FE nodes).               */
+int tg_mt_vec(const tg_win* h_wM, const tg_win* h_wT, const double* Mvals,
+              const double* b, double* out, void* stream);
+
+/* ---- (ii) Gauss-point assembly ----------------------------------------- */
+
+/* Evaluate per-Gauss-point coefficient slots with a small register-machine
+ * program (stands in for the FFC-generated tabulate_tensor of
+ * common.py:1215-1216; geometry per calculusUtils.py:18-24,56-69,255-276).
+ * Inputs of the program (registers 0..): xi_1..xi_dim, wq, then one register
+ * per requested jet (function f, multi-index alpha).
+ * h_coefs[f]: device pointer of function f's coefficients, ncomp[f] components
+ * interleaved ([n_global][ncomp]); h_jets: njets x (f, comp, a1, a2, a3).
+ * prog: nprog x (op,dst,a,b) int32 on device.  out[cell-cell0][slot][qp].   */
+int tg_qp_eval(const tg_basis* h_B, int32_t nfun, const double* const* h_coefs,
+               const int32_t* h_ncomp, int32_t njets, const int32_t* h_jets,
+               const int32_t* prog, int32_t nprog, const double* consts,
+               int32_t nreg, int32_t nout, const int32_t* h_outregs,
+               int64_t cell0, int64_t ncells, double* out, void* stream);
+
+/* A[I,J] += sum_q sum_{s,t} coef[cell][s*nT+t][q] D^{aS_s}psi_I D^{aT_t}psi_J
+ * element by element, colours processed one launch each, no atomics
+ * (dolfin::Assembler behind common.py:1215-1216).  Row = test function.
+ * With B = Lagrange basis this is A_FE; with B = extracted basis it is
+ * sum_e M_e^T K_e M_e written straight into C.                               */
+int tg_assemble_matrix(const tg_basis* h_B, const tg_win* h_W,
+                       int32_t nS, const int32_t* h_alphaS,
+                       int32_t nT, const int32_t* h_alphaT,
+                       const double* coef, int64_t cell0, int64_t ncells,
+                       double* vals, void* stream);
+
+/* same with explicit colour strides per direction (2 suffices for the CG
+ * Lagrange basis; nloc is always safe and is the default above).            */
+int tg_assemble_matrix_ex(const tg_basis* h_B, const tg_win* h_W,
+                          int32_t nS, const int32_t* h_alphaS,
+                          int32_t nT, const int32_t* h_alphaT,
+                          const int32_t* h_stride,
+                          const double* coef, int64_t cell0, int64_t ncells,
+                          double* vals, void* stream);
+
+/* b[I] += sum_q sum_s coef[cell][s][q] D^{aS_s}psi_I  (common.py:1169)       */
+int tg_assemble_vector(const tg_basis* h_B, int32_t nS, const int32_t* h_alphaS,
+                       const double* coef, int64_t cell0, int64_t ncells,
+                       double* b, void* stream);
+
+int tg_assemble_vector_ex(const tg_basis* h_B, int32_t nS, const int32_t* h_alphaS,
+                          const int32_t* h_stride, const double* coef,
+                          int64_t cell0, int64_t ncells, double* b, void* stream);
+
+/* sum over all entries (functional assembly, poisson.py:132); result on device */
+int tg_sum(const double* x, int64_t n, double* out1, void* stream);
+
+/* ---- (iii) triple product, BCs, solve ---------------------------------- */
+
+/* AP = A M on its window (first half of MatPtAP, common.py:1194-1195).
+ * h_wMT: transposed ranges of M.                                            */
+int tg_ptap_ap(const tg_win* h_wA, const double* Avals,
+               const tg_win* h_wM, const double* Mvals, const tg_win* h_wMT,
+               const tg_win* h_wP, double* APvals, void* stream);
+/* C = M^T (AP).  h_wPT: transposed ranges of AP.                             */
+int tg_ptap_c(const tg_win* h_wM, const double* Mvals, const tg_win* h_wMT,
+              const tg_win* h_wP, const double* APvals, const tg_win* h_wPT,
+              const tg_win* h_wC, double* Cvals, void* stream);
+
+/* zeroRowsColumns(zeroDofs, diag) (common.py:1199-1200); mask[i]!=0 marks a
+ * constrained DoF.                                                          */
+int tg_zero_rows_cols(const int64_t* rowptr, const int32_t* cols, double* vals,
+                      int64_t nrows, const uint8_t* mask, double diag, void* stream);
+/* b[zeroDofs] = 0 (common.py:1154-1158) */
+int tg_zero_entries(double* b, const uint8_t* mask, int64_t n, void* stream);
+
+/* dinv[i] = 1/C[i,i] */
+int tg_diag_inv(const int64_t* rowptr, const int32_t* cols, const double* vals,
+                int64_t nrows, int64_t row0, double* dinv, void* stream);
+
+/* Jacobi-preconditioned CG, all iteration state on the device, one host
+ * check every `check_every` iterations (solve() of common.py:1255-1258).
+ * work: 4*n + tg_cg_scratch_len() + 8 doubles.  Synchronises before
+ * returning.  Reductions are two-stage on a fixed grid: deterministic.     */
+int tg_cg_scratch_len(void);
+int tg_solve_cg(const int64_t* rowptr, const int32_t* cols, const double* vals,
+                const double* b, double* x, int64_t n,
+                double rtol, double atol, int32_t maxit, int32_t check_every,
+                double* work, int32_t* h_iters, double* h_relres, void* stream);
+
+/* CG building blocks for the row-distributed multi-GPU solver (the host
+ * interleaves torch.distributed halo exchange / all-reduce between them).
+ * scratch: tg_cg_scratch_len() doubles.
+ *   spmv_dot : y = A x (local rows; cols index the extended vector x),
+ *              out1[0] = sum_r x[xoff+r]*y[r]
+ *   init     : r = b - y ; p = dinv r ; out2 = {r.dinv.r, r.r}
+ *   axpy_dot : a = num[0]/den[0]; x += a p; r -= a q; out2 = {r.dinv.r, r.r}
+ *   xpby     : p = dinv*r + (num[0]/den[0]) p
+ *   dot      : out1[0] = a.b                                               */
+int tg_cg_spmv_dot(const int64_t* rowptr, const int32_t* cols, const double* vals,
+                   const double* x, int64_t xoff, double* y, int64_t nrows,
+                   double* scratch, double* out1, void* stream);
+int tg_cg_init(const double* b, const double* y, const double* dinv, double* r,
+               double* p, int64_t n, double* scratch, double* out2, void* stream);
+int tg_cg_axpy_dot(double* x, double* r, const double* p, const double* q,
+                   const double* dinv, int64_t n, const double* num, const double* den,
+                   double* scratch, double* out2, void* stream);
+int tg_cg_xpby(double* p, const double* r, const double* dinv, int64_t n,
+               const double* num, const double* den, void* stream);
+int tg_dot(const double* a, const double* b, int64_t n, double* scratch,
+           double* out1, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,22 @@
+// Error state and small queries of the C-ABI.
+#include "tg_common.cuh"
+#include <stdarg.h>
+
+static thread_local char g_err[1024] = "";
+
+void tg_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* tg_last_error(void) { return g_err; }
+extern "C" int tg_version(void) { return 100; }
+
+extern "C" int tg_device_sm_count(void) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  return sms;
+}

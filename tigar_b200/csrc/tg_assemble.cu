@@ -1,0 +1,376 @@
+// Gauss-point assembly of element matrices/vectors on a tensor-product basis,
+// written into a windowed CSR matrix by colouring (no atomics).
+// Reference: dolfin::Assembler behind common.py:1215-1216 (matrix) and
+// :1169 (vector).  With the extracted basis (tabN) this computes
+// sum_e M_e^T K_e M_e directly (the element-fused M^T A M of SURVEY 7.1-5b).
+#include "tg_common.cuh"
+
+struct TgAlpha {
+  int n;
+  signed char al[TG_MAXJET][3];
+};
+
+struct TgColour {
+  int k[3];       // first cell of this colour per direction
+  int cnt[3];     // cells of this colour per direction
+  int stride[3];
+};
+
+__device__ inline double tg_jet1(const TgBasis& B, const int* e, const int* q, const int* a,
+                                 const signed char* al) {
+  const int nd = B.nder + 1;
+  double v = B.tab[0][(((int64_t)e[0] * B.nq[0] + q[0]) * B.nloc[0] + a[0]) * nd + al[0]];
+  if (B.dim > 1) v *= B.tab[1][(((int64_t)e[1] * B.nq[1] + q[1]) * B.nloc[1] + a[1]) * nd + al[1]];
+  if (B.dim > 2) v *= B.tab[2][(((int64_t)e[2] * B.nq[2] + q[2]) * B.nloc[2] + a[2]) * nd + al[2]];
+  return v;
+}
+
+__device__ inline void tg_colour_cell(const TgColour& C, int dim, int64_t bid, int* e) {
+  int m0 = (int)(bid % C.cnt[0]);
+  int64_t r = bid / C.cnt[0];
+  int m1 = (int)(r % C.cnt[1]);
+  int m2 = (int)(r / C.cnt[1]);
+  e[0] = C.k[0] + C.stride[0] * m0;
+  e[1] = (dim > 1) ? C.k[1] + C.stride[1] * m1 : 0;
+  e[2] = (dim > 2) ? C.k[2] + C.stride[2] * m2 : 0;
+}
+
+template <int NACC>
+__global__ void __launch_bounds__(256)
+k_assemble_matrix(TgBasis B, TgWin W, TgAlpha S, TgAlpha T, int sameST,
+                  const double* __restrict__ coef, int64_t cell0, TgColour C, int QC,
+                  double* __restrict__ vals) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nen = B.nloc[0] * B.nloc[1] * B.nloc[2];
+  const int nqp = B.nq[0] * B.nq[1] * B.nq[2];
+  const int nS = S.n, nT = T.n;
+  const int tid = threadIdx.x, nth = blockDim.x;
+
+  int e[3];
+  tg_colour_cell(C, B.dim, blockIdx.x, e);
+  const int64_t cell = e[0] + (int64_t)B.nel[0] * (e[1] + (int64_t)B.nel[1] * e[2]);
+  const double* cc = coef + (cell - cell0) * (int64_t)nS * nT * nqp;
+
+  // smem carve-up
+  double* BJS = (double*)smem_raw;                 // [QC][nS][nen]
+  double* BJT = sameST ? BJS : BJS + (size_t)QC * nS * nen;   // [QC][nT][nen]
+  double* G = BJT + (size_t)QC * nT * nen;         // [QC][nS][nen]
+  double* cs = G + (size_t)QC * nS * nen;          // [QC][nS*nT]
+  long long* rbase = (long long*)(cs + (size_t)QC * nS * nT);   // [nen]
+  int* gc = (int*)(rbase + nen);                   // [nen][3]
+  int* rlo = gc + 3 * nen;                         // [nen][3]
+  int* rlen = rlo + 3 * nen;                       // [nen][3]
+
+  for (int a = tid; a < nen; a += nth) {
+    int al[3];
+    tg_decode(a, B.nloc, B.dim, al);
+    int g[3] = {0, 0, 0};
+    for (int d = 0; d < B.dim; d++) g[d] = B.idx[d][e[d] * B.nloc[d] + al[d]];
+    int64_t row = g[0] + (int64_t)W.nr[0] * (g[1] + (int64_t)W.nr[1] * g[2]);
+    TgRowWin rw = tg_row_window(W, g);
+    rbase[a] = W.rowptr[row];
+    for (int d = 0; d < 3; d++) {
+      gc[3 * a + d] = g[d];
+      rlo[3 * a + d] = rw.lo[d];
+      rlen[3 * a + d] = rw.len[d];
+    }
+  }
+
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; i++) acc[i] = 0.0;
+
+  for (int q0 = 0; q0 < nqp; q0 += QC) {
+    const int nqc = min(QC, nqp - q0);
+    __syncthreads();
+    for (int i = tid; i < nqc * nS * nen; i += nth) {
+      int a = i % nen;
+      int t = i / nen;
+      int s = t % nS;
+      int ql = t / nS;
+      int q[3], al[3];
+      tg_decode(q0 + ql, B.nq, B.dim, q);
+      tg_decode(a, B.nloc, B.dim, al);
+      BJS[i] = tg_jet1(B, e, q, al, S.al[s]);
+    }
+    if (!sameST) {
+      for (int i = tid; i < nqc * nT * nen; i += nth) {
+        int a = i % nen;
+        int t = i / nen;
+        int s = t % nT;
+        int ql = t / nT;
+        int q[3], al[3];
+        tg_decode(q0 + ql, B.nq, B.dim, q);
+        tg_decode(a, B.nloc, B.dim, al);
+        BJT[i] = tg_jet1(B, e, q, al, T.al[s]);
+      }
+    }
+    for (int i = tid; i < nqc * nS * nT; i += nth) {
+      int st = i % (nS * nT);
+      int ql = i / (nS * nT);
+      cs[i] = cc[(int64_t)st * nqp + q0 + ql];
+    }
+    __syncthreads();
+    for (int i = tid; i < nqc * nS * nen; i += nth) {
+      int b = i % nen;
+      int t = i / nen;
+      int s = t % nS;
+      int ql = t / nS;
+      double g = 0.0;
+      for (int tt = 0; tt < nT; tt++)
+        g += cs[(ql * nS + s) * nT + tt] * BJT[(ql * nT + tt) * nen + b];
+      G[i] = g;
+    }
+    __syncthreads();
+    const int nk = nqc * nS;
+#pragma unroll
+    for (int i = 0; i < NACC; i++) {
+      int pair = tid + i * nth;
+      if (pair < nen * nen) {
+        int a = pair / nen, b = pair - a * nen;
+        double s = 0.0;
+        for (int k = 0; k < nk; k++) s += BJS[k * nen + a] * G[k * nen + b];
+        acc[i] += s;
+      }
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < NACC; i++) {
+    int pair = tid + i * nth;
+    if (pair < nen * nen) {
+      int a = pair / nen, b = pair - a * nen;
+      int pos = ((gc[3 * b + 2] - rlo[3 * a + 2]) * rlen[3 * a + 1] +
+                 (gc[3 * b + 1] - rlo[3 * a + 1])) * rlen[3 * a + 0] +
+                (gc[3 * b + 0] - rlo[3 * a + 0]);
+      vals[rbase[a] + pos] += acc[i];
+    }
+  }
+}
+
+static int tg_colour_setup(const tg_basis* h_B, const int32_t* h_stride, int64_t cell0,
+                           int64_t ncells, int* elo, int* ehi) {
+  int dim = h_B->dim;
+  int64_t slab = 1;
+  for (int d = 0; d < dim - 1; d++) slab *= h_B->nel[d];
+  TG_REQUIRE(cell0 % slab == 0 && ncells % slab == 0,
+             "cell range must be whole slabs of the last direction");
+  *elo = (int)(cell0 / slab);
+  *ehi = (int)((cell0 + ncells) / slab);
+  TG_REQUIRE(*ehi <= h_B->nel[dim - 1], "cell range exceeds patch");
+  for (int d = 0; d < dim; d++) TG_REQUIRE(h_stride[d] >= 1, "colour stride");
+  return 0;
+}
+
+// iterate colours; fn(colour) launches one kernel
+template <class F>
+static int tg_for_colours(const tg_basis* h_B, const int32_t* h_stride, int elo, int ehi, F fn) {
+  int dim = h_B->dim;
+  int st[3] = {1, 1, 1}, lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+  for (int d = 0; d < dim; d++) {
+    st[d] = h_stride[d];
+    hi[d] = h_B->nel[d];
+  }
+  lo[dim - 1] = elo;
+  hi[dim - 1] = ehi;
+  for (int k2 = 0; k2 < st[2]; k2++)
+    for (int k1 = 0; k1 < st[1]; k1++)
+      for (int k0 = 0; k0 < st[0]; k0++) {
+        TgColour C;
+        int kk[3] = {k0, k1, k2};
+        int64_t n = 1;
+        for (int d = 0; d < 3; d++) {
+          // first cell >= lo[d] congruent to kk[d] mod st[d]
+          int first = lo[d] + ((kk[d] - lo[d]) % st[d] + st[d]) % st[d];
+          C.k[d] = first;
+          C.stride[d] = st[d];
+          C.cnt[d] = (first < hi[d]) ? (hi[d] - first + st[d] - 1) / st[d] : 0;
+          n *= C.cnt[d];
+        }
+        if (n == 0) continue;
+        int rc = fn(C, n);
+        if (rc) return rc;
+      }
+  return 0;
+}
+
+static int g_smem_optin = -1;
+static int tg_smem_limit() {
+  if (g_smem_optin < 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  }
+  return g_smem_optin;
+}
+
+extern "C" int tg_assemble_matrix_ex(const tg_basis* h_B, const tg_win* h_W, int32_t nS,
+                                     const int32_t* h_alphaS, int32_t nT,
+                                     const int32_t* h_alphaT, const int32_t* h_stride,
+                                     const double* coef, int64_t cell0, int64_t ncells,
+                                     double* vals, void* stream) {
+  TG_REQUIRE(nS >= 1 && nS <= TG_MAXJET && nT >= 1 && nT <= TG_MAXJET, "jet count");
+  TgBasis B = tg_basis_dev(h_B);
+  TgWin W = tg_win_dev(h_W);
+  TgAlpha S, T;
+  S.n = nS;
+  T.n = nT;
+  int same = (nS == nT);
+  for (int s = 0; s < nS; s++)
+    for (int d = 0; d < 3; d++) {
+      S.al[s][d] = (signed char)h_alphaS[3 * s + d];
+      TG_REQUIRE(h_alphaS[3 * s + d] <= h_B->nder, "derivative order not tabulated");
+    }
+  for (int s = 0; s < nT; s++)
+    for (int d = 0; d < 3; d++) {
+      T.al[s][d] = (signed char)h_alphaT[3 * s + d];
+      TG_REQUIRE(h_alphaT[3 * s + d] <= h_B->nder, "derivative order not tabulated");
+      if (same && T.al[s][d] != S.al[s][d]) same = 0;
+    }
+  int elo, ehi;
+  int rc = tg_colour_setup(h_B, h_stride, cell0, ncells, &elo, &ehi);
+  if (rc) return rc;
+  const int nen = B.nloc[0] * B.nloc[1] * B.nloc[2];
+  const int nqp = B.nq[0] * B.nq[1] * B.nq[2];
+  const int nth = 256;
+  // q-chunk so that smem fits (target <= ~100 KB to keep 2 CTAs/SM when possible)
+  size_t fixed = (size_t)nen * (8 + 9 * 4) + 64;
+  size_t perq = ((size_t)nS * nen * (same ? 2 : 1) + (same ? 0 : (size_t)nT * nen) +
+                 (size_t)nS * nen * (same ? 0 : 1) + (size_t)nS * nT) * 8;
+  // (same: BJS + G ; distinct: BJS + BJT + G)
+  perq = ((size_t)nS * nen + (same ? 0 : (size_t)nT * nen) + (size_t)nS * nen + (size_t)nS * nT) * 8;
+  size_t budget = 100 * 1024;
+  int limit = tg_smem_limit();
+  int QC = (int)((budget - fixed) / perq);
+  if (QC < 1) {
+    QC = (int)(((size_t)limit - fixed) / perq);
+    TG_REQUIRE(QC >= 1, "element too large for shared memory");
+  }
+  if (QC > nqp) QC = nqp;
+  size_t smem = fixed + perq * QC;
+  int npair = nen * nen;
+  int nacc = (npair + nth - 1) / nth;
+  cudaStream_t s = tg_stream(stream);
+
+#define TG_LAUNCH_ASM(N)                                                                      \
+  {                                                                                           \
+    TG_CHECK(cudaFuncSetAttribute(k_assemble_matrix<N>,                                       \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    rc = tg_for_colours(h_B, h_stride, elo, ehi, [&](const TgColour& C, int64_t n) -> int {   \
+      k_assemble_matrix<N><<<(unsigned)n, nth, smem, s>>>(B, W, S, T, same, coef, cell0, C,   \
+                                                          QC, vals);                          \
+      TG_LAUNCH_CHECK();                                                                      \
+      return 0;                                                                               \
+    });                                                                                       \
+  }
+  if (nacc <= 1) TG_LAUNCH_ASM(1)
+  else if (nacc <= 2) TG_LAUNCH_ASM(2)
+  else if (nacc <= 4) TG_LAUNCH_ASM(4)
+  else if (nacc <= 8) TG_LAUNCH_ASM(8)
+  else if (nacc <= 16) TG_LAUNCH_ASM(16)
+  else if (nacc <= 32) TG_LAUNCH_ASM(32)
+  else if (nacc <= 64) TG_LAUNCH_ASM(64)
+  else if (nacc <= 184) TG_LAUNCH_ASM(184)
+  else {
+    tg_set_error("element with %d local functions is too large", nen);
+    return 2;
+  }
+#undef TG_LAUNCH_ASM
+  return rc;
+}
+
+extern "C" int tg_assemble_matrix(const tg_basis* h_B, const tg_win* h_W, int32_t nS,
+                                  const int32_t* h_alphaS, int32_t nT, const int32_t* h_alphaT,
+                                  const double* coef, int64_t cell0, int64_t ncells,
+                                  double* vals, void* stream) {
+  int32_t stride[3];
+  for (int d = 0; d < 3; d++) stride[d] = (d < h_B->dim) ? h_B->nloc[d] : 1;
+  return tg_assemble_matrix_ex(h_B, h_W, nS, h_alphaS, nT, h_alphaT, stride, coef, cell0,
+                               ncells, vals, stream);
+}
+
+// element vector: one block per cell, threads over local functions
+__global__ void k_assemble_vector(TgBasis B, TgAlpha S, const double* __restrict__ coef,
+                                  int64_t cell0, TgColour C, double* __restrict__ bvec) {
+  const int nen = B.nloc[0] * B.nloc[1] * B.nloc[2];
+  const int nqp = B.nq[0] * B.nq[1] * B.nq[2];
+  int e[3];
+  tg_colour_cell(C, B.dim, blockIdx.x, e);
+  const int64_t cell = e[0] + (int64_t)B.nel[0] * (e[1] + (int64_t)B.nel[1] * e[2]);
+  const double* cc = coef + (cell - cell0) * (int64_t)S.n * nqp;
+  for (int a = threadIdx.x; a < nen; a += blockDim.x) {
+    int al[3];
+    tg_decode(a, B.nloc, B.dim, al);
+    double acc = 0.0;
+    for (int qp = 0; qp < nqp; qp++) {
+      int q[3];
+      tg_decode(qp, B.nq, B.dim, q);
+      for (int s = 0; s < S.n; s++) acc += cc[(int64_t)s * nqp + qp] * tg_jet1(B, e, q, al, S.al[s]);
+    }
+    int64_t g = 0, mul = 1;
+    for (int d = 0; d < B.dim; d++) {
+      g += mul * B.idx[d][e[d] * B.nloc[d] + al[d]];
+      mul *= B.n[d];
+    }
+    bvec[g] += acc;
+  }
+}
+
+extern "C" int tg_assemble_vector_ex(const tg_basis* h_B, int32_t nS, const int32_t* h_alphaS,
+                                     const int32_t* h_stride, const double* coef,
+                                     int64_t cell0, int64_t ncells, double* b, void* stream) {
+  TG_REQUIRE(nS >= 1 && nS <= TG_MAXJET, "jet count");
+  TgBasis B = tg_basis_dev(h_B);
+  TgAlpha S;
+  S.n = nS;
+  for (int s = 0; s < nS; s++)
+    for (int d = 0; d < 3; d++) {
+      S.al[s][d] = (signed char)h_alphaS[3 * s + d];
+      TG_REQUIRE(h_alphaS[3 * s + d] <= h_B->nder, "derivative order not tabulated");
+    }
+  int elo, ehi;
+  int rc = tg_colour_setup(h_B, h_stride, cell0, ncells, &elo, &ehi);
+  if (rc) return rc;
+  const int nen = B.nloc[0] * B.nloc[1] * B.nloc[2];
+  int nth = nen < 32 ? 32 : (nen > 256 ? 256 : ((nen + 31) / 32) * 32);
+  cudaStream_t s = tg_stream(stream);
+  return tg_for_colours(h_B, h_stride, elo, ehi, [&](const TgColour& C, int64_t n) -> int {
+    k_assemble_vector<<<(unsigned)n, nth, 0, s>>>(B, S, coef, cell0, C, b);
+    TG_LAUNCH_CHECK();
+    return 0;
+  });
+}
+
+extern "C" int tg_assemble_vector(const tg_basis* h_B, int32_t nS, const int32_t* h_alphaS,
+                                  const double* coef, int64_t cell0, int64_t ncells, double* b,
+                                  void* stream) {
+  int32_t stride[3];
+  for (int d = 0; d < 3; d++) stride[d] = (d < h_B->dim) ? h_B->nloc[d] : 1;
+  return tg_assemble_vector_ex(h_B, nS, h_alphaS, stride, coef, cell0, ncells, b, stream);
+}
+
+__global__ void k_sum(const double* __restrict__ x, int64_t n, double* __restrict__ out) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    acc += x[i];
+  acc = tg_warp_sum(acc);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sh[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    acc = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+    acc = tg_warp_sum(acc);
+    if (lane == 0) atomicAdd(out, acc);
+  }
+}
+
+extern "C" int tg_sum(const double* x, int64_t n, double* out1, void* stream) {
+  TG_CHECK(cudaMemsetAsync(out1, 0, sizeof(double), tg_stream(stream)));
+  if (n == 0) return 0;
+  int grid = (int)(tg_cdiv(n, 256) < 1184 ? tg_cdiv(n, 256) : 1184);
+  k_sum<<<grid, 256, 0, tg_stream(stream)>>>(x, n, out1);
+  TG_LAUNCH_CHECK();
+  return 0;
+}
