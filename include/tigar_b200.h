@@ -98,6 +98,11 @@ int tg_tabulate_1d(const double* ghostKnots, int32_t nGhost, int32_t p, int32_t 
 
 /* windowed-CSR pattern helpers */
 int tg_win_rowlen(const tg_win* h_w, int64_t* rowlen, void* stream);
+/* rowptr[nrows+1] from the exclusive prefix sums S_d[nr_d+1] (device, int64)
+ * of the per-direction window lengths (PETSc MatSetPreallocation equivalent,
+ * common.py:1483-1492): closed form, no scan.                                */
+int tg_win_rowptr(const tg_win* h_w, const int64_t* const* h_S, int64_t* rowptr,
+                  void* stream);
 int tg_win_fill_cols(const tg_win* h_w, int32_t* cols, void* stream);
 
 /* Global extraction operator values, M = M_w (x) M_v (x) M_u on its window
@@ -176,6 +181,26 @@ int tg_ptap_ap(const tg_win* h_wA, const double* Avals,
 int tg_ptap_c(const tg_win* h_wM, const double* Mvals, const tg_win* h_wMT,
               const tg_win* h_wP, const double* APvals, const tg_win* h_wPT,
               const tg_win* h_wC, double* Cvals, void* stream);
+
+/* ---- windowed-CSR operators (no column array: 8 B per non-zero) ---------- */
+/* y = C x  (MatMult inside KSP, common.py:1255-1258; M*U, common.py:379,1259) */
+int tg_win_spmv(const tg_win* h_w, const double* vals, const double* x, double* y,
+                void* stream);
+/* y = C x and out1[0] = sum_r x[xoff+r] y[r]; scratch: tg_cg_scratch_len()   */
+int tg_win_spmv_dot(const tg_win* h_w, const double* vals, const double* x, int64_t xoff,
+                    double* y, double* scratch, double* out1, void* stream);
+/* zeroRowsColumns on the window pattern; rowmask over local rows, colmask over
+ * columns; col_shift = offset of the row's own column in the last direction
+ * (0 unless the block is a slab of a row-distributed matrix).                */
+int tg_win_zero_rows_cols(const tg_win* h_w, double* vals, const uint8_t* rowmask,
+                          const uint8_t* colmask, double diag, int32_t col_shift,
+                          void* stream);
+int tg_win_diag_inv(const tg_win* h_w, const double* vals, int32_t col_shift, double* dinv,
+                    void* stream);
+/* Jacobi-CG on a windowed matrix; same contract as tg_solve_cg.             */
+int tg_win_solve_cg(const tg_win* h_w, const double* vals, const double* b, double* x,
+                    double rtol, double atol, int32_t maxit, int32_t check_every,
+                    double* work, int32_t* h_iters, double* h_relres, void* stream);
 
 /* zeroRowsColumns(zeroDofs, diag) (common.py:1199-1200); mask[i]!=0 marks a
  * constrained DoF.                                                          */

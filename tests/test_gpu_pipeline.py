@@ -1,0 +1,212 @@
+"""GPU parity, layers (ii)+(iii): Gauss-point assembly, M^T A M / M^T b, BCs
+and the solve, against the oracle on the same inputs.
+
+Tolerances (floating point; stated per north_star): matrices/vectors agree to
+1e-12 relative (different summation order), solutions to 1e-10 relative in the
+IGA DoF vector (BASELINE.json: ||u_new - u_ref|| / ||u_ref|| < 1e-10)."""
+import math
+
+import numpy as np
+import pytest
+
+from gpu_util import make_pair, uk, rel, relm
+
+pytestmark = pytest.mark.gpu
+
+PI = math.pi
+
+
+def poisson_forms(spline, kind="sin"):
+    from tIGAr import TrialFunction, TestFunction, inner, sin
+    u, v = TrialFunction(spline.V), TestFunction(spline.V)
+    x = spline.spatialCoordinates()
+    if kind == "sin":
+        f = 1.0
+        for d in range(len(x)):
+            f = f * sin(PI * x[d])
+        f = f * (len(x) * PI ** 2)
+    else:
+        f = x[0] * x[0] + 1.0
+    a = inner(spline.grad(u), spline.grad(v)) * spline.dx
+    L = inner(f, v) * spline.dx
+    return a, L
+
+
+def f_np(kind, dim):
+    if kind == "sin":
+        return lambda X: dim * PI ** 2 * np.prod(np.sin(PI * X[..., :dim]), axis=-1)
+    return lambda X: X[..., 0] ** 2 + 1.0
+
+
+CASES = [([2, 2], [6, 5]), ([3, 3], [4, 5]), ([2, 3], [4, 4]), ([2, 2, 2], [3, 2, 3]),
+         ([3, 3, 3], [2, 3, 2]), ([2], [7])]
+
+
+@pytest.mark.parametrize("deg,nels", CASES)
+def test_fe_assembly_and_ptap_match_oracle(deg, nels):
+    from tigar_b200 import dev
+    kv = [uk(p, n) for p, n in zip(deg, nels)]
+    gen, spline, pr = make_pair(deg, kv, mode="csr")
+    a, L = poisson_forms(spline, "poly")
+    pr.extract()
+    pr.assemble(f_np("poly", len(deg)))
+    pr.ptap()
+    # cpFuncs = M_control * P  (common.py:367-380)
+    for i in range(spline.nsd + 1):
+        assert np.abs(spline.cpFuncs[i].vector().get_local() - pr.cpn[:, i]).max() < 1e-14
+    A = spline._assemble_kind(a, "fe")
+    assert relm(A.to_scipy(), pr.Afe) < 1e-12
+    b = spline._assemble_kind(L, "fe")
+    assert rel(dev.to_np(b), pr.bfe) < 1e-12
+    C0 = spline.extractMatrix(A, applyBCs=False)
+    assert relm(C0.to_scipy(), pr.C0) < 1e-12
+    MTb0 = spline.extractVector(b, applyBCs=False)
+    assert rel(MTb0.get_local(), pr.b0) < 1e-12
+    C = spline.assembleMatrix(a, diag=3.5)
+    pr.ptap(diag=3.5)
+    assert relm(C.to_scipy(), pr.C) < 1e-12
+    Cd = C.to_scipy().toarray()
+    z = np.unique(pr.zeroDofs)
+    assert np.all(Cd[z, z] == 3.5)
+    MTb = spline.assembleVector(L)
+    assert rel(MTb.get_local(), pr.b) < 1e-12
+    assert not MTb.get_local()[z].any()
+
+
+@pytest.mark.parametrize("deg,nels", CASES)
+def test_fused_equals_csr_path(deg, nels):
+    kv = [uk(p, n) for p, n in zip(deg, nels)]
+    gen, spline, pr = make_pair(deg, kv, mode="fused")
+    a, L = poisson_forms(spline, "sin")
+    pr.extract()
+    pr.assemble(f_np("sin", len(deg)))
+    pr.ptap()
+    C = spline.assembleMatrix(a)
+    assert relm(C.to_scipy(), pr.C) < 1e-12
+    MTb = spline.assembleVector(L)
+    assert rel(MTb.get_local(), pr.b) < 1e-12
+
+
+@pytest.mark.parametrize("mode", ["csr", "fused"])
+@pytest.mark.parametrize("deg,nels", [([2, 2], [16, 16]), ([3, 3], [10, 10]), ([3, 3, 3], [5, 4, 5]),
+                                      ([2, 2, 2], [8, 8, 8])])
+def test_poisson_solution_matches_oracle(deg, nels, mode):
+    from tIGAr import Function, assemble
+    kv = [uk(p, n) for p, n in zip(deg, nels)]
+    gen, spline, pr = make_pair(deg, kv, mode=mode)
+    a, L = poisson_forms(spline, "sin")
+    u = Function(spline.V)
+    MTU = spline.solveLinearVariationalProblem(a == L, u)
+    Uo = pr.run(f_np("sin", len(deg)))             # oracle: sparse LU
+    assert rel(MTU.get_local(), Uo) < 1e-10        # the north_star tolerance
+    # FE representation u = M U (common.py:1259)
+    assert rel(u.vector().get_local(), pr.M @ Uo) < 1e-10
+    # L2 error functional (poisson.py:132)
+    x = spline.spatialCoordinates()
+    from tIGAr import sin
+    soln = 1.0
+    for d in range(len(deg)):
+        soln = soln * sin(PI * x[d])
+    err = math.sqrt(assemble(((u - soln) ** 2) * spline.dx))
+    exact = lambda X: np.prod(np.sin(PI * X[..., :len(deg)]), axis=-1)
+    erro = pr.error(Uo, "l2", exact)
+    assert abs(err - erro) / erro < 1e-7
+
+
+def test_biharmonic_matches_oracle():
+    from tIGAr import TrialFunction, TestFunction, Function, inner, cos, assemble
+    deg, nels = [4, 4], [8, 8]
+    kv = [uk(p, n, -1.0, 1.0) for p, n in zip(deg, nels)]
+    for mode in ("csr", "fused"):
+        gen, spline, pr = make_pair(deg, kv, nLayers=2, form="biharmonic", mode=mode)
+        u, v = TrialFunction(spline.V), TestFunction(spline.V)
+        lap = lambda w: spline.div(spline.grad(w))
+        x = spline.spatialCoordinates()
+        cx, cy = cos(PI * x[0]), cos(PI * x[1])
+        f = PI ** 4 * (cx * (cy + 1.0) + 2.0 * cx * cy + (cx + 1.0) * cy)
+        res = inner(lap(u), lap(v)) * spline.dx - inner(f, v) * spline.dx
+        uh = Function(spline.V)
+        MTU = spline.solveLinearVariationalProblem(res, uh)
+        fo = lambda X: PI ** 4 * (np.cos(PI * X[..., 0]) * (np.cos(PI * X[..., 1]) + 1)
+                                  + 2 * np.cos(PI * X[..., 0]) * np.cos(PI * X[..., 1])
+                                  + (np.cos(PI * X[..., 0]) + 1) * np.cos(PI * X[..., 1]))
+        Uo = pr.run(fo)
+        assert relm(spline.assembleMatrix(inner(lap(u), lap(v)) * spline.dx).to_scipy(), pr.C) < 1e-11
+        assert rel(MTU.get_local(), Uo) < 1e-8      # cond ~ h^-4: looser than Poisson
+        soln = (cx + 1.0) * (cy + 1.0)
+        en = math.sqrt(assemble((lap(uh - soln) ** 2) * spline.dx))
+        lapo = lambda X: -PI ** 2 * (np.cos(PI * X[..., 0]) * (np.cos(PI * X[..., 1]) + 1)
+                                     + (np.cos(PI * X[..., 0]) + 1) * np.cos(PI * X[..., 1]))
+        eo = pr.error(Uo, "energy", lapo)
+        assert abs(en - eo) / eo < 1e-5
+
+
+def test_manufactured_force_from_div_grad():
+    """f = -div(grad(soln)) as the demo writes it (poisson.py:112-114) equals
+    the closed form."""
+    from tIGAr import TestFunction, inner, sin
+    deg, nels = [3, 3], [6, 6]
+    kv = [uk(p, n) for p, n in zip(deg, nels)]
+    gen, spline, pr = make_pair(deg, kv, mode="csr")
+    v = TestFunction(spline.V)
+    x = spline.spatialCoordinates()
+    soln = sin(PI * x[0]) * sin(PI * x[1])
+    f = -spline.div(spline.grad(soln))
+    b1 = spline.assembleVector(inner(f, v) * spline.dx, applyBCs=False).get_local()
+    b2 = spline.assembleVector(inner(2 * PI ** 2 * soln, v) * spline.dx, applyBCs=False).get_local()
+    assert rel(b1, b2) < 1e-9
+
+
+def test_generic_csr_kernels_match_windowed():
+    """tg_spmv / tg_zero_rows_cols / tg_solve_cg (general CSR) against the
+    windowed variants and scipy."""
+    import ctypes as C
+    from tigar_b200 import dev
+    from tigar_b200._lib import lib, check
+    deg, nels = [2, 2], [7, 6]
+    kv = [uk(p, n) for p, n in zip(deg, nels)]
+    gen, spline, pr = make_pair(deg, kv, mode="csr")
+    a, L = poisson_forms(spline, "sin")
+    Cm = spline.assembleMatrix(a)
+    b = spline.assembleVector(L)
+    w = Cm.window
+    rp, cols = w.rowptr(), w.columns()
+    n = w.nrows
+    rng = np.random.RandomState(1)
+    x = dev.from_np(rng.rand(n))
+    y1, y2 = dev.empty(n), dev.empty(n)
+    check(lib.tg_spmv(dev.ptr(rp), dev.ptr(cols), dev.ptr(Cm.vals), dev.ptr(x), dev.ptr(y1), n,
+                      dev.stream()))
+    Cm.matvec(x, y2)
+    assert np.abs(dev.to_np(y1) - dev.to_np(y2)).max() < 1e-12
+    assert np.abs(dev.to_np(y1) - Cm.to_scipy() @ dev.to_np(x)).max() < 1e-12
+    sol = dev.zeros(n)
+    work = dev.empty(4 * n + lib.tg_cg_scratch_len() + 8)
+    its, relres = C.c_int32(0), C.c_double(0)
+    check(lib.tg_solve_cg(dev.ptr(rp), dev.ptr(cols), dev.ptr(Cm.vals), dev.ptr(b.t), dev.ptr(sol),
+                          n, 1e-13, 0.0, 10000, 10, dev.ptr(work), C.byref(its), C.byref(relres),
+                          dev.stream()))
+    import scipy.sparse.linalg as spla
+    ref = spla.spsolve(Cm.to_scipy().tocsc(), b.get_local())
+    assert rel(dev.to_np(sol), ref) < 1e-10 and its.value > 0
+    # general-CSR zeroRowsColumns
+    A2 = spline.assembleMatrix(a, applyBCs=False)
+    check(lib.tg_zero_rows_cols(dev.ptr(rp), dev.ptr(cols), dev.ptr(A2.vals), n,
+                                dev.ptr(spline._bc_mask()), 1.0, dev.stream()))
+    assert np.array_equal(dev.to_np(A2.vals), dev.to_np(Cm.vals))
+
+
+def test_write_and_read_extraction(tmp_path):
+    from tIGAr import ExtractedSpline, Function
+    deg, nels = [2, 2], [5, 5]
+    kv = [uk(p, n) for p, n in zip(deg, nels)]
+    gen, spline, pr = make_pair(deg, kv, mode="csr")
+    d = str(tmp_path / "extraction")
+    gen.writeExtraction(d)
+    sp2 = ExtractedSpline(d, 4, mode="csr")
+    a, L = poisson_forms(spline, "sin")
+    a2, L2 = poisson_forms(sp2, "sin")
+    u1, u2 = Function(spline.V), Function(sp2.V)
+    U1 = spline.solveLinearVariationalProblem(a == L, u1).get_local()
+    U2 = sp2.solveLinearVariationalProblem(a2 == L2, u2).get_local()
+    assert rel(U1, U2) < 1e-12

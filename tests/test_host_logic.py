@@ -1,0 +1,176 @@
+"""CPU tests of the product's host logic (no device work): knot bookkeeping vs
+the reference golden, symbolic compiler vs direct evaluation, form language,
+C-ABI surface."""
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tigar_b200 import bsplines as PB
+from tigar_b200 import symbolic as S
+from tigar_b200 import ufl_lite as U
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_uniform_knots_and_spline1_state(golden):
+    for i, a in enumerate(golden["uk_args"]):
+        got = PB.uniformKnots(int(a[0]), a[1], a[2], int(a[3]), bool(a[4]), int(a[5]))
+        assert np.array_equal(np.array(got, dtype=float), golden["uk_%d" % i])
+    for name in golden["s1_names"]:
+        pre = "s1_%s_" % name
+        s = PB.BSpline1(int(golden[pre + "p"]), golden[pre + "knots"])
+        assert s.nel == int(golden[pre + "nel"]) and s.ncp == int(golden[pre + "ncp"])
+        assert np.array_equal(s.uniqueKnots, golden[pre + "uniqueKnots"])
+        assert np.array_equal(s.multiplicities, golden[pre + "multiplicities"])
+        assert np.array_equal(s.ghostKnots, golden[pre + "ghostKnots"])
+        assert np.array_equal(s.grevilleAll(), golden[pre + "greville"])
+        assert s.isDiscontinuous() == bool(golden[pre + "disc"])
+
+
+def test_tensor_bookkeeping(golden):
+    for name in golden["tp_names"]:
+        pre = "tp_%s_" % name
+        deg = [int(x) for x in golden[pre + "deg"]]
+        kv = [golden[pre + "kv%d" % d] for d in range(len(deg))]
+        b = PB.BSpline(deg, kv)
+        assert b.getNcp() == int(golden[pre + "ncp"]) and b.nel == int(golden[pre + "nel"])
+        assert b.getDegree() == int(golden[pre + "degree"])
+        assert b.getPrealloc() == int(golden[pre + "prealloc"])
+        for d in range(len(deg)):
+            for side in (0, 1):
+                for nl in (1, 2):
+                    assert np.array_equal(np.array(b.getSideDofs(d, side, nl)),
+                                          golden[pre + "side_%d_%d_%d" % (d, side, nl)])
+        extra = int(golden[pre + "nsd"]) - len(deg)
+        cm = PB.ExplicitBSplineControlMesh(deg, kv, extraDim=extra)
+        assert np.array_equal(cm.controlNet(), golden[pre + "P"])
+        P1 = np.array([[cm.getHomogeneousCoordinate(n, d) for d in range(cm.getNsd() + 1)]
+                       for n in range(0, b.getNcp(), 5)])
+        assert np.array_equal(P1, golden[pre + "P"][::5])
+
+
+# ---- interpreter for compiled programs (test infrastructure) -------------------
+def run_program(prog, xi, wq, jetvals):
+    R = np.zeros(prog.nreg)
+    R[:prog.dim] = xi
+    R[prog.dim] = wq
+    for k, j in enumerate(prog.jets):
+        R[prog.dim + 1 + k] = jetvals[j]
+    f1 = dict(neg=lambda a: -a, sin=math.sin, cos=math.cos, exp=math.exp, log=math.log,
+              sqrt=math.sqrt, abs=abs, tan=math.tan, tanh=math.tanh, sinh=math.sinh,
+              cosh=math.cosh, atan=math.atan, mov=lambda a: a)
+    f2 = dict(add=lambda a, b: a + b, sub=lambda a, b: a - b, mul=lambda a, b: a * b,
+              div=lambda a, b: a / b, pow=lambda a, b: a ** b, max=max, min=min,
+              gt=lambda a, b: float(a > b))
+    names = {v: k for k, v in S.OPCODES.items()}
+    for op, dst, a, b in prog.prog:
+        n = names[op]
+        if n == "const":
+            R[dst] = prog.consts[a]
+        elif n in f1:
+            R[dst] = f1[n](R[a])
+        else:
+            R[dst] = f2[n](R[a], R[b])
+    return [R[r] for r in prog.outregs]
+
+
+def test_symbolic_compile_and_diff():
+    x, y = S.xi(0), S.xi(1)
+    u = S.jet(1, 0, (0, 0, 0))
+    e = S.func("sin", x * 3.0) * S.func("exp", y) + u * u / (x + 2.0) - S.power(y + 1.5, S.const(2.5))
+    de = S.diff(e, 0)
+    prog = S.compile_program([e, de, S.diff(e, 1)], 2)
+    jv = {(1, 0, (0, 0, 0)): 0.7, (1, 0, (1, 0, 0)): -0.3, (1, 0, (0, 1, 0)): 1.1}
+    X, Y = 0.4, 0.9
+
+    def ev(X, Y, U0):
+        return math.sin(3 * X) * math.exp(Y) + U0 * U0 / (X + 2.0) - (Y + 1.5) ** 2.5
+    got = run_program(prog, [X, Y], 1.0, jv)
+    assert abs(got[0] - ev(X, Y, 0.7)) < 1e-14
+    # d/dx with u depending on x through its jet (1,0,0)
+    ex = 3 * math.cos(3 * X) * math.exp(Y) + 2 * 0.7 * (-0.3) / (X + 2) - 0.49 / (X + 2) ** 2
+    ey = math.sin(3 * X) * math.exp(Y) + 2 * 0.7 * 1.1 / (X + 2) - 2.5 * (Y + 1.5) ** 1.5
+    assert abs(got[1] - ex) < 1e-13 and abs(got[2] - ey) < 1e-13
+    assert prog.nreg < 40
+
+
+def test_hash_consing_and_folding():
+    a = S.xi(0) + S.xi(1)
+    b = S.xi(1) + S.xi(0)
+    assert a is b
+    assert S.mul(S.const(2.0), S.const(3.0)) is S.const(6.0)
+    assert S.sub(a, a) is S.ZERO and S.mul(a, S.ZERO) is S.ZERO
+
+
+def test_form_language_poisson_keys():
+    # identity geometry written by hand: grad u . grad v
+    u = U.Tensor(U.Scalar({(None, U.ZERO3): S.ONE}))
+    v = U.Tensor(U.Scalar({(U.ZERO3, None): S.ONE}))
+    gu, gv = U.parametric_grad(u, 2), U.parametric_grad(v, 2)
+    a = U.inner(gu, gv).a[()]
+    assert set(a.terms) == {((1, 0, 0), (1, 0, 0)), ((0, 1, 0), (0, 1, 0))}
+    assert a.arity() == 2
+    f = U.sin(U.Tensor(U.Scalar.coef(S.xi(0))))
+    L = (f * v).a[()]
+    assert L.arity() == 1 and list(L.terms) == [(U.ZERO3, None)]
+    with pytest.raises(ValueError):
+        (u * u)
+    res = U.Form([(a, None)]) - U.Form([(L, None)])
+    assert U.lhs(res).arity() == 2 and U.rhs(res).arity() == 1
+    r = U.rhs(res).scalar().terms[(U.ZERO3, None)]
+    assert r is L.terms[(U.ZERO3, None)]
+
+
+def test_tensor_algebra_det_inv():
+    m = U.as_matrix([[2.0, 1.0], [0.5, 3.0]])
+    assert abs(U.det(m).a[()].node().args[0] - 5.5) < 1e-15
+    mi = U.inv(m)
+    ref = np.linalg.inv(np.array([[2.0, 1.0], [0.5, 3.0]]))
+    for i in range(2):
+        for j in range(2):
+            assert abs(mi.a[i, j].node().args[0] - ref[i, j]) < 1e-15
+    m3 = np.array([[2.0, 1.0, 0.3], [0.5, 3.0, -1.0], [0.2, 0.1, 1.5]])
+    mi3 = U.inv(U.as_matrix(m3.tolist()))
+    for i in range(3):
+        for j in range(3):
+            assert abs(mi3.a[i, j].node().args[0] - np.linalg.inv(m3)[i, j]) < 1e-14
+
+
+def test_cabi_exports_every_declared_symbol():
+    import ctypes
+    hdr = open(os.path.join(ROOT, "include", "tigar_b200.h")).read()
+    names = set(re.findall(r"\b(tg_[a-z0-9_]+)\s*\(", hdr))
+    names -= {"tg_basis", "tg_win"}
+    assert len(names) > 30
+    lib = ctypes.CDLL(os.path.join(ROOT, "tigar_b200", "libtigar_b200.so"))
+    for n in sorted(names):
+        assert hasattr(lib, n), "missing export " + n
+    from tigar_b200 import _lib
+    assert set(_lib.SIGNATURES) == names
+    assert lib.tg_version() >= 100
+
+
+def test_product_does_not_import_oracle():
+    import subprocess
+    import sys
+    code = ("import sys; import tigar_b200.api, tigar_b200.engine, tIGAr; "
+            "bad=[m for m in sys.modules if m=='oracle' or m.startswith('oracle.')]; "
+            "assert not bad, bad")
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "tigar_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tigar_b200.engine import TensorPatch
+    with pytest.raises(RuntimeError):
+        TensorPatch([2, 2], [PB.uniformKnots(2, 0.0, 1.0, 4)] * 2)

@@ -51,6 +51,13 @@ SIGNATURES = {
                        c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "tg_win_rowlen": [PW, c_vp, c_vp],
     "tg_win_fill_cols": [PW, c_vp, c_vp],
+    "tg_win_rowptr": [PW, PVP, c_vp, c_vp],
+    "tg_win_spmv": [PW, c_vp, c_vp, c_vp, c_vp],
+    "tg_win_spmv_dot": [PW, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp],
+    "tg_win_zero_rows_cols": [PW, c_vp, c_vp, c_vp, c_dbl, c_i32, c_vp],
+    "tg_win_diag_inv": [PW, c_vp, c_i32, c_vp, c_vp],
+    "tg_win_solve_cg": [PW, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_i32, c_i32, c_vp, PI32,
+                        C.POINTER(c_dbl), c_vp],
     "tg_m_fill": [PW, PVP, PVP, PI32, c_vp, c_vp],
     "tg_spmv": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
     "tg_mt_vec": [PW, PW, c_vp, c_vp, c_vp, c_vp],

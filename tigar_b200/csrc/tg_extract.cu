@@ -21,6 +21,54 @@ extern "C" int tg_win_rowlen(const tg_win* h_w, int64_t* rowlen, void* stream) {
   return 0;
 }
 
+struct TgPrefix {
+  const int64_t* S[3];
+  int64_t T[3];   // totals
+};
+
+// rowptr(r0,r1,r2) = S0[r0] len1 len2 + T0 (S1[r1] len2 + T1 S2[r2])
+__global__ void k_win_rowptr(TgWin w, TgPrefix P, int64_t nrows, int64_t* __restrict__ rowptr) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r > nrows) return;
+  if (r == nrows) {
+    rowptr[r] = P.T[0] * P.T[1] * P.T[2];
+    return;
+  }
+  int rc[3];
+  tg_decode(r, w.nr, w.dim, rc);
+  int64_t len1 = 1, len2 = 1, s1 = 0, s2 = 0;
+  if (w.dim > 1) {
+    len1 = w.hi[1][rc[1]] - w.lo[1][rc[1]] + 1;
+    s1 = P.S[1][rc[1]];
+  }
+  if (w.dim > 2) {
+    len2 = w.hi[2][rc[2]] - w.lo[2][rc[2]] + 1;
+    s2 = P.S[2][rc[2]];
+  }
+  rowptr[r] = P.S[0][rc[0]] * len1 * len2 + P.T[0] * (s1 * len2 + P.T[1] * s2);
+}
+
+extern "C" int tg_win_rowptr(const tg_win* h_w, const int64_t* const* h_S, int64_t* rowptr,
+                             void* stream) {
+  int64_t nrows = tg_win_nrows(h_w);
+  TgPrefix P;
+  cudaStream_t st = tg_stream(stream);
+  for (int d = 0; d < 3; d++) {
+    P.S[d] = nullptr;
+    P.T[d] = 1;
+    if (d < h_w->dim) {
+      P.S[d] = h_S[d];
+      TG_CHECK(cudaMemcpyAsync(&P.T[d], h_S[d] + h_w->nr[d], sizeof(int64_t),
+                               cudaMemcpyDeviceToHost, st));
+    }
+  }
+  TG_CHECK(cudaStreamSynchronize(st));
+  k_win_rowptr<<<(unsigned)tg_cdiv(nrows + 1, 256), 256, 0, st>>>(tg_win_dev(h_w), P, nrows,
+                                                                  rowptr);
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
 // one warp per row
 __global__ void k_win_fill_cols(TgWin w, int64_t nrows, int32_t* __restrict__ cols) {
   int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;

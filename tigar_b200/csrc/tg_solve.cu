@@ -252,12 +252,14 @@ extern "C" int tg_dot(const double* a, const double* b, int64_t n, double* scrat
   return 0;
 }
 
-// Single-GPU driver.  work: r[n] p[n] q[n] dinv[n] scratch[tg_cg_scratch_len()] s[8]
+// Single-GPU driver shared by the general-CSR and the windowed-CSR solvers.
+// work: r[n] p[n] q[n] dinv[n] scratch[tg_cg_scratch_len()] s[8]
 // s: 0 rz_a, 1 rr_a, 2 pAp, 3 rz_b, 4 rr_b, 5 bb
-extern "C" int tg_solve_cg(const int64_t* rowptr, const int32_t* cols, const double* vals,
-                           const double* b, double* x, int64_t n, double rtol, double atol,
-                           int32_t maxit, int32_t check_every, double* work, int32_t* h_iters,
-                           double* h_relres, void* stream) {
+// SPMV(x, y, dot_out): y = A x, dot_out[0] = x.y ; DIAG(dinv): dinv = 1/diag(A)
+template <class SPMV, class DIAG>
+static int tg_cg_driver(SPMV spmv, DIAG diag, const double* b, double* x, int64_t n,
+                        double rtol, double atol, int32_t maxit, int32_t check_every,
+                        double* work, int32_t* h_iters, double* h_relres, void* stream) {
   cudaStream_t st = tg_stream(stream);
   double* r = work;
   double* p = work + n;
@@ -267,10 +269,10 @@ extern "C" int tg_solve_cg(const int64_t* rowptr, const int32_t* cols, const dou
   double* s = scratch + tg_cg_scratch_len();
   if (check_every < 1) check_every = 1;
   int rc;
-  if ((rc = tg_diag_inv(rowptr, cols, vals, n, 0, dinv, stream))) return rc;
+  if ((rc = diag(dinv))) return rc;
   if ((rc = tg_dot(b, b, n, scratch, s + 5, stream))) return rc;
   // q = A x0 ; r = b - q ; p = dinv r
-  if ((rc = tg_cg_spmv_dot(rowptr, cols, vals, x, 0, q, n, scratch, s + 2, stream))) return rc;
+  if ((rc = spmv(x, q, s + 2))) return rc;
   if ((rc = tg_cg_init(b, q, dinv, r, p, n, scratch, s + 0, stream))) return rc;
   double hs[6];
   TG_CHECK(cudaMemcpyAsync(hs, s, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -286,7 +288,7 @@ extern "C" int tg_solve_cg(const int64_t* rowptr, const int32_t* cols, const dou
     for (int k = 0; k < nstep; k++, it++) {
       double* cur = (it & 1) ? s + 3 : s + 0;   // rz, rr of current residual
       double* nxt = (it & 1) ? s + 0 : s + 3;
-      if ((rc = tg_cg_spmv_dot(rowptr, cols, vals, p, 0, q, n, scratch, s + 2, stream))) return rc;
+      if ((rc = spmv(p, q, s + 2))) return rc;
       if ((rc = tg_cg_axpy_dot(x, r, p, q, dinv, n, cur, s + 2, scratch, nxt, stream))) return rc;
       if ((rc = tg_cg_xpby(p, r, dinv, n, nxt, cur, stream))) return rc;
     }
@@ -302,4 +304,46 @@ extern "C" int tg_solve_cg(const int64_t* rowptr, const int32_t* cols, const dou
   if (h_iters) *h_iters = it;
   if (h_relres) *h_relres = (bb > 0.0) ? sqrt(rr / bb) : 0.0;
   return 0;
+}
+
+extern "C" int tg_solve_cg(const int64_t* rowptr, const int32_t* cols, const double* vals,
+                           const double* b, double* x, int64_t n, double rtol, double atol,
+                           int32_t maxit, int32_t check_every, double* work, int32_t* h_iters,
+                           double* h_relres, void* stream) {
+  double* scratch = work + 4 * n;
+  return tg_cg_driver(
+      [&](const double* xx, double* yy, double* dot) {
+        return tg_cg_spmv_dot(rowptr, cols, vals, xx, 0, yy, n, scratch, dot, stream);
+      },
+      [&](double* dinv) { return tg_diag_inv(rowptr, cols, vals, n, 0, dinv, stream); }, b, x, n,
+      rtol, atol, maxit, check_every, work, h_iters, h_relres, stream);
+}
+
+// windowed-CSR variant (tg_winops.cu)
+int tg_win_spmv_launch(const tg_win* h_w, const double* vals, const double* x, int64_t xoff,
+                       double* y, double* part, cudaStream_t st);
+int tg_ws_grid_size();
+
+extern "C" int tg_win_spmv_dot(const tg_win* h_w, const double* vals, const double* x,
+                               int64_t xoff, double* y, double* scratch, double* out1,
+                               void* stream) {
+  int rc = tg_win_spmv_launch(h_w, vals, x, xoff, y, scratch, tg_stream(stream));
+  if (rc) return rc;
+  k_final_reduce<<<1, 256, 0, tg_stream(stream)>>>(scratch, tg_ws_grid_size(), 1, out1);
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tg_win_solve_cg(const tg_win* h_w, const double* vals, const double* b,
+                               double* x, double rtol, double atol, int32_t maxit,
+                               int32_t check_every, double* work, int32_t* h_iters,
+                               double* h_relres, void* stream) {
+  int64_t n = tg_win_nrows(h_w);
+  double* scratch = work + 4 * n;
+  return tg_cg_driver(
+      [&](const double* xx, double* yy, double* dot) {
+        return tg_win_spmv_dot(h_w, vals, xx, 0, yy, scratch, dot, stream);
+      },
+      [&](double* dinv) { return tg_win_diag_inv(h_w, vals, 0, dinv, stream); }, b, x, n, rtol,
+      atol, maxit, check_every, work, h_iters, h_relres, stream);
 }

@@ -1,0 +1,506 @@
+"""
+Host-side driver of the CUDA hot path on one tensor-product B-spline patch:
+
+  extraction   M = M_w (x) M_v (x) M_u          (common.py:1460-1578)
+  assembly     A_FE, b_FE on the Q_pf Lagrange mesh (common.py:1169,1215-1216)
+  extraction   M^T A M, M^T b, zero BCs         (common.py:1142-1204)
+  solve        Jacobi-CG                        (common.py:1236-1263)
+
+and the element-fused variant  C = sum_e M_e^T K_e M_e  that never forms the
+global A_FE / M (mandatory at 256^3 and beyond).
+
+Everything numerical happens in libtigar_b200.so; this module only builds
+descriptors (window ranges, multi-index lists, register programs) and
+launches.  Matrices are "windowed CSR": each row stores the dense
+tensor-product box of its columns, so no column index array exists (8 B/nnz).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import dev
+from . import symbolic as S
+from ._lib import lib, check, tg_basis, tg_win, i32arr, vparr, c_vp
+from .bsplines import BSpline1
+
+IGNORE_EPS = 1e-15          # DEFAULT_BASIS_FUNC_IGNORE_EPS, common.py:56
+
+
+# --------------------------------------------------------------------------
+def gauss_rule01(nq):
+    x, w = np.polynomial.legendre.leggauss(nq)
+    return 0.5 * (x + 1.0), 0.5 * w
+
+
+def lagrange_jets01(pf, t, nder):
+    """d^k/dt^k of the equispaced degree-pf Lagrange basis on [0,1] at points
+    t: [len(t), pf+1, nder+1].  Reference-element constants (FIAT's role)."""
+    nodes = np.arange(pf + 1) / float(pf)
+    out = np.zeros((len(t), pf + 1, nder + 1))
+    for a in range(pf + 1):
+        others = np.delete(nodes, a)
+        poly = np.poly1d(others, r=True) / np.prod(nodes[a] - others)
+        for k in range(nder + 1):
+            out[:, a, k] = np.polyder(poly, k)(t) if k else poly(t)
+    return out
+
+
+class Window(object):
+    """Tensor-product row windows of a sparse matrix + its device descriptor."""
+
+    def __init__(self, nr, nc, lo, hi):
+        self.dim = len(nr)
+        self.nr = [int(x) for x in nr]
+        self.nc = [int(x) for x in nc]
+        self.lo = [np.ascontiguousarray(a, dtype=np.int32) for a in lo]
+        self.hi = [np.ascontiguousarray(a, dtype=np.int32) for a in hi]
+        for d in range(self.dim):
+            assert len(self.lo[d]) == self.nr[d] and len(self.hi[d]) == self.nr[d]
+            assert np.all(self.lo[d] >= 0) and np.all(self.hi[d] < self.nc[d])
+            assert np.all(self.hi[d] >= self.lo[d])
+        self.len = [(h - l + 1).astype(np.int64) for l, h in zip(self.lo, self.hi)]
+        self.nrows = int(np.prod(self.nr))
+        self.ncols = int(np.prod(self.nc))
+        self.nnz = int(np.prod([int(l.sum()) for l in self.len]))
+        self._d = None
+
+    def transpose(self):
+        lo, hi = [], []
+        for d in range(self.dim):
+            l = np.full(self.nc[d], np.iinfo(np.int32).max, dtype=np.int64)
+            h = np.full(self.nc[d], -1, dtype=np.int64)
+            # a column c is covered by every row r with lo[r] <= c <= hi[r]
+            for rr in range(self.nr[d]):
+                a, b = self.lo[d][rr], self.hi[d][rr]
+                l[a:b + 1] = np.minimum(l[a:b + 1], rr)
+                h[a:b + 1] = np.maximum(h[a:b + 1], rr)
+            lo.append(l)
+            hi.append(h)
+        return Window(self.nc, self.nr, lo, hi)
+
+    def compose(self, other):
+        """Window of the product (self) * (other)."""
+        lo, hi = [], []
+        for d in range(self.dim):
+            assert self.nc[d] == other.nr[d]
+            l = np.array([other.lo[d][a:b + 1].min() for a, b in zip(self.lo[d], self.hi[d])])
+            h = np.array([other.hi[d][a:b + 1].max() for a, b in zip(self.lo[d], self.hi[d])])
+            lo.append(l)
+            hi.append(h)
+        return Window(self.nr, other.nc, lo, hi)
+
+    # device descriptor (lazily uploaded)
+    def dev(self):
+        if self._d is None:
+            w = tg_win()
+            w.dim = self.dim
+            keep = []
+            S_ptrs = []
+            for d in range(3):
+                if d < self.dim:
+                    w.nr[d], w.nc[d] = self.nr[d], self.nc[d]
+                    tl, th = dev.from_np(self.lo[d]), dev.from_np(self.hi[d])
+                    ts = dev.from_np(np.concatenate([[0], np.cumsum(self.len[d])]).astype(np.int64))
+                    keep += [tl, th, ts]
+                    w.lo[d], w.hi[d] = dev.ptr(tl), dev.ptr(th)
+                    S_ptrs.append(dev.ptr(ts))
+                else:
+                    w.nr[d], w.nc[d] = 1, 1
+                    w.lo[d], w.hi[d] = None, None
+                    S_ptrs.append(0)
+            rowptr = dev.empty(self.nrows + 1, dev.I64)
+            w.rowptr = dev.ptr(rowptr)
+            check(lib.tg_win_rowptr(C.byref(w), (c_vp * 3)(*S_ptrs), dev.ptr(rowptr),
+                                    dev.stream()))
+            keep.append(rowptr)
+            self._d = (w, keep, rowptr)
+        return self._d[0]
+
+    def ref(self):
+        return C.byref(self.dev())
+
+    def rowptr(self):
+        self.dev()
+        return self._d[2]
+
+    def columns(self):
+        """Explicit CSR column array (only for export / generic CSR kernels)."""
+        cols = dev.empty(self.nnz, dev.I32)
+        check(lib.tg_win_fill_cols(self.ref(), dev.ptr(cols), dev.stream()))
+        return cols
+
+
+class WinMatrix(object):
+    """Values on a Window.  ``to_scipy`` exports a standard CSR for checking."""
+
+    def __init__(self, window, vals=None):
+        self.window = window
+        self.vals = dev.zeros(window.nnz) if vals is None else vals
+
+    @property
+    def shape(self):
+        return (self.window.nrows, self.window.ncols)
+
+    def matvec(self, x, y=None):
+        y = dev.empty(self.window.nrows) if y is None else y
+        check(lib.tg_win_spmv(self.window.ref(), dev.ptr(self.vals), dev.ptr(x), dev.ptr(y),
+                              dev.stream()))
+        return y
+
+    def to_scipy(self, drop_eps=None):
+        import scipy.sparse as sp
+        w = self.window
+        rp = dev.to_np(w.rowptr())
+        cols = dev.to_np(w.columns())
+        vals = dev.to_np(self.vals)
+        A = sp.csr_matrix((vals, cols, rp), shape=self.shape)
+        if drop_eps is not None:
+            A.data[np.abs(A.data) <= drop_eps] = 0.0
+            A.eliminate_zeros()
+        A.sort_indices()
+        return A
+
+    def copy(self):
+        return WinMatrix(self.window, self.vals.clone())
+
+
+# --------------------------------------------------------------------------
+class Dir1D(object):
+    """One parametric direction: knot data, 1-D extraction rows, per-element
+    tables at the Gauss points."""
+
+    def __init__(self, spline1, pf, nq, eps=IGNORE_EPS):
+        s = spline1
+        self.s = s
+        self.p, self.pf, self.nq = s.p, int(pf), int(nq)
+        self.nel, self.ncp = s.nel, s.ncp
+        self.nfe = s.nel * self.pf + 1
+        if s.multiplicities[0] != s.p + 1 or s.multiplicities[-1] != s.p + 1:
+            raise NotImplementedError(
+                "tigar_b200 tensor-product fast path needs open (non-periodic) knot vectors")
+        if s.isDiscontinuous():
+            raise NotImplementedError("discontinuous B-splines need DG extraction (not built)")
+        self.d_uk = dev.from_np(s.uniqueKnots)
+        self.d_espan = dev.from_np(s.elementSpans())
+        self.tables = {}
+        # 1-D extraction rows at the FE nodes (reference per-node evaluation)
+        x = dev.empty(self.nfe)
+        check(lib.tg_fe_nodes_1d(dev.ptr(self.d_uk), self.nel, self.pf, dev.ptr(x), dev.stream()))
+        self.x_fe = x
+        span, nodes, vals = s.evalBatch(x)
+        self.m_first = (span - self.p).contiguous()          # int32 [nfe]
+        self.m_vals = vals.contiguous()                      # [nfe, p+1]
+        hv = dev.to_np(vals)
+        hf = dev.to_np(self.m_first).astype(np.int64)
+        keep = np.abs(hv) > eps
+        first_kept = keep.argmax(axis=1)
+        last_kept = self.p - keep[:, ::-1].argmax(axis=1)
+        width = keep.sum(axis=1)
+        if not np.all(width == last_kept - first_kept + 1):
+            raise RuntimeError("non-contiguous 1-D extraction row")
+        self.m_lo = hf + first_kept
+        self.m_hi = hf + last_kept
+
+    def table(self, nder):
+        """Device tables tabulated up to derivative order ``nder``."""
+        nder = int(nder)
+        if nder not in self.tables:
+            s = self.s
+            tq, gw = gauss_rule01(self.nq)
+            lag = lagrange_jets01(self.pf, tq, nder)
+            dk, dg = s.deviceKnots()
+            np1, nf, nd = self.p + 1, self.pf + 1, nder + 1
+            t = dict(
+                Me=dev.empty(self.nel * nf * np1),
+                tabN=dev.empty(self.nel * self.nq * np1 * nd),
+                idxN=dev.empty(self.nel * np1, dev.I32),
+                tabL=dev.empty(self.nel * self.nq * nf * nd),
+                idxL=dev.empty(self.nel * nf, dev.I32),
+                wq=dev.empty(self.nel * self.nq),
+                xq=dev.empty(self.nel * self.nq),
+                lag=dev.from_np(lag), tq=dev.from_np(tq), gw=dev.from_np(gw))
+            check(lib.tg_tabulate_1d(
+                dev.ptr(dg), s.nGhost, self.p, self.ncp, dev.ptr(self.d_uk),
+                dev.ptr(self.d_espan), self.nel, self.pf, self.nq, nder,
+                dev.ptr(t["lag"]), dev.ptr(t["tq"]), dev.ptr(t["gw"]),
+                dev.ptr(t["Me"]), dev.ptr(t["tabN"]), dev.ptr(t["idxN"]),
+                dev.ptr(t["tabL"]), dev.ptr(t["idxL"]), dev.ptr(t["wq"]), dev.ptr(t["xq"]),
+                dev.stream()))
+            self.tables[nder] = t
+        return self.tables[nder]
+
+
+class Basis(object):
+    """ctypes tg_basis + the tensors it points to."""
+
+    def __init__(self, dirs, kind, nder):
+        b = tg_basis()
+        b.dim = len(dirs)
+        b.nder = nder
+        self.keep = []
+        for d in range(3):
+            if d < len(dirs):
+                D = dirs[d]
+                t = D.table(nder)
+                self.keep.append(t)
+                b.nel[d], b.nq[d] = D.nel, D.nq
+                if kind == "fe":
+                    b.n[d], b.nloc[d] = D.nfe, D.pf + 1
+                    b.tab[d], b.idx[d] = dev.ptr(t["tabL"]), dev.ptr(t["idxL"])
+                else:
+                    b.n[d], b.nloc[d] = D.ncp, D.p + 1
+                    b.tab[d], b.idx[d] = dev.ptr(t["tabN"]), dev.ptr(t["idxN"])
+                b.wq[d], b.xq[d] = dev.ptr(t["wq"]), dev.ptr(t["xq"])
+            else:
+                b.n[d] = b.nel[d] = b.nloc[d] = b.nq[d] = 1
+        self.c = b
+        self.kind = kind
+        self.nder = nder
+        self.nloc = [b.nloc[d] for d in range(b.dim)]
+        self.ntot = int(np.prod([b.n[d] for d in range(b.dim)]))
+        self.nqp = int(np.prod([b.nq[d] for d in range(b.dim)]))
+        self.nen = int(np.prod(self.nloc))
+
+    def ref(self):
+        return C.byref(self.c)
+
+
+def pad3(alpha):
+    a = tuple(int(x) for x in alpha)
+    return a + (0,) * (3 - len(a))
+
+
+class TensorPatch(object):
+    """A tensor-product B-spline patch and its Q_pf Lagrange background mesh."""
+
+    def __init__(self, degrees, kvecs, quadDeg=None, eps=IGNORE_EPS, splines=None):
+        dev.require_cuda()
+        self.dim = len(degrees)
+        self.splines = splines or [BSpline1(p, k) for p, k in zip(degrees, kvecs)]
+        self.degrees = [s.p for s in self.splines]
+        self.pf = max(self.degrees)                     # BSplines.py:580-588 (useRect)
+        self.quadDeg = 2 * self.pf if quadDeg is None else int(quadDeg)
+        self.nq = self.quadDeg // 2 + 1                 # Gauss-Legendre points / direction
+        self.eps = eps
+        self.dirs = [Dir1D(s, self.pf, self.nq, eps) for s in self.splines]
+        self.nel = [D.nel for D in self.dirs]
+        self.ncp = [D.ncp for D in self.dirs]
+        self.nfe = [D.nfe for D in self.dirs]
+        self.ncells = int(np.prod(self.nel))
+        self.n_iga = int(np.prod(self.ncp))
+        self.n_fe = int(np.prod(self.nfe))
+        self._bases = {}
+        self._win = {}
+        self.launches = 0
+
+    # ---- descriptors -------------------------------------------------------
+    def basis(self, kind, nder):
+        key = (kind, int(nder))
+        if key not in self._bases:
+            self._bases[key] = Basis(self.dirs, kind, int(nder))
+        return self._bases[key]
+
+    def window(self, name):
+        """'M' FExIGA, 'MT' IGAxFE, 'A' FExFE, 'P' = A*M, 'PT', 'C' IGAxIGA."""
+        if name not in self._win:
+            if name == "M":
+                w = Window(self.nfe, self.ncp, [D.m_lo for D in self.dirs],
+                           [D.m_hi for D in self.dirs])
+            elif name == "MT":
+                w = self.window("M").transpose()
+            elif name == "A":
+                lo, hi = [], []
+                for D in self.dirs:
+                    g = np.arange(D.nfe)
+                    e_lo = np.maximum((g - 1) // D.pf, 0)          # leftmost cell touching g
+                    e_hi = np.minimum(g // D.pf, D.nel - 1)        # rightmost cell
+                    lo.append(e_lo * D.pf)
+                    hi.append((e_hi + 1) * D.pf)
+                w = Window(self.nfe, self.nfe, lo, hi)
+            elif name == "P":
+                w = self.window("A").compose(self.window("M"))
+            elif name == "PT":
+                w = self.window("P").transpose()
+            elif name == "C":
+                w = self.window("MT").compose(self.window("P"))
+            else:
+                raise KeyError(name)
+            self._win[name] = w
+        return self._win[name]
+
+    # ---- (i) extraction ----------------------------------------------------
+    def build_M(self):
+        """Global extraction operator on its window (generateM)."""
+        w = self.window("M")
+        M = WinMatrix(w, dev.empty(w.nnz))
+        firsts = vparr([dev.ptr(D.m_first) for D in self.dirs])
+        vals = vparr([dev.ptr(D.m_vals) for D in self.dirs])
+        check(lib.tg_m_fill(w.ref(), firsts, vals, i32arr(self.degrees), dev.ptr(M.vals),
+                            dev.stream()))
+        return M
+
+    def mt_vec(self, M, b):
+        """M^T b (multTranspose, common.py:97-109)."""
+        out = dev.empty(self.n_iga)
+        check(lib.tg_mt_vec(self.window("M").ref(), self.window("MT").ref(), dev.ptr(M.vals),
+                            dev.ptr(b), dev.ptr(out), dev.stream()))
+        return out
+
+    def fe_node_coords(self):
+        """[n_fe, dim] FE node coordinates (tabulate_dof_coordinates)."""
+        xs = [dev.to_np(D.x_fe) for D in self.dirs]
+        g = np.meshgrid(*xs, indexing="ij")
+        return np.stack([a.ravel(order="F") for a in g], axis=1)
+
+    # ---- (ii) Gauss-point assembly ----------------------------------------
+    def _cell_chunks(self, bytes_per_cell, budget=1 << 29):
+        """Chunks of whole slabs of the last direction."""
+        slab = self.ncells // self.nel[-1]
+        per = max(1, int(budget // max(1, slab * bytes_per_cell)))
+        k = 0
+        while k < self.nel[-1]:
+            n = min(per, self.nel[-1] - k)
+            yield k * slab, n * slab
+            k += n
+
+    def _qp_setup(self, outputs, funcs):
+        """Compile ``outputs`` (symbolic Nodes) -> device program + jet table.
+        funcs: {fid: device vector}."""
+        prog = S.compile_program(outputs, self.dim)
+        fids = sorted(set(j[0] for j in prog.jets))
+        fpos = {f: i for i, f in enumerate(fids)}
+        for f in fids:
+            if f not in funcs:
+                raise KeyError("coefficient function %r has no data in this basis" % (f,))
+        jets = []
+        for (f, comp, al) in prog.jets:
+            jets += [fpos[f], comp] + list(pad3(al))
+        nder = max([max(al) for (_, _, al) in prog.jets] + [0])
+        P = dict(prog=prog, fids=fids, njets=len(prog.jets), jets=i32arr(jets),
+                 coefs=vparr([dev.ptr(funcs[f]) for f in fids]),
+                 keep=[funcs[f] for f in fids],
+                 ncomp=i32arr([1] * len(fids)),
+                 d_prog=dev.from_np(np.array(prog.prog, dtype=np.int32).reshape(-1, 4))
+                 if prog.prog else dev.zeros(4, dev.I32),
+                 d_consts=dev.from_np(np.array(prog.consts or [0.0], dtype=np.float64)),
+                 outregs=i32arr(prog.outregs), nout=len(prog.outregs), nder=nder)
+        return P
+
+    def _qp_eval(self, B, P, cell0, ncells, out):
+        check(lib.tg_qp_eval(B.ref(), len(P["fids"]), P["coefs"], P["ncomp"], P["njets"],
+                             P["jets"], dev.ptr(P["d_prog"]), len(P["prog"].prog),
+                             dev.ptr(P["d_consts"]), P["prog"].nreg, P["nout"], P["outregs"],
+                             cell0, ncells, dev.ptr(out), dev.stream()))
+
+    @staticmethod
+    def jet_order(nodes):
+        return S.max_order(nodes)
+
+    def assemble_matrix(self, terms, funcs, kind="fe", out=None):
+        """terms: {(alphaTest, alphaTrial): Node} (coefficient already includes
+        J and the quadrature weight).  kind 'fe' -> A_FE on the Lagrange
+        basis; kind 'iga' -> sum_e M_e^T K_e M_e on the spline basis."""
+        alS = sorted(set(pad3(k[0]) for k in terms))
+        alT = sorted(set(pad3(k[1]) for k in terms))
+        nS, nT = len(alS), len(alT)
+        grid = [[S.ZERO] * nT for _ in range(nS)]
+        for (a, b), node in terms.items():
+            grid[alS.index(pad3(a))][alT.index(pad3(b))] = node
+        outputs = [grid[s][t] for s in range(nS) for t in range(nT)]
+        P = self._qp_setup(outputs, funcs)
+        nder = max(P["nder"], max(max(a) for a in alS + alT))
+        B = self.basis(kind, nder)
+        W = self.window("A" if kind == "fe" else "C")
+        A = WinMatrix(W) if out is None else out
+        stride = i32arr([2] * self.dim if kind == "fe" else B.nloc)
+        aS = i32arr([x for a in alS for x in a])
+        aT = i32arr([x for a in alT for x in a])
+        per_cell = nS * nT * B.nqp * 8
+        buf = None
+        for cell0, nc in self._cell_chunks(per_cell):
+            if buf is None or buf.numel() < nc * nS * nT * B.nqp:
+                buf = dev.empty(nc * nS * nT * B.nqp)
+            self._qp_eval(B, P, cell0, nc, buf)
+            check(lib.tg_assemble_matrix_ex(B.ref(), W.ref(), nS, aS, nT, aT, stride,
+                                            dev.ptr(buf), cell0, nc, dev.ptr(A.vals),
+                                            dev.stream()))
+        return A
+
+    def assemble_vector(self, terms, funcs, kind="fe", out=None):
+        """terms: {alphaTest: Node}."""
+        alS = sorted(set(pad3(k) for k in terms))
+        nS = len(alS)
+        outputs = [S.ZERO] * nS
+        for a, node in terms.items():
+            outputs[alS.index(pad3(a))] = node
+        P = self._qp_setup(outputs, funcs)
+        nder = max(P["nder"], max(max(a) for a in alS))
+        B = self.basis(kind, nder)
+        b = dev.zeros(B.ntot) if out is None else out
+        stride = i32arr([2] * self.dim if kind == "fe" else B.nloc)
+        aS = i32arr([x for a in alS for x in a])
+        buf = None
+        for cell0, nc in self._cell_chunks(nS * B.nqp * 8):
+            if buf is None or buf.numel() < nc * nS * B.nqp:
+                buf = dev.empty(nc * nS * B.nqp)
+            self._qp_eval(B, P, cell0, nc, buf)
+            check(lib.tg_assemble_vector_ex(B.ref(), nS, aS, stride, dev.ptr(buf), cell0, nc,
+                                            dev.ptr(b), dev.stream()))
+        return b
+
+    def assemble_scalar(self, node, funcs, kind="fe"):
+        """sum over all Gauss points of ``node`` (functional assembly)."""
+        P = self._qp_setup([node], funcs)
+        B = self.basis(kind, P["nder"])
+        tot = 0.0
+        acc = dev.zeros(1)
+        buf = None
+        for cell0, nc in self._cell_chunks(B.nqp * 8):
+            if buf is None or buf.numel() < nc * B.nqp:
+                buf = dev.empty(nc * B.nqp)
+            self._qp_eval(B, P, cell0, nc, buf)
+            check(lib.tg_sum(dev.ptr(buf), nc * B.nqp, dev.ptr(acc), dev.stream()))
+            tot += float(acc.item())
+        return tot
+
+    # ---- (iii) triple product, BCs, solve -----------------------------------
+    def ptap(self, A, M, keep_AP=False):
+        """C = M^T A M on windowed operands (MatPtAP, common.py:1194-1195)."""
+        wA, wM, wMT = self.window("A"), self.window("M"), self.window("MT")
+        wP, wPT, wC = self.window("P"), self.window("PT"), self.window("C")
+        AP = dev.empty(wP.nnz)
+        check(lib.tg_ptap_ap(wA.ref(), dev.ptr(A.vals), wM.ref(), dev.ptr(M.vals), wMT.ref(),
+                             wP.ref(), dev.ptr(AP), dev.stream()))
+        Cm = WinMatrix(wC, dev.empty(wC.nnz))
+        check(lib.tg_ptap_c(wM.ref(), dev.ptr(M.vals), wMT.ref(), wP.ref(), dev.ptr(AP),
+                            wPT.ref(), wC.ref(), dev.ptr(Cm.vals), dev.stream()))
+        if keep_AP:
+            return Cm, WinMatrix(wP, AP)
+        return Cm
+
+    def bc_mask(self, zeroDofs):
+        m = np.zeros(self.n_iga, dtype=np.uint8)
+        z = np.asarray(zeroDofs, dtype=np.int64)
+        if z.size:
+            m[z] = 1
+        return dev.from_np(m)
+
+    def apply_bcs_matrix(self, Cm, mask, diag=1.0):
+        check(lib.tg_win_zero_rows_cols(Cm.window.ref(), dev.ptr(Cm.vals), dev.ptr(mask),
+                                        dev.ptr(mask), float(diag), 0, dev.stream()))
+        return Cm
+
+    def apply_bcs_vector(self, b, mask):
+        check(lib.tg_zero_entries(dev.ptr(b), dev.ptr(mask), b.numel(), dev.stream()))
+        return b
+
+    def solve_cg(self, Cm, b, x=None, rtol=1e-12, atol=0.0, maxit=100000, check_every=25):
+        n = Cm.window.nrows
+        x = dev.zeros(n) if x is None else x
+        work = dev.empty(4 * n + lib.tg_cg_scratch_len() + 8)
+        its = C.c_int32(0)
+        rel = C.c_double(0.0)
+        check(lib.tg_win_solve_cg(Cm.window.ref(), dev.ptr(Cm.vals), dev.ptr(b), dev.ptr(x),
+                                  float(rtol), float(atol), int(maxit), int(check_every),
+                                  dev.ptr(work), C.byref(its), C.byref(rel), dev.stream()))
+        return x, its.value, rel.value
