@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""
+bench.py -- the reference's hot path (extract -> assemble -> M^T A M / M^T b ->
+BCs -> solve) on synthetic tensor-product B-spline patches.
+
+  python bench.py --gpus N --steps K --warmup W            (our CUDA path)
+  python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm)
+
+Metric (BASELINE.json): IGA DoF/s end to end.  One "step" = one complete pass
+of the hot path over the patch.  Workload at N=1: BASELINE configs[1], 3-D
+cubic B-spline Poisson on 256^3 cells (17.4 M IGA DoFs), element-fused path
+(global A_FE would be 682 GB).
+
+  value     device-timed throughput, control net / knots already resident in HBM
+  e2e       same pass through the tIGAr API from HOST buffers (pinned control
+            net H2D, solution vector D2H inside the timed region)
+  roofline  the dominant kernel (windowed SpMV inside CG, HBM-bound), timed
+            live with CUDA events on the solver stream
+  cpu_baseline  the numpy/scipy oracle ("port") on a bounded sample, host cores
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "DoF/s end-to-end (extract+assemble+PtAP+solve)"
+UNIT = "DoF/s"
+P = 3
+CG_RTOL = 1e-10
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs")), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ problem
+def build_inputs(nel):
+    """Host-side inputs of one step: knot vectors, Greville control net (pinned),
+    zero-DoF lists.  Built once; they are the step's INPUT, not its work."""
+    import numpy as np
+    import torch
+    from tIGAr.BSplines import ExplicitBSplineControlMesh, uniformKnots
+    kv = [uniformKnots(P, 0.0, 1.0, nel) for _ in range(3)]
+    cm = ExplicitBSplineControlMesh([P] * 3, kv)
+    net = cm.controlNet()
+    pinned = torch.from_numpy(net)
+    if torch.cuda.is_available():
+        pinned = pinned.pin_memory()
+    return kv, cm, pinned
+
+
+def one_step(kv, cm, control_net, mode, rtol, to_host):
+    """One pass of the hot path through the tIGAr API.  Returns
+    (n_dofs, cg_iterations, stage event list, result)."""
+    import torch
+    from tIGAr import (EqualOrderSpline, ExtractedSpline, TrialFunction, TestFunction,
+                       Function, KrylovSolver, inner, sin, pi)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    ev[0].record()
+    gen = EqualOrderSpline(1, cm)
+    sp = gen.getScalarSpline(0)
+    for d in range(3):
+        for side in (0, 1):
+            gen.addZeroDofs(0, sp.getSideDofs(d, side))
+    spline = ExtractedSpline(gen, 2 * P, mode=mode, controlNet=control_net)
+    ks = KrylovSolver("cg", "jacobi")
+    ks.parameters["relative_tolerance"] = rtol
+    spline.setSolverOptions(linearSolver=ks)
+    ev[1].record()                                              # extract done
+    u, v = TrialFunction(spline.V), TestFunction(spline.V)
+    x = spline.spatialCoordinates()
+    f = 3 * pi ** 2 * sin(pi * x[0]) * sin(pi * x[1]) * sin(pi * x[2])
+    a = inner(spline.grad(u), spline.grad(v)) * spline.dx
+    L = inner(f, v) * spline.dx
+    MTAM, MTb = spline.assembleLinearSystem(a, L)
+    ev[2].record()                                              # assemble + PtAP + BCs done
+    uh = Function(spline.V)
+    U = spline.solveLinearSystem(MTAM, MTb, uh)
+    ev[3].record()                                              # solve done
+    res = U.get_local() if to_host else U.t
+    ev[4].record()
+    return spline._patch.n_iga, spline.lastSolve["iterations"], ev, res, MTAM
+
+
+def spmv_bytes(W):
+    """Algorithmic bytes of one windowed SpMV launch: values once (8 B/nnz, no
+    column indices exist), row pointer + x read + y write per row."""
+    return 8 * W.nnz + (8 + 8 + 8) * W.nrows
+
+
+# ------------------------------------------------------------------ CPU arm
+def cpu_port_step(nel):
+    import numpy as np
+    from oracle import pipeline as OP
+    from oracle import bsplines as OB
+    kv = [OB.uniform_knots(P, 0.0, 1.0, nel)] * 3
+    pr = OP.Problem([P] * 3, kv)
+    f = lambda X: 3 * math.pi ** 2 * np.prod(np.sin(math.pi * X), axis=-1)
+    t = time.perf_counter()
+    pr.extract()
+    pr.assemble(f)
+    pr.ptap()
+    pr.solve("cg", CG_RTOL)
+    return pr.ts.ncp, time.perf_counter() - t, pr.iters
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nel = args.ref_nel
+    cores = os.cpu_count()
+    for _ in range(args.warmup):
+        cpu_port_step(nel)
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(args.steps):
+        nd, _, its = cpu_port_step(nel)
+        n += nd
+    dt = time.perf_counter() - t0
+    val = n / dt
+    sample = "3-D cubic B-spline Poisson, %d^3 cells (%d DoFs) per step, CG rtol %g" % (
+        nel, nd, CG_RTOL)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3D cubic B-spline Poisson %d^3 cells" % args.nel,
+                   "note": "CPU arm runs a bounded sample of the workload: " + sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample + "; numpy/scipy oracle (FEniCS/PETSc absent); "
+                                            "BLAS may use all %d host threads" % cores},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from tigar_b200._lib import lib
+    import ctypes as C
+
+    if world > 1:
+        from tigar_b200 import multigpu
+        return multigpu.bench(args, METRIC, UNIT, CG_RTOL)
+
+    nel = args.nel
+    mode = args.mode
+    kv, cm, pinned = build_inputs(nel)
+    dev_cols = [pinned[:, i].contiguous().cuda() for i in range(4)]    # resident inputs
+
+    def barrier():
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step(kv, cm, dev_cols, mode, CG_RTOL, False)
+    barrier()
+
+    # ---- device-resident timing (value) + live SpMV timing --------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    lib.tg_prof_enable(1)
+    l0 = lib.tg_launch_count()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    stages = []
+    for _ in range(args.steps):
+        n_dofs, iters, ev, _, MTAM = one_step(kv, cm, dev_cols, mode, CG_RTOL, False)
+        stages.append(ev)
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    launches = lib.tg_launch_count() - l0
+    spmv_ms, spmv_n = C.c_double(0), C.c_int64(0)
+    lib.tg_prof_get(C.byref(spmv_ms), C.byref(spmv_n))
+    lib.tg_prof_enable(0)
+    clocks = sampler.stop()
+    W = MTAM.window
+    stage_ms = {"extract": 0.0, "assemble_ptap_bcs": 0.0, "solve": 0.0}
+    for ev in stages:
+        stage_ms["extract"] += ev[0].elapsed_time(ev[1])
+        stage_ms["assemble_ptap_bcs"] += ev[1].elapsed_time(ev[2])
+        stage_ms["solve"] += ev[2].elapsed_time(ev[3])
+    for k in stage_ms:
+        stage_ms[k] /= max(args.steps, 1)
+    del MTAM, stages
+    value = n_dofs * args.steps / (ms * 1e-3)
+
+    # ---- end to end from host buffers -----------------------------------------
+    for _ in range(1):
+        one_step(kv, cm, pinned, mode, CG_RTOL, True)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, _, _, res, MT = one_step(kv, cm, pinned, mode, CG_RTOL, True)
+        del MT
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - wall0))
+    e2e = {"value": n_dofs * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": int(pinned.numel() * 8 + sum(len(k) for k in kv) * 8),
+           "d2h_bytes_per_step": int(n_dofs * 8)}
+
+    peak, which = measured_peaks()
+    bytes_per_launch = spmv_bytes(W)
+    avg_ms = spmv_ms.value / max(spmv_n.value, 1)
+    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_win_spmv<true> (CG matvec + p.Ap partials)",
+                "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
+                "launches_timed": int(spmv_n.value),
+                "share_of_step": spmv_ms.value / ms if ms > 0 else None}
+    tfile = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    if os.path.exists(tfile):
+        try:
+            with open(tfile) as f:
+                roofline["traffic"] = json.load(f).get(str(nel))
+        except Exception:
+            pass
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3D cubic B-spline Poisson %d^3 cells, 1 GPU (BASELINE configs[1])"
+                               % nel if nel == 256 else
+                               "3D cubic B-spline Poisson %d^3 cells" % nel,
+                   "degree": P, "cells": nel ** 3, "iga_dofs": n_dofs, "path": mode,
+                   "quad_degree": 2 * P, "cg_rtol": CG_RTOL, "cg_iterations": iters,
+                   "preconditioner": "jacobi",
+                   "l2": "inputs larger than L2 (matrix %.1f GB streamed every CG iteration)"
+                         % (8e-9 * W.nnz)},
+        "stage_ms": stage_ms, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline}
+
+    if not args.no_ptap:
+        out["ptap"] = ptap_roofline(args.ptap_nel, peak)
+    if not args.no_cpu:
+        nd, dt, its = cpu_port_step(args.cpu_nel)
+        out["cpu_baseline"] = {
+            "value": nd / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": "same problem at %d^3 cells (%d DoFs), one pass, %.1f s, CG its %d; "
+                      "numpy/scipy oracle" % (args.cpu_nel, nd, dt, its)}
+    print(json.dumps(out))
+
+
+def ptap_roofline(nel, peak):
+    """The global-CSR M^T A M (MatPtAP) at the largest 3-D cubic size that is
+    cheap to hold: achieved HBM GB/s of the two kernels (BASELINE.json's second
+    metric).  Algorithmic bytes: each operand streamed once, outputs written
+    once, 8 B per stored value (windowed CSR stores no column indices)."""
+    import torch
+    from tigar_b200.engine import TensorPatch, WinMatrix
+    from tigar_b200 import dev
+    from tIGAr.BSplines import uniformKnots
+    kv = [uniformKnots(P, 0.0, 1.0, nel)] * 3
+    patch = TensorPatch([P] * 3, kv)
+    M = patch.build_M()
+    A = WinMatrix(patch.window("A"))
+    A.vals.fill_(1.0)
+    ts = []
+    for rep in range(4):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        e[0].record()
+        Cm = patch.ptap(A, M)
+        e[1].record()
+        torch.cuda.synchronize()
+        ts.append(e[0].elapsed_time(e[1]))
+        del Cm
+    ms = min(ts[1:])
+    wA, wM, wP, wC = (patch.window(k) for k in "AMPC")
+    b = 8 * (wA.nnz + wM.nnz + 2 * wP.nnz + wM.nnz + wC.nnz)
+    return {"workload": "3D cubic %d^3 global-CSR PtAP (AP=A*M then C=M^T*AP)" % nel,
+            "ms": ms, "bytes": b, "achieved": b / (ms * 1e-3) / 1e9, "unit": "GB/s",
+            "frac": b / (ms * 1e-3) / 1e9 / peak,
+            "nnz": {"A": wA.nnz, "M": wM.nnz, "AP": wP.nnz, "C": wC.nnz}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nel", type=int, default=256)
+    ap.add_argument("--mode", default="fused", choices=["fused", "csr"])
+    ap.add_argument("--cpu-nel", type=int, default=20)
+    ap.add_argument("--ref-nel", type=int, default=16)
+    ap.add_argument("--ptap-nel", type=int, default=48)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ptap", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -58,6 +58,8 @@ typedef struct {
 
 const char* tg_last_error(void);
 int tg_version(void);
+/* kernels launched by this library so far (bench.py's gpu_launches claim) */
+int64_t tg_launch_count(void);
 /* number of SMs of the current device (grid sizing) */
 int tg_device_sm_count(void);
 
@@ -222,6 +224,12 @@ int tg_solve_cg(const int64_t* rowptr, const int32_t* cols, const double* vals,
                 const double* b, double* x, int64_t n,
                 double rtol, double atol, int32_t maxit, int32_t check_every,
                 double* work, int32_t* h_iters, double* h_relres, void* stream);
+
+/* Live timing of the SpMV launches inside the CG drivers (CUDA events on the
+ * solver's stream, collected at the host checks): the roofline numerator of
+ * bench.py.  enable(1) resets the counters.                                  */
+void tg_prof_enable(int on);
+void tg_prof_get(double* spmv_ms, int64_t* spmv_launches);
 
 /* CG building blocks for the row-distributed multi-GPU solver (the host
  * interleaves torch.distributed halo exchange / all-reduce between them).

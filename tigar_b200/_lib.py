@@ -44,6 +44,7 @@ SIGNATURES = {
     "tg_last_error": [],
     "tg_version": [],
     "tg_device_sm_count": [],
+    "tg_launch_count": [],
     "tg_bspline_eval_batch": [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32,
                               c_vp, c_i64, c_vp, c_vp, c_vp, c_vp],
     "tg_fe_nodes_1d": [c_vp, c_i32, c_i32, c_vp, c_vp],
@@ -77,13 +78,15 @@ SIGNATURES = {
     "tg_cg_scratch_len": [],
     "tg_solve_cg": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_i32, c_i32,
                     c_vp, PI32, C.POINTER(c_dbl), c_vp],
+    "tg_prof_enable": [c_i32],
+    "tg_prof_get": [C.POINTER(c_dbl), C.POINTER(c_i64)],
     "tg_cg_spmv_dot": [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp],
     "tg_cg_init": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
     "tg_cg_axpy_dot": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp],
     "tg_cg_xpby": [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
     "tg_dot": [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
 }
-_RESTYPES = {"tg_last_error": C.c_char_p}
+_RESTYPES = {"tg_last_error": C.c_char_p, "tg_prof_enable": None, "tg_prof_get": None, "tg_launch_count": c_i64}
 
 for _name, _args in SIGNATURES.items():
     _f = getattr(lib, _name)          # AttributeError if a symbol is missing

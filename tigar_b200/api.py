@@ -519,7 +519,12 @@ class ExtractedSpline(object):
     """common.py:667-1433."""
 
     def __init__(self, sourceArg, quadDeg, mesh=None, doPermutation=DEFAULT_DO_PERMUTATION,
-                 comm=worldcomm, mode=None):
+                 comm=worldcomm, mode=None, controlNet=None):
+        """``mode`` ("csr" / "fused") and ``controlNet`` (a ready [ncp, nsd+1]
+        homogeneous control net, host array or list of device tensors, instead
+        of the generator's per-node loop) are extensions of the reference
+        signature (common.py:676-706)."""
+        self._controlNetArg = controlNet
         if isinstance(sourceArg, AbstractExtractionGenerator):
             self.initFromGenerator(sourceArg, quadDeg, doPermutation)
         else:
@@ -546,7 +551,7 @@ class ExtractedSpline(object):
         self.V = FunctionSpace(self, self.nFields)
         self.V_control = FunctionSpace(self, 1, control=True)
         self.VE, self.VE_control = generator.VE, generator.VE_control
-        P = generator.controlNet()
+        P = self._controlNetArg if self._controlNetArg is not None else generator.controlNet()
         self._set_control_net(P)
         self.zeroDofs = np.unique(np.array(generator.zeroDofs, dtype=np.int64))
         self._M = None
@@ -580,11 +585,22 @@ class ExtractedSpline(object):
         self._M = None
 
     def _set_control_net(self, P):
-        self.controlNet = np.asarray(P, dtype=np.float64)
+        """P: [ncp, nsd+1] host array (torch pinned or numpy), or a list of
+        nsd+1 device tensors (already resident)."""
+        import torch
         self.cpFuncs = []
+        if isinstance(P, (list, tuple)):
+            cols = list(P)
+            self.controlNet = None
+        else:
+            t = P if isinstance(P, torch.Tensor) else torch.from_numpy(
+                np.ascontiguousarray(P, dtype=np.float64))
+            self.controlNet = t
+            d = t.to(dev.device(), non_blocking=True)            # one H2D copy
+            cols = [d[:, i].contiguous() for i in range(self.nsd + 1)]
         for i in range(self.nsd + 1):
             f = Function(self.V_control)
-            f.set_iga(dev.from_np(self.controlNet[:, i].copy()))
+            f.set_iga(cols[i])
             self.cpFuncs.append(f)
 
     def patch(self):

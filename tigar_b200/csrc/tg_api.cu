@@ -20,3 +20,8 @@ extern "C" int tg_device_sm_count(void) {
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
   return sms;
 }
+
+// number of kernels this library has launched (bench.py's gpu_launches)
+static long long g_launches = 0;
+void tg_count_launch() { g_launches++; }
+extern "C" int64_t tg_launch_count(void) { return (int64_t)g_launches; }

@@ -17,7 +17,12 @@ void tg_set_error(const char* fmt, ...);
     }                                                                         \
   } while (0)
 
-#define TG_LAUNCH_CHECK() TG_CHECK(cudaGetLastError())
+void tg_count_launch();
+#define TG_LAUNCH_CHECK()            \
+  do {                               \
+    tg_count_launch();               \
+    TG_CHECK(cudaGetLastError());    \
+  } while (0)
 
 #define TG_REQUIRE(cond, msg)                                                 \
   do {                                                                        \

@@ -3,6 +3,7 @@
 // :1236-1263 (solveLinearSystem; DOLFIN/PETSc solve()).
 // All reductions are two-stage with a fixed grid -> deterministic, no atomics.
 #include "tg_common.cuh"
+#include <stdlib.h>
 
 #define TG_CG_BLOCK 256
 static int g_cg_grid = 0;
@@ -252,6 +253,41 @@ extern "C" int tg_dot(const double* a, const double* b, int64_t n, double* scrat
   return 0;
 }
 
+// ---- optional live timing of the SpMV launches (bench.py roofline) -----------
+static int g_prof_on = 0;
+static double g_prof_spmv_ms = 0.0;
+static int64_t g_prof_spmv_n = 0;
+static cudaEvent_t* g_prof_ev = nullptr;
+static int g_prof_cap = 0;
+
+extern "C" void tg_prof_enable(int on) {
+  g_prof_on = on;
+  g_prof_spmv_ms = 0.0;
+  g_prof_spmv_n = 0;
+}
+extern "C" void tg_prof_get(double* spmv_ms, int64_t* spmv_launches) {
+  if (spmv_ms) *spmv_ms = g_prof_spmv_ms;
+  if (spmv_launches) *spmv_launches = g_prof_spmv_n;
+}
+static int tg_prof_reserve(int n) {
+  if (n <= g_prof_cap) return 0;
+  cudaEvent_t* ev = (cudaEvent_t*)realloc(g_prof_ev, sizeof(cudaEvent_t) * n);
+  if (!ev) return 1;
+  g_prof_ev = ev;
+  for (int i = g_prof_cap; i < n; i++) TG_CHECK(cudaEventCreate(&g_prof_ev[i]));
+  g_prof_cap = n;
+  return 0;
+}
+static void tg_prof_collect(int npairs) {
+  for (int k = 0; k < npairs; k++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof_ev[2 * k], g_prof_ev[2 * k + 1]) == cudaSuccess) {
+      g_prof_spmv_ms += ms;
+      g_prof_spmv_n++;
+    }
+  }
+}
+
 // Single-GPU driver shared by the general-CSR and the windowed-CSR solvers.
 // work: r[n] p[n] q[n] dinv[n] scratch[tg_cg_scratch_len()] s[8]
 // s: 0 rz_a, 1 rr_a, 2 pAp, 3 rz_b, 4 rr_b, 5 bb
@@ -269,6 +305,8 @@ static int tg_cg_driver(SPMV spmv, DIAG diag, const double* b, double* x, int64_
   double* s = scratch + tg_cg_scratch_len();
   if (check_every < 1) check_every = 1;
   int rc;
+  const int prof = g_prof_on;
+  if (prof && tg_prof_reserve(2 * check_every)) return 1;
   if ((rc = diag(dinv))) return rc;
   if ((rc = tg_dot(b, b, n, scratch, s + 5, stream))) return rc;
   // q = A x0 ; r = b - q ; p = dinv r
@@ -288,13 +326,16 @@ static int tg_cg_driver(SPMV spmv, DIAG diag, const double* b, double* x, int64_
     for (int k = 0; k < nstep; k++, it++) {
       double* cur = (it & 1) ? s + 3 : s + 0;   // rz, rr of current residual
       double* nxt = (it & 1) ? s + 0 : s + 3;
+      if (prof) cudaEventRecord(g_prof_ev[2 * k], st);
       if ((rc = spmv(p, q, s + 2))) return rc;
+      if (prof) cudaEventRecord(g_prof_ev[2 * k + 1], st);
       if ((rc = tg_cg_axpy_dot(x, r, p, q, dinv, n, cur, s + 2, scratch, nxt, stream))) return rc;
       if ((rc = tg_cg_xpby(p, r, dinv, n, nxt, cur, stream))) return rc;
     }
     double* last = (it & 1) ? s + 3 : s + 0;
     TG_CHECK(cudaMemcpyAsync(hs, last, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     TG_CHECK(cudaStreamSynchronize(st));
+    if (prof) tg_prof_collect(nstep);
     rr = hs[1];
     if (!(rr == rr)) {
       tg_set_error("CG produced NaN at iteration %d", it);
