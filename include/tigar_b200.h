@@ -160,6 +160,16 @@ int tg_assemble_matrix_ex(const tg_basis* h_B, const tg_win* h_W,
                           const double* coef, int64_t cell0, int64_t ncells,
                           double* vals, void* stream);
 
+/* Sum-factorised variant of tg_assemble_matrix_ex for 3-D bases with the same
+ * nloc = nq in {3,4,5} per direction (tg_assemble_sf_supported).  Only the
+ * listed terms are processed: h_terms = nterms x (slot, aS[3], aT[3]) where
+ * slot indexes coef[cell][slot][qp] (nslots slots per cell).                 */
+int tg_assemble_sf_supported(const tg_basis* h_B);
+int tg_assemble_matrix_terms(const tg_basis* h_B, const tg_win* h_W, int32_t nterms,
+                             const int32_t* h_terms, int32_t nslots,
+                             const int32_t* h_stride, const double* coef,
+                             int64_t cell0, int64_t ncells, double* vals, void* stream);
+
 /* b[I] += sum_q sum_s coef[cell][s][q] D^{aS_s}psi_I  (common.py:1169)       */
 int tg_assemble_vector(const tg_basis* h_B, int32_t nS, const int32_t* h_alphaS,
                        const double* coef, int64_t cell0, int64_t ncells,

@@ -67,6 +67,9 @@ SIGNATURES = {
     "tg_assemble_matrix": [PB, PW, c_i32, PI32, c_i32, PI32, c_vp, c_i64, c_i64, c_vp, c_vp],
     "tg_assemble_matrix_ex": [PB, PW, c_i32, PI32, c_i32, PI32, PI32, c_vp, c_i64, c_i64,
                               c_vp, c_vp],
+    "tg_assemble_sf_supported": [PB],
+    "tg_assemble_matrix_terms": [PB, PW, c_i32, PI32, c_i32, PI32, c_vp, c_i64, c_i64, c_vp,
+                                 c_vp],
     "tg_assemble_vector": [PB, c_i32, PI32, c_vp, c_i64, c_i64, c_vp, c_vp],
     "tg_assemble_vector_ex": [PB, c_i32, PI32, PI32, c_vp, c_i64, c_i64, c_vp, c_vp],
     "tg_sum": [c_vp, c_i64, c_vp, c_vp],

@@ -289,6 +289,186 @@ extern "C" int tg_assemble_matrix(const tg_basis* h_B, const tg_win* h_W, int32_
                                ncells, vals, stream);
 }
 
+// ---------------------------------------------------------------------------
+// Sum-factorised element matrices, 3-D, NL local functions and NQ Gauss points
+// per direction.  One CTA per cell, NL^4 threads: thread = (b1,a1,b2,a2) owns
+// the NL x NL block of (a3,b3) entries.  Per term (D^s v, D^t u, coefficient G):
+//   T1[a1,b1,q2,q3] = sum_q1 S1[q1,a1] T1[q1,b1] G[q1,q2,q3]      (shared)
+//   t2[q3]          = sum_q2 S2[q2,a2] T2[q2,b2] T1[a1,b1,q2,q3]  (registers)
+//   acc[a3][b3]    += sum_q3 S3[q3,a3] T3[q3,b3] t2[q3]
+// 3*NL^2*NQ^2 ... ~100 DFMA per thread per term instead of NQ^3 per entry.
+struct TgTerms {
+  int n;
+  int nslots;
+  short slot[TG_MAXJET * TG_MAXJET];
+  signed char aS[TG_MAXJET * TG_MAXJET][3];
+  signed char aT[TG_MAXJET * TG_MAXJET][3];
+};
+
+template <int NL, int NQ>
+__global__ void __launch_bounds__(NL* NL* NL* NL)
+k_assemble_matrix_sf3(TgBasis B, TgWin W, TgTerms TT, const double* __restrict__ coef,
+                      int64_t cell0, TgColour C, double* __restrict__ vals) {
+  constexpr int NT = NL * NL * NL * NL;
+  constexpr int NQP = NQ * NQ * NQ;
+  constexpr int NEN = NL * NL * NL;
+  constexpr int MAXD = 5;                       // derivative orders 0..4
+  __shared__ double G[NQP];
+  __shared__ double T1[NQ * NQ * NL * NL];      // [q3][q2][a1][b1]
+  __shared__ double tabs[3][MAXD][NQ][NL];      // [d][k][q][a]
+  __shared__ long long rbase[NEN];
+  __shared__ int gidx[3][NL], rlo[3][NL], rlen[3][NL];
+
+  const int tid = threadIdx.x;
+  const int b1 = tid % NL, a1 = (tid / NL) % NL, b2 = (tid / (NL * NL)) % NL,
+            a2 = tid / (NL * NL * NL);
+  int e[3];
+  tg_colour_cell(C, 3, blockIdx.x, e);
+  const int64_t cell = e[0] + (int64_t)B.nel[0] * (e[1] + (int64_t)B.nel[1] * e[2]);
+  const double* cc = coef + (cell - cell0) * (int64_t)TT.nslots * NQP;
+  const int nd = B.nder + 1;
+
+  for (int i = tid; i < 3 * nd * NQ * NL; i += NT) {
+    int a = i % NL, t = i / NL, q = t % NQ;
+    t /= NQ;
+    int k = t % nd, d = t / nd;
+    tabs[d][k][q][a] = B.tab[d][(((int64_t)e[d] * NQ + q) * NL + a) * nd + k];
+  }
+  if (tid < 3 * NL) {
+    int d = tid / NL, a = tid % NL;
+    int g = B.idx[d][e[d] * NL + a];
+    gidx[d][a] = g;
+    int lo = W.lo[d][g];
+    rlo[d][a] = lo;
+    rlen[d][a] = W.hi[d][g] - lo + 1;
+  }
+  __syncthreads();
+  for (int a = tid; a < NEN; a += NT) {
+    int l0 = a % NL, l1 = (a / NL) % NL, l2 = a / (NL * NL);
+    int64_t row = gidx[0][l0] + (int64_t)W.nr[0] * (gidx[1][l1] + (int64_t)W.nr[1] * gidx[2][l2]);
+    rbase[a] = W.rowptr[row];
+  }
+
+  double acc[NL][NL];
+#pragma unroll
+  for (int i = 0; i < NL; i++)
+#pragma unroll
+    for (int j = 0; j < NL; j++) acc[i][j] = 0.0;
+
+  for (int term = 0; term < TT.n; term++) {
+    const int s0 = TT.aS[term][0], s1 = TT.aS[term][1], s2 = TT.aS[term][2];
+    const int t0 = TT.aT[term][0], t1 = TT.aT[term][1], t2o = TT.aT[term][2];
+    const double* g = cc + (int64_t)TT.slot[term] * NQP;
+    __syncthreads();                           // previous term done with G / T1
+    for (int i = tid; i < NQP; i += NT) G[i] = g[i];
+    __syncthreads();
+    for (int o = tid; o < NQ * NQ * NL * NL; o += NT) {
+      int ob1 = o % NL, oa1 = (o / NL) % NL, q23 = o / (NL * NL);
+      double v = 0.0;
+#pragma unroll
+      for (int q1 = 0; q1 < NQ; q1++)
+        v += tabs[0][s0][q1][oa1] * tabs[0][t0][q1][ob1] * G[q23 * NQ + q1];
+      T1[o] = v;
+    }
+    __syncthreads();
+    double w2[NQ];
+#pragma unroll
+    for (int q2 = 0; q2 < NQ; q2++) w2[q2] = tabs[1][s1][q2][a2] * tabs[1][t1][q2][b2];
+    double t2[NQ];
+#pragma unroll
+    for (int q3 = 0; q3 < NQ; q3++) {
+      double v = 0.0;
+#pragma unroll
+      for (int q2 = 0; q2 < NQ; q2++) v += w2[q2] * T1[((q3 * NQ + q2) * NL + a1) * NL + b1];
+      t2[q3] = v;
+    }
+    double vv[NL][NQ];
+#pragma unroll
+    for (int b3 = 0; b3 < NL; b3++)
+#pragma unroll
+      for (int q3 = 0; q3 < NQ; q3++) vv[b3][q3] = tabs[2][t2o][q3][b3];
+#pragma unroll
+    for (int a3 = 0; a3 < NL; a3++) {
+      double w[NQ];
+#pragma unroll
+      for (int q3 = 0; q3 < NQ; q3++) w[q3] = t2[q3] * tabs[2][s2][q3][a3];
+#pragma unroll
+      for (int b3 = 0; b3 < NL; b3++) {
+        double v = acc[a3][b3];
+#pragma unroll
+        for (int q3 = 0; q3 < NQ; q3++) v += w[q3] * vv[b3][q3];
+        acc[a3][b3] = v;
+      }
+    }
+  }
+
+  // scatter: rows a = (a1,a2,a3), columns b = (b1,b2,b3)
+  const int d0 = gidx[0][b1] - rlo[0][a1];
+  const int d1 = gidx[1][b2] - rlo[1][a2];
+  const int len0 = rlen[0][a1], len1 = rlen[1][a2];
+#pragma unroll
+  for (int a3 = 0; a3 < NL; a3++) {
+    const int64_t base = rbase[a1 + NL * (a2 + NL * a3)];
+#pragma unroll
+    for (int b3 = 0; b3 < NL; b3++) {
+      const int d2 = gidx[2][b3] - rlo[2][a3];
+      const int64_t p = base + ((int64_t)d2 * len1 + d1) * len0 + d0;
+      vals[p] += acc[a3][b3];
+    }
+  }
+}
+
+extern "C" int tg_assemble_sf_supported(const tg_basis* h_B) {
+  if (h_B->dim != 3 || h_B->nder > 4) return 0;
+  int nl = h_B->nloc[0], nq = h_B->nq[0];
+  for (int d = 1; d < 3; d++)
+    if (h_B->nloc[d] != nl || h_B->nq[d] != nq) return 0;
+  return (nl == nq && (nl == 3 || nl == 4 || nl == 5)) ? 1 : 0;
+}
+
+extern "C" int tg_assemble_matrix_terms(const tg_basis* h_B, const tg_win* h_W, int32_t nterms,
+                                        const int32_t* h_terms, int32_t nslots,
+                                        const int32_t* h_stride, const double* coef,
+                                        int64_t cell0, int64_t ncells, double* vals,
+                                        void* stream) {
+  TG_REQUIRE(tg_assemble_sf_supported(h_B), "basis not supported by the sum-factorised kernel");
+  TG_REQUIRE(nterms >= 0 && nterms <= TG_MAXJET * TG_MAXJET, "term count");
+  if (nterms == 0 || ncells == 0) return 0;
+  TgBasis B = tg_basis_dev(h_B);
+  TgWin W = tg_win_dev(h_W);
+  TgTerms TT;
+  TT.n = nterms;
+  TT.nslots = nslots;
+  for (int i = 0; i < nterms; i++) {
+    const int32_t* t = h_terms + 7 * i;
+    TG_REQUIRE(t[0] >= 0 && t[0] < nslots, "term slot");
+    TT.slot[i] = (short)t[0];
+    for (int d = 0; d < 3; d++) {
+      TG_REQUIRE(t[1 + d] >= 0 && t[1 + d] <= h_B->nder && t[4 + d] >= 0 && t[4 + d] <= h_B->nder,
+                 "derivative order not tabulated");
+      TT.aS[i][d] = (signed char)t[1 + d];
+      TT.aT[i][d] = (signed char)t[4 + d];
+    }
+  }
+  int elo, ehi;
+  int rc = tg_colour_setup(h_B, h_stride, cell0, ncells, &elo, &ehi);
+  if (rc) return rc;
+  cudaStream_t s = tg_stream(stream);
+  const int nl = h_B->nloc[0];
+#define TG_LAUNCH_SF(N)                                                                        \
+  rc = tg_for_colours(h_B, h_stride, elo, ehi, [&](const TgColour& C, int64_t n) -> int {      \
+    k_assemble_matrix_sf3<N, N><<<(unsigned)n, N * N * N * N, 0, s>>>(B, W, TT, coef, cell0, C, \
+                                                                      vals);                   \
+    TG_LAUNCH_CHECK();                                                                         \
+    return 0;                                                                                  \
+  });
+  if (nl == 3) { TG_LAUNCH_SF(3) }
+  else if (nl == 4) { TG_LAUNCH_SF(4) }
+  else { TG_LAUNCH_SF(5) }
+#undef TG_LAUNCH_SF
+  return rc;
+}
+
 // element vector: one block per cell, threads over local functions
 __global__ void k_assemble_vector(TgBasis B, TgAlpha S, const double* __restrict__ coef,
                                   int64_t cell0, TgColour C, double* __restrict__ bvec) {

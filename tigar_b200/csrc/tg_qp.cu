@@ -28,55 +28,92 @@ struct TgOutSpec {
   int reg[TG_MAXOUT];
 };
 
+// One CTA per cell, one thread per Gauss point.  Jets are sum-factorised
+// through shared memory (3 small contractions per jet instead of a
+// nen-term sum per point), then every thread interprets the program.
 template <int NREG>
 __global__ void k_qp_eval(TgBasis B, TgJetSpec J, const int4* __restrict__ prog, int nprog,
                           const double* __restrict__ consts, TgOutSpec O, int64_t cell0,
                           int64_t ncells, int nqp, double* __restrict__ out) {
-  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t >= ncells * nqp) return;
-  int64_t cl = t / nqp;
-  int qp = (int)(t - cl * nqp);
-  int e[3], q[3];
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int64_t cl = blockIdx.x;
+  const int n0 = B.nloc[0], n1 = B.nloc[1], n2 = B.nloc[2];
+  const int q0n = B.nq[0], q1n = B.nq[1], q2n = B.nq[2];
+  const int nen = n0 * n1 * n2;
+  const int nd = B.nder + 1;
+  int e[3];
   tg_decode(cell0 + cl, B.nel, B.dim, e);
-  tg_decode(qp, B.nq, B.dim, q);
+
+  // smem: tabs[3][nq][nloc][nd] | c[nen] | s1[q0n*n1*n2] | s2[q0n*q1n*n2]
+  double* tb0 = sm;
+  double* tb1 = tb0 + q0n * n0 * nd;
+  double* tb2 = tb1 + q1n * n1 * nd;
+  double* cf = tb2 + q2n * n2 * nd;
+  double* s1 = cf + nen;
+  double* s2 = s1 + q0n * n1 * n2;
+  for (int i = tid; i < q0n * n0 * nd; i += nth) tb0[i] = B.tab[0][(int64_t)e[0] * q0n * n0 * nd + i];
+  for (int i = tid; i < q1n * n1 * nd; i += nth)
+    tb1[i] = (B.dim > 1) ? B.tab[1][(int64_t)e[1] * q1n * n1 * nd + i] : 1.0;
+  for (int i = tid; i < q2n * n2 * nd; i += nth)
+    tb2[i] = (B.dim > 2) ? B.tab[2][(int64_t)e[2] * q2n * n2 * nd + i] : 1.0;
+
+  const bool active = tid < nqp;
+  int q[3] = {0, 0, 0};
+  if (active) tg_decode(tid, B.nq, B.dim, q);
 
   double R[NREG];
-  double wq = 1.0;
-  const int nd = B.nder + 1;
-  const double* tb[3];
-  const int32_t* ix[3];
-  for (int d = 0; d < 3; d++) {
-    if (d < B.dim) {
+  if (active) {
+    double wq = 1.0;
+    for (int d = 0; d < B.dim; d++) {
       R[d] = B.xq[d][e[d] * B.nq[d] + q[d]];
       wq *= B.wq[d][e[d] * B.nq[d] + q[d]];
-      tb[d] = B.tab[d] + ((int64_t)e[d] * B.nq[d] + q[d]) * B.nloc[d] * nd;
-      ix[d] = B.idx[d] + e[d] * B.nloc[d];
-    } else {
-      tb[d] = nullptr;
-      ix[d] = nullptr;
     }
+    R[B.dim] = wq;
   }
-  R[B.dim] = wq;
   const int r0 = B.dim + 1;
-  for (int j = 0; j < J.njets; j++) R[r0 + j] = 0.0;
-
-  // jets: sum over local basis functions
-  const int n0 = B.nloc[0], n1 = B.nloc[1], n2 = B.nloc[2];
-  for (int a2 = 0; a2 < n2; a2++) {
-    int64_t g2 = (B.dim > 2) ? ix[2][a2] : 0;
-    for (int a1 = 0; a1 < n1; a1++) {
-      int64_t g1 = (B.dim > 1) ? ix[1][a1] : 0;
-      for (int a0 = 0; a0 < n0; a0++) {
-        int64_t g = ix[0][a0] + (int64_t)B.n[0] * (g1 + (int64_t)B.n[1] * g2);
-        for (int j = 0; j < J.njets; j++) {
-          double wgt = tb[0][a0 * nd + J.al[j][0]];
-          if (B.dim > 1) wgt *= tb[1][a1 * nd + J.al[j][1]];
-          if (B.dim > 2) wgt *= tb[2][a2 * nd + J.al[j][2]];
-          R[r0 + j] += wgt * J.coef[j][g * J.ncomp[j] + J.comp[j]];
-        }
+  const double* lastc = nullptr;
+  int lastcomp = -1;
+  for (int j = 0; j < J.njets; j++) {
+    const int a0 = J.al[j][0], a1 = (B.dim > 1) ? J.al[j][1] : 0, a2 = (B.dim > 2) ? J.al[j][2] : 0;
+    __syncthreads();
+    if (J.coef[j] != lastc || J.comp[j] != lastcomp) {
+      lastc = J.coef[j];
+      lastcomp = J.comp[j];
+      for (int a = tid; a < nen; a += nth) {
+        int l0 = a % n0, t = a / n0, l1 = t % n1, l2 = t / n1;
+        int64_t g = B.idx[0][e[0] * n0 + l0];
+        if (B.dim > 1) g += (int64_t)B.n[0] * B.idx[1][e[1] * n1 + l1];
+        if (B.dim > 2) g += (int64_t)B.n[0] * B.n[1] * B.idx[2][e[2] * n2 + l2];
+        cf[a] = lastc[g * J.ncomp[j] + lastcomp];
       }
+      __syncthreads();
+    }
+    // s1[(l2*n1 + l1)*q0n + q0] = sum_l0 c[l0,l1,l2] tab0[q0][l0][a0]
+    for (int o = tid; o < q0n * n1 * n2; o += nth) {
+      int qq = o % q0n, r = o / q0n;
+      double acc = 0.0;
+      for (int l0 = 0; l0 < n0; l0++) acc += cf[r * n0 + l0] * tb0[(qq * n0 + l0) * nd + a0];
+      s1[o] = acc;
+    }
+    __syncthreads();
+    // s2[(l2*q1n + q1)*q0n + q0] = sum_l1 s1[l2,l1,q0] tab1[q1][l1][a1]
+    for (int o = tid; o < q0n * q1n * n2; o += nth) {
+      int qq0 = o % q0n, t = o / q0n, qq1 = t % q1n, l2 = t / q1n;
+      double acc = 0.0;
+      for (int l1 = 0; l1 < n1; l1++)
+        acc += s1[(l2 * n1 + l1) * q0n + qq0] * tb1[(qq1 * n1 + l1) * nd + a1];
+      s2[o] = acc;
+    }
+    __syncthreads();
+    if (active) {
+      double acc = 0.0;
+      for (int l2 = 0; l2 < n2; l2++)
+        acc += s2[(l2 * q1n + q[1]) * q0n + q[0]] * tb2[(q[2] * n2 + l2) * nd + a2];
+      R[r0 + j] = acc;
     }
   }
+  if (!active) return;
 
   for (int pc = 0; pc < nprog; pc++) {
     int4 in = __ldg(&prog[pc]);
@@ -112,7 +149,7 @@ __global__ void k_qp_eval(TgBasis B, TgJetSpec J, const int4* __restrict__ prog,
     }
     R[in.y] = r;
   }
-  double* o = out + cl * (int64_t)O.nout * nqp + qp;
+  double* o = out + cl * (int64_t)O.nout * nqp + tid;
   for (int s = 0; s < O.nout; s++) o[(int64_t)s * nqp] = R[O.reg[s]];
 }
 
@@ -142,20 +179,32 @@ extern "C" int tg_qp_eval(const tg_basis* h_B, int32_t nfun, const double* const
   O.nout = nout;
   for (int s = 0; s < nout; s++) O.reg[s] = h_outregs[s];
   int nqp = B.nq[0] * B.nq[1] * B.nq[2];
-  int64_t nt = ncells * nqp;
-  if (nt == 0) return 0;
-  int bs = 128;
-  unsigned grid = (unsigned)tg_cdiv(nt, bs);
+  if (ncells == 0) return 0;
+  TG_REQUIRE(nqp <= 1024, "too many Gauss points per cell");
+  TG_REQUIRE(ncells < (int64_t)2147483647, "too many cells per launch");
+  // jets of one function must be adjacent so its coefficient tile is loaded once
+  int bs = ((nqp + 31) / 32) * 32;
+  unsigned grid = (unsigned)ncells;
+  const int nd = B.nder + 1;
+  size_t smem = 0;
+  for (int d = 0; d < 3; d++) smem += (size_t)B.nq[d] * B.nloc[d] * nd;
+  smem += (size_t)B.nloc[0] * B.nloc[1] * B.nloc[2];
+  smem += (size_t)B.nq[0] * B.nloc[1] * B.nloc[2];
+  smem += (size_t)B.nq[0] * B.nq[1] * B.nloc[2];
+  smem *= sizeof(double);
+  TG_REQUIRE(smem <= 48 * 1024, "element too large for the qp-eval shared-memory tiles");
   cudaStream_t s = tg_stream(stream);
   const int4* p4 = (const int4*)prog;
   if (nreg <= 32)
-    k_qp_eval<32><<<grid, bs, 0, s>>>(B, J, p4, nprog, consts, O, cell0, ncells, nqp, out);
+    k_qp_eval<32><<<grid, bs, smem, s>>>(B, J, p4, nprog, consts, O, cell0, ncells, nqp, out);
+  else if (nreg <= 64)
+    k_qp_eval<64><<<grid, bs, smem, s>>>(B, J, p4, nprog, consts, O, cell0, ncells, nqp, out);
   else if (nreg <= 128)
-    k_qp_eval<128><<<grid, bs, 0, s>>>(B, J, p4, nprog, consts, O, cell0, ncells, nqp, out);
+    k_qp_eval<128><<<grid, bs, smem, s>>>(B, J, p4, nprog, consts, O, cell0, ncells, nqp, out);
   else if (nreg <= 512)
-    k_qp_eval<512><<<grid, bs, 0, s>>>(B, J, p4, nprog, consts, O, cell0, ncells, nqp, out);
+    k_qp_eval<512><<<grid, bs, smem, s>>>(B, J, p4, nprog, consts, O, cell0, ncells, nqp, out);
   else if (nreg <= 2048)
-    k_qp_eval<2048><<<grid, bs, 0, s>>>(B, J, p4, nprog, consts, O, cell0, ncells, nqp, out);
+    k_qp_eval<2048><<<grid, bs, smem, s>>>(B, J, p4, nprog, consts, O, cell0, ncells, nqp, out);
   else {
     tg_set_error("qp program needs %d registers (max 2048)", nreg);
     return 2;

@@ -403,16 +403,34 @@ class TensorPatch(object):
         alS = sorted(set(pad3(k[0]) for k in terms))
         alT = sorted(set(pad3(k[1]) for k in terms))
         nS, nT = len(alS), len(alT)
+        W = self.window("A" if kind == "fe" else "C")
+        A = WinMatrix(W) if out is None else out
+        order = max(max(max(a) for a in alS + alT), self.jet_order(list(terms.values())))
+        B = self.basis(kind, order)
+        stride = i32arr([2] * self.dim if kind == "fe" else B.nloc)
+        if lib.tg_assemble_sf_supported(B.ref()):
+            # sum-factorised kernel: one coefficient slot per non-zero term
+            keys = sorted(terms, key=lambda k: (pad3(k[0]), pad3(k[1])))
+            P = self._qp_setup([terms[k] for k in keys], funcs)
+            tl = []
+            for i, k in enumerate(keys):
+                tl += [i] + list(pad3(k[0])) + list(pad3(k[1]))
+            h_terms = i32arr(tl)
+            nslots = len(keys)
+            buf = None
+            for cell0, nc in self._cell_chunks(nslots * B.nqp * 8):
+                if buf is None or buf.numel() < nc * nslots * B.nqp:
+                    buf = dev.empty(nc * nslots * B.nqp)
+                self._qp_eval(B, P, cell0, nc, buf)
+                check(lib.tg_assemble_matrix_terms(B.ref(), W.ref(), nslots, h_terms, nslots,
+                                                   stride, dev.ptr(buf), cell0, nc,
+                                                   dev.ptr(A.vals), dev.stream()))
+            return A
         grid = [[S.ZERO] * nT for _ in range(nS)]
         for (a, b), node in terms.items():
             grid[alS.index(pad3(a))][alT.index(pad3(b))] = node
         outputs = [grid[s][t] for s in range(nS) for t in range(nT)]
         P = self._qp_setup(outputs, funcs)
-        nder = max(P["nder"], max(max(a) for a in alS + alT))
-        B = self.basis(kind, nder)
-        W = self.window("A" if kind == "fe" else "C")
-        A = WinMatrix(W) if out is None else out
-        stride = i32arr([2] * self.dim if kind == "fe" else B.nloc)
         aS = i32arr([x for a in alS for x in a])
         aT = i32arr([x for a in alT for x in a])
         per_cell = nS * nT * B.nqp * 8
