@@ -54,6 +54,7 @@ typedef struct {
   const int32_t* lo[TG_MAXDIM];
   const int32_t* hi[TG_MAXDIM];
   const int64_t* rowptr;     /* [nrows+1]                                    */
+  int32_t w0max;             /* max over rows of the first-direction window length */
 } tg_win;
 
 const char* tg_last_error(void);

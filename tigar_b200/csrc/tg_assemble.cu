@@ -469,30 +469,72 @@ extern "C" int tg_assemble_matrix_terms(const tg_basis* h_B, const tg_win* h_W, 
   return rc;
 }
 
-// element vector: one block per cell, threads over local functions
+// element vector, sum-factorised through shared memory: one CTA per cell.
+//   u1[a0,q1,q2] = sum_q0 tab0[q0][a0][s0] c[q0,q1,q2]
+//   u2[a0,a1,q2] = sum_q1 tab1[q1][a1][s1] u1[a0,q1,q2]
+//   b[a0,a1,a2] += sum_q2 tab2[q2][a2][s2] u2[a0,a1,q2]
 __global__ void k_assemble_vector(TgBasis B, TgAlpha S, const double* __restrict__ coef,
                                   int64_t cell0, TgColour C, double* __restrict__ bvec) {
-  const int nen = B.nloc[0] * B.nloc[1] * B.nloc[2];
-  const int nqp = B.nq[0] * B.nq[1] * B.nq[2];
+  extern __shared__ double smv[];
+  const int n0 = B.nloc[0], n1 = B.nloc[1], n2 = B.nloc[2];
+  const int q0n = B.nq[0], q1n = B.nq[1], q2n = B.nq[2];
+  const int nen = n0 * n1 * n2;
+  const int nqp = q0n * q1n * q2n;
+  const int nd = B.nder + 1;
+  const int tid = threadIdx.x, nth = blockDim.x;
   int e[3];
   tg_colour_cell(C, B.dim, blockIdx.x, e);
   const int64_t cell = e[0] + (int64_t)B.nel[0] * (e[1] + (int64_t)B.nel[1] * e[2]);
   const double* cc = coef + (cell - cell0) * (int64_t)S.n * nqp;
-  for (int a = threadIdx.x; a < nen; a += blockDim.x) {
+  double* tb0 = smv;
+  double* tb1 = tb0 + q0n * n0 * nd;
+  double* tb2 = tb1 + q1n * n1 * nd;
+  double* cq = tb2 + q2n * n2 * nd;        // [nqp]
+  double* u1 = cq + nqp;                   // [q2][q1][a0]
+  double* u2 = u1 + n0 * q1n * q2n;        // [q2][a1][a0]
+  double* acc = u2 + n0 * n1 * q2n;        // [nen]
+  for (int i = tid; i < q0n * n0 * nd; i += nth) tb0[i] = B.tab[0][(int64_t)e[0] * q0n * n0 * nd + i];
+  for (int i = tid; i < q1n * n1 * nd; i += nth)
+    tb1[i] = (B.dim > 1) ? B.tab[1][(int64_t)e[1] * q1n * n1 * nd + i] : 1.0;
+  for (int i = tid; i < q2n * n2 * nd; i += nth)
+    tb2[i] = (B.dim > 2) ? B.tab[2][(int64_t)e[2] * q2n * n2 * nd + i] : 1.0;
+  for (int a = tid; a < nen; a += nth) acc[a] = 0.0;
+  for (int s = 0; s < S.n; s++) {
+    const int s0 = S.al[s][0], s1 = (B.dim > 1) ? S.al[s][1] : 0, s2 = (B.dim > 2) ? S.al[s][2] : 0;
+    __syncthreads();
+    for (int i = tid; i < nqp; i += nth) cq[i] = cc[(int64_t)s * nqp + i];
+    __syncthreads();
+    for (int o = tid; o < n0 * q1n * q2n; o += nth) {
+      int a0 = o % n0, r = o / n0;                     // r = q2*q1n + q1
+      double v = 0.0;
+      for (int q = 0; q < q0n; q++) v += tb0[(q * n0 + a0) * nd + s0] * cq[r * q0n + q];
+      u1[o] = v;
+    }
+    __syncthreads();
+    for (int o = tid; o < n0 * n1 * q2n; o += nth) {
+      int a0 = o % n0, t = o / n0, a1 = t % n1, q2 = t / n1;
+      double v = 0.0;
+      for (int q = 0; q < q1n; q++) v += tb1[(q * n1 + a1) * nd + s1] * u1[(q2 * q1n + q) * n0 + a0];
+      u2[o] = v;
+    }
+    __syncthreads();
+    for (int a = tid; a < nen; a += nth) {
+      int a01 = a % (n0 * n1), a2 = a / (n0 * n1);
+      double v = 0.0;
+      for (int q = 0; q < q2n; q++) v += tb2[(q * n2 + a2) * nd + s2] * u2[q * n0 * n1 + a01];
+      acc[a] += v;
+    }
+  }
+  __syncthreads();
+  for (int a = tid; a < nen; a += nth) {
     int al[3];
     tg_decode(a, B.nloc, B.dim, al);
-    double acc = 0.0;
-    for (int qp = 0; qp < nqp; qp++) {
-      int q[3];
-      tg_decode(qp, B.nq, B.dim, q);
-      for (int s = 0; s < S.n; s++) acc += cc[(int64_t)s * nqp + qp] * tg_jet1(B, e, q, al, S.al[s]);
-    }
     int64_t g = 0, mul = 1;
     for (int d = 0; d < B.dim; d++) {
       g += mul * B.idx[d][e[d] * B.nloc[d] + al[d]];
       mul *= B.n[d];
     }
-    bvec[g] += acc;
+    bvec[g] += acc[a];
   }
 }
 
@@ -513,9 +555,18 @@ extern "C" int tg_assemble_vector_ex(const tg_basis* h_B, int32_t nS, const int3
   if (rc) return rc;
   const int nen = B.nloc[0] * B.nloc[1] * B.nloc[2];
   int nth = nen < 32 ? 32 : (nen > 256 ? 256 : ((nen + 31) / 32) * 32);
+  const int nd = B.nder + 1;
+  size_t smem = 0;
+  for (int d = 0; d < 3; d++) smem += (size_t)B.nq[d] * B.nloc[d] * nd;
+  smem += (size_t)B.nq[0] * B.nq[1] * B.nq[2];
+  smem += (size_t)B.nloc[0] * B.nq[1] * B.nq[2];
+  smem += (size_t)B.nloc[0] * B.nloc[1] * B.nq[2];
+  smem += (size_t)nen;
+  smem *= sizeof(double);
+  TG_REQUIRE(smem <= 48 * 1024, "element too large for the vector-assembly tiles");
   cudaStream_t s = tg_stream(stream);
   return tg_for_colours(h_B, h_stride, elo, ehi, [&](const TgColour& C, int64_t n) -> int {
-    k_assemble_vector<<<(unsigned)n, nth, 0, s>>>(B, S, coef, cell0, C, b);
+    k_assemble_vector<<<(unsigned)n, nth, smem, s>>>(B, S, coef, cell0, C, b);
     TG_LAUNCH_CHECK();
     return 0;
   });

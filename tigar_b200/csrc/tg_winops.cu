@@ -21,7 +21,7 @@ int tg_ws_grid_size() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    g_ws_grid = sms * 8;   // 8 CTAs x 256 threads = 64 warps/SM, one wave
+    g_ws_grid = sms * 4;   // 4 CTAs x 256 threads resident per SM, one wave
   }
   return g_ws_grid;
 }
@@ -41,16 +41,32 @@ __device__ inline double tg_block_sum_ws(double v, double* sh) {
 }
 
 // DOT: also accumulate sum_r x[xoff + r] * y[r] into part[blockIdx.x]
+//
+// A CTA walks items (32 consecutive rows of one line).  For the line's window
+// shape (w0max x len1 x len2) it keeps in shared memory the x-offset of every
+// window position, so the fast path of a row is: lanes stride the row's
+// contiguous value array (fully coalesced 256 B loads), look the x offset up in
+// shared memory and gather x from L1/L2.  No integer divisions in the loop.
+// Rows whose first-direction window is clipped by the patch boundary take the
+// generic path.
+#define TG_WS_MAXTAB 1024
 template <bool DOT>
-__global__ void __launch_bounds__(TG_WS_BLOCK)
+__global__ void __launch_bounds__(TG_WS_BLOCK, 4)
 k_win_spmv(TgWin w, const double* __restrict__ vals, const double* __restrict__ x,
-           int64_t xoff, double* __restrict__ y, int nchunk, int nitems,
+           int64_t xoff, double* __restrict__ y, int nchunk, int nitems, int w0max,
            double* __restrict__ part) {
   __shared__ double sh[32];
+  __shared__ int xtab[TG_WS_MAXTAB];
+  __shared__ int tab_len1, tab_len2;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nr0 = w.nr[0], nr1 = w.nr[1];
-  const int64_t nc0 = w.nc[0];
-  const int64_t pl = nc0 * w.nc[1];          // x plane stride
+  const int nc0 = w.nc[0];
+  const int64_t pl = (int64_t)nc0 * w.nc[1];          // x plane stride
+  if (threadIdx.x == 0) {
+    tab_len1 = -1;
+    tab_len2 = -1;
+  }
+  __syncthreads();
   double dot = 0.0;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int line = item / nchunk;
@@ -66,22 +82,46 @@ k_win_spmv(TgWin w, const double* __restrict__ vals, const double* __restrict__ 
       lo2 = __ldg(w.lo[2] + r2);
       len2 = __ldg(w.hi[2] + r2) - lo2 + 1;
     }
+    const int tile = len1 * len2;
+    const int ntab = w0max * tile;
+    const bool usetab = ntab <= TG_WS_MAXTAB;
+    if (usetab && (tab_len1 != len1 || tab_len2 != len2)) {      // uniform branch
+      __syncthreads();
+      for (int p = threadIdx.x; p < ntab; p += TG_WS_BLOCK) {
+        int c0 = p % w0max, t = p / w0max, c1 = t % len1, c2 = t / len1;
+        xtab[p] = c0 + nc0 * c1 + (int)pl * c2;
+      }
+      if (threadIdx.x == 0) {
+        tab_len1 = len1;
+        tab_len2 = len2;
+      }
+      __syncthreads();
+    }
     const int rend = min(nr0, ch * TG_WS_ROWS + TG_WS_ROWS);
-    const double* xb = x + nc0 * lo1 + pl * lo2;
+    const double* xb = x + (int64_t)nc0 * lo1 + pl * lo2;
     for (int r0 = ch * TG_WS_ROWS + wid; r0 < rend; r0 += TG_WS_BLOCK / 32) {
       const int64_t row = r0 + (int64_t)nr0 * line;
       const int lo0 = __ldg(w.lo[0] + r0);
       const int len0 = __ldg(w.hi[0] + r0) - lo0 + 1;
-      const int tile = len0 * len1;
       const double* __restrict__ av = vals + __ldg(w.rowptr + row);
+      const double* xr = xb + lo0;
+      const int n = len0 * tile;
       double acc = 0.0;
-      for (int t = lane; t < tile; t += 32) {
-        const int c1 = t / len0;
-        const int c0 = t - c1 * len0;
-        const double* xv = xb + lo0 + c0 + nc0 * c1;
-        const double* a = av + t;
-#pragma unroll 7
-        for (int c2 = 0; c2 < len2; c2++) acc += a[(int64_t)c2 * tile] * xv[c2 * pl];
+      if (usetab && len0 == w0max) {
+        double acc2 = 0.0;
+        int p = lane;
+        for (; p + 32 < n; p += 64) {
+          double a0 = __ldcs(av + p), a1 = __ldcs(av + p + 32);
+          acc += a0 * xr[xtab[p]];
+          acc2 += a1 * xr[xtab[p + 32]];
+        }
+        if (p < n) acc += __ldcs(av + p) * xr[xtab[p]];
+        acc += acc2;
+      } else {
+        for (int p = lane; p < n; p += 32) {
+          int c0 = p % len0, t = p / len0, c1 = t % len1, c2 = t / len1;
+          acc += av[p] * xr[c0 + nc0 * c1 + pl * c2];
+        }
       }
       acc = tg_warp_sum(acc);
       if (lane == 0) {
@@ -111,11 +151,13 @@ int tg_win_spmv_launch(const tg_win* h_w, const double* vals, const double* x, i
   if (nitems == 0) return 0;
   int g = tg_ws_grid_size();
   TgWin w = tg_win_dev(h_w);
+  TG_REQUIRE(h_w->w0max >= 1, "window descriptor lacks w0max");
   if (part)
-    k_win_spmv<true><<<g, TG_WS_BLOCK, 0, st>>>(w, vals, x, xoff, y, nchunk, (int)nitems, part);
+    k_win_spmv<true><<<g, TG_WS_BLOCK, 0, st>>>(w, vals, x, xoff, y, nchunk, (int)nitems,
+                                                h_w->w0max, part);
   else
     k_win_spmv<false><<<g, TG_WS_BLOCK, 0, st>>>(w, vals, x, xoff, y, nchunk, (int)nitems,
-                                                 nullptr);
+                                                 h_w->w0max, nullptr);
   TG_LAUNCH_CHECK();
   return 0;
 }

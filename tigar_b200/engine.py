@@ -110,6 +110,7 @@ class Window(object):
                     S_ptrs.append(0)
             rowptr = dev.empty(self.nrows + 1, dev.I64)
             w.rowptr = dev.ptr(rowptr)
+            w.w0max = int(self.len[0].max())
             check(lib.tg_win_rowptr(C.byref(w), (c_vp * 3)(*S_ptrs), dev.ptr(rowptr),
                                     dev.stream()))
             keep.append(rowptr)
@@ -353,7 +354,7 @@ class TensorPatch(object):
         return np.stack([a.ravel(order="F") for a in g], axis=1)
 
     # ---- (ii) Gauss-point assembly ----------------------------------------
-    def _cell_chunks(self, bytes_per_cell, budget=1 << 29):
+    def _cell_chunks(self, bytes_per_cell, budget=3 << 29):
         """Chunks of whole slabs of the last direction."""
         slab = self.ncells // self.nel[-1]
         per = max(1, int(budget // max(1, slab * bytes_per_cell)))
