@@ -179,6 +179,13 @@ int tg_assemble_vector(const tg_basis* h_B, int32_t nS, const int32_t* h_alphaS,
 int tg_assemble_vector_ex(const tg_basis* h_B, int32_t nS, const int32_t* h_alphaS,
                           const int32_t* h_stride, const double* coef,
                           int64_t cell0, int64_t ncells, double* b, void* stream);
+/* same, reading term s from coef[cell][h_slots[s]][qp] with nslots slots per
+ * cell (lets the matrix and the vector of one linear system share a single
+ * Gauss-point pass: assembleLinearSystem, common.py:1223-1234).             */
+int tg_assemble_vector_slots(const tg_basis* h_B, int32_t nS, const int32_t* h_alphaS,
+                             const int32_t* h_slots, int32_t nslots,
+                             const int32_t* h_stride, const double* coef,
+                             int64_t cell0, int64_t ncells, double* b, void* stream);
 
 /* sum over all entries (functional assembly, poisson.py:132); result on device */
 int tg_sum(const double* x, int64_t n, double* out1, void* stream);

@@ -72,6 +72,8 @@ SIGNATURES = {
                                  c_vp],
     "tg_assemble_vector": [PB, c_i32, PI32, c_vp, c_i64, c_i64, c_vp, c_vp],
     "tg_assemble_vector_ex": [PB, c_i32, PI32, PI32, c_vp, c_i64, c_i64, c_vp, c_vp],
+    "tg_assemble_vector_slots": [PB, c_i32, PI32, PI32, c_i32, PI32, c_vp, c_i64, c_i64, c_vp,
+                                 c_vp],
     "tg_sum": [c_vp, c_i64, c_vp, c_vp],
     "tg_ptap_ap": [PW, c_vp, PW, c_vp, PW, PW, c_vp, c_vp],
     "tg_ptap_c": [PW, c_vp, PW, PW, c_vp, PW, PW, c_vp, c_vp],

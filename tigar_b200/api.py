@@ -761,7 +761,21 @@ class ExtractedSpline(object):
         return MTAM
 
     def assembleLinearSystem(self, lhsForm, rhsForm, applyBCs=True):
-        return (self.assembleMatrix(lhsForm, applyBCs), self.assembleVector(rhsForm, applyBCs))
+        """common.py:1223-1234.  Matrix and vector share one Gauss-point pass."""
+        kind = "fe" if self.mode == "csr" else "iga"
+        ms, vs = lhsForm.scalar(), rhsForm.scalar()
+        if ms.arity() != 2 or vs.arity() != 1 or any(k[0] is None for k in vs.terms):
+            return (self.assembleMatrix(lhsForm, applyBCs),
+                    self.assembleVector(rhsForm, applyBCs))
+        mt = {(k[0], k[1]): n for k, n in self._weighted(ms).items()}
+        vt = {k[0]: n for k, n in self._weighted(vs).items()}
+        A, b = self._patch.assemble_system(mt, vt, self._funcs(kind), kind)
+        if self.mode == "csr":
+            return (self.extractMatrix(A, applyBCs), self.extractVector(b, applyBCs))
+        if applyBCs:
+            self._patch.apply_bcs_matrix(A, self._bc_mask(), 1)
+            self._patch.apply_bcs_vector(b, self._bc_mask())
+        return A, DeviceVector(b)
 
     def solveLinearSystem(self, MTAM, MTb, u):
         """common.py:1236-1263: returns the IGA DoF vector, updates ``u``."""

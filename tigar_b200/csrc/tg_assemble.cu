@@ -313,7 +313,7 @@ k_assemble_matrix_sf3(TgBasis B, TgWin W, TgTerms TT, const double* __restrict__
   constexpr int NQP = NQ * NQ * NQ;
   constexpr int NEN = NL * NL * NL;
   constexpr int MAXD = 5;                       // derivative orders 0..4
-  __shared__ double G[NQP];
+  extern __shared__ double Gall[];               // [nterms][NQP]
   __shared__ double T1[NQ * NQ * NL * NL];      // [q3][q2][a1][b1]
   __shared__ double tabs[3][MAXD][NQ][NL];      // [d][k][q][a]
   __shared__ long long rbase[NEN];
@@ -328,6 +328,10 @@ k_assemble_matrix_sf3(TgBasis B, TgWin W, TgTerms TT, const double* __restrict__
   const double* cc = coef + (cell - cell0) * (int64_t)TT.nslots * NQP;
   const int nd = B.nder + 1;
 
+  for (int i = tid; i < TT.n * NQP; i += NT) {
+    int term = i / NQP;
+    Gall[i] = __ldcs(cc + (int64_t)TT.slot[term] * NQP + (i - term * NQP));
+  }
   for (int i = tid; i < 3 * nd * NQ * NL; i += NT) {
     int a = i % NL, t = i / NL, q = t % NQ;
     t /= NQ;
@@ -358,10 +362,8 @@ k_assemble_matrix_sf3(TgBasis B, TgWin W, TgTerms TT, const double* __restrict__
   for (int term = 0; term < TT.n; term++) {
     const int s0 = TT.aS[term][0], s1 = TT.aS[term][1], s2 = TT.aS[term][2];
     const int t0 = TT.aT[term][0], t1 = TT.aT[term][1], t2o = TT.aT[term][2];
-    const double* g = cc + (int64_t)TT.slot[term] * NQP;
-    __syncthreads();                           // previous term done with G / T1
-    for (int i = tid; i < NQP; i += NT) G[i] = g[i];
-    __syncthreads();
+    const double* G = Gall + term * NQP;
+    __syncthreads();                           // previous term done with T1 (and Gall loaded)
     for (int o = tid; o < NQ * NQ * NL * NL; o += NT) {
       int ob1 = o % NL, oa1 = (o / NL) % NL, q23 = o / (NL * NL);
       double v = 0.0;
@@ -406,16 +408,25 @@ k_assemble_matrix_sf3(TgBasis B, TgWin W, TgTerms TT, const double* __restrict__
   const int d0 = gidx[0][b1] - rlo[0][a1];
   const int d1 = gidx[1][b2] - rlo[1][a2];
   const int len0 = rlen[0][a1], len1 = rlen[1][a2];
+  double* ptr[NL][NL];
 #pragma unroll
   for (int a3 = 0; a3 < NL; a3++) {
     const int64_t base = rbase[a1 + NL * (a2 + NL * a3)];
 #pragma unroll
     for (int b3 = 0; b3 < NL; b3++) {
       const int d2 = gidx[2][b3] - rlo[2][a3];
-      const int64_t p = base + ((int64_t)d2 * len1 + d1) * len0 + d0;
-      vals[p] += acc[a3][b3];
+      ptr[a3][b3] = vals + base + ((int64_t)d2 * len1 + d1) * len0 + d0;
     }
   }
+  // colouring guarantees exclusive ownership: all loads first, then all stores
+#pragma unroll
+  for (int a3 = 0; a3 < NL; a3++)
+#pragma unroll
+    for (int b3 = 0; b3 < NL; b3++) acc[a3][b3] += *ptr[a3][b3];
+#pragma unroll
+  for (int a3 = 0; a3 < NL; a3++)
+#pragma unroll
+    for (int b3 = 0; b3 < NL; b3++) *ptr[a3][b3] = acc[a3][b3];
 }
 
 extern "C" int tg_assemble_sf_supported(const tg_basis* h_B) {
@@ -455,10 +466,12 @@ extern "C" int tg_assemble_matrix_terms(const tg_basis* h_B, const tg_win* h_W, 
   if (rc) return rc;
   cudaStream_t s = tg_stream(stream);
   const int nl = h_B->nloc[0];
+  const size_t gsm = (size_t)nterms * nl * nl * nl * sizeof(double);
+  TG_REQUIRE(gsm <= 40 * 1024, "too many terms for the coefficient tile");
 #define TG_LAUNCH_SF(N)                                                                        \
   rc = tg_for_colours(h_B, h_stride, elo, ehi, [&](const TgColour& C, int64_t n) -> int {      \
-    k_assemble_matrix_sf3<N, N><<<(unsigned)n, N * N * N * N, 0, s>>>(B, W, TT, coef, cell0, C, \
-                                                                      vals);                   \
+    k_assemble_matrix_sf3<N, N><<<(unsigned)n, N * N * N * N, gsm, s>>>(B, W, TT, coef, cell0,  \
+                                                                        C, vals);              \
     TG_LAUNCH_CHECK();                                                                         \
     return 0;                                                                                  \
   });
@@ -473,7 +486,12 @@ extern "C" int tg_assemble_matrix_terms(const tg_basis* h_B, const tg_win* h_W, 
 //   u1[a0,q1,q2] = sum_q0 tab0[q0][a0][s0] c[q0,q1,q2]
 //   u2[a0,a1,q2] = sum_q1 tab1[q1][a1][s1] u1[a0,q1,q2]
 //   b[a0,a1,a2] += sum_q2 tab2[q2][a2][s2] u2[a0,a1,q2]
-__global__ void k_assemble_vector(TgBasis B, TgAlpha S, const double* __restrict__ coef,
+struct TgSlots {
+  int nslots;
+  short slot[TG_MAXJET];
+};
+
+__global__ void k_assemble_vector(TgBasis B, TgAlpha S, TgSlots SL, const double* __restrict__ coef,
                                   int64_t cell0, TgColour C, double* __restrict__ bvec) {
   extern __shared__ double smv[];
   const int n0 = B.nloc[0], n1 = B.nloc[1], n2 = B.nloc[2];
@@ -485,7 +503,7 @@ __global__ void k_assemble_vector(TgBasis B, TgAlpha S, const double* __restrict
   int e[3];
   tg_colour_cell(C, B.dim, blockIdx.x, e);
   const int64_t cell = e[0] + (int64_t)B.nel[0] * (e[1] + (int64_t)B.nel[1] * e[2]);
-  const double* cc = coef + (cell - cell0) * (int64_t)S.n * nqp;
+  const double* cc = coef + (cell - cell0) * (int64_t)SL.nslots * nqp;
   double* tb0 = smv;
   double* tb1 = tb0 + q0n * n0 * nd;
   double* tb2 = tb1 + q1n * n1 * nd;
@@ -502,7 +520,7 @@ __global__ void k_assemble_vector(TgBasis B, TgAlpha S, const double* __restrict
   for (int s = 0; s < S.n; s++) {
     const int s0 = S.al[s][0], s1 = (B.dim > 1) ? S.al[s][1] : 0, s2 = (B.dim > 2) ? S.al[s][2] : 0;
     __syncthreads();
-    for (int i = tid; i < nqp; i += nth) cq[i] = cc[(int64_t)s * nqp + i];
+    for (int i = tid; i < nqp; i += nth) cq[i] = cc[(int64_t)SL.slot[s] * nqp + i];
     __syncthreads();
     for (int o = tid; o < n0 * q1n * q2n; o += nth) {
       int a0 = o % n0, r = o / n0;                     // r = q2*q1n + q1
@@ -538,10 +556,31 @@ __global__ void k_assemble_vector(TgBasis B, TgAlpha S, const double* __restrict
   }
 }
 
+extern "C" int tg_assemble_vector_slots(const tg_basis* h_B, int32_t nS, const int32_t* h_alphaS,
+                                        const int32_t* h_slots, int32_t nslots,
+                                        const int32_t* h_stride, const double* coef,
+                                        int64_t cell0, int64_t ncells, double* b, void* stream);
+
 extern "C" int tg_assemble_vector_ex(const tg_basis* h_B, int32_t nS, const int32_t* h_alphaS,
                                      const int32_t* h_stride, const double* coef,
                                      int64_t cell0, int64_t ncells, double* b, void* stream) {
+  int32_t slots[TG_MAXJET];
+  for (int i = 0; i < TG_MAXJET; i++) slots[i] = i;
+  return tg_assemble_vector_slots(h_B, nS, h_alphaS, slots, nS, h_stride, coef, cell0, ncells, b,
+                                  stream);
+}
+
+extern "C" int tg_assemble_vector_slots(const tg_basis* h_B, int32_t nS, const int32_t* h_alphaS,
+                                        const int32_t* h_slots, int32_t nslots,
+                                        const int32_t* h_stride, const double* coef,
+                                        int64_t cell0, int64_t ncells, double* b, void* stream) {
   TG_REQUIRE(nS >= 1 && nS <= TG_MAXJET, "jet count");
+  TgSlots SL;
+  SL.nslots = nslots;
+  for (int i = 0; i < nS; i++) {
+    TG_REQUIRE(h_slots[i] >= 0 && h_slots[i] < nslots, "slot index");
+    SL.slot[i] = (short)h_slots[i];
+  }
   TgBasis B = tg_basis_dev(h_B);
   TgAlpha S;
   S.n = nS;
@@ -566,7 +605,7 @@ extern "C" int tg_assemble_vector_ex(const tg_basis* h_B, int32_t nS, const int3
   TG_REQUIRE(smem <= 48 * 1024, "element too large for the vector-assembly tiles");
   cudaStream_t s = tg_stream(stream);
   return tg_for_colours(h_B, h_stride, elo, ehi, [&](const TgColour& C, int64_t n) -> int {
-    k_assemble_vector<<<(unsigned)n, nth, smem, s>>>(B, S, coef, cell0, C, b);
+    k_assemble_vector<<<(unsigned)n, nth, smem, s>>>(B, S, SL, coef, cell0, C, b);
     TG_LAUNCH_CHECK();
     return 0;
   });

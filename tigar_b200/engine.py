@@ -445,6 +445,46 @@ class TensorPatch(object):
                                             dev.stream()))
         return A
 
+    def assemble_system(self, mterms, vterms, funcs, kind="fe"):
+        """Matrix and vector of one linear system from a single Gauss-point
+        pass (the geometry sub-expressions are shared by hash-consing).
+        Returns (WinMatrix, vector)."""
+        alS = sorted(set(pad3(k) for k in vterms))
+        mk = sorted(mterms, key=lambda k: (pad3(k[0]), pad3(k[1])))
+        nodes = [mterms[k] for k in mk] + [vterms[a] for a in
+                                           sorted(vterms, key=lambda a: pad3(a))]
+        order = max([max(pad3(k[0]) + pad3(k[1])) for k in mk] + [max(a) for a in alS]
+                    + [self.jet_order(nodes)])
+        B = self.basis(kind, order)
+        if not lib.tg_assemble_sf_supported(B.ref()):
+            return (self.assemble_matrix(mterms, funcs, kind),
+                    self.assemble_vector(vterms, funcs, kind))
+        W = self.window("A" if kind == "fe" else "C")
+        A = WinMatrix(W)
+        b = dev.zeros(B.ntot)
+        P = self._qp_setup(nodes, funcs)
+        nm, nv = len(mk), len(alS)
+        nslots = nm + nv
+        tl = []
+        for i, k in enumerate(mk):
+            tl += [i] + list(pad3(k[0])) + list(pad3(k[1]))
+        h_terms = i32arr(tl)
+        aS = i32arr([x for a in alS for x in a])
+        vslots = i32arr([nm + i for i in range(nv)])
+        stride = i32arr([2] * self.dim if kind == "fe" else B.nloc)
+        buf = None
+        for cell0, nc in self._cell_chunks(nslots * B.nqp * 8):
+            if buf is None or buf.numel() < nc * nslots * B.nqp:
+                buf = dev.empty(nc * nslots * B.nqp)
+            self._qp_eval(B, P, cell0, nc, buf)
+            check(lib.tg_assemble_matrix_terms(B.ref(), W.ref(), nm, h_terms, nslots, stride,
+                                               dev.ptr(buf), cell0, nc, dev.ptr(A.vals),
+                                               dev.stream()))
+            check(lib.tg_assemble_vector_slots(B.ref(), nv, aS, vslots, nslots, stride,
+                                               dev.ptr(buf), cell0, nc, dev.ptr(b),
+                                               dev.stream()))
+        return A, b
+
     def assemble_vector(self, terms, funcs, kind="fe", out=None):
         """terms: {alphaTest: Node}."""
         alS = sorted(set(pad3(k) for k in terms))
