@@ -55,6 +55,8 @@ typedef struct {
   const int32_t* hi[TG_MAXDIM];
   const int64_t* rowptr;     /* [nrows+1]                                    */
   int32_t w0max;             /* max over rows of the first-direction window length */
+  const int64_t* S[TG_MAXDIM]; /* exclusive prefix sums of the window lengths,
+                                  [nr_d+1]: rowptr in closed form             */
 } tg_win;
 
 const char* tg_last_error(void);

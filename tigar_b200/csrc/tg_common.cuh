@@ -44,6 +44,7 @@ struct TgWin {
   const int32_t* lo[3];
   const int32_t* hi[3];
   const int64_t* rowptr;
+  const int64_t* S[3];
 };
 
 static inline TgWin tg_win_dev(const tg_win* w) {
@@ -54,6 +55,7 @@ static inline TgWin tg_win_dev(const tg_win* w) {
     d.nc[k] = (k < w->dim) ? w->nc[k] : 1;
     d.lo[k] = (k < w->dim) ? w->lo[k] : nullptr;
     d.hi[k] = (k < w->dim) ? w->hi[k] : nullptr;
+    d.S[k] = (k < w->dim) ? w->S[k] : nullptr;
   }
   d.rowptr = w->rowptr;
   return d;

@@ -99,24 +99,37 @@ k_win_spmv(TgWin w, const double* __restrict__ vals, const double* __restrict__ 
     }
     const int rend = min(nr0, ch * TG_WS_ROWS + TG_WS_ROWS);
     const double* xb = x + (int64_t)nc0 * lo1 + pl * lo2;
+    // rowptr in closed form: S0[r0]*len1*len2 + T0*(S1[r1]*len2 + T1*S2[r2])
+    int64_t linebase = 0;
+    if (w.dim > 1) {
+      const int64_t T0 = __ldg(w.S[0] + nr0);
+      int64_t inner = __ldg(w.S[1] + r1) * len2;
+      if (w.dim > 2) inner += __ldg(w.S[1] + nr1) * __ldg(w.S[2] + r2);
+      linebase = T0 * inner;
+    }
     for (int r0 = ch * TG_WS_ROWS + wid; r0 < rend; r0 += TG_WS_BLOCK / 32) {
       const int64_t row = r0 + (int64_t)nr0 * line;
       const int lo0 = __ldg(w.lo[0] + r0);
       const int len0 = __ldg(w.hi[0] + r0) - lo0 + 1;
-      const double* __restrict__ av = vals + __ldg(w.rowptr + row);
+      const double* __restrict__ av = vals + linebase + __ldg(w.S[0] + r0) * tile;
       const double* xr = xb + lo0;
       const int n = len0 * tile;
       double acc = 0.0;
       if (usetab && len0 == w0max) {
-        double acc2 = 0.0;
+        double acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
         int p = lane;
-        for (; p + 32 < n; p += 64) {
-          double a0 = __ldcs(av + p), a1 = __ldcs(av + p + 32);
-          acc += a0 * xr[xtab[p]];
-          acc2 += a1 * xr[xtab[p + 32]];
+        for (; p + 96 < n; p += 128) {
+          double a0 = __ldcs(av + p), a1 = __ldcs(av + p + 32), a2 = __ldcs(av + p + 64),
+                 a3 = __ldcs(av + p + 96);
+          double x0 = xr[xtab[p]], x1 = xr[xtab[p + 32]], x2 = xr[xtab[p + 64]],
+                 x3 = xr[xtab[p + 96]];
+          acc += a0 * x0;
+          acc1 += a1 * x1;
+          acc2 += a2 * x2;
+          acc3 += a3 * x3;
         }
-        if (p < n) acc += __ldcs(av + p) * xr[xtab[p]];
-        acc += acc2;
+        for (; p < n; p += 32) acc += __ldcs(av + p) * xr[xtab[p]];
+        acc += (acc1 + acc2) + acc3;
       } else {
         for (int p = lane; p < n; p += 32) {
           int c0 = p % len0, t = p / len0, c1 = t % len1, c2 = t / len1;

@@ -103,10 +103,12 @@ class Window(object):
                     ts = dev.from_np(np.concatenate([[0], np.cumsum(self.len[d])]).astype(np.int64))
                     keep += [tl, th, ts]
                     w.lo[d], w.hi[d] = dev.ptr(tl), dev.ptr(th)
+                    w.S[d] = dev.ptr(ts)
                     S_ptrs.append(dev.ptr(ts))
                 else:
                     w.nr[d], w.nc[d] = 1, 1
                     w.lo[d], w.hi[d] = None, None
+                    w.S[d] = None
                     S_ptrs.append(0)
             rowptr = dev.empty(self.nrows + 1, dev.I64)
             w.rowptr = dev.ptr(rowptr)
