@@ -57,6 +57,10 @@ typedef struct {
   int32_t w0max;             /* max over rows of the first-direction window length */
   const int64_t* S[TG_MAXDIM]; /* exclusive prefix sums of the window lengths,
                                   [nr_d+1]: rowptr in closed form             */
+  int32_t maxrow;            /* longest row (values); 0 = unknown: the TMA-staged
+                                SpMV is then not used.  The value array must be
+                                readable up to the next 16-byte boundary past
+                                its end (any separate allocation is).         */
 } tg_win;
 
 const char* tg_last_error(void);

@@ -31,7 +31,7 @@ class tg_basis(C.Structure):
 
 class tg_win(C.Structure):
     _fields_ = [("dim", c_i32), ("nr", c_i32 * 3), ("nc", c_i32 * 3),
-                ("lo", c_vp * 3), ("hi", c_vp * 3), ("rowptr", c_vp), ("w0max", c_i32), ("S", c_vp * 3)]
+                ("lo", c_vp * 3), ("hi", c_vp * 3), ("rowptr", c_vp), ("w0max", c_i32), ("S", c_vp * 3), ("maxrow", c_i32)]
 
 
 PB = C.POINTER(tg_basis)

@@ -11,6 +11,7 @@
 // pointer increments, so the inner loop is 2 loads + 1 DFMA, no index math.
 // HBM-bound: the value array is streamed exactly once, x is served by L1/L2.
 #include "tg_common.cuh"
+#include <stdlib.h>
 
 #define TG_WS_BLOCK 256
 #define TG_WS_ROWS 32   // rows of one line per item
@@ -149,6 +150,242 @@ k_win_spmv(TgWin w, const double* __restrict__ vals, const double* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------
+// TMA-staged variant: the value array of a windowed matrix is one contiguous
+// stream in row order, so each CTA owns a contiguous range of rows and a
+// producer warp pulls it through a ring of shared-memory stages with 1-D bulk
+// async copies (cp.async.bulk, SASS UBLKCP) completing on mbarriers; eight
+// consumer warps each reduce one row per stage out of shared memory while x is
+// gathered through L1/L2.  Keeps NS x 22 KB per CTA in flight, independent of
+// occupancy.
+#define TG_TMA_ROWS 8
+#define TG_TMA_CONSUMERS (TG_TMA_ROWS * 32)
+#define TG_TMA_THREADS (TG_TMA_CONSUMERS + 32)
+
+__device__ __forceinline__ uint32_t tg_smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void tg_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tg_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tg_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tg_smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tg_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tg_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tg_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  const uint32_t a = tg_smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tg_bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(tg_smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(tg_smem_u32(bar))
+      : "memory");
+}
+
+template <bool DOT>
+__global__ void __launch_bounds__(TG_TMA_THREADS)
+k_win_spmv_tma(TgWin w, const double* __restrict__ vals, const double* __restrict__ x,
+               int64_t xoff, double* __restrict__ y, int64_t nrows, int w0max, int NS,
+               int stage_doubles, double* __restrict__ part) {
+  extern __shared__ __align__(128) unsigned char tsm[];
+  double* bufs = (double*)tsm;                                       // [NS][stage_doubles]
+  long long* offs = (long long*)(bufs + (size_t)NS * stage_doubles);  // [NS][TG_TMA_ROWS + 2]
+  uint64_t* full = (uint64_t*)(offs + (size_t)NS * (TG_TMA_ROWS + 2));
+  uint64_t* empty = full + NS;
+  int* xtab = (int*)(empty + NS);                                    // [TG_WS_MAXTAB]
+  __shared__ double sh[32];
+  __shared__ int tab_len1, tab_len2;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nr0 = w.nr[0], nr1 = w.nr[1];
+  const int nc0 = w.nc[0];
+  const int64_t pl = (int64_t)nc0 * w.nc[1];
+  // contiguous row range of this CTA, in whole stages
+  const int64_t nstage_tot = (nrows + TG_TMA_ROWS - 1) / TG_TMA_ROWS;
+  const int64_t st0 = nstage_tot * blockIdx.x / gridDim.x;
+  const int64_t st1 = nstage_tot * (blockIdx.x + 1) / gridDim.x;
+  const int nst = (int)(st1 - st0);
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; s++) {
+      tg_mbar_init(&full[s], 1);
+      tg_mbar_init(&empty[s], TG_TMA_ROWS);
+    }
+    tab_len1 = -1;
+    tab_len2 = -1;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  double dot = 0.0;
+  if (wid == TG_TMA_ROWS) {
+    // ---------------- producer warp ----------------
+    for (int t = 0; t < nst; t++) {
+      const int s = t % NS;
+      const int k = t / NS;
+      if (k > 0) tg_mbar_wait(&empty[s], (uint32_t)((k - 1) & 1));
+      const int64_t rb = (st0 + t) * TG_TMA_ROWS;
+      const int64_t re = min(rb + (int64_t)TG_TMA_ROWS, nrows);
+      long long* o = offs + (size_t)s * (TG_TMA_ROWS + 2);
+      long long v = 0;
+      if (lane <= (int)(re - rb)) v = __ldg(w.rowptr + rb + lane);
+      const long long start = __shfl_sync(0xffffffffu, v, 0);
+      const long long end = __shfl_sync(0xffffffffu, v, (int)(re - rb));
+      const long long astart = start & ~1LL;                    // 16-byte aligned
+      if (lane <= TG_TMA_ROWS) o[lane] = v - astart;
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t bytes = (uint32_t)((((end - astart) * 8) + 15) & ~15LL);
+        tg_mbar_expect_tx(&full[s], bytes);
+        tg_bulk_g2s(bufs + (size_t)s * stage_doubles, vals + astart, bytes, &full[s]);
+      }
+    }
+  } else {
+    // ---------------- consumer warps: one row per stage each ----------------
+    for (int t = 0; t < nst; t++) {
+      const int s = t % NS;
+      const int k = t / NS;
+      const int64_t rb = (st0 + t) * TG_TMA_ROWS;
+      const int64_t re = min(rb + (int64_t)TG_TMA_ROWS, nrows);
+      // window shape of the stage's first row decides the shared x-offset table
+      {
+        const unsigned line = (unsigned)(rb / nr0);
+        const int r2 = (int)(line / (unsigned)nr1), r1 = (int)(line - (unsigned)r2 * nr1);
+        int len1 = 1, len2 = 1;
+        if (w.dim > 1) len1 = __ldg(w.hi[1] + r1) - __ldg(w.lo[1] + r1) + 1;
+        if (w.dim > 2) len2 = __ldg(w.hi[2] + r2) - __ldg(w.lo[2] + r2) + 1;
+        const int ntab = w0max * len1 * len2;
+        if (ntab <= TG_WS_MAXTAB && (tab_len1 != len1 || tab_len2 != len2)) {
+          asm volatile("bar.sync 1, %0;" ::"n"(TG_TMA_CONSUMERS) : "memory");
+          for (int p = tid; p < ntab; p += TG_TMA_CONSUMERS) {
+            int c0 = p % w0max, tt = p / w0max, c1 = tt % len1, c2 = tt / len1;
+            xtab[p] = c0 + nc0 * c1 + (int)pl * c2;
+          }
+          if (tid == 0) {
+            tab_len1 = len1;
+            tab_len2 = len2;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(TG_TMA_CONSUMERS) : "memory");
+        }
+      }
+      tg_mbar_wait(&full[s], (uint32_t)(k & 1));
+      const int64_t row = rb + wid;
+      if (row < re) {
+        const long long* o = offs + (size_t)s * (TG_TMA_ROWS + 2);
+        const double* sv = bufs + (size_t)s * stage_doubles + o[wid];
+        const unsigned line = (unsigned)(row / nr0);
+        const int r0 = (int)(row - (int64_t)line * nr0);
+        const int r2 = (int)(line / (unsigned)nr1), r1 = (int)(line - (unsigned)r2 * nr1);
+        int lo1 = 0, len1 = 1, lo2 = 0, len2 = 1;
+        if (w.dim > 1) {
+          lo1 = __ldg(w.lo[1] + r1);
+          len1 = __ldg(w.hi[1] + r1) - lo1 + 1;
+        }
+        if (w.dim > 2) {
+          lo2 = __ldg(w.lo[2] + r2);
+          len2 = __ldg(w.hi[2] + r2) - lo2 + 1;
+        }
+        const int lo0 = __ldg(w.lo[0] + r0);
+        const int len0 = __ldg(w.hi[0] + r0) - lo0 + 1;
+        const double* xr = x + lo0 + (int64_t)nc0 * lo1 + pl * lo2;
+        const int n = len0 * len1 * len2;
+        double acc = 0.0;
+        if (len0 == w0max && len1 == tab_len1 && len2 == tab_len2) {
+          double acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+          int p = lane;
+          for (; p + 96 < n; p += 128) {
+            double x0 = xr[xtab[p]], x1 = xr[xtab[p + 32]], x2 = xr[xtab[p + 64]],
+                   x3 = xr[xtab[p + 96]];
+            acc += sv[p] * x0;
+            acc1 += sv[p + 32] * x1;
+            acc2 += sv[p + 64] * x2;
+            acc3 += sv[p + 96] * x3;
+          }
+          for (; p < n; p += 32) acc += sv[p] * xr[xtab[p]];
+          acc += (acc1 + acc2) + acc3;
+        } else {
+          for (int p = lane; p < n; p += 32) {
+            int c0 = p % len0, tt = p / len0, c1 = tt % len1, c2 = tt / len1;
+            acc += sv[p] * xr[c0 + nc0 * c1 + pl * c2];
+          }
+        }
+        acc = tg_warp_sum(acc);
+        if (lane == 0) {
+          y[row] = acc;
+          if (DOT) dot += x[xoff + row] * acc;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) tg_mbar_arrive(&empty[s]);
+    }
+  }
+  if (DOT) {
+    dot = tg_block_sum_ws(dot, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = dot;
+  }
+}
+
+static int g_tma_smem_ok = -1;
+
+// returns 1 if launched, 0 if the shape does not fit the staged kernel
+static int tg_win_spmv_tma_try(const tg_win* h_w, const double* vals, const double* x,
+                               int64_t xoff, double* y, double* part, cudaStream_t st,
+                               int* launched) {
+  *launched = 0;
+  if (getenv("TIGAR_B200_NO_TMA")) return 0;
+  // largest row: w0max * max len1 * max len2 is not known on the host without the
+  // lo/hi arrays; S totals bound it: use nnz/nrows-free bound passed by the caller
+  if (h_w->maxrow <= 0 || (((uintptr_t)vals) & 15) != 0) return 0;
+  const int64_t nrows = tg_win_nrows(h_w);
+  if (nrows >= (int64_t)1 << 31) return 0;
+  int stage_doubles = (int)(((int64_t)TG_TMA_ROWS * h_w->maxrow + 2 + 15) & ~15);
+  size_t stage_bytes = (size_t)stage_doubles * 8;
+  const size_t budget = 100 * 1024;
+  int NS = (int)(budget / stage_bytes);
+  if (NS < 2) return 0;
+  if (NS > 6) NS = 6;
+  if ((int64_t)h_w->w0max * (h_w->maxrow / h_w->w0max) > TG_WS_MAXTAB) return 0;
+  size_t smem = (size_t)NS * stage_bytes + (size_t)NS * (TG_TMA_ROWS + 2) * 8 + 2 * NS * 8 +
+                TG_WS_MAXTAB * 4 + 128;
+  if (g_tma_smem_ok < 0) {
+    cudaError_t e1 = cudaFuncSetAttribute(k_win_spmv_tma<true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    cudaError_t e2 = cudaFuncSetAttribute(k_win_spmv_tma<false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    g_tma_smem_ok = (e1 == cudaSuccess && e2 == cudaSuccess) ? 1 : 0;
+  }
+  if (!g_tma_smem_ok) return 0;
+  int g = tg_ws_grid_size() / 2;          // 2 CTAs per SM
+  TgWin w = tg_win_dev(h_w);
+  if (part) {
+    // unused partial sums of the wider reduction grid must be zero
+    TG_CHECK(cudaMemsetAsync(part, 0, sizeof(double) * tg_ws_grid_size(), st));
+    k_win_spmv_tma<true><<<g, TG_TMA_THREADS, smem, st>>>(w, vals, x, xoff, y, nrows, h_w->w0max,
+                                                          NS, stage_doubles, part);
+  } else {
+    k_win_spmv_tma<false><<<g, TG_TMA_THREADS, smem, st>>>(w, vals, x, xoff, y, nrows,
+                                                           h_w->w0max, NS, stage_doubles, nullptr);
+  }
+  TG_LAUNCH_CHECK();
+  *launched = 1;
+  return 0;
+}
+
 static inline int64_t tg_win_lines(const tg_win* w) {
   int64_t n = 1;
   for (int d = 1; d < w->dim; d++) n *= w->nr[d];
@@ -158,6 +395,11 @@ static inline int64_t tg_win_lines(const tg_win* w) {
 int tg_win_spmv_launch(const tg_win* h_w, const double* vals, const double* x, int64_t xoff,
                        double* y, double* part, cudaStream_t st) {
   TG_REQUIRE(h_w->dim >= 1 && h_w->dim <= 3, "dim");
+  {
+    int launched = 0;
+    int rc = tg_win_spmv_tma_try(h_w, vals, x, xoff, y, part, st, &launched);
+    if (rc || launched) return rc;
+  }
   int nchunk = (int)tg_cdiv(h_w->nr[0], TG_WS_ROWS);
   int64_t nitems = tg_win_lines(h_w) * nchunk;
   TG_REQUIRE(nitems < (int64_t)2147483647, "too many row items");

@@ -113,6 +113,7 @@ class Window(object):
             rowptr = dev.empty(self.nrows + 1, dev.I64)
             w.rowptr = dev.ptr(rowptr)
             w.w0max = int(self.len[0].max())
+            w.maxrow = int(np.prod([int(l.max()) for l in self.len]))
             check(lib.tg_win_rowptr(C.byref(w), (c_vp * 3)(*S_ptrs), dev.ptr(rowptr),
                                     dev.stream()))
             keep.append(rowptr)
