@@ -235,6 +235,10 @@ k_win_spmv_tma(TgWin w, const double* __restrict__ vals, const double* __restric
   double dot = 0.0;
   if (wid == TG_TMA_ROWS) {
     // ---------------- producer warp ----------------
+    const long long T0 = __ldg(w.S[0] + nr0);
+    const long long T1 = (w.dim > 1) ? __ldg(w.S[1] + nr1) : 1;
+    const long long T2 = (w.dim > 2) ? __ldg(w.S[2] + w.nr[2]) : 1;
+    const long long nnz_total = T0 * T1 * T2;
     for (int t = 0; t < nst; t++) {
       const int s = t % NS;
       const int k = t / NS;
@@ -242,8 +246,27 @@ k_win_spmv_tma(TgWin w, const double* __restrict__ vals, const double* __restric
       const int64_t rb = (st0 + t) * TG_TMA_ROWS;
       const int64_t re = min(rb + (int64_t)TG_TMA_ROWS, nrows);
       long long* o = offs + (size_t)s * (TG_TMA_ROWS + 2);
+      // row offsets in closed form from the 1-D prefix sums (L1-resident):
+      // S0[r0]*len1*len2 + T0*(S1[r1]*len2 + T1*S2[r2]); no DRAM round trip.
       long long v = 0;
-      if (lane <= (int)(re - rb)) v = __ldg(w.rowptr + rb + lane);
+      if (lane <= (int)(re - rb)) {
+        const int64_t row = rb + lane;
+        if (row >= nrows) {
+          v = nnz_total;
+        } else {
+          const unsigned line = (unsigned)(row / nr0);
+          const int r0 = (int)(row - (int64_t)line * nr0);
+          const int r2 = (int)(line / (unsigned)nr1), r1 = (int)(line - (unsigned)r2 * nr1);
+          long long len1 = 1, len2 = 1, inner = 0;
+          if (w.dim > 2) len2 = __ldg(w.hi[2] + r2) - __ldg(w.lo[2] + r2) + 1;
+          if (w.dim > 1) {
+            len1 = __ldg(w.hi[1] + r1) - __ldg(w.lo[1] + r1) + 1;
+            inner = __ldg(w.S[1] + r1) * len2;
+            if (w.dim > 2) inner += T1 * __ldg(w.S[2] + r2);
+          }
+          v = __ldg(w.S[0] + r0) * len1 * len2 + T0 * inner;
+        }
+      }
       const long long start = __shfl_sync(0xffffffffu, v, 0);
       const long long end = __shfl_sync(0xffffffffu, v, (int)(re - rb));
       const long long astart = start & ~1LL;                    // 16-byte aligned
@@ -347,7 +370,10 @@ static int tg_win_spmv_tma_try(const tg_win* h_w, const double* vals, const doub
                                int64_t xoff, double* y, double* part, cudaStream_t st,
                                int* launched) {
   *launched = 0;
-  if (getenv("TIGAR_B200_NO_TMA")) return 0;
+  // Opt-in: on B200 the staged kernel reaches ~34 % of HBM peak (consumer warps
+  // are latency-bound on the x gathers at 16 warps/SM, profiles/r1_ncu_spmv_tma.txt)
+  // against ~63 % for the direct-load kernel below, so the latter is the default.
+  if (!getenv("TIGAR_B200_TMA_SPMV")) return 0;
   // largest row: w0max * max len1 * max len2 is not known on the host without the
   // lo/hi arrays; S totals bound it: use nnz/nrows-free bound passed by the caller
   if (h_w->maxrow <= 0 || (((uintptr_t)vals) & 15) != 0) return 0;
