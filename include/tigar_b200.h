@@ -57,6 +57,9 @@ typedef struct {
   int32_t w0max;             /* max over rows of the first-direction window length */
   const int64_t* S[TG_MAXDIM]; /* exclusive prefix sums of the window lengths,
                                   [nr_d+1]: rowptr in closed form             */
+  int32_t row0[TG_MAXDIM];   /* row-distributed blocks: global coordinate of local row /    */
+  int32_t col0[TG_MAXDIM];   /* column 0 per direction (0 for a whole matrix).  Assembly
+                                skips rows outside [row0, row0+nr).                        */
   int32_t maxrow;            /* longest row (values); 0 = unknown: the TMA-staged
                                 SpMV is then not used.  The value array must be
                                 readable up to the next 16-byte boundary past
@@ -192,6 +195,15 @@ int tg_assemble_vector_slots(const tg_basis* h_B, int32_t nS, const int32_t* h_a
                              const int32_t* h_slots, int32_t nslots,
                              const int32_t* h_stride, const double* coef,
                              int64_t cell0, int64_t ncells, double* b, void* stream);
+
+/* vector assembly into a slab of the global vector: only entries whose
+ * coordinate in direction d lies in [h_row0[d], h_row0[d]+h_nr[d]) are written,
+ * at local index (coordinate - row0), local sizes h_nr.                      */
+int tg_assemble_vector_part(const tg_basis* h_B, int32_t nS, const int32_t* h_alphaS,
+                            const int32_t* h_slots, int32_t nslots,
+                            const int32_t* h_stride, const int32_t* h_row0,
+                            const int32_t* h_nr, const double* coef,
+                            int64_t cell0, int64_t ncells, double* b, void* stream);
 
 /* sum over all entries (functional assembly, poisson.py:132); result on device */
 int tg_sum(const double* x, int64_t n, double* out1, void* stream);

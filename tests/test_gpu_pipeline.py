@@ -210,3 +210,53 @@ def test_write_and_read_extraction(tmp_path):
     U1 = spline.solveLinearVariationalProblem(a == L, u1).get_local()
     U2 = sp2.solveLinearVariationalProblem(a2 == L2, u2).get_local()
     assert rel(U1, U2) < 1e-12
+
+
+@pytest.mark.parametrize("size", [2, 3])
+@pytest.mark.parametrize("deg,nels", [([2, 2, 2], [3, 4, 5]), ([3, 3, 3], [3, 2, 6]), ([2, 2], [5, 7])])
+def test_slab_partitioned_assembly_matches_global(deg, nels, size):
+    """Every rank's block of the row-distributed system (assembled with halo
+    cell layers, rows it does not own skipped) equals the corresponding rows of
+    the oracle's global M^T A M / M^T b, BCs included.  Ranks are emulated one
+    after the other on one GPU (no communication is needed for assembly)."""
+    from tIGAr import EqualOrderSpline, ExtractedSpline
+    from tIGAr.BSplines import ExplicitBSplineControlMesh
+    from tigar_b200.api import _Comm
+
+    class FakeComm(_Comm):
+        def __init__(self, r, n):
+            _Comm.__init__(self, False)
+            self._r, self._n = r, n
+        rank = property(lambda self: self._r)
+        size = property(lambda self: self._n)
+
+    kv = [uk(p, n) for p, n in zip(deg, nels)]
+    _, _, pr = make_pair(deg, kv, mode="fused")
+    pr.extract()
+    pr.assemble(f_np("sin", len(deg)))
+    pr.ptap(diag=2.0)
+    Cg = pr.C.tocsr()
+    rows_seen = 0
+    for r in range(size):
+        gen = EqualOrderSpline(FakeComm(r, size), 1, ExplicitBSplineControlMesh(deg, kv))
+        sp = gen.getScalarSpline(0)
+        for d in range(len(deg)):
+            for side in (0, 1):
+                gen.addZeroDofs(0, sp.getSideDofs(d, side))
+        spline = ExtractedSpline(gen, 2 * max(deg))
+        assert spline.mode == "fused"
+        a, L = poisson_forms(spline, "sin")
+        patch = spline.patch()
+        pp, pl = patch.pp, patch.plane
+        A, b = spline.assembleLinearSystem(a, L)
+        # same diag as the oracle run
+        A2 = spline.assembleMatrix(a, diag=2.0)
+        r0, r1, c0, c1 = pp["k0"] * pl, pp["k1"] * pl, pp["c0"] * pl, pp["c1"] * pl
+        ref = Cg[r0:r1, c0:c1]
+        assert Cg[r0:r1].nnz == ref.nnz
+        assert relm(A2.to_scipy(), ref) < 1e-12
+        assert rel(b.get_local(), pr.b[r0:r1]) < 1e-12
+        b2 = spline.assembleVector(L)
+        assert rel(b2.get_local(), pr.b[r0:r1]) < 1e-12
+        rows_seen += r1 - r0
+    assert rows_seen == Cg.shape[0]

@@ -31,7 +31,8 @@ class tg_basis(C.Structure):
 
 class tg_win(C.Structure):
     _fields_ = [("dim", c_i32), ("nr", c_i32 * 3), ("nc", c_i32 * 3),
-                ("lo", c_vp * 3), ("hi", c_vp * 3), ("rowptr", c_vp), ("w0max", c_i32), ("S", c_vp * 3), ("maxrow", c_i32)]
+                ("lo", c_vp * 3), ("hi", c_vp * 3), ("rowptr", c_vp), ("w0max", c_i32), ("S", c_vp * 3), ("row0", c_i32 * 3), ("col0", c_i32 * 3),
+                ("maxrow", c_i32)]
 
 
 PB = C.POINTER(tg_basis)
@@ -74,6 +75,8 @@ SIGNATURES = {
     "tg_assemble_vector_ex": [PB, c_i32, PI32, PI32, c_vp, c_i64, c_i64, c_vp, c_vp],
     "tg_assemble_vector_slots": [PB, c_i32, PI32, PI32, c_i32, PI32, c_vp, c_i64, c_i64, c_vp,
                                  c_vp],
+    "tg_assemble_vector_part": [PB, c_i32, PI32, PI32, c_i32, PI32, PI32, PI32, c_vp, c_i64,
+                                c_i64, c_vp, c_vp],
     "tg_sum": [c_vp, c_i64, c_vp, c_vp],
     "tg_ptap_ap": [PW, c_vp, PW, c_vp, PW, PW, c_vp, c_vp],
     "tg_ptap_c": [PW, c_vp, PW, PW, c_vp, PW, PW, c_vp, c_vp],

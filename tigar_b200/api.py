@@ -529,6 +529,10 @@ class ExtractedSpline(object):
             self.initFromGenerator(sourceArg, quadDeg, doPermutation)
         else:
             self.initFromFilesystem(sourceArg, quadDeg, comm, mesh)
+        if self._patch.part is not None:
+            if mode not in (None, "fused"):
+                raise NotImplementedError("multi-GPU runs use the element-fused path")
+            mode = "fused"
         self.mode = mode or os.environ.get("TIGAR_B200_MODE") or self._auto_mode()
         if self.mode not in ("csr", "fused"):
             raise ValueError("mode must be 'csr' or 'fused'")
@@ -546,8 +550,9 @@ class ExtractedSpline(object):
         self.mesh = generator.mesh
         self.comm = generator.getComm()
         sp = generator._tensor_spline(-1)
+        part = (self.comm.rank, self.comm.size) if self.comm.size > 1 else None
         self._patch = TensorPatch([s.p for s in sp.splines], None, quadDeg=quadDeg,
-                                  splines=sp.splines, eps=generator.getIgnoreEps())
+                                  splines=sp.splines, eps=generator.getIgnoreEps(), part=part)
         self.V = FunctionSpace(self, self.nFields)
         self.V_control = FunctionSpace(self, 1, control=True)
         self.VE, self.VE_control = generator.VE, generator.VE_control
@@ -787,6 +792,9 @@ class ExtractedSpline(object):
         x0 = None if u.iga is None else u.iga.clone()
         x, its, rel = self._patch.solve_cg(MTAM, MTb.t, x0, rtol, atol, maxit)
         self.lastSolve = dict(iterations=its, relative_residual=rel)
+        if self._patch.part is not None:       # replicate the IGA DoF vector on every rank
+            from .multigpu import gather_planes
+            x = gather_planes(x, self._patch)
         u.set_iga(x)
         return DeviceVector(x)
 

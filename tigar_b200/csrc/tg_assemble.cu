@@ -64,16 +64,25 @@ k_assemble_matrix(TgBasis B, TgWin W, TgAlpha S, TgAlpha T, int sameST,
   for (int a = tid; a < nen; a += nth) {
     int al[3];
     tg_decode(a, B.nloc, B.dim, al);
-    int g[3] = {0, 0, 0};
-    for (int d = 0; d < B.dim; d++) g[d] = B.idx[d][e[d] * B.nloc[d] + al[d]];
-    int64_t row = g[0] + (int64_t)W.nr[0] * (g[1] + (int64_t)W.nr[1] * g[2]);
-    TgRowWin rw = tg_row_window(W, g);
-    rbase[a] = W.rowptr[row];
-    for (int d = 0; d < 3; d++) {
-      gc[3 * a + d] = g[d];
-      rlo[3 * a + d] = rw.lo[d];
-      rlen[3 * a + d] = rw.len[d];
+    int g[3] = {0, 0, 0}, rr[3] = {0, 0, 0};
+    bool valid = true;
+    for (int d = 0; d < B.dim; d++) {
+      g[d] = B.idx[d][e[d] * B.nloc[d] + al[d]];
+      rr[d] = g[d] - W.row0[d];
+      valid = valid && rr[d] >= 0 && rr[d] < W.nr[d];
     }
+    if (valid) {
+      int64_t row = rr[0] + (int64_t)W.nr[0] * (rr[1] + (int64_t)W.nr[1] * rr[2]);
+      TgRowWin rw = tg_row_window(W, rr);
+      rbase[a] = W.rowptr[row];
+      for (int d = 0; d < 3; d++) {
+        rlo[3 * a + d] = rw.lo[d];
+        rlen[3 * a + d] = rw.len[d];
+      }
+    } else {
+      rbase[a] = -1;
+    }
+    for (int d = 0; d < 3; d++) gc[3 * a + d] = g[d] - W.col0[d];
   }
 
   double acc[NACC];
@@ -140,6 +149,7 @@ k_assemble_matrix(TgBasis B, TgWin W, TgAlpha S, TgAlpha T, int sameST,
     int pair = tid + i * nth;
     if (pair < nen * nen) {
       int a = pair / nen, b = pair - a * nen;
+      if (rbase[a] < 0) continue;
       int pos = ((gc[3 * b + 2] - rlo[3 * a + 2]) * rlen[3 * a + 1] +
                  (gc[3 * b + 1] - rlo[3 * a + 1])) * rlen[3 * a + 0] +
                 (gc[3 * b + 0] - rlo[3 * a + 0]);
@@ -317,7 +327,7 @@ k_assemble_matrix_sf3(TgBasis B, TgWin W, TgTerms TT, const double* __restrict__
   __shared__ double T1[NQ * NQ * NL * NL];      // [q3][q2][a1][b1]
   __shared__ double tabs[3][MAXD][NQ][NL];      // [d][k][q][a]
   __shared__ long long rbase[NEN];
-  __shared__ int gidx[3][NL], rlo[3][NL], rlen[3][NL];
+  __shared__ int gidx[3][NL], rlo[3][NL], rlen[3][NL], ridx[3][NL];
 
   const int tid = threadIdx.x;
   const int b1 = tid % NL, a1 = (tid / NL) % NL, b2 = (tid / (NL * NL)) % NL,
@@ -341,16 +351,24 @@ k_assemble_matrix_sf3(TgBasis B, TgWin W, TgTerms TT, const double* __restrict__
   if (tid < 3 * NL) {
     int d = tid / NL, a = tid % NL;
     int g = B.idx[d][e[d] * NL + a];
-    gidx[d][a] = g;
-    int lo = W.lo[d][g];
+    gidx[d][a] = g - W.col0[d];              // column coordinate (local)
+    int r = g - W.row0[d];                   // row coordinate (local), -1 if not owned
+    if (r < 0 || r >= W.nr[d]) r = -1;
+    ridx[d][a] = r;
+    int lo = (r >= 0) ? W.lo[d][r] : 0;
     rlo[d][a] = lo;
-    rlen[d][a] = W.hi[d][g] - lo + 1;
+    rlen[d][a] = (r >= 0) ? W.hi[d][r] - lo + 1 : 1;
   }
   __syncthreads();
   for (int a = tid; a < NEN; a += NT) {
     int l0 = a % NL, l1 = (a / NL) % NL, l2 = a / (NL * NL);
-    int64_t row = gidx[0][l0] + (int64_t)W.nr[0] * (gidx[1][l1] + (int64_t)W.nr[1] * gidx[2][l2]);
-    rbase[a] = W.rowptr[row];
+    int r0 = ridx[0][l0], r1 = ridx[1][l1], r2 = ridx[2][l2];
+    if (r0 < 0 || r1 < 0 || r2 < 0) {
+      rbase[a] = -1;
+    } else {
+      int64_t row = r0 + (int64_t)W.nr[0] * (r1 + (int64_t)W.nr[1] * r2);
+      rbase[a] = W.rowptr[row];
+    }
   }
 
   double acc[NL][NL];
@@ -415,18 +433,20 @@ k_assemble_matrix_sf3(TgBasis B, TgWin W, TgTerms TT, const double* __restrict__
 #pragma unroll
     for (int b3 = 0; b3 < NL; b3++) {
       const int d2 = gidx[2][b3] - rlo[2][a3];
-      ptr[a3][b3] = vals + base + ((int64_t)d2 * len1 + d1) * len0 + d0;
+      ptr[a3][b3] = (base >= 0) ? vals + base + ((int64_t)d2 * len1 + d1) * len0 + d0 : nullptr;
     }
   }
   // colouring guarantees exclusive ownership: all loads first, then all stores
 #pragma unroll
   for (int a3 = 0; a3 < NL; a3++)
 #pragma unroll
-    for (int b3 = 0; b3 < NL; b3++) acc[a3][b3] += *ptr[a3][b3];
+    for (int b3 = 0; b3 < NL; b3++)
+      if (ptr[a3][b3]) acc[a3][b3] += *ptr[a3][b3];
 #pragma unroll
   for (int a3 = 0; a3 < NL; a3++)
 #pragma unroll
-    for (int b3 = 0; b3 < NL; b3++) *ptr[a3][b3] = acc[a3][b3];
+    for (int b3 = 0; b3 < NL; b3++)
+      if (ptr[a3][b3]) *ptr[a3][b3] = acc[a3][b3];
 }
 
 extern "C" int tg_assemble_sf_supported(const tg_basis* h_B) {
@@ -489,6 +509,7 @@ extern "C" int tg_assemble_matrix_terms(const tg_basis* h_B, const tg_win* h_W, 
 struct TgSlots {
   int nslots;
   short slot[TG_MAXJET];
+  int row0[3], nr[3];       // slab of the global vector that is written
 };
 
 __global__ void k_assemble_vector(TgBasis B, TgAlpha S, TgSlots SL, const double* __restrict__ coef,
@@ -548,11 +569,14 @@ __global__ void k_assemble_vector(TgBasis B, TgAlpha S, TgSlots SL, const double
     int al[3];
     tg_decode(a, B.nloc, B.dim, al);
     int64_t g = 0, mul = 1;
+    bool valid = true;
     for (int d = 0; d < B.dim; d++) {
-      g += mul * B.idx[d][e[d] * B.nloc[d] + al[d]];
-      mul *= B.n[d];
+      int r = B.idx[d][e[d] * B.nloc[d] + al[d]] - SL.row0[d];
+      valid = valid && r >= 0 && r < SL.nr[d];
+      g += mul * r;
+      mul *= SL.nr[d];
     }
-    bvec[g] += acc[a];
+    if (valid) bvec[g] += acc[a];
   }
 }
 
@@ -574,9 +598,24 @@ extern "C" int tg_assemble_vector_slots(const tg_basis* h_B, int32_t nS, const i
                                         const int32_t* h_slots, int32_t nslots,
                                         const int32_t* h_stride, const double* coef,
                                         int64_t cell0, int64_t ncells, double* b, void* stream) {
+  int32_t row0[3] = {0, 0, 0}, nr[3] = {1, 1, 1};
+  for (int d = 0; d < h_B->dim; d++) nr[d] = h_B->n[d];
+  return tg_assemble_vector_part(h_B, nS, h_alphaS, h_slots, nslots, h_stride, row0, nr, coef,
+                                 cell0, ncells, b, stream);
+}
+
+extern "C" int tg_assemble_vector_part(const tg_basis* h_B, int32_t nS, const int32_t* h_alphaS,
+                                       const int32_t* h_slots, int32_t nslots,
+                                       const int32_t* h_stride, const int32_t* h_row0,
+                                       const int32_t* h_nr, const double* coef, int64_t cell0,
+                                       int64_t ncells, double* b, void* stream) {
   TG_REQUIRE(nS >= 1 && nS <= TG_MAXJET, "jet count");
   TgSlots SL;
   SL.nslots = nslots;
+  for (int d = 0; d < 3; d++) {
+    SL.row0[d] = (d < h_B->dim) ? h_row0[d] : 0;
+    SL.nr[d] = (d < h_B->dim) ? h_nr[d] : 1;
+  }
   for (int i = 0; i < nS; i++) {
     TG_REQUIRE(h_slots[i] >= 0 && h_slots[i] < nslots, "slot index");
     SL.slot[i] = (short)h_slots[i];

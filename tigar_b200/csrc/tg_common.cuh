@@ -45,6 +45,7 @@ struct TgWin {
   const int32_t* hi[3];
   const int64_t* rowptr;
   const int64_t* S[3];
+  int row0[3], col0[3];
 };
 
 static inline TgWin tg_win_dev(const tg_win* w) {
@@ -56,6 +57,8 @@ static inline TgWin tg_win_dev(const tg_win* w) {
     d.lo[k] = (k < w->dim) ? w->lo[k] : nullptr;
     d.hi[k] = (k < w->dim) ? w->hi[k] : nullptr;
     d.S[k] = (k < w->dim) ? w->S[k] : nullptr;
+    d.row0[k] = (k < w->dim) ? w->row0[k] : 0;
+    d.col0[k] = (k < w->dim) ? w->col0[k] : 0;
   }
   d.rowptr = w->rowptr;
   return d;

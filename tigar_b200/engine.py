@@ -62,7 +62,27 @@ class Window(object):
         self.nrows = int(np.prod(self.nr))
         self.ncols = int(np.prod(self.nc))
         self.nnz = int(np.prod([int(l.sum()) for l in self.len]))
+        self.row0 = [0] * self.dim
+        self.col0 = [0] * self.dim
         self._d = None
+
+    def slab(self, k0, k1, c0, c1):
+        """Rows [k0,k1) of the last direction, columns restricted to [c0,c1)
+        (must contain every window of those rows): one rank's block of a
+        row-distributed matrix."""
+        L = self.dim - 1
+        lo = list(self.lo)
+        hi = list(self.hi)
+        lo[L] = self.lo[L][k0:k1] - c0
+        hi[L] = self.hi[L][k0:k1] - c0
+        nr = list(self.nr)
+        nc = list(self.nc)
+        nr[L] = k1 - k0
+        nc[L] = c1 - c0
+        w = Window(nr, nc, lo, hi)
+        w.row0[L] = k0
+        w.col0[L] = c0
+        return w
 
     def transpose(self):
         lo, hi = [], []
@@ -99,6 +119,7 @@ class Window(object):
             for d in range(3):
                 if d < self.dim:
                     w.nr[d], w.nc[d] = self.nr[d], self.nc[d]
+                    w.row0[d], w.col0[d] = self.row0[d], self.col0[d]
                     tl, th = dev.from_np(self.lo[d]), dev.from_np(self.hi[d])
                     ts = dev.from_np(np.concatenate([[0], np.cumsum(self.len[d])]).astype(np.int64))
                     keep += [tl, th, ts]
@@ -277,7 +298,9 @@ def pad3(alpha):
 class TensorPatch(object):
     """A tensor-product B-spline patch and its Q_pf Lagrange background mesh."""
 
-    def __init__(self, degrees, kvecs, quadDeg=None, eps=IGNORE_EPS, splines=None):
+    def __init__(self, degrees, kvecs, quadDeg=None, eps=IGNORE_EPS, splines=None, part=None):
+        """``part=(rank, size)``: this process owns one slab of IGA planes of
+        the last parametric direction (fused path only); see multigpu.py."""
         dev.require_cuda()
         self.dim = len(degrees)
         self.splines = splines or [BSpline1(p, k) for p, k in zip(degrees, kvecs)]
@@ -296,6 +319,27 @@ class TensorPatch(object):
         self._bases = {}
         self._win = {}
         self.launches = 0
+        self.part = part
+        self.slab_lo, self.slab_hi = 0, self.nel[-1]
+        if part is not None and part[1] > 1:
+            from .multigpu import plane_partition
+            D = self.dirs[-1]
+            plane = self.n_iga // D.ncp
+            first = D.s.elementSpans().astype(np.int64) - D.p      # first function of a cell
+            self.pp = plane_partition(D.ncp, first, first + D.p, self.window_global_C_last(),
+                                      part[0], part[1])
+            self.slab_lo, self.slab_hi = self.pp["cells"]
+            self.plane = plane
+            self.n_loc = plane * (self.pp["k1"] - self.pp["k0"])
+            self.n_ext = plane * (self.pp["c1"] - self.pp["c0"])
+            self.xoff = plane * (self.pp["k0"] - self.pp["c0"])
+        else:
+            self.part = None
+
+    def window_global_C_last(self):
+        """(lo, hi) of the global C window in the last direction."""
+        w = self._global_window("C")
+        return w.lo[-1], w.hi[-1]
 
     # ---- descriptors -------------------------------------------------------
     def basis(self, kind, nder):
@@ -305,13 +349,23 @@ class TensorPatch(object):
         return self._bases[key]
 
     def window(self, name):
-        """'M' FExIGA, 'MT' IGAxFE, 'A' FExFE, 'P' = A*M, 'PT', 'C' IGAxIGA."""
+        """'M' FExIGA, 'MT' IGAxFE, 'A' FExFE, 'P' = A*M, 'PT', 'C' IGAxIGA.
+        With a slab partition, 'C' is this rank's block of rows."""
+        if name == "C" and getattr(self, "part", None) is not None:
+            if "Cloc" not in self._win:
+                pp = self.pp
+                self._win["Cloc"] = self._global_window("C").slab(pp["k0"], pp["k1"], pp["c0"],
+                                                                  pp["c1"])
+            return self._win["Cloc"]
+        return self._global_window(name)
+
+    def _global_window(self, name):
         if name not in self._win:
             if name == "M":
                 w = Window(self.nfe, self.ncp, [D.m_lo for D in self.dirs],
                            [D.m_hi for D in self.dirs])
             elif name == "MT":
-                w = self.window("M").transpose()
+                w = self._global_window("M").transpose()
             elif name == "A":
                 lo, hi = [], []
                 for D in self.dirs:
@@ -322,11 +376,11 @@ class TensorPatch(object):
                     hi.append((e_hi + 1) * D.pf)
                 w = Window(self.nfe, self.nfe, lo, hi)
             elif name == "P":
-                w = self.window("A").compose(self.window("M"))
+                w = self._global_window("A").compose(self._global_window("M"))
             elif name == "PT":
-                w = self.window("P").transpose()
+                w = self._global_window("P").transpose()
             elif name == "C":
-                w = self.window("MT").compose(self.window("P"))
+                w = self._global_window("MT").compose(self._global_window("P"))
             else:
                 raise KeyError(name)
             self._win[name] = w
@@ -361,9 +415,9 @@ class TensorPatch(object):
         """Chunks of whole slabs of the last direction."""
         slab = self.ncells // self.nel[-1]
         per = max(1, int(budget // max(1, slab * bytes_per_cell)))
-        k = 0
-        while k < self.nel[-1]:
-            n = min(per, self.nel[-1] - k)
+        k = self.slab_lo
+        while k < self.slab_hi:
+            n = min(per, self.slab_hi - k)
             yield k * slab, n * slab
             k += n
 
@@ -464,7 +518,16 @@ class TensorPatch(object):
                     self.assemble_vector(vterms, funcs, kind))
         W = self.window("A" if kind == "fe" else "C")
         A = WinMatrix(W)
-        b = dev.zeros(B.ntot)
+        if self.part is not None:
+            if kind != "iga":
+                raise NotImplementedError("slab partition exists for the fused path only")
+            b = dev.zeros(self.n_loc)
+            vrow0 = i32arr([0] * (self.dim - 1) + [self.pp["k0"]])
+            vnr = i32arr(self.ncp[:-1] + [self.pp["k1"] - self.pp["k0"]])
+        else:
+            b = dev.zeros(B.ntot)
+            vrow0 = i32arr([0] * self.dim)
+            vnr = i32arr([B.c.n[d] for d in range(self.dim)])
         P = self._qp_setup(nodes, funcs)
         nm, nv = len(mk), len(alS)
         nslots = nm + nv
@@ -483,9 +546,9 @@ class TensorPatch(object):
             check(lib.tg_assemble_matrix_terms(B.ref(), W.ref(), nm, h_terms, nslots, stride,
                                                dev.ptr(buf), cell0, nc, dev.ptr(A.vals),
                                                dev.stream()))
-            check(lib.tg_assemble_vector_slots(B.ref(), nv, aS, vslots, nslots, stride,
-                                               dev.ptr(buf), cell0, nc, dev.ptr(b),
-                                               dev.stream()))
+            check(lib.tg_assemble_vector_part(B.ref(), nv, aS, vslots, nslots, stride, vrow0, vnr,
+                                              dev.ptr(buf), cell0, nc, dev.ptr(b),
+                                              dev.stream()))
         return A, b
 
     def assemble_vector(self, terms, funcs, kind="fe", out=None):
@@ -498,16 +561,27 @@ class TensorPatch(object):
         P = self._qp_setup(outputs, funcs)
         nder = max(P["nder"], max(max(a) for a in alS))
         B = self.basis(kind, nder)
-        b = dev.zeros(B.ntot) if out is None else out
+        if self.part is not None:
+            if kind != "iga":
+                raise NotImplementedError("slab partition exists for the fused path only")
+            b = dev.zeros(self.n_loc) if out is None else out
+            vrow0 = i32arr([0] * (self.dim - 1) + [self.pp["k0"]])
+            vnr = i32arr(self.ncp[:-1] + [self.pp["k1"] - self.pp["k0"]])
+        else:
+            b = dev.zeros(B.ntot) if out is None else out
+            vrow0 = i32arr([0] * self.dim)
+            vnr = i32arr([B.c.n[d] for d in range(self.dim)])
         stride = i32arr([2] * self.dim if kind == "fe" else B.nloc)
         aS = i32arr([x for a in alS for x in a])
+        slots = i32arr(list(range(nS)))
         buf = None
         for cell0, nc in self._cell_chunks(nS * B.nqp * 8):
             if buf is None or buf.numel() < nc * nS * B.nqp:
                 buf = dev.empty(nc * nS * B.nqp)
             self._qp_eval(B, P, cell0, nc, buf)
-            check(lib.tg_assemble_vector_ex(B.ref(), nS, aS, stride, dev.ptr(buf), cell0, nc,
-                                            dev.ptr(b), dev.stream()))
+            check(lib.tg_assemble_vector_part(B.ref(), nS, aS, slots, nS, stride, vrow0, vnr,
+                                              dev.ptr(buf), cell0, nc, dev.ptr(b),
+                                              dev.stream()))
         return b
 
     def assemble_scalar(self, node, funcs, kind="fe"):
@@ -517,12 +591,25 @@ class TensorPatch(object):
         tot = 0.0
         acc = dev.zeros(1)
         buf = None
-        for cell0, nc in self._cell_chunks(B.nqp * 8):
-            if buf is None or buf.numel() < nc * B.nqp:
-                buf = dev.empty(nc * B.nqp)
-            self._qp_eval(B, P, cell0, nc, buf)
-            check(lib.tg_sum(dev.ptr(buf), nc * B.nqp, dev.ptr(acc), dev.stream()))
-            tot += float(acc.item())
+        saved = (self.slab_lo, self.slab_hi)
+        if self.part is not None:      # disjoint cell layers per rank, then all-reduce
+            r, n = self.part
+            self.slab_lo, self.slab_hi = (self.nel[-1] * r) // n, (self.nel[-1] * (r + 1)) // n
+        try:
+            for cell0, nc in self._cell_chunks(B.nqp * 8):
+                if buf is None or buf.numel() < nc * B.nqp:
+                    buf = dev.empty(nc * B.nqp)
+                self._qp_eval(B, P, cell0, nc, buf)
+                check(lib.tg_sum(dev.ptr(buf), nc * B.nqp, dev.ptr(acc), dev.stream()))
+                tot += float(acc.item())
+        finally:
+            self.slab_lo, self.slab_hi = saved
+        if self.part is not None:
+            import torch
+            import torch.distributed as dist
+            t = torch.tensor([tot], dtype=torch.float64, device=dev.device())
+            dist.all_reduce(t)
+            tot = float(t.item())
         return tot
 
     # ---- (iii) triple product, BCs, solve -----------------------------------
@@ -548,15 +635,30 @@ class TensorPatch(object):
         return dev.from_np(m)
 
     def apply_bcs_matrix(self, Cm, mask, diag=1.0):
+        if self.part is not None:
+            pp, pl = self.pp, self.plane
+            rowmask = mask[pp["k0"] * pl:pp["k1"] * pl]
+            colmask = mask[pp["c0"] * pl:pp["c1"] * pl]
+            check(lib.tg_win_zero_rows_cols(Cm.window.ref(), dev.ptr(Cm.vals), dev.ptr(rowmask),
+                                            dev.ptr(colmask), float(diag),
+                                            pp["k0"] - pp["c0"], dev.stream()))
+            return Cm
         check(lib.tg_win_zero_rows_cols(Cm.window.ref(), dev.ptr(Cm.vals), dev.ptr(mask),
                                         dev.ptr(mask), float(diag), 0, dev.stream()))
         return Cm
 
     def apply_bcs_vector(self, b, mask):
+        if self.part is not None:
+            mask = mask[self.pp["k0"] * self.plane:self.pp["k1"] * self.plane]
         check(lib.tg_zero_entries(dev.ptr(b), dev.ptr(mask), b.numel(), dev.stream()))
         return b
 
     def solve_cg(self, Cm, b, x=None, rtol=1e-12, atol=0.0, maxit=100000, check_every=25):
+        if self.part is not None:
+            from .multigpu import DeviceOps, dist_cg
+            ops = DeviceOps(self, Cm)
+            xl, its, rel = dist_cg(ops, b, rtol, atol, maxit, check_every)
+            return xl, its, rel
         n = Cm.window.nrows
         x = dev.zeros(n) if x is None else x
         work = dev.empty(4 * n + lib.tg_cg_scratch_len() + 8)
