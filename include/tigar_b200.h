@@ -220,6 +220,21 @@ int tg_ptap_c(const tg_win* h_wM, const double* Mvals, const tg_win* h_wMT,
               const tg_win* h_wP, const double* APvals, const tg_win* h_wPT,
               const tg_win* h_wC, double* Cvals, void* stream);
 
+/* Kronecker-structured M^T A M for tensor-product bases (M = M_2 (x) M_1 (x) M_0;
+ * the global M is never read).  h_tabs[d]: device array [n_fe_d][10][10] with
+ * tab[I][J-loA_d(I)][j-loP_d(I)] = M_d[J,j]; box >= prod_d max(lenA_d, lenP_d)
+ * (shared-memory tile per row).  AP = A*M, one pass over A.                  */
+int tg_ptap_kron_ap(const tg_win* h_wA, const double* Avals, const double* const* h_tabs,
+                    const tg_win* h_wP, double* APvals, int32_t box, void* stream);
+/* Y[(..i_d..),:] = sum_I M_d[I,i_d] X[(..I_d..),:] : turns direction d of the row
+ * grid from FE nodes into IGA functions.  mfirst/mvals: the 1-D extraction
+ * rows of direction d ([n_fe_d] and [n_fe_d][np1]); supp_lo/hi[i]: FE support
+ * of function i.  Apply for d = 0,1,2 to get C = M^T (AP).                   */
+int tg_win_rowcombine(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY,
+                      double* Yvals, int32_t d, const int32_t* mfirst, const double* mvals,
+                      int32_t np1, const int32_t* supp_lo, const int32_t* supp_hi,
+                      void* stream);
+
 /* ---- windowed-CSR operators (no column array: 8 B per non-zero) ---------- */
 /* y = C x  (MatMult inside KSP, common.py:1255-1258; M*U, common.py:379,1259) */
 int tg_win_spmv(const tg_win* h_w, const double* vals, const double* x, double* y,

@@ -260,3 +260,26 @@ def test_slab_partitioned_assembly_matches_global(deg, nels, size):
         assert rel(b2.get_local(), pr.b[r0:r1]) < 1e-12
         rows_seen += r1 - r0
     assert rows_seen == Cg.shape[0]
+
+
+@pytest.mark.parametrize("deg,nels", [([2], [9]), ([3, 2], [4, 5]), ([3, 3, 3], [3, 4, 3]), ([4, 4], [4, 3]),
+                                      ([2, 3, 2], [3, 3, 4])])
+def test_kronecker_ptap_equals_generic_ptap_and_scipy(deg, nels):
+    """tg_ptap_kron_ap + tg_win_rowcombine (M never read) against the generic
+    box-intersection kernels and scipy's M^T A M on a random windowed A."""
+    from tigar_b200.engine import TensorPatch, WinMatrix
+    from tigar_b200 import dev
+    kv = [uk(p, n, -1.0, 2.0) for p, n in zip(deg, nels)]
+    patch = TensorPatch(deg, kv)
+    assert patch.kron_supported()
+    A = WinMatrix(patch.window("A"))
+    rng = np.random.RandomState(5)
+    A.vals.copy_(dev.from_np(rng.randn(A.window.nnz)))
+    M = patch.build_M()
+    Ck = patch.ptap_kron(A)
+    Cg, AP = patch.ptap(A, M, keep_AP=True)            # generic kernels
+    As, Ms = A.to_scipy(), M.to_scipy()
+    ref = (Ms.T @ As @ Ms).tocsr()
+    assert relm(Ck.to_scipy(), ref) < 1e-13
+    assert relm(Cg.to_scipy(), ref) < 1e-13
+    assert relm(AP.to_scipy(), (As @ Ms).tocsr()) < 1e-13

@@ -80,6 +80,8 @@ SIGNATURES = {
     "tg_sum": [c_vp, c_i64, c_vp, c_vp],
     "tg_ptap_ap": [PW, c_vp, PW, c_vp, PW, PW, c_vp, c_vp],
     "tg_ptap_c": [PW, c_vp, PW, PW, c_vp, PW, PW, c_vp, c_vp],
+    "tg_ptap_kron_ap": [PW, c_vp, PVP, PW, c_vp, c_i32, c_vp],
+    "tg_win_rowcombine": [PW, c_vp, PW, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp],
     "tg_zero_rows_cols": [c_vp, c_vp, c_vp, c_i64, c_vp, c_dbl, c_vp],
     "tg_zero_entries": [c_vp, c_vp, c_i64, c_vp],
     "tg_diag_inv": [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp],

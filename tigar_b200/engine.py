@@ -15,6 +15,7 @@ launches.  Matrices are "windowed CSR": each row stores the dense
 tensor-product box of its columns, so no column index array exists (8 B/nnz).
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -613,8 +614,79 @@ class TensorPatch(object):
         return tot
 
     # ---- (iii) triple product, BCs, solve -----------------------------------
-    def ptap(self, A, M, keep_AP=False):
+    KRON_KB = 10
+
+    def _kron_tabs(self):
+        """Per-direction blocks tab[I][J-loA(I)][j-loP(I)] = M_d[J,j] for
+        tg_ptap_kron_ap, and host copies of the 1-D extraction rows."""
+        if getattr(self, "_ktabs", None) is None:
+            KB = self.KRON_KB
+            wA, wP = self._global_window("A"), self._global_window("P")
+            tabs = []
+            for d, D in enumerate(self.dirs):
+                first = dev.to_np(D.m_first).astype(np.int64)
+                vals = dev.to_np(D.m_vals)
+                t = np.zeros((D.nfe, KB, KB))
+                for I in range(D.nfe):
+                    for J in range(wA.lo[d][I], wA.hi[d][I] + 1):
+                        for k in range(D.p + 1):
+                            j = first[J] + k
+                            if D.m_lo[J] <= j <= D.m_hi[J]:
+                                t[I, J - wA.lo[d][I], j - wP.lo[d][I]] = vals[J, k]
+                tabs.append(dev.from_np(t))
+            self._ktabs = tabs
+        return self._ktabs
+
+    def kron_supported(self):
+        KB = self.KRON_KB
+        wA, wP = self._global_window("A"), self._global_window("P")
+        return all(int(wA.len[d].max()) <= KB and int(wP.len[d].max()) <= KB
+                   for d in range(self.dim))
+
+    def ptap_kron(self, A, keep=False):
+        """C = M^T A M without reading the global M: tg_ptap_kron_ap (one pass
+        over A) followed by one tg_win_rowcombine per direction."""
+        wA, wP, wC, wMT = (self._global_window(k) for k in ("A", "P", "C", "MT"))
+        tabs = self._kron_tabs()
+        box = int(np.prod([max(int(wA.len[d].max()), int(wP.len[d].max()))
+                           for d in range(self.dim)]))
+        X = WinMatrix(wP, dev.empty(wP.nnz))
+        check(lib.tg_ptap_kron_ap(wA.ref(), dev.ptr(A.vals), vparr([dev.ptr(t) for t in tabs]),
+                                  wP.ref(), dev.ptr(X.vals), box, dev.stream()))
+        stages = [X]
+        for d, D in enumerate(self.dirs):
+            key = "K%d" % d
+            if key not in self._win:
+                wX = stages[-1].window
+                nr = list(wX.nr)
+                nr[d] = D.ncp
+                lo = list(wX.lo)
+                hi = list(wX.hi)
+                lo[d], hi[d] = wC.lo[d], wC.hi[d]
+                self._win[key] = Window(nr, wX.nc, lo, hi)
+            wY = self._win[key]
+            Y = WinMatrix(wY, dev.empty(wY.nnz))
+            if not hasattr(D, "d_slo"):
+                D.d_slo = dev.from_np(wMT.lo[d].astype(np.int32))
+                D.d_shi = dev.from_np(wMT.hi[d].astype(np.int32))
+            check(lib.tg_win_rowcombine(stages[-1].window.ref(), dev.ptr(stages[-1].vals),
+                                        wY.ref(), dev.ptr(Y.vals), d, dev.ptr(D.m_first),
+                                        dev.ptr(D.m_vals), D.p + 1, dev.ptr(D.d_slo),
+                                        dev.ptr(D.d_shi), dev.stream()))
+            stages.append(Y)
+            if not keep and len(stages) > 2:
+                stages[-2] = None
+        Cw = stages[-1]
+        out = WinMatrix(wC, Cw.vals)          # same pattern as the global C window
+        assert Cw.window.nnz == wC.nnz
+        return (out, [s for s in stages if s is not None]) if keep else out
+
+    def ptap(self, A, M=None, keep_AP=False):
         """C = M^T A M on windowed operands (MatPtAP, common.py:1194-1195)."""
+        if not keep_AP and self.kron_supported() and not os.environ.get("TIGAR_B200_PTAP_GENERIC"):
+            return self.ptap_kron(A)
+        if M is None:
+            M = self.build_M()
         wA, wM, wMT = self.window("A"), self.window("M"), self.window("MT")
         wP, wPT, wC = self.window("P"), self.window("PT"), self.window("C")
         AP = dev.empty(wP.nnz)
