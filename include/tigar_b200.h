@@ -150,6 +150,16 @@ int tg_qp_eval(const tg_basis* h_B, int32_t nfun, const double* const* h_coefs,
                int32_t nreg, int32_t nout, const int32_t* h_outregs,
                int64_t cell0, int64_t ncells, double* out, void* stream);
 
+/* Run-time compiled Gauss-point kernels (FFC/dijitso's role behind
+ * dolfin.assemble, common.py:1215-1216): CUDA C source -> NVRTC -> sm_100a.
+ * tg_jit_check only compiles (no GPU needed); tg_jit_launch passes ONE POD
+ * parameter block by value.                                                  */
+int tg_jit_check(const char* src, int64_t* cubin_bytes);
+int tg_jit_compile(const char* src, const char* kernel_name, void** handle);
+int tg_jit_launch(void* handle, int64_t grid, int32_t block, int32_t smem_bytes,
+                  const void* param, int32_t param_bytes, void* stream);
+int tg_jit_free(void* handle);
+
 /* A[I,J] += sum_q sum_{s,t} coef[cell][s*nT+t][q] D^{aS_s}psi_I D^{aT_t}psi_J
  * element by element, colours processed one launch each, no atomics
  * (dolfin::Assembler behind common.py:1215-1216).  Row = test function.

@@ -283,3 +283,25 @@ def test_kronecker_ptap_equals_generic_ptap_and_scipy(deg, nels):
     assert relm(Ck.to_scipy(), ref) < 1e-13
     assert relm(Cg.to_scipy(), ref) < 1e-13
     assert relm(AP.to_scipy(), (As @ Ms).tocsr()) < 1e-13
+
+
+def test_jit_kernel_equals_interpreter():
+    """NVRTC-compiled Gauss-point kernel vs the register-machine interpreter
+    (tg_qp_eval) on the same forms: identical systems to rounding (the JIT may
+    contract a*b+c into FMAs)."""
+    import os
+    deg, nels = [3, 3, 3], [3, 4, 3]
+    kv = [uk(p, n) for p, n in zip(deg, nels)]
+    out = {}
+    for flag in ("jit", "interp"):
+        if flag == "interp":
+            os.environ["TIGAR_B200_NO_JIT"] = "1"
+        try:
+            gen, spline, pr = make_pair(deg, kv, mode="fused")
+            a, L = poisson_forms(spline, "sin")
+            A, b = spline.assembleLinearSystem(a, L)
+            out[flag] = (A.to_scipy(), b.get_local())
+        finally:
+            os.environ.pop("TIGAR_B200_NO_JIT", None)
+    assert relm(out["jit"][0], out["interp"][0]) < 1e-14
+    assert rel(out["jit"][1], out["interp"][1]) < 1e-14

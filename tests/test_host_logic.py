@@ -174,3 +174,23 @@ def test_no_gpu_means_loud_failure():
     from tigar_b200.engine import TensorPatch
     with pytest.raises(RuntimeError):
         TensorPatch([2, 2], [PB.uniformKnots(2, 0.0, 1.0, 4)] * 2)
+
+
+def test_generated_qp_kernel_compiles_for_sm100a():
+    """The form compiler's CUDA output goes through NVRTC (sm_100a) without a
+    GPU; 2-D and 3-D shapes, derivative orders up to 2."""
+    from tigar_b200 import jit
+    x, y, z = S.xi(0), S.xi(1), S.xi(2)
+    u = [S.jet(1, 0, a) for a in [(0, 0, 0), (1, 0, 0), (0, 2, 0), (0, 1, 1)]]
+    g = S.jet(2, 0, (0, 0, 1))
+    e = S.func("sin", x * y) * u[0] + u[1] * u[2] / (S.func("sqrt", u[3] * u[3] + 1.0)) + g * S.wq() + z
+    prog = S.compile_program([e, S.diff(e, 0), S.ZERO], 3)
+    fids = sorted(set(j[0] for j in prog.jets))
+    jets = [(fids.index(f), c, al) for (f, c, al) in prog.jets]
+    src, nth = jit.generate(prog, 3, [4, 4, 4], [4, 4, 4], 4, jets, len(fids))
+    assert nth == 64 and jit.check_source(src) > 1000
+    prog2 = S.compile_program([S.func("cos", x) * S.jet(7, 0, (1, 1, 0))], 2)
+    src2, nth2 = jit.generate(prog2, 2, [3, 5, 1], [3, 3, 1], 3, [(0, 0, (1, 1, 0))], 1)
+    assert nth2 == 32 and jit.check_source(src2) > 1000
+    with pytest.raises(Exception):
+        jit.check_source("this is not CUDA")

@@ -65,6 +65,10 @@ SIGNATURES = {
     "tg_mt_vec": [PW, PW, c_vp, c_vp, c_vp, c_vp],
     "tg_qp_eval": [PB, c_i32, PVP, PI32, c_i32, PI32, c_vp, c_i32, c_vp, c_i32, c_i32,
                    PI32, c_i64, c_i64, c_vp, c_vp],
+    "tg_jit_check": [C.c_char_p, C.POINTER(c_i64)],
+    "tg_jit_compile": [C.c_char_p, C.c_char_p, C.POINTER(c_vp)],
+    "tg_jit_launch": [c_vp, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp],
+    "tg_jit_free": [c_vp],
     "tg_assemble_matrix": [PB, PW, c_i32, PI32, c_i32, PI32, c_vp, c_i64, c_i64, c_vp, c_vp],
     "tg_assemble_matrix_ex": [PB, PW, c_i32, PI32, c_i32, PI32, PI32, c_vp, c_i64, c_i64,
                               c_vp, c_vp],

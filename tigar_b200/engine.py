@@ -446,6 +446,19 @@ class TensorPatch(object):
         return P
 
     def _qp_eval(self, B, P, cell0, ncells, out):
+        from . import jit
+        if jit.enabled() and len(P["fids"]) <= jit.MAXFUN:
+            k = P.setdefault("jit", {}).get(B.nder)
+            if k is None:
+                fpos = {f: i for i, f in enumerate(P["fids"])}
+                jets = [(fpos[f], comp, pad3(al)) for (f, comp, al) in P["prog"].jets]
+                nloc = B.nloc + [1] * (3 - self.dim)
+                nq = [B.c.nq[d] for d in range(3)]
+                k = jit.get_kernel(P["prog"], self.dim, nloc, nq, B.nder + 1, jets,
+                                   len(P["fids"]))
+                P["jit"][B.nder] = k
+            jit.launch(k, B, [dev.ptr(t) for t in P["keep"]], cell0, ncells, out)
+            return
         check(lib.tg_qp_eval(B.ref(), len(P["fids"]), P["coefs"], P["ncomp"], P["njets"],
                              P["jets"], dev.ptr(P["d_prog"]), len(P["prog"].prog),
                              dev.ptr(P["d_consts"]), P["prog"].nreg, P["nout"], P["outregs"],

@@ -1,0 +1,194 @@
+"""
+Form compiler back end: turns a compiled Gauss-point program
+(tigar_b200.symbolic.Program) plus the element shape into CUDA C and has the
+library compile it with NVRTC for sm_100a (``tg_jit_compile``).  This is the
+role FFC/dijitso play behind ``dolfin.assemble`` in the reference
+(common.py:1215-1216): one generated kernel per integrand, cached.
+
+Generated kernel: one CTA per cell, one thread per Gauss point.  Jets of the
+coefficient functions are sum-factorised through shared memory with every loop
+bound a compile-time constant; the scalar program is emitted as straight-line
+FP64 code (no interpreter, no local-memory register file).
+"""
+import ctypes as C
+import hashlib
+import os
+
+from . import dev
+from . import symbolic as S
+from ._lib import lib, check, c_vp, c_i32, c_i64
+
+_UN = {"neg": "-(%s)", "sin": "sin(%s)", "cos": "cos(%s)", "exp": "exp(%s)", "log": "log(%s)",
+       "sqrt": "sqrt(%s)", "abs": "fabs(%s)", "tan": "tan(%s)", "tanh": "tanh(%s)",
+       "sinh": "sinh(%s)", "cosh": "cosh(%s)", "atan": "atan(%s)", "mov": "(%s)"}
+_BIN = {"add": "(%s + %s)", "sub": "(%s - %s)", "mul": "(%s * %s)", "div": "(%s / %s)",
+        "pow": "pow(%s, %s)", "max": "fmax(%s, %s)", "min": "fmin(%s, %s)",
+        "gt": "((%s > %s) ? 1.0 : 0.0)"}
+_NAMES = {v: k for k, v in S.OPCODES.items()}
+
+MAXFUN = 16
+
+
+class QpArgs(C.Structure):
+    _fields_ = [("tab", c_vp * 3), ("idx", c_vp * 3), ("wq", c_vp * 3), ("xq", c_vp * 3),
+                ("coef", c_vp * MAXFUN), ("n", c_i32 * 3), ("nel", c_i32 * 3),
+                ("cell0", c_i64), ("out", c_vp)]
+
+
+_PRELUDE = r"""
+struct QpArgs {
+  const double* tab[3]; const int* idx[3]; const double* wq[3]; const double* xq[3];
+  const double* coef[%(MAXFUN)d]; int n[3]; int nel[3]; long long cell0; double* out;
+};
+"""
+
+
+def generate(prog, dim, nloc, nq, nd, jets, nfun):
+    """CUDA source of the kernel for ``prog``.  jets: list of (fpos, comp, al3)
+    in register order; nloc/nq: per-direction sizes (padded to 3 with 1)."""
+    n0, n1, n2 = nloc
+    q0, q1, q2 = nq
+    nen, nqp = n0 * n1 * n2, q0 * q1 * q2
+    nth = ((nqp + 31) // 32) * 32
+    L = []
+    w = L.append
+    w(_PRELUDE % dict(MAXFUN=MAXFUN))
+    w("#define N0 %d\n#define N1 %d\n#define N2 %d\n#define Q0 %d\n#define Q1 %d\n#define Q2 %d"
+      % (n0, n1, n2, q0, q1, q2))
+    w("#define ND %d\n#define NEN %d\n#define NQP %d\n#define NTH %d\n#define DIM %d"
+      % (nd, nen, nqp, nth, dim))
+    w('extern "C" __global__ void __launch_bounds__(NTH) tigar_qp(const QpArgs A) {')
+    w("  __shared__ double tb0[Q0*N0*ND], tb1[Q1*N1*ND], tb2[Q2*N2*ND];")
+    w("  __shared__ double cf[NEN], s1[Q0*N1*N2], s2[Q0*Q1*N2];")
+    w("  const int tid = threadIdx.x;")
+    w("  const long long cl = blockIdx.x;")
+    w("  long long c = A.cell0 + cl;")
+    w("  int e0 = (int)(c % A.nel[0]), e1 = 0, e2 = 0;")
+    if dim > 1:
+        w("  { long long r = c / A.nel[0]; e1 = (int)(r % A.nel[1]); " +
+          ("e2 = (int)(r / A.nel[1]);" if dim > 2 else "") + " }")
+    w("  for (int i = tid; i < Q0*N0*ND; i += NTH) tb0[i] = A.tab[0][(long long)e0*Q0*N0*ND + i];")
+    if dim > 1:
+        w("  for (int i = tid; i < Q1*N1*ND; i += NTH) tb1[i] = A.tab[1][(long long)e1*Q1*N1*ND + i];")
+    else:
+        w("  for (int i = tid; i < Q1*N1*ND; i += NTH) tb1[i] = 1.0;")
+    if dim > 2:
+        w("  for (int i = tid; i < Q2*N2*ND; i += NTH) tb2[i] = A.tab[2][(long long)e2*Q2*N2*ND + i];")
+    else:
+        w("  for (int i = tid; i < Q2*N2*ND; i += NTH) tb2[i] = 1.0;")
+    w("  const bool active = tid < NQP;")
+    w("  const int qa = tid %% Q0, qb = (tid / Q0) %% Q1, qc = tid / (Q0*Q1);" .replace("%%", "%"))
+    # jets, grouped by function, then by a0, then by (a0,a1)
+    w("  double %s;" % ", ".join("j%d = 0.0" % k for k in range(max(len(jets), 1))))
+    byf = {}
+    for k, (f, comp, al) in enumerate(jets):
+        byf.setdefault((f, comp), []).append((k, al))
+    for (f, comp), lst in byf.items():
+        w("  __syncthreads();")
+        w("  for (int a = tid; a < NEN; a += NTH) {")
+        w("    int l0 = a %% N0, t = a / N0, l1 = t %% N1, l2 = t / N1;".replace("%%", "%"))
+        w("    long long g = A.idx[0][e0*N0 + l0];")
+        if dim > 1:
+            w("    g += (long long)A.n[0] * A.idx[1][e1*N1 + l1];")
+        if dim > 2:
+            w("    g += (long long)A.n[0] * A.n[1] * A.idx[2][e2*N2 + l2];")
+        w("    cf[a] = A.coef[%d][g];" % f)
+        w("  }")
+        a0s = sorted(set(al[0] for _, al in lst))
+        for a0 in a0s:
+            w("  __syncthreads();")
+            w("  for (int o = tid; o < Q0*N1*N2; o += NTH) {")
+            w("    int qq = o %% Q0, r = o / Q0; double acc = 0.0;".replace("%%", "%"))
+            w("    #pragma unroll\n    for (int l = 0; l < N0; l++) acc += cf[r*N0 + l] * tb0[(qq*N0 + l)*ND + %d];" % a0)
+            w("    s1[o] = acc;\n  }")
+            a1s = sorted(set(al[1] for _, al in lst if al[0] == a0))
+            for a1 in a1s:
+                w("  __syncthreads();")
+                w("  for (int o = tid; o < Q0*Q1*N2; o += NTH) {")
+                w("    int x0 = o %% Q0, t = o / Q0, x1 = t %% Q1, l2 = t / Q1; double acc = 0.0;"
+                  .replace("%%", "%"))
+                w("    #pragma unroll\n    for (int l = 0; l < N1; l++) acc += s1[(l2*N1 + l)*Q0 + x0] * tb1[(x1*N1 + l)*ND + %d];" % a1)
+                w("    s2[o] = acc;\n  }")
+                w("  __syncthreads();")
+                for k, al in lst:
+                    if al[0] == a0 and al[1] == a1:
+                        w("  if (active) { double acc = 0.0;")
+                        w("    #pragma unroll\n    for (int l = 0; l < N2; l++) acc += s2[(l*Q1 + qb)*Q0 + qa] * tb2[(qc*N2 + l)*ND + %d];" % al[2])
+                        w("    j%d = acc; }" % k)
+    w("  if (!active) return;")
+    # fixed registers
+    names = {}
+    for d in range(dim):
+        q = ("qa", "qb", "qc")[d]
+        e = ("e0", "e1", "e2")[d]
+        Q = ("Q0", "Q1", "Q2")[d]
+        w("  const double x%d = A.xq[%d][%s*%s + %s];" % (d, d, e, Q, q))
+        names[d] = "x%d" % d
+    w("  const double wqv = %s;" % " * ".join(
+        "A.wq[%d][%s*%s + %s]" % (d, ("e0", "e1", "e2")[d], ("Q0", "Q1", "Q2")[d],
+                                  ("qa", "qb", "qc")[d]) for d in range(dim)))
+    names[dim] = "wqv"
+    for k in range(len(jets)):
+        names[dim + 1 + k] = "j%d" % k
+    # straight-line program in SSA form (registers are re-used by the allocator,
+    # so every definition gets a fresh C variable)
+    ver = 0
+    for (op, dst, a, b) in prog.prog:
+        nm = _NAMES[op]
+        var = "t%d" % ver
+        ver += 1
+        if nm == "const":
+            expr = repr(float(prog.consts[a]))
+            if expr in ("inf", "-inf", "nan"):
+                raise ValueError("non-finite constant in form")
+        elif nm in _UN:
+            expr = _UN[nm] % names[a]
+        else:
+            expr = _BIN[nm] % (names[a], names[b])
+        w("  const double %s = %s;" % (var, expr))
+        names[dst] = var
+    w("  double* o = A.out + cl * (long long)%d * NQP + tid;" % len(prog.outregs))
+    for s, r in enumerate(prog.outregs):
+        w("  o[%d * NQP] = %s;" % (s, names[r]))
+    w("}")
+    return "\n".join(L), nth
+
+
+_cache = {}
+
+
+def enabled():
+    return not os.environ.get("TIGAR_B200_NO_JIT")
+
+
+def get_kernel(prog, dim, nloc, nq, nd, jets, nfun):
+    src, nth = generate(prog, dim, nloc, nq, nd, jets, nfun)
+    key = hashlib.sha1(src.encode()).hexdigest()
+    k = _cache.get(key)
+    if k is None:
+        h = C.c_void_p()
+        check(lib.tg_jit_compile(src.encode(), b"tigar_qp", C.byref(h)))
+        k = (h, nth)
+        _cache[key] = k
+    return k
+
+
+def check_source(src):
+    """Compile only (no GPU needed); returns the cubin size."""
+    n = c_i64(0)
+    check(lib.tg_jit_check(src.encode(), C.byref(n)))
+    return n.value
+
+
+def launch(kernel, B, coef_ptrs, cell0, ncells, out):
+    h, nth = kernel
+    a = QpArgs()
+    b = B.c
+    for d in range(3):
+        a.tab[d], a.idx[d], a.wq[d], a.xq[d] = b.tab[d], b.idx[d], b.wq[d], b.xq[d]
+        a.n[d], a.nel[d] = b.n[d], b.nel[d]
+    for i, p in enumerate(coef_ptrs):
+        a.coef[i] = p
+    a.cell0 = cell0
+    a.out = dev.ptr(out)
+    check(lib.tg_jit_launch(h, ncells, nth, 0, C.byref(a), C.sizeof(a), dev.stream()))
