@@ -89,10 +89,10 @@ def test_nurbs_like_geometry_ptap_equals_direct():
     pr.assemble(f)
     pr.ptap(applyBCs=False)
     Ad, bd = pr.direct_iga(f)
-    # FE-interpolated rational geometry differs from the exact NURBS map by
-    # interpolation error (the reference has the same property, common.py:917-921),
-    # so only a loose agreement is expected here.
-    assert spla.norm(pr.C0 - Ad) / spla.norm(Ad) < 5e-2
+    # numerator and weight are splines, hence represented EXACTLY in the FE
+    # space (common.py:917-921): the rational map agrees point-wise
+    assert spla.norm(pr.C0 - Ad) / spla.norm(Ad) < 1e-11
+    assert np.linalg.norm(pr.b0 - bd) / np.linalg.norm(bd) < 1e-11
 
 
 def test_bcs():
