@@ -315,8 +315,11 @@ struct TgTerms {
   signed char aT[TG_MAXJET * TG_MAXJET][3];
 };
 
+__device__ __forceinline__ int l1i(int a, int NL) { return (a / NL) % NL; }
+__device__ __forceinline__ int l2i(int a, int NL) { return a / (NL * NL); }
+
 template <int NL, int NQ>
-__global__ void __launch_bounds__(NL* NL* NL* NL)
+__global__ void __launch_bounds__(NL* NL* NL* NL, (NL == 4) ? 3 : 1)
 k_assemble_matrix_sf3(TgBasis B, TgWin W, TgTerms TT, const double* __restrict__ coef,
                       int64_t cell0, TgColour C, double* __restrict__ vals) {
   constexpr int NT = NL * NL * NL * NL;
@@ -324,7 +327,7 @@ k_assemble_matrix_sf3(TgBasis B, TgWin W, TgTerms TT, const double* __restrict__
   constexpr int NEN = NL * NL * NL;
   constexpr int MAXD = 5;                       // derivative orders 0..4
   extern __shared__ double Gall[];               // [nterms][NQP]
-  __shared__ double T1[NQ * NQ * NL * NL];      // [q3][q2][a1][b1]
+  __shared__ double T1[2 * NQ * NQ * NL * NL];  // 2 x [q3][q2][a1][b1]
   __shared__ double tabs[3][MAXD][NQ][NL];      // [d][k][q][a]
   __shared__ long long rbase[NEN];
   __shared__ int gidx[3][NL], rlo[3][NL], rlen[3][NL], ridx[3][NL];
@@ -366,8 +369,11 @@ k_assemble_matrix_sf3(TgBasis B, TgWin W, TgTerms TT, const double* __restrict__
     if (r0 < 0 || r1 < 0 || r2 < 0) {
       rbase[a] = -1;
     } else {
-      int64_t row = r0 + (int64_t)W.nr[0] * (r1 + (int64_t)W.nr[1] * r2);
-      rbase[a] = W.rowptr[row];
+      // rowptr in closed form from the 1-D prefix sums (L1/L2 resident):
+      // S0[r0]*len1*len2 + T0*(S1[r1]*len2 + T1*S2[r2])
+      const long long l1 = rlen[1][l1i(a, NL)], l2 = rlen[2][l2i(a, NL)];
+      const long long T0 = W.S[0][W.nr[0]], T1 = W.S[1][W.nr[1]];
+      rbase[a] = W.S[0][r0] * l1 * l2 + T0 * (W.S[1][r1] * l2 + T1 * W.S[2][r2]);
     }
   }
 
@@ -377,31 +383,39 @@ k_assemble_matrix_sf3(TgBasis B, TgWin W, TgTerms TT, const double* __restrict__
 #pragma unroll
     for (int j = 0; j < NL; j++) acc[i][j] = 0.0;
 
+  // Terms arrive sorted by their last-direction orders (aS[2], aT[2]); terms of
+  // one group share the stage-3 tables, so their t2[] are summed first and the
+  // most expensive contraction runs once per group instead of once per term.
+  double t2[NQ];
+#pragma unroll
+  for (int q3 = 0; q3 < NQ; q3++) t2[q3] = 0.0;
   for (int term = 0; term < TT.n; term++) {
     const int s0 = TT.aS[term][0], s1 = TT.aS[term][1], s2 = TT.aS[term][2];
     const int t0 = TT.aT[term][0], t1 = TT.aT[term][1], t2o = TT.aT[term][2];
     const double* G = Gall + term * NQP;
-    __syncthreads();                           // previous term done with T1 (and Gall loaded)
+    double* T1b = T1 + (term & 1) * (NQ * NQ * NL * NL);       // double buffered
+    if (term == 0) __syncthreads();                            // Gall, tabs loaded
     for (int o = tid; o < NQ * NQ * NL * NL; o += NT) {
       int ob1 = o % NL, oa1 = (o / NL) % NL, q23 = o / (NL * NL);
       double v = 0.0;
 #pragma unroll
       for (int q1 = 0; q1 < NQ; q1++)
         v += tabs[0][s0][q1][oa1] * tabs[0][t0][q1][ob1] * G[q23 * NQ + q1];
-      T1[o] = v;
+      T1b[o] = v;
     }
     __syncthreads();
     double w2[NQ];
 #pragma unroll
     for (int q2 = 0; q2 < NQ; q2++) w2[q2] = tabs[1][s1][q2][a2] * tabs[1][t1][q2][b2];
-    double t2[NQ];
 #pragma unroll
     for (int q3 = 0; q3 < NQ; q3++) {
-      double v = 0.0;
+      double v = t2[q3];
 #pragma unroll
-      for (int q2 = 0; q2 < NQ; q2++) v += w2[q2] * T1[((q3 * NQ + q2) * NL + a1) * NL + b1];
+      for (int q2 = 0; q2 < NQ; q2++) v += w2[q2] * T1b[((q3 * NQ + q2) * NL + a1) * NL + b1];
       t2[q3] = v;
     }
+    const bool last = (term + 1 == TT.n) || TT.aS[term + 1][2] != s2 || TT.aT[term + 1][2] != t2o;
+    if (!last) continue;
     double vv[NL][NQ];
 #pragma unroll
     for (int b3 = 0; b3 < NL; b3++)
@@ -420,6 +434,8 @@ k_assemble_matrix_sf3(TgBasis B, TgWin W, TgTerms TT, const double* __restrict__
         acc[a3][b3] = v;
       }
     }
+#pragma unroll
+    for (int q3 = 0; q3 < NQ; q3++) t2[q3] = 0.0;
   }
 
   // scatter: rows a = (a1,a2,a3), columns b = (b1,b2,b3)

@@ -468,6 +468,14 @@ class TensorPatch(object):
     def jet_order(nodes):
         return S.max_order(nodes)
 
+    @staticmethod
+    def _sf_key(k):
+        """Order terms so that those sharing the last-direction derivative
+        orders are adjacent (the sum-factorised kernel runs its last stage once
+        per such group)."""
+        a, b = pad3(k[0]), pad3(k[1])
+        return (a[2], b[2], a[1], b[1], a[0], b[0])
+
     def assemble_matrix(self, terms, funcs, kind="fe", out=None):
         """terms: {(alphaTest, alphaTrial): Node} (coefficient already includes
         J and the quadrature weight).  kind 'fe' -> A_FE on the Lagrange
@@ -482,7 +490,7 @@ class TensorPatch(object):
         stride = i32arr([2] * self.dim if kind == "fe" else B.nloc)
         if lib.tg_assemble_sf_supported(B.ref()):
             # sum-factorised kernel: one coefficient slot per non-zero term
-            keys = sorted(terms, key=lambda k: (pad3(k[0]), pad3(k[1])))
+            keys = sorted(terms, key=self._sf_key)
             P = self._qp_setup([terms[k] for k in keys], funcs)
             tl = []
             for i, k in enumerate(keys):
@@ -521,7 +529,7 @@ class TensorPatch(object):
         pass (the geometry sub-expressions are shared by hash-consing).
         Returns (WinMatrix, vector)."""
         alS = sorted(set(pad3(k) for k in vterms))
-        mk = sorted(mterms, key=lambda k: (pad3(k[0]), pad3(k[1])))
+        mk = sorted(mterms, key=self._sf_key)
         nodes = [mterms[k] for k in mk] + [vterms[a] for a in
                                            sorted(vterms, key=lambda a: pad3(a))]
         order = max([max(pad3(k[0]) + pad3(k[1])) for k in mk] + [max(a) for a in alS]
