@@ -318,7 +318,8 @@ class AbstractExtractionGenerator(object):
         self.zeroDofs += newDofs
 
     def addZeroDofs(self, field, newDofs):
-        self.addZeroDofsGlobal([self.globalDof(field, d) for d in newDofs])
+        off = self.globalDof(field, 0)
+        self.addZeroDofsGlobal(list(newDofs) if off == 0 else [d + off for d in newDofs])
 
     def getPrealloc(self, control):
         return DEFAULT_PREALLOC

@@ -303,17 +303,20 @@ class BSpline(AbstractScalarBasis):
             elif self.nvar == 2:
                 M = shape[0]
                 if direction == 0:
-                    out += [ij2dof(i, j, M) for j in range(shape[1])]
+                    out += (np.arange(shape[1]) * M + i).tolist()
                 else:
-                    out += [ij2dof(j, i, M) for j in range(shape[0])]
+                    out += (i * M + np.arange(shape[0])).tolist()
             else:
                 M, N, O = shape
-                if direction == 0:
-                    out += [ijk2dof(i, j, k, M, N) for j in range(N) for k in range(O)]
+                if direction == 0:      # j outer, k inner
+                    jj, kk = np.arange(N)[:, None], np.arange(O)[None, :]
+                    out += (kk * (M * N) + jj * M + i).ravel().tolist()
                 elif direction == 1:
-                    out += [ijk2dof(j, i, k, M, N) for j in range(M) for k in range(O)]
+                    jj, kk = np.arange(M)[:, None], np.arange(O)[None, :]
+                    out += (kk * (M * N) + i * M + jj).ravel().tolist()
                 else:
-                    out += [ijk2dof(j, k, i, M, N) for j in range(M) for k in range(N)]
+                    jj, kk = np.arange(M)[:, None], np.arange(N)[None, :]
+                    out += (i * (M * N) + kk * M + jj).ravel().tolist()
         return out
 
 

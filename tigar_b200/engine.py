@@ -746,7 +746,7 @@ class TensorPatch(object):
         check(lib.tg_zero_entries(dev.ptr(b), dev.ptr(mask), b.numel(), dev.stream()))
         return b
 
-    def solve_cg(self, Cm, b, x=None, rtol=1e-12, atol=0.0, maxit=100000, check_every=25):
+    def solve_cg(self, Cm, b, x=None, rtol=1e-12, atol=0.0, maxit=100000, check_every=5):
         if self.part is not None:
             from .multigpu import DeviceOps, dist_cg
             ops = DeviceOps(self, Cm)
