@@ -151,9 +151,10 @@ def one_step(kv, cm, control_net, mode, rtol, to_host):
 
 
 def spmv_bytes(W):
-    """Algorithmic bytes of one windowed SpMV launch: values once (8 B/nnz, no
-    column indices exist), row pointer + x read + y write per row."""
-    return 8 * W.nnz + (8 + 8 + 8) * W.nrows
+    """Algorithmic bytes of one windowed SpMV launch: the exact non-zeros once
+    (8 B/nnz, no column indices exist; SELL padding is NOT counted), x read + y
+    write per row (+ row pointer for the row-major layout)."""
+    return 8 * W.nnz + (16 if W.layout == 1 else 24) * W.nrows
 
 
 # ------------------------------------------------------------------ CPU arm
@@ -287,7 +288,8 @@ def run_ours(args):
     bytes_per_launch = spmv_bytes(W)
     avg_ms = spmv_ms.value / max(spmv_n.value, 1)
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_win_spmv<true> (CG matvec + p.Ap partials)",
+    roofline = {"bound": "hbm", "kernel": ("k_sell_spmv<7,true>" if W.layout == 1 else "k_win_spmv<true>")
+                + " (CG matvec + p.Ap partials)",
                 "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None,
                 "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,

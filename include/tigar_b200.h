@@ -60,6 +60,18 @@ typedef struct {
   int32_t row0[TG_MAXDIM];   /* row-distributed blocks: global coordinate of local row /    */
   int32_t col0[TG_MAXDIM];   /* column 0 per direction (0 for a whole matrix).  Assembly
                                 skips rows outside [row0, row0+nr).                        */
+  int32_t layout;            /* 0: rows contiguous (rowptr[row] + pos).
+                                1: SELL-H: rows of one (r1,r2) line are grouped H at a time
+                                and stored slot-major, entry (row, slot) at
+                                  linebase(r1,r2) + (r0/H)*H*slots + slot*H + r0%H,
+                                slot = ((c2-lo2)*len1 + (c1-lo1))*w0max + (c0 - bs0[r0]),
+                                slots = w0max*len1*len2,
+                                linebase = H*ceil(nr0/H)*w0max*(S1[r1]*len2 + T1*S2[r2]);
+                                first-direction windows are padded to the uniform band
+                                [bs0[r0], bs0[r0]+w0max) with zeros.  Used for the IGA
+                                system matrix: lanes = rows, fully coalesced SpMV.       */
+  int32_t H;
+  const int32_t* bs0;        /* [nr0] band start (layout 1)                              */
   int32_t maxrow;            /* longest row (values); 0 = unknown: the TMA-staged
                                 SpMV is then not used.  The value array must be
                                 readable up to the next 16-byte boundary past
@@ -264,6 +276,14 @@ int tg_win_diag_inv(const tg_win* h_w, const double* vals, int32_t col_shift, do
 int tg_win_solve_cg(const tg_win* h_w, const double* vals, const double* b, double* x,
                     double rtol, double atol, int32_t maxit, int32_t check_every,
                     double* work, int32_t* h_iters, double* h_relres, void* stream);
+
+/* layout conversion of a windowed matrix's values: exact row-major CSR order
+ * (rowptr) <-> the window's own layout.  export: out_csr[rowptr[r]+pos] =
+ * vals(r,pos); import: the inverse, padding zero-filled.                     */
+int tg_win_export_vals(const tg_win* h_w, const double* vals, double* out_csr, void* stream);
+int tg_win_import_vals(const tg_win* h_w, const double* in_csr, double* vals, void* stream);
+/* number of doubles the value array of a window occupies in its layout       */
+int64_t tg_win_storage(const tg_win* h_w, const int64_t* h_T);
 
 /* zeroRowsColumns(zeroDofs, diag) (common.py:1199-1200); mask[i]!=0 marks a
  * constrained DoF.                                                          */

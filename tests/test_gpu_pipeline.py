@@ -171,11 +171,12 @@ def test_generic_csr_kernels_match_windowed():
     b = spline.assembleVector(L)
     w = Cm.window
     rp, cols = w.rowptr(), w.columns()
+    cv = Cm.csr_values()              # exact CSR order (the window may be SELL)
     n = w.nrows
     rng = np.random.RandomState(1)
     x = dev.from_np(rng.rand(n))
     y1, y2 = dev.empty(n), dev.empty(n)
-    check(lib.tg_spmv(dev.ptr(rp), dev.ptr(cols), dev.ptr(Cm.vals), dev.ptr(x), dev.ptr(y1), n,
+    check(lib.tg_spmv(dev.ptr(rp), dev.ptr(cols), dev.ptr(cv), dev.ptr(x), dev.ptr(y1), n,
                       dev.stream()))
     Cm.matvec(x, y2)
     assert np.abs(dev.to_np(y1) - dev.to_np(y2)).max() < 1e-12
@@ -183,17 +184,17 @@ def test_generic_csr_kernels_match_windowed():
     sol = dev.zeros(n)
     work = dev.empty(4 * n + lib.tg_cg_scratch_len() + 8)
     its, relres = C.c_int32(0), C.c_double(0)
-    check(lib.tg_solve_cg(dev.ptr(rp), dev.ptr(cols), dev.ptr(Cm.vals), dev.ptr(b.t), dev.ptr(sol),
+    check(lib.tg_solve_cg(dev.ptr(rp), dev.ptr(cols), dev.ptr(cv), dev.ptr(b.t), dev.ptr(sol),
                           n, 1e-13, 0.0, 10000, 10, dev.ptr(work), C.byref(its), C.byref(relres),
                           dev.stream()))
     import scipy.sparse.linalg as spla
     ref = spla.spsolve(Cm.to_scipy().tocsc(), b.get_local())
     assert rel(dev.to_np(sol), ref) < 1e-10 and its.value > 0
     # general-CSR zeroRowsColumns
-    A2 = spline.assembleMatrix(a, applyBCs=False)
-    check(lib.tg_zero_rows_cols(dev.ptr(rp), dev.ptr(cols), dev.ptr(A2.vals), n,
+    A2 = spline.assembleMatrix(a, applyBCs=False).csr_values()
+    check(lib.tg_zero_rows_cols(dev.ptr(rp), dev.ptr(cols), dev.ptr(A2), n,
                                 dev.ptr(spline._bc_mask()), 1.0, dev.stream()))
-    assert np.array_equal(dev.to_np(A2.vals), dev.to_np(Cm.vals))
+    assert np.array_equal(dev.to_np(A2), dev.to_np(cv))
 
 
 def test_write_and_read_extraction(tmp_path):
@@ -305,3 +306,35 @@ def test_jit_kernel_equals_interpreter():
             os.environ.pop("TIGAR_B200_NO_JIT", None)
     assert relm(out["jit"][0], out["interp"][0]) < 1e-14
     assert rel(out["jit"][1], out["interp"][1]) < 1e-14
+
+
+@pytest.mark.parametrize("deg,nels", [([2], [40]), ([3, 2], [37, 5]), ([3, 3, 3], [11, 3, 4]), ([2, 2, 2], [2, 2, 2])])
+def test_sell_and_row_major_layouts_agree(deg, nels):
+    """The IGA system matrix in SELL-H layout (default) and in row-major layout
+    (TIGAR_B200_LAYOUT=0): identical CSR export, SpMV, BCs, diagonal and CG."""
+    import os
+    from tigar_b200 import dev
+    kv = [uk(p, n) for p, n in zip(deg, nels)]
+    res = {}
+    for layout in ("1", "0"):
+        os.environ["TIGAR_B200_LAYOUT"] = layout
+        try:
+            gen, spline, pr = make_pair(deg, kv, mode="fused")
+            assert spline.patch().window("C").layout == int(layout)
+            a, L = poisson_forms(spline, "sin")
+            C0 = spline.assembleMatrix(a, applyBCs=False)
+            C = spline.assembleMatrix(a, diag=2.5)
+            b = spline.assembleVector(L)
+            rng = np.random.RandomState(2)
+            x = rng.rand(C.window.ncols)
+            y = dev.to_np(C0.matvec(dev.from_np(x)))
+            sol, its, relres = spline.patch().solve_cg(C, b.t, rtol=1e-13)
+            res[layout] = (C0.to_scipy(), C.to_scipy(), y, dev.to_np(sol), x)
+        finally:
+            os.environ.pop("TIGAR_B200_LAYOUT", None)
+    s, r = res["1"], res["0"]
+    assert abs(s[0] - r[0]).max() == 0.0 and abs(s[1] - r[1]).max() == 0.0   # same entries
+    assert np.abs(s[2] - s[0] @ s[4]).max() < 1e-12 and np.abs(r[2] - r[0] @ r[4]).max() < 1e-12
+    assert rel(s[3], r[3]) < 1e-10
+    import scipy.sparse.linalg as spla
+    assert (s[1].diagonal()[np.unique(spline.zeroDofs)] == 2.5).all()

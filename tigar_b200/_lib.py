@@ -32,7 +32,7 @@ class tg_basis(C.Structure):
 class tg_win(C.Structure):
     _fields_ = [("dim", c_i32), ("nr", c_i32 * 3), ("nc", c_i32 * 3),
                 ("lo", c_vp * 3), ("hi", c_vp * 3), ("rowptr", c_vp), ("w0max", c_i32), ("S", c_vp * 3), ("row0", c_i32 * 3), ("col0", c_i32 * 3),
-                ("maxrow", c_i32)]
+                ("layout", c_i32), ("H", c_i32), ("bs0", c_vp), ("maxrow", c_i32)]
 
 
 PB = C.POINTER(tg_basis)
@@ -86,6 +86,9 @@ SIGNATURES = {
     "tg_ptap_c": [PW, c_vp, PW, PW, c_vp, PW, PW, c_vp, c_vp],
     "tg_ptap_kron_ap": [PW, c_vp, PVP, PW, c_vp, c_i32, c_vp],
     "tg_win_rowcombine": [PW, c_vp, PW, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp],
+    "tg_win_export_vals": [PW, c_vp, c_vp, c_vp],
+    "tg_win_import_vals": [PW, c_vp, c_vp, c_vp],
+    "tg_win_storage": [PW, C.POINTER(c_i64)],
     "tg_zero_rows_cols": [c_vp, c_vp, c_vp, c_i64, c_vp, c_dbl, c_vp],
     "tg_zero_entries": [c_vp, c_vp, c_i64, c_vp],
     "tg_diag_inv": [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp],
@@ -100,7 +103,7 @@ SIGNATURES = {
     "tg_cg_xpby": [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
     "tg_dot": [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
 }
-_RESTYPES = {"tg_last_error": C.c_char_p, "tg_prof_enable": None, "tg_prof_get": None, "tg_launch_count": c_i64}
+_RESTYPES = {"tg_last_error": C.c_char_p, "tg_prof_enable": None, "tg_prof_get": None, "tg_launch_count": c_i64, "tg_win_storage": c_i64}
 
 for _name, _args in SIGNATURES.items():
     _f = getattr(lib, _name)          # AttributeError if a symbol is missing

@@ -60,6 +60,7 @@ k_assemble_matrix(TgBasis B, TgWin W, TgAlpha S, TgAlpha T, int sameST,
   int* gc = (int*)(rbase + nen);                   // [nen][3]
   int* rlo = gc + 3 * nen;                         // [nen][3]
   int* rlen = rlo + 3 * nen;                       // [nen][3]
+  int* rstride = rlen + 3 * nen;                   // [nen]
 
   for (int a = tid; a < nen; a += nth) {
     int al[3];
@@ -72,13 +73,16 @@ k_assemble_matrix(TgBasis B, TgWin W, TgAlpha S, TgAlpha T, int sameST,
       valid = valid && rr[d] >= 0 && rr[d] < W.nr[d];
     }
     if (valid) {
-      int64_t row = rr[0] + (int64_t)W.nr[0] * (rr[1] + (int64_t)W.nr[1] * rr[2]);
       TgRowWin rw = tg_row_window(W, rr);
-      rbase[a] = W.rowptr[row];
+      TgRowAddr ra = tg_row_addr(W, rr, rw);
+      rbase[a] = ra.base;
+      rstride[a] = ra.stride;
       for (int d = 0; d < 3; d++) {
         rlo[3 * a + d] = rw.lo[d];
         rlen[3 * a + d] = rw.len[d];
       }
+      rlo[3 * a + 0] = ra.lo0;
+      rlen[3 * a + 0] = ra.len0;
     } else {
       rbase[a] = -1;
     }
@@ -153,7 +157,7 @@ k_assemble_matrix(TgBasis B, TgWin W, TgAlpha S, TgAlpha T, int sameST,
       int pos = ((gc[3 * b + 2] - rlo[3 * a + 2]) * rlen[3 * a + 1] +
                  (gc[3 * b + 1] - rlo[3 * a + 1])) * rlen[3 * a + 0] +
                 (gc[3 * b + 0] - rlo[3 * a + 0]);
-      vals[rbase[a] + pos] += acc[i];
+      vals[rbase[a] + (long long)pos * rstride[a]] += acc[i];
     }
   }
 }
@@ -244,7 +248,7 @@ extern "C" int tg_assemble_matrix_ex(const tg_basis* h_B, const tg_win* h_W, int
   const int nqp = B.nq[0] * B.nq[1] * B.nq[2];
   const int nth = 256;
   // q-chunk so that smem fits (target <= ~100 KB to keep 2 CTAs/SM when possible)
-  size_t fixed = (size_t)nen * (8 + 9 * 4) + 64;
+  size_t fixed = (size_t)nen * (8 + 10 * 4) + 64;
   size_t perq = ((size_t)nS * nen * (same ? 2 : 1) + (same ? 0 : (size_t)nT * nen) +
                  (size_t)nS * nen * (same ? 0 : 1) + (size_t)nS * nT) * 8;
   // (same: BJS + G ; distinct: BJS + BJT + G)
@@ -331,6 +335,7 @@ k_assemble_matrix_sf3(TgBasis B, TgWin W, TgTerms TT, const double* __restrict__
   __shared__ double tabs[3][MAXD][NQ][NL];      // [d][k][q][a]
   __shared__ long long rbase[NEN];
   __shared__ int gidx[3][NL], rlo[3][NL], rlen[3][NL], ridx[3][NL];
+  __shared__ int rstr;
 
   const int tid = threadIdx.x;
   const int b1 = tid % NL, a1 = (tid / NL) % NL, b2 = (tid / (NL * NL)) % NL,
@@ -369,11 +374,27 @@ k_assemble_matrix_sf3(TgBasis B, TgWin W, TgTerms TT, const double* __restrict__
     if (r0 < 0 || r1 < 0 || r2 < 0) {
       rbase[a] = -1;
     } else {
-      // rowptr in closed form from the 1-D prefix sums (L1/L2 resident):
-      // S0[r0]*len1*len2 + T0*(S1[r1]*len2 + T1*S2[r2])
       const long long l1 = rlen[1][l1i(a, NL)], l2 = rlen[2][l2i(a, NL)];
-      const long long T0 = W.S[0][W.nr[0]], T1 = W.S[1][W.nr[1]];
-      rbase[a] = W.S[0][r0] * l1 * l2 + T0 * (W.S[1][r1] * l2 + T1 * W.S[2][r2]);
+      const long long T1 = W.S[1][W.nr[1]];
+      if (W.layout == 0) {
+        // rowptr in closed form from the 1-D prefix sums (L1/L2 resident):
+        // S0[r0]*len1*len2 + T0*(S1[r1]*len2 + T1*S2[r2])
+        const long long T0 = W.S[0][W.nr[0]];
+        rbase[a] = W.S[0][r0] * l1 * l2 + T0 * (W.S[1][r1] * l2 + T1 * W.S[2][r2]);
+      } else {
+        const int H = W.H, chunk = r0 / H;
+        const long long nchunk = (W.nr[0] + H - 1) / H;
+        rbase[a] = (long long)H * nchunk * W.w0max * (W.S[1][r1] * l2 + T1 * W.S[2][r2]) +
+                   (long long)chunk * H * (W.w0max * l1 * l2) + (r0 - chunk * H);
+      }
+    }
+  }
+  if (tid == 0) rstr = (W.layout == 0) ? 1 : W.H;
+  if (W.layout != 0 && tid < NL) {        // SELL: uniform band in the first direction
+    const int r = ridx[0][tid];
+    if (r >= 0) {
+      rlo[0][tid] = W.bs0[r];
+      rlen[0][tid] = W.w0max;
     }
   }
 
@@ -449,7 +470,8 @@ k_assemble_matrix_sf3(TgBasis B, TgWin W, TgTerms TT, const double* __restrict__
 #pragma unroll
     for (int b3 = 0; b3 < NL; b3++) {
       const int d2 = gidx[2][b3] - rlo[2][a3];
-      ptr[a3][b3] = (base >= 0) ? vals + base + ((int64_t)d2 * len1 + d1) * len0 + d0 : nullptr;
+      ptr[a3][b3] =
+          (base >= 0) ? vals + base + (((int64_t)d2 * len1 + d1) * len0 + d0) * rstr : nullptr;
     }
   }
   // colouring guarantees exclusive ownership: all loads first, then all stores

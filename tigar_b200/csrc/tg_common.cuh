@@ -46,6 +46,8 @@ struct TgWin {
   const int64_t* rowptr;
   const int64_t* S[3];
   int row0[3], col0[3];
+  int layout, H, w0max;
+  const int32_t* bs0;
 };
 
 static inline TgWin tg_win_dev(const tg_win* w) {
@@ -61,6 +63,10 @@ static inline TgWin tg_win_dev(const tg_win* w) {
     d.col0[k] = (k < w->dim) ? w->col0[k] : 0;
   }
   d.rowptr = w->rowptr;
+  d.layout = w->layout;
+  d.H = w->H;
+  d.w0max = w->w0max;
+  d.bs0 = w->bs0;
   return d;
 }
 
@@ -129,6 +135,37 @@ __device__ inline TgRowWin tg_row_window(const TgWin& w, const int* r) {
     }
   }
   return rw;
+}
+
+// Address of entry (d0,d1,d2) of a row (offsets inside its window):
+//   base + ((d2*len1 + d1)*len0 + d0) * stride,  d0 = c0 - lo0
+struct TgRowAddr {
+  long long base;
+  int stride, len0, lo0;
+};
+
+__device__ inline TgRowAddr tg_row_addr(const TgWin& w, const int* rc, const TgRowWin& rw) {
+  TgRowAddr a;
+  if (w.layout == 0) {
+    const long long row = rc[0] + (long long)w.nr[0] * (rc[1] + (long long)w.nr[1] * rc[2]);
+    a.base = w.rowptr[row];
+    a.stride = 1;
+    a.len0 = rw.len[0];
+    a.lo0 = rw.lo[0];
+  } else {
+    const int H = w.H;
+    const int chunk = rc[0] / H, lane = rc[0] - chunk * H;
+    const long long nchunk = (w.nr[0] + H - 1) / H;
+    const long long slots = (long long)w.w0max * rw.len[1] * rw.len[2];
+    long long inner = 0;
+    if (w.dim > 1) inner = w.S[1][rc[1]] * rw.len[2];
+    if (w.dim > 2) inner += w.S[1][w.nr[1]] * w.S[2][rc[2]];
+    a.base = (long long)H * nchunk * w.w0max * inner + (long long)chunk * H * slots + lane;
+    a.stride = H;
+    a.len0 = w.w0max;
+    a.lo0 = w.bs0[rc[0]];
+  }
+  return a;
 }
 
 // position of column c inside the window (caller guarantees containment)

@@ -18,7 +18,7 @@ static int tg_cg_grid_size() {
   return g_cg_grid;
 }
 
-extern "C" int tg_cg_scratch_len(void) { return 2 * tg_cg_grid_size() + 8; }
+extern "C" int tg_cg_scratch_len(void) { return 2 * tg_cg_grid_size() + 8; }   // >= 2*ws grid
 
 __device__ inline double tg_block_sum(double v, double* sh) {
   v = tg_warp_sum(v);
@@ -370,7 +370,8 @@ extern "C" int tg_win_spmv_dot(const tg_win* h_w, const double* vals, const doub
                                void* stream) {
   int rc = tg_win_spmv_launch(h_w, vals, x, xoff, y, scratch, tg_stream(stream));
   if (rc) return rc;
-  k_final_reduce<<<1, 256, 0, tg_stream(stream)>>>(scratch, tg_ws_grid_size(), 1, out1);
+  k_final_reduce<<<1, 256, 0, tg_stream(stream)>>>(
+      scratch, (h_w->layout == 1) ? 2 * tg_ws_grid_size() : tg_ws_grid_size(), 1, out1);
   TG_LAUNCH_CHECK();
   return 0;
 }

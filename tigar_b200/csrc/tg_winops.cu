@@ -13,6 +13,7 @@
 #include "tg_common.cuh"
 #include <stdlib.h>
 
+static inline int64_t tg_win_lines(const tg_win* w);
 #define TG_WS_BLOCK 256
 #define TG_WS_ROWS 32   // rows of one line per item
 
@@ -412,6 +413,98 @@ static int tg_win_spmv_tma_try(const tg_win* h_w, const double* vals, const doub
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// SELL-H layout (tg_win.layout == 1): lanes = rows.  A warp owns one
+// (line, chunk) item = H consecutive rows; per slot the 32 lanes read 32
+// consecutive values (one coalesced line of the stream) and 32 consecutive x
+// entries.  No reduction, no per-row index math, W0 independent loads in flight
+// per lane per inner iteration.
+template <int W0, bool DOT>
+__global__ void __launch_bounds__(256)
+k_sell_spmv(TgWin w, const double* __restrict__ vals, const double* __restrict__ x, int64_t xoff,
+            double* __restrict__ y, int nchunk, int64_t nitems, double* __restrict__ part) {
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31;
+  const int H = w.H;
+  const int w0 = (W0 > 0) ? W0 : w.w0max;
+  const int nr0 = w.nr[0], nr1 = w.nr[1];
+  const int64_t nc0 = w.nc[0];
+  const int64_t pl = nc0 * w.nc[1];
+  const int64_t T1 = (w.dim > 1) ? w.S[1][nr1] : 1;
+  const int64_t linemul = (int64_t)H * nchunk * w0;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double dot = 0.0;
+  for (int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < nitems;
+       item += nwarps) {
+    const int64_t line = item / nchunk;
+    const int ch = (int)(item - line * nchunk);
+    const int r2 = (int)(line / nr1);
+    const int r1 = (int)(line - (int64_t)r2 * nr1);
+    int lo1 = 0, len1 = 1, lo2 = 0, len2 = 1;
+    int64_t inner = 0;
+    if (w.dim > 1) {
+      lo1 = __ldg(w.lo[1] + r1);
+      len1 = __ldg(w.hi[1] + r1) - lo1 + 1;
+    }
+    if (w.dim > 2) {
+      lo2 = __ldg(w.lo[2] + r2);
+      len2 = __ldg(w.hi[2] + r2) - lo2 + 1;
+    }
+    if (w.dim > 1) inner = __ldg(w.S[1] + r1) * len2;
+    if (w.dim > 2) inner += T1 * __ldg(w.S[2] + r2);
+    const int64_t slots = (int64_t)w0 * len1 * len2;
+    const int r0 = ch * H + lane;
+    const bool valid = lane < H && r0 < nr0;
+    if (valid) {
+      const double* __restrict__ a = vals + linemul * inner + (int64_t)ch * H * slots + lane;
+      const double* xb = x + __ldg(w.bs0 + r0) + nc0 * lo1 + pl * lo2;
+      double acc0 = 0.0, acc1 = 0.0;
+      for (int c2 = 0; c2 < len2; c2++) {
+        const double* xp = xb + pl * c2;
+        for (int c1 = 0; c1 < len1; c1++) {
+          if (W0 > 0) {
+            double av[W0 > 0 ? W0 : 1], xv[W0 > 0 ? W0 : 1];
+#pragma unroll
+            for (int k = 0; k < W0; k++) av[k] = __ldcs(a + (int64_t)k * H);
+#pragma unroll
+            for (int k = 0; k < W0; k++) xv[k] = xp[k];
+#pragma unroll
+            for (int k = 0; k < W0; k++) {
+              if (k & 1) acc1 += av[k] * xv[k];
+              else acc0 += av[k] * xv[k];
+            }
+          } else {
+            for (int k = 0; k < w0; k++) acc0 += __ldcs(a + (int64_t)k * H) * xp[k];
+          }
+          a += (int64_t)w0 * H;
+          xp += nc0;
+        }
+      }
+      const double acc = acc0 + acc1;
+      const int64_t row = r0 + (int64_t)nr0 * line;
+      y[row] = acc;
+      if (DOT) dot += x[xoff + row] * acc;
+    }
+  }
+  if (DOT) {
+    dot = tg_block_sum_ws(dot, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = dot;
+  }
+}
+
+template <bool DOT>
+static void tg_sell_launch(int w0, int g, cudaStream_t st, const TgWin& w, const double* vals,
+                           const double* x, int64_t xoff, double* y, int nchunk, int64_t nitems,
+                           double* part) {
+  switch (w0) {
+    case 3: k_sell_spmv<3, DOT><<<g, 256, 0, st>>>(w, vals, x, xoff, y, nchunk, nitems, part); break;
+    case 5: k_sell_spmv<5, DOT><<<g, 256, 0, st>>>(w, vals, x, xoff, y, nchunk, nitems, part); break;
+    case 7: k_sell_spmv<7, DOT><<<g, 256, 0, st>>>(w, vals, x, xoff, y, nchunk, nitems, part); break;
+    case 9: k_sell_spmv<9, DOT><<<g, 256, 0, st>>>(w, vals, x, xoff, y, nchunk, nitems, part); break;
+    default: k_sell_spmv<0, DOT><<<g, 256, 0, st>>>(w, vals, x, xoff, y, nchunk, nitems, part); break;
+  }
+}
+
 static inline int64_t tg_win_lines(const tg_win* w) {
   int64_t n = 1;
   for (int d = 1; d < w->dim; d++) n *= w->nr[d];
@@ -421,6 +514,23 @@ static inline int64_t tg_win_lines(const tg_win* w) {
 int tg_win_spmv_launch(const tg_win* h_w, const double* vals, const double* x, int64_t xoff,
                        double* y, double* part, cudaStream_t st) {
   TG_REQUIRE(h_w->dim >= 1 && h_w->dim <= 3, "dim");
+  if (h_w->layout == 1) {
+    TG_REQUIRE(h_w->H >= 1 && h_w->H <= 32 && h_w->bs0 != nullptr, "SELL descriptor");
+    int nchunk = (int)tg_cdiv(h_w->nr[0], h_w->H);
+    int64_t nitems = tg_win_lines(h_w) * nchunk;
+    if (nitems == 0) return 0;
+    int g = tg_ws_grid_size() * 2;          // 8 CTAs of 256 threads per SM
+    if ((int64_t)g * 8 > nitems) g = (int)tg_cdiv(nitems, 8);
+    TgWin w = tg_win_dev(h_w);
+    if (part) {
+      TG_CHECK(cudaMemsetAsync(part, 0, sizeof(double) * tg_ws_grid_size() * 2, st));
+      tg_sell_launch<true>(h_w->w0max, g, st, w, vals, x, xoff, y, nchunk, nitems, part);
+    } else {
+      tg_sell_launch<false>(h_w->w0max, g, st, w, vals, x, xoff, y, nchunk, nitems, nullptr);
+    }
+    TG_LAUNCH_CHECK();
+    return 0;
+  }
   {
     int launched = 0;
     int rc = tg_win_spmv_tma_try(h_w, vals, x, xoff, y, part, st, &launched);
@@ -455,26 +565,38 @@ __global__ void k_win_zero_rows_cols(TgWin w, double* __restrict__ vals, int64_t
                                      const uint8_t* __restrict__ rowmask,
                                      const uint8_t* __restrict__ colmask, double diag,
                                      int col_shift) {
-  int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
+  // layout 0: one warp per row, lanes over its entries.
+  // layout 1: one thread per row (consecutive threads = consecutive rows of a
+  //           chunk, so every slot access is coalesced).
+  int64_t r;
+  int lane, step;
+  if (w.layout == 0) {
+    r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    lane = threadIdx.x & 31;
+    step = 32;
+  } else {
+    r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    lane = 0;
+    step = 1;
+  }
   if (r >= nrows) return;
   int rc[3];
   tg_decode(r, w.nr, w.dim, rc);
   TgRowWin rw = tg_row_window(w, rc);
+  TgRowAddr ra = tg_row_addr(w, rc, rw);
   int cc[3] = {rc[0], rc[1], rc[2]};
   cc[w.dim - 1] += col_shift;
   const int64_t mycol = cc[0] + (int64_t)w.nc[0] * (cc[1] + (int64_t)w.nc[1] * cc[2]);
   const bool mr = rowmask[r] != 0;
-  const int64_t base = w.rowptr[r];
-  const int tot = rw.len[0] * rw.len[1] * rw.len[2];
-  for (int pos = lane; pos < tot; pos += 32) {
-    int c0 = pos % rw.len[0];
-    int t = pos / rw.len[0];
+  const int tot = ra.len0 * rw.len[1] * rw.len[2];
+  for (int pos = lane; pos < tot; pos += step) {
+    int c0 = pos % ra.len0;
+    int t = pos / ra.len0;
     int c1 = t % rw.len[1];
     int c2 = t / rw.len[1];
-    int64_t col = (rw.lo[0] + c0) +
+    int64_t col = (ra.lo0 + c0) +
                   (int64_t)w.nc[0] * ((rw.lo[1] + c1) + (int64_t)w.nc[1] * (rw.lo[2] + c2));
-    if (mr || colmask[col]) vals[base + pos] = (mr && col == mycol) ? diag : 0.0;
+    if (mr || colmask[col]) vals[ra.base + (int64_t)pos * ra.stride] = (mr && col == mycol) ? diag : 0.0;
   }
 }
 
@@ -483,7 +605,8 @@ extern "C" int tg_win_zero_rows_cols(const tg_win* h_w, double* vals, const uint
                                      void* stream) {
   int64_t nrows = tg_win_nrows(h_w);
   if (nrows == 0) return 0;
-  k_win_zero_rows_cols<<<(unsigned)tg_cdiv(nrows * 32, 256), 256, 0, tg_stream(stream)>>>(
+  const int64_t nthreads = (h_w->layout == 0) ? nrows * 32 : nrows;
+  k_win_zero_rows_cols<<<(unsigned)tg_cdiv(nthreads, 256), 256, 0, tg_stream(stream)>>>(
       tg_win_dev(h_w), vals, nrows, rowmask, colmask, diag, col_shift);
   TG_LAUNCH_CHECK();
   return 0;
@@ -496,9 +619,12 @@ __global__ void k_win_diag_inv(TgWin w, const double* __restrict__ vals, int64_t
   int rc[3];
   tg_decode(r, w.nr, w.dim, rc);
   TgRowWin rw = tg_row_window(w, rc);
+  TgRowAddr ra = tg_row_addr(w, rc, rw);
   int cc[3] = {rc[0], rc[1], rc[2]};
   cc[w.dim - 1] += col_shift;
-  double d = vals[w.rowptr[r] + tg_win_pos(rw, cc)];
+  const int64_t pos = ((int64_t)(cc[2] - rw.lo[2]) * rw.len[1] + (cc[1] - rw.lo[1])) * ra.len0 +
+                      (cc[0] - ra.lo0);
+  double d = vals[ra.base + pos * ra.stride];
   dinv[r] = (d != 0.0) ? 1.0 / d : 1.0;
 }
 
@@ -508,6 +634,57 @@ extern "C" int tg_win_diag_inv(const tg_win* h_w, const double* vals, int32_t co
   if (nrows == 0) return 0;
   k_win_diag_inv<<<(unsigned)tg_cdiv(nrows, 256), 256, 0, tg_stream(stream)>>>(
       tg_win_dev(h_w), vals, nrows, col_shift, dinv);
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+
+// ---- layout conversion: exact row-major CSR order <-> the window's layout -----
+template <bool EXPORT>
+__global__ void k_win_convert(TgWin w, const double* __restrict__ src, double* __restrict__ dst,
+                              int64_t nrows) {
+  int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= nrows) return;
+  int rc[3];
+  tg_decode(r, w.nr, w.dim, rc);
+  TgRowWin rw = tg_row_window(w, rc);
+  TgRowAddr ra = tg_row_addr(w, rc, rw);
+  const int64_t base = w.rowptr[r];
+  const int tot = rw.len[0] * rw.len[1] * rw.len[2];
+  for (int pos = lane; pos < tot; pos += 32) {
+    int c0 = pos % rw.len[0];
+    int t = pos / rw.len[0];           // = c2*len1 + c1
+    int64_t p = ra.base + ((int64_t)t * ra.len0 + (rw.lo[0] + c0 - ra.lo0)) * ra.stride;
+    if (EXPORT) dst[base + pos] = src[p];
+    else dst[p] = src[base + pos];
+  }
+}
+
+extern "C" int64_t tg_win_storage(const tg_win* h_w, const int64_t* h_T) {
+  // h_T: totals of the per-direction window lengths (exact nnz = T0*T1*T2)
+  int64_t T[3] = {1, 1, 1};
+  for (int d = 0; d < h_w->dim; d++) T[d] = h_T[d];
+  if (h_w->layout == 0) return T[0] * T[1] * T[2];
+  return (int64_t)h_w->H * tg_cdiv(h_w->nr[0], h_w->H) * h_w->w0max * T[1] * T[2];
+}
+
+extern "C" int tg_win_export_vals(const tg_win* h_w, const double* vals, double* out_csr,
+                                  void* stream) {
+  int64_t nrows = tg_win_nrows(h_w);
+  if (nrows == 0) return 0;
+  k_win_convert<true><<<(unsigned)tg_cdiv(nrows * 32, 256), 256, 0, tg_stream(stream)>>>(
+      tg_win_dev(h_w), vals, out_csr, nrows);
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tg_win_import_vals(const tg_win* h_w, const double* in_csr, double* vals,
+                                  void* stream) {
+  int64_t nrows = tg_win_nrows(h_w);
+  if (nrows == 0) return 0;
+  k_win_convert<false><<<(unsigned)tg_cdiv(nrows * 32, 256), 256, 0, tg_stream(stream)>>>(
+      tg_win_dev(h_w), in_csr, vals, nrows);
   TG_LAUNCH_CHECK();
   return 0;
 }

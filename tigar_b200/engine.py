@@ -65,7 +65,30 @@ class Window(object):
         self.nnz = int(np.prod([int(l.sum()) for l in self.len]))
         self.row0 = [0] * self.dim
         self.col0 = [0] * self.dim
+        self.layout = 0
+        self.H = 1
         self._d = None
+
+    def sell(self):
+        """Switch to the SELL-H layout (lanes = rows; see tg_win.layout in
+        include/tigar_b200.h).  Returns self."""
+        assert self._d is None
+        nr0 = self.nr[0]
+        nchunk = (nr0 + 31) // 32
+        self.H = (nr0 + nchunk - 1) // nchunk
+        self.layout = 1
+        w0 = int(self.len[0].max())
+        self.bs0 = np.minimum(self.lo[0].astype(np.int64), self.nc[0] - w0).astype(np.int32)
+        assert np.all(self.bs0 >= 0)
+        return self
+
+    def storage(self):
+        """Doubles occupied by the value array in this layout."""
+        if self.layout == 0:
+            return self.nnz
+        nchunk = (self.nr[0] + self.H - 1) // self.H
+        rest = int(np.prod([int(l.sum()) for l in self.len[1:]])) if self.dim > 1 else 1
+        return self.H * nchunk * int(self.len[0].max()) * rest
 
     def slab(self, k0, k1, c0, c1):
         """Rows [k0,k1) of the last direction, columns restricted to [c0,c1)
@@ -83,6 +106,8 @@ class Window(object):
         w = Window(nr, nc, lo, hi)
         w.row0[L] = k0
         w.col0[L] = c0
+        if self.layout == 1:
+            w.sell()
         return w
 
     def transpose(self):
@@ -136,6 +161,11 @@ class Window(object):
             w.rowptr = dev.ptr(rowptr)
             w.w0max = int(self.len[0].max())
             w.maxrow = int(np.prod([int(l.max()) for l in self.len]))
+            w.layout, w.H = self.layout, self.H
+            if self.layout == 1:
+                tb = dev.from_np(self.bs0)
+                keep.append(tb)
+                w.bs0 = dev.ptr(tb)
             check(lib.tg_win_rowptr(C.byref(w), (c_vp * 3)(*S_ptrs), dev.ptr(rowptr),
                                     dev.stream()))
             keep.append(rowptr)
@@ -161,7 +191,25 @@ class WinMatrix(object):
 
     def __init__(self, window, vals=None):
         self.window = window
-        self.vals = dev.zeros(window.nnz) if vals is None else vals
+        self.vals = dev.zeros(window.storage()) if vals is None else vals
+
+    @staticmethod
+    def from_csr_values(window, csr_vals):
+        """Values given in exact row-major CSR order -> the window's layout."""
+        if window.layout == 0:
+            return WinMatrix(window, csr_vals)
+        m = WinMatrix(window)
+        check(lib.tg_win_import_vals(window.ref(), dev.ptr(csr_vals), dev.ptr(m.vals),
+                                     dev.stream()))
+        return m
+
+    def csr_values(self):
+        w = self.window
+        if w.layout == 0:
+            return self.vals
+        out = dev.empty(w.nnz)
+        check(lib.tg_win_export_vals(w.ref(), dev.ptr(self.vals), dev.ptr(out), dev.stream()))
+        return out
 
     @property
     def shape(self):
@@ -178,7 +226,7 @@ class WinMatrix(object):
         w = self.window
         rp = dev.to_np(w.rowptr())
         cols = dev.to_np(w.columns())
-        vals = dev.to_np(self.vals)
+        vals = dev.to_np(self.csr_values())
         A = sp.csr_matrix((vals, cols, rp), shape=self.shape)
         if drop_eps is not None:
             A.data[np.abs(A.data) <= drop_eps] = 0.0
@@ -355,10 +403,23 @@ class TensorPatch(object):
         if name == "C" and getattr(self, "part", None) is not None:
             if "Cloc" not in self._win:
                 pp = self.pp
-                self._win["Cloc"] = self._global_window("C").slab(pp["k0"], pp["k1"], pp["c0"],
-                                                                  pp["c1"])
+                self._win["Cloc"] = self._system_window().slab(pp["k0"], pp["k1"], pp["c0"],
+                                                               pp["c1"])
             return self._win["Cloc"]
+        if name == "C":
+            return self._system_window()
         return self._global_window(name)
+
+    def _system_window(self):
+        """The IGA system matrix window, in the SELL-H layout unless
+        TIGAR_B200_LAYOUT=0 (row-major)."""
+        if "Csys" not in self._win:
+            g = self._global_window("C")
+            w = Window(g.nr, g.nc, g.lo, g.hi)
+            if os.environ.get("TIGAR_B200_LAYOUT", "1") != "0":
+                w.sell()
+            self._win["Csys"] = w
+        return self._win["Csys"]
 
     def _global_window(self, name):
         if name not in self._win:
@@ -698,8 +759,8 @@ class TensorPatch(object):
             if not keep and len(stages) > 2:
                 stages[-2] = None
         Cw = stages[-1]
-        out = WinMatrix(wC, Cw.vals)          # same pattern as the global C window
-        assert Cw.window.nnz == wC.nnz
+        assert Cw.window.nnz == wC.nnz        # same pattern as the global C window
+        out = WinMatrix.from_csr_values(self.window("C"), Cw.vals)
         return (out, [s for s in stages if s is not None]) if keep else out
 
     def ptap(self, A, M=None, keep_AP=False):
@@ -709,13 +770,14 @@ class TensorPatch(object):
         if M is None:
             M = self.build_M()
         wA, wM, wMT = self.window("A"), self.window("M"), self.window("MT")
-        wP, wPT, wC = self.window("P"), self.window("PT"), self.window("C")
+        wP, wPT, wC = self.window("P"), self.window("PT"), self._global_window("C")
         AP = dev.empty(wP.nnz)
         check(lib.tg_ptap_ap(wA.ref(), dev.ptr(A.vals), wM.ref(), dev.ptr(M.vals), wMT.ref(),
                              wP.ref(), dev.ptr(AP), dev.stream()))
         Cm = WinMatrix(wC, dev.empty(wC.nnz))
         check(lib.tg_ptap_c(wM.ref(), dev.ptr(M.vals), wMT.ref(), wP.ref(), dev.ptr(AP),
                             wPT.ref(), wC.ref(), dev.ptr(Cm.vals), dev.stream()))
+        Cm = WinMatrix.from_csr_values(self.window("C"), Cm.vals)
         if keep_AP:
             return Cm, WinMatrix(wP, AP)
         return Cm
