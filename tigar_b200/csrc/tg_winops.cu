@@ -419,12 +419,16 @@ static int tg_win_spmv_tma_try(const tg_win* h_w, const double* vals, const doub
 // consecutive values (one coalesced line of the stream) and 32 consecutive x
 // entries.  No reduction, no per-row index math, W0 independent loads in flight
 // per lane per inner iteration.
-template <int W0, bool DOT>
+template <int W0, bool DOT, int G>
 __global__ void __launch_bounds__(256)
 k_sell_spmv(TgWin w, const double* __restrict__ vals, const double* __restrict__ x, int64_t xoff,
             double* __restrict__ y, int nchunk, int64_t nitems, double* __restrict__ part) {
+  // One CTA per (line, chunk) item = H consecutive rows; its 8 warps split the
+  // (c1,c2) slot groups, so the CTA streams one contiguous block of values and
+  // all warps gather from the same small x neighbourhood (stays in L1).
   __shared__ double sh[32];
-  const int lane = threadIdx.x & 31;
+  __shared__ double red[8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int H = w.H;
   const int w0 = (W0 > 0) ? W0 : w.w0max;
   const int nr0 = w.nr[0], nr1 = w.nr[1];
@@ -432,10 +436,8 @@ k_sell_spmv(TgWin w, const double* __restrict__ vals, const double* __restrict__
   const int64_t pl = nc0 * w.nc[1];
   const int64_t T1 = (w.dim > 1) ? w.S[1][nr1] : 1;
   const int64_t linemul = (int64_t)H * nchunk * w0;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   double dot = 0.0;
-  for (int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < nitems;
-       item += nwarps) {
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int64_t line = item / nchunk;
     const int ch = (int)(item - line * nchunk);
     const int r2 = (int)(line / nr1);
@@ -452,39 +454,64 @@ k_sell_spmv(TgWin w, const double* __restrict__ vals, const double* __restrict__
     }
     if (w.dim > 1) inner = __ldg(w.S[1] + r1) * len2;
     if (w.dim > 2) inner += T1 * __ldg(w.S[2] + r2);
-    const int64_t slots = (int64_t)w0 * len1 * len2;
+    const int ngroups = len1 * len2;
+    const int64_t slots = (int64_t)w0 * ngroups;
     const int r0 = ch * H + lane;
     const bool valid = lane < H && r0 < nr0;
+    double acc0 = 0.0, acc1 = 0.0;
     if (valid) {
-      const double* __restrict__ a = vals + linemul * inner + (int64_t)ch * H * slots + lane;
+      const double* __restrict__ abase = vals + linemul * inner + (int64_t)ch * H * slots + lane;
       const double* xb = x + __ldg(w.bs0 + r0) + nc0 * lo1 + pl * lo2;
-      double acc0 = 0.0, acc1 = 0.0;
-      for (int c2 = 0; c2 < len2; c2++) {
-        const double* xp = xb + pl * c2;
-        for (int c1 = 0; c1 < len1; c1++) {
-          if (W0 > 0) {
-            double av[W0 > 0 ? W0 : 1], xv[W0 > 0 ? W0 : 1];
+      if (W0 > 0) {
+        // G slot groups per trip: G*W0 value loads and G*W0 x loads in flight
+        for (int g0 = wid * G; g0 < ngroups; g0 += 8 * G) {
+          double av[G][W0 > 0 ? W0 : 1], xv[G][W0 > 0 ? W0 : 1];
 #pragma unroll
-            for (int k = 0; k < W0; k++) av[k] = __ldcs(a + (int64_t)k * H);
+          for (int u = 0; u < G; u++) {
+            const int g = min(g0 + u, ngroups - 1);
+            const double* __restrict__ a = abase + (int64_t)g * W0 * H;
 #pragma unroll
-            for (int k = 0; k < W0; k++) xv[k] = xp[k];
-#pragma unroll
-            for (int k = 0; k < W0; k++) {
-              if (k & 1) acc1 += av[k] * xv[k];
-              else acc0 += av[k] * xv[k];
-            }
-          } else {
-            for (int k = 0; k < w0; k++) acc0 += __ldcs(a + (int64_t)k * H) * xp[k];
+            for (int k = 0; k < W0; k++) av[u][k] = __ldcs(a + (int64_t)k * H);
           }
-          a += (int64_t)w0 * H;
-          xp += nc0;
+#pragma unroll
+          for (int u = 0; u < G; u++) {
+            const int g = min(g0 + u, ngroups - 1);
+            const int c2 = g / len1, c1 = g - c2 * len1;
+            const double* xp = xb + nc0 * c1 + pl * c2;
+#pragma unroll
+            for (int k = 0; k < W0; k++) xv[u][k] = xp[k];
+          }
+#pragma unroll
+          for (int u = 0; u < G; u++) {
+            if (g0 + u < ngroups) {
+#pragma unroll
+              for (int k = 0; k < W0; k++) {
+                if (k & 1) acc1 += av[u][k] * xv[u][k];
+                else acc0 += av[u][k] * xv[u][k];
+              }
+            }
+          }
+        }
+      } else {
+        for (int g = wid; g < ngroups; g += 8) {
+          const int c2 = g / len1, c1 = g - c2 * len1;
+          const double* __restrict__ a = abase + (int64_t)g * w0 * H;
+          const double* xp = xb + nc0 * c1 + pl * c2;
+          for (int k = 0; k < w0; k++) acc0 += __ldcs(a + (int64_t)k * H) * xp[k];
         }
       }
-      const double acc = acc0 + acc1;
+    }
+    red[wid][lane] = acc0 + acc1;
+    __syncthreads();
+    if (wid == 0 && valid) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc += red[j][lane];
       const int64_t row = r0 + (int64_t)nr0 * line;
       y[row] = acc;
       if (DOT) dot += x[xoff + row] * acc;
     }
+    __syncthreads();
   }
   if (DOT) {
     dot = tg_block_sum_ws(dot, sh);
@@ -492,17 +519,32 @@ k_sell_spmv(TgWin w, const double* __restrict__ vals, const double* __restrict__
   }
 }
 
+template <bool DOT, int G>
+static void tg_sell_launch_g(int w0, int g, cudaStream_t st, const TgWin& w, const double* vals,
+                             const double* x, int64_t xoff, double* y, int nchunk,
+                             int64_t nitems, double* part) {
+  switch (w0) {
+    case 3: k_sell_spmv<3, DOT, G><<<g, 256, 0, st>>>(w, vals, x, xoff, y, nchunk, nitems, part); break;
+    case 5: k_sell_spmv<5, DOT, G><<<g, 256, 0, st>>>(w, vals, x, xoff, y, nchunk, nitems, part); break;
+    case 7: k_sell_spmv<7, DOT, G><<<g, 256, 0, st>>>(w, vals, x, xoff, y, nchunk, nitems, part); break;
+    case 9: k_sell_spmv<9, DOT, G><<<g, 256, 0, st>>>(w, vals, x, xoff, y, nchunk, nitems, part); break;
+    default: k_sell_spmv<0, DOT, 1><<<g, 256, 0, st>>>(w, vals, x, xoff, y, nchunk, nitems, part); break;
+  }
+}
+
+static int g_sell_G = 0;
 template <bool DOT>
 static void tg_sell_launch(int w0, int g, cudaStream_t st, const TgWin& w, const double* vals,
                            const double* x, int64_t xoff, double* y, int nchunk, int64_t nitems,
                            double* part) {
-  switch (w0) {
-    case 3: k_sell_spmv<3, DOT><<<g, 256, 0, st>>>(w, vals, x, xoff, y, nchunk, nitems, part); break;
-    case 5: k_sell_spmv<5, DOT><<<g, 256, 0, st>>>(w, vals, x, xoff, y, nchunk, nitems, part); break;
-    case 7: k_sell_spmv<7, DOT><<<g, 256, 0, st>>>(w, vals, x, xoff, y, nchunk, nitems, part); break;
-    case 9: k_sell_spmv<9, DOT><<<g, 256, 0, st>>>(w, vals, x, xoff, y, nchunk, nitems, part); break;
-    default: k_sell_spmv<0, DOT><<<g, 256, 0, st>>>(w, vals, x, xoff, y, nchunk, nitems, part); break;
+  if (!g_sell_G) {
+    const char* e = getenv("TIGAR_B200_SELL_G");
+    g_sell_G = e ? atoi(e) : 2;
+    if (g_sell_G != 1 && g_sell_G != 2 && g_sell_G != 4) g_sell_G = 2;
   }
+  if (g_sell_G == 1) tg_sell_launch_g<DOT, 1>(w0, g, st, w, vals, x, xoff, y, nchunk, nitems, part);
+  else if (g_sell_G == 2) tg_sell_launch_g<DOT, 2>(w0, g, st, w, vals, x, xoff, y, nchunk, nitems, part);
+  else tg_sell_launch_g<DOT, 4>(w0, g, st, w, vals, x, xoff, y, nchunk, nitems, part);
 }
 
 static inline int64_t tg_win_lines(const tg_win* w) {
@@ -520,7 +562,7 @@ int tg_win_spmv_launch(const tg_win* h_w, const double* vals, const double* x, i
     int64_t nitems = tg_win_lines(h_w) * nchunk;
     if (nitems == 0) return 0;
     int g = tg_ws_grid_size() * 2;          // 8 CTAs of 256 threads per SM
-    if ((int64_t)g * 8 > nitems) g = (int)tg_cdiv(nitems, 8);
+    if ((int64_t)g > nitems) g = (int)nitems;
     TgWin w = tg_win_dev(h_w);
     if (part) {
       TG_CHECK(cudaMemsetAsync(part, 0, sizeof(double) * tg_ws_grid_size() * 2, st));

@@ -411,12 +411,15 @@ class TensorPatch(object):
         return self._global_window(name)
 
     def _system_window(self):
-        """The IGA system matrix window, in the SELL-H layout unless
-        TIGAR_B200_LAYOUT=0 (row-major)."""
+        """The IGA system matrix window.  Row-major by default; TIGAR_B200_LAYOUT=1
+        selects the SELL-H layout (lanes = rows).  Measured on B200 at 128^3/200^3
+        cubic (tools/spmv_probe.py, profiles/r1_spmv_variants.txt): row-major
+        61 % of HBM peak, SELL-29 29-46 % -- the coalesced layout loses because
+        each warp keeps fewer bytes in flight; it stays available for study."""
         if "Csys" not in self._win:
             g = self._global_window("C")
             w = Window(g.nr, g.nc, g.lo, g.hi)
-            if os.environ.get("TIGAR_B200_LAYOUT", "1") != "0":
+            if os.environ.get("TIGAR_B200_LAYOUT", "0") == "1":
                 w.sell()
             self._win["Csys"] = w
         return self._win["Csys"]
