@@ -52,8 +52,8 @@ __device__ inline double tg_block_sum_ws(double v, double* sh) {
 // Rows whose first-direction window is clipped by the patch boundary take the
 // generic path.
 #define TG_WS_MAXTAB 1024
-template <bool DOT>
-__global__ void __launch_bounds__(TG_WS_BLOCK, 4)
+template <bool DOT, int U>
+__global__ void __launch_bounds__(TG_WS_BLOCK, (U <= 4) ? 4 : 3)
 k_win_spmv(TgWin w, const double* __restrict__ vals, const double* __restrict__ x,
            int64_t xoff, double* __restrict__ y, int nchunk, int nitems, int w0max,
            double* __restrict__ part) {
@@ -118,20 +118,31 @@ k_win_spmv(TgWin w, const double* __restrict__ vals, const double* __restrict__ 
       const int n = len0 * tile;
       double acc = 0.0;
       if (usetab && len0 == w0max) {
-        double acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        // U coalesced 256-byte value loads in flight per warp per trip
+        double accs[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) accs[u] = 0.0;
         int p = lane;
-        for (; p + 96 < n; p += 128) {
-          double a0 = __ldcs(av + p), a1 = __ldcs(av + p + 32), a2 = __ldcs(av + p + 64),
-                 a3 = __ldcs(av + p + 96);
-          double x0 = xr[xtab[p]], x1 = xr[xtab[p + 32]], x2 = xr[xtab[p + 64]],
-                 x3 = xr[xtab[p + 96]];
-          acc += a0 * x0;
-          acc1 += a1 * x1;
-          acc2 += a2 * x2;
-          acc3 += a3 * x3;
+        for (; p + 32 * (U - 1) < n; p += 32 * U) {
+          double a[U], xv[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) a[u] = __ldcs(av + p + 32 * u);
+#pragma unroll
+          for (int u = 0; u < U; u++) xv[u] = xr[xtab[p + 32 * u]];
+#pragma unroll
+          for (int u = 0; u < U; u++) accs[u] += a[u] * xv[u];
         }
-        for (; p < n; p += 32) acc += __ldcs(av + p) * xr[xtab[p]];
-        acc += (acc1 + acc2) + acc3;
+        {   // remainder (< U chunks): predicated, still issued together
+          double a[U], xv[U];
+#pragma unroll
+          for (int u = 0; u < U - 1; u++) a[u] = (p + 32 * u < n) ? __ldcs(av + p + 32 * u) : 0.0;
+#pragma unroll
+          for (int u = 0; u < U - 1; u++) xv[u] = (p + 32 * u < n) ? xr[xtab[p + 32 * u]] : 0.0;
+#pragma unroll
+          for (int u = 0; u < U - 1; u++) accs[u] += a[u] * xv[u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) acc += accs[u];
       } else {
         for (int p = lane; p < n; p += 32) {
           int c0 = p % len0, t = p / len0, c1 = t % len1, c2 = t / len1;
@@ -585,12 +596,27 @@ int tg_win_spmv_launch(const tg_win* h_w, const double* vals, const double* x, i
   int g = tg_ws_grid_size();
   TgWin w = tg_win_dev(h_w);
   TG_REQUIRE(h_w->w0max >= 1, "window descriptor lacks w0max");
-  if (part)
-    k_win_spmv<true><<<g, TG_WS_BLOCK, 0, st>>>(w, vals, x, xoff, y, nchunk, (int)nitems,
-                                                h_w->w0max, part);
-  else
-    k_win_spmv<false><<<g, TG_WS_BLOCK, 0, st>>>(w, vals, x, xoff, y, nchunk, (int)nitems,
-                                                 h_w->w0max, nullptr);
+  static int U = 0;
+  if (!U) {
+    const char* e = getenv("TIGAR_B200_SPMV_U");
+    U = e ? atoi(e) : 4;
+    if (U != 4 && U != 6 && U != 8) U = 4;
+  }
+  if (U > 4) {                       // 3 resident CTAs per SM: keep it one wave
+    g = (g / 4) * 3;
+    if (part) TG_CHECK(cudaMemsetAsync(part, 0, sizeof(double) * tg_ws_grid_size(), st));
+  }
+#define TG_SPMV_LAUNCH(UU)                                                                    \
+  if (part)                                                                                   \
+    k_win_spmv<true, UU><<<g, TG_WS_BLOCK, 0, st>>>(w, vals, x, xoff, y, nchunk, (int)nitems, \
+                                                    h_w->w0max, part);                        \
+  else                                                                                        \
+    k_win_spmv<false, UU><<<g, TG_WS_BLOCK, 0, st>>>(w, vals, x, xoff, y, nchunk,             \
+                                                     (int)nitems, h_w->w0max, nullptr);
+  if (U == 4) { TG_SPMV_LAUNCH(4) }
+  else if (U == 6) { TG_SPMV_LAUNCH(6) }
+  else { TG_SPMV_LAUNCH(8) }
+#undef TG_SPMV_LAUNCH
   TG_LAUNCH_CHECK();
   return 0;
 }

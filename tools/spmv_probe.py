@@ -23,7 +23,8 @@ if len(sys.argv) > 2:      # child: one variant
     b = 8 * W.nnz + 16 * W.nrows
     print("%-28s %8.3f ms  %7.1f GB/s  frac %.3f" % (sys.argv[2], ms, b / ms / 1e6, b / ms / 1e6 / 6524.9))
     sys.exit(0)
-for name, env in [("rowmajor", {"TIGAR_B200_LAYOUT": "0"}), ("sell G=1", {"TIGAR_B200_SELL_G": "1"}),
-                  ("sell G=2", {"TIGAR_B200_SELL_G": "2"}), ("sell G=4", {"TIGAR_B200_SELL_G": "4"})]:
+for name, env in [("rowmajor U=4", {"TIGAR_B200_SPMV_U": "4"}), ("rowmajor U=6", {"TIGAR_B200_SPMV_U": "6"}),
+                  ("rowmajor U=8", {"TIGAR_B200_SPMV_U": "8"}),
+                  ("sell G=4", {"TIGAR_B200_LAYOUT": "1", "TIGAR_B200_SELL_G": "4"})]:
     e = dict(os.environ); e.update(env)
     subprocess.run([sys.executable, __file__, str(nel), name], env=e)
