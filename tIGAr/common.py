@@ -7,7 +7,7 @@ from numpy import array, zeros, arange                          # noqa: F401
 from tigar_b200.api import (                                    # noqa: F401
     AbstractExtractionGenerator, AbstractCoordinateChartSpline, AbstractMultiFieldSpline,
     EqualOrderSpline, FieldListSpline, ExtractedSpline, FunctionSpace, Function,
-    TrialFunction, TestFunction, assemble, File, KrylovSolver, PETScKrylovSolver, SubDomain,
+    TrialFunction, TestFunction, assemble, derivative, File, KrylovSolver, PETScKrylovSolver, SubDomain,
     MPI, worldcomm, selfcomm, mpisize, mpirank, norm, INDEX_TYPE, DEFAULT_PREALLOC,
     DEFAULT_DO_PERMUTATION, DEFAULT_BASIS_FUNC_IGNORE_EPS, USE_DG_DEFAULT, FORM_MT,
     EXTRACTION_DATA_FILE, EXTRACTION_INFO_FILE, EXTRACTION_ZERO_DOFS_FILE,

@@ -194,3 +194,29 @@ def test_generated_qp_kernel_compiles_for_sm100a():
     assert nth2 == 32 and jit.check_source(src2) > 1000
     with pytest.raises(Exception):
         jit.check_source("this is not CUDA")
+
+
+def test_gateaux_derivative_matches_finite_difference():
+    """derivative(F, u) of a nonlinear scalar form: symbolic d/du against a
+    finite difference of the compiled integrand."""
+    v = U.Tensor(U.Scalar({(U.ZERO3, None): S.ONE}))
+    u0 = S.jet(11, 0, (0, 0, 0))
+    ux = S.jet(11, 0, (1, 0, 0))
+    g = S.jet(12, 0, (0, 0, 0))
+    uT = U.Tensor(U.Scalar.coef(u0))
+    uxT = U.Tensor(U.Scalar.coef(ux))
+    F = U.Form([(((1.0 + uT * uT) * uxT * v.dx(0) + U.sin(uT) * U.Tensor(U.Scalar.coef(g)) * v).a[()], None)])
+    J = U.gateaux(F, 11).scalar()
+    keys = set(J.terms)
+    assert keys == {((1, 0, 0), (0, 0, 0)), ((1, 0, 0), (1, 0, 0)), ((0, 0, 0), (0, 0, 0))}
+    vals = {(11, 0, (0, 0, 0)): 0.3, (11, 0, (1, 0, 0)): -0.8, (12, 0, (0, 0, 0)): 1.7}
+
+    def ev(node, vv):
+        prog = S.compile_program([node], 2)
+        return run_program(prog, [0.0, 0.0], 1.0, vv)[0]
+    # d/du0 of (1+u0^2) ux  = 2 u0 ux ; d/dux = 1+u0^2 ; d/du0 of sin(u0) g = cos(u0) g
+    assert abs(ev(J.terms[((1, 0, 0), (0, 0, 0))], vals) - 2 * 0.3 * -0.8) < 1e-14
+    assert abs(ev(J.terms[((1, 0, 0), (1, 0, 0))], vals) - (1 + 0.09)) < 1e-14
+    assert abs(ev(J.terms[((0, 0, 0), (0, 0, 0))], vals) - math.cos(0.3) * 1.7) < 1e-14
+    with pytest.raises(ValueError):
+        U.gateaux(U.Form([((U.Tensor(U.Scalar({(None, U.ZERO3): S.ONE})) * v).a[()], None)]), 11)

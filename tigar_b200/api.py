@@ -218,6 +218,14 @@ def TestFunction(V):
     return U.Tensor(U.Scalar({(U.ZERO3, None): S.ONE}))
 
 
+def derivative(form, u, du=None):
+    """UFL ``derivative``: Gateaux derivative of ``form`` with respect to the
+    Function ``u`` in the direction of a trial function (poisson-nonzero-bc.py:103)."""
+    if not isinstance(u, Function):
+        raise TypeError("derivative() is taken with respect to a Function")
+    return U.gateaux(form, u.fid)
+
+
 def assemble(form, tensor=None):
     """dolfin.assemble on the FE space: float / FE vector / FE matrix."""
     owner = form.owner()

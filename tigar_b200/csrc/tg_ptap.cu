@@ -164,10 +164,11 @@ struct TgKronTabs {
   const double* tab[3];   // [n_d][TG_KB][TG_KB]: tab[I][J - loA(I)][j - loP(I)]
 };
 
+template <int KE>
 __global__ void __launch_bounds__(TG_KAP_WARPS * 32)
 k_ptap_kron_ap(TgWin wA, const double* __restrict__ Av, TgKronTabs T, TgWin wP,
                double* __restrict__ APv, int64_t nrows, int box) {
-  extern __shared__ double smk[];           // [TG_KAP_WARPS][3][box]
+  extern __shared__ double smk[];           // [TG_KAP_WARPS][3*box + 3*KB*KB]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t I = blockIdx.x * (int64_t)TG_KAP_WARPS + wid;
   if (I >= nrows) return;
@@ -177,50 +178,73 @@ k_ptap_kron_ap(TgWin wA, const double* __restrict__ Av, TgKronTabs T, TgWin wP,
   const TgRowWin rp = tg_row_window(wP, Ic);
   const int L0 = ra.len[0], L1 = ra.len[1], L2 = ra.len[2];
   const int K0 = rp.len[0], K1 = rp.len[1], K2 = rp.len[2];
-  double* a = smk + (size_t)wid * 3 * box;
+  double* a = smk + (size_t)wid * (3 * box + 3 * TG_KB * TG_KB);
   double* s1 = a + box;
   double* s2 = s1 + box;
+  double* tb = s2 + box;                    // the three per-row 1-D blocks
   const double* __restrict__ arow = Av + wA.rowptr[I];
   const int n = L0 * L1 * L2;
   for (int p = lane; p < n; p += 32) a[p] = __ldcs(arow + p);
-  const double* t0 = T.tab[0] + (int64_t)Ic[0] * TG_KB * TG_KB;
-  const double* t1 = (wA.dim > 1) ? T.tab[1] + (int64_t)Ic[1] * TG_KB * TG_KB : nullptr;
-  const double* t2 = (wA.dim > 2) ? T.tab[2] + (int64_t)Ic[2] * TG_KB * TG_KB : nullptr;
+  for (int d = 0; d < wA.dim; d++) {
+    const double* t = T.tab[d] + (int64_t)Ic[d] * TG_KB * TG_KB;
+    for (int p = lane; p < TG_KB * TG_KB; p += 32) tb[d * TG_KB * TG_KB + p] = __ldg(t + p);
+  }
+  const double* t0 = tb;
+  const double* t1 = tb + TG_KB * TG_KB;
+  const double* t2 = tb + 2 * TG_KB * TG_KB;
   __syncwarp();
-  // stage 1: s1[t*K0 + j0] = sum_J0 a[t*L0 + J0] t0[J0][j0],  t = (J2*L1 + J1)
-  const int n1 = K0 * L1 * L2;
-  for (int o = lane; o < n1; o += 32) {
-    const int t = o / K0, j0 = o - t * K0;
-    double v = 0.0;
-    for (int J = 0; J < L0; J++) v += a[t * L0 + J] * __ldg(t0 + J * TG_KB + j0);
-    s1[o] = v;
+  // stage 1: one lane per (J1,J2) pair t: s1[t*K0 + j0] = sum_J a[t*L0 + J] t0[J][j0]
+  const int nt = L1 * L2;
+  for (int t = lane; t < nt; t += 32) {
+    double av[KE];
+#pragma unroll
+    for (int J = 0; J < KE; J++) av[J] = (J < L0) ? a[t * L0 + J] : 0.0;
+    for (int j0 = 0; j0 < K0; j0++) {
+      double v = 0.0;
+#pragma unroll
+      for (int J = 0; J < KE; J++) v += av[J] * t0[J * TG_KB + j0];
+      s1[t * K0 + j0] = v;
+    }
   }
   __syncwarp();
   double* out = APv + wP.rowptr[I];
+  const int n1 = K0 * L1 * L2;
   if (wA.dim == 1) {
     for (int o = lane; o < n1; o += 32) out[o] = s1[o];
     return;
   }
-  // stage 2: s2[(J2*K1 + j1)*K0 + j0] = sum_J1 s1[(J2*L1 + J1)*K0 + j0] t1[J1][j1]
-  const int n2 = K0 * K1 * L2;
-  for (int o = lane; o < n2; o += 32) {
-    const int j0 = o % K0, r = o / K0, j1 = r % K1, J2 = r / K1;
-    double v = 0.0;
-    for (int J = 0; J < L1; J++) v += s1[(J2 * L1 + J) * K0 + j0] * __ldg(t1 + J * TG_KB + j1);
-    s2[o] = v;
+  // stage 2: one lane per (j0,J2): s2[(J2*K1 + j1)*K0 + j0] = sum_J s1[(J2*L1 + J)*K0 + j0] t1[J][j1]
+  const int n02 = K0 * L2;
+  for (int o = lane; o < n02; o += 32) {
+    const int J2 = o / K0, j0 = o - J2 * K0;
+    double sv[KE];
+#pragma unroll
+    for (int J = 0; J < KE; J++) sv[J] = (J < L1) ? s1[(J2 * L1 + J) * K0 + j0] : 0.0;
+    for (int j1 = 0; j1 < K1; j1++) {
+      double v = 0.0;
+#pragma unroll
+      for (int J = 0; J < KE; J++) v += sv[J] * t1[J * TG_KB + j1];
+      s2[(J2 * K1 + j1) * K0 + j0] = v;
+    }
   }
   __syncwarp();
+  const int n2 = K0 * K1 * L2;
   if (wA.dim == 2) {
     for (int o = lane; o < n2; o += 32) out[o] = s2[o];
     return;
   }
-  // stage 3: out[(j2*K1 + j1)*K0 + j0] = sum_J2 s2[(J2*K1 + j1)*K0 + j0] t2[J2][j2]
-  const int n3 = K0 * K1 * K2, k01 = K0 * K1;
-  for (int o = lane; o < n3; o += 32) {
-    const int j01 = o % k01, j2 = o / k01;
-    double v = 0.0;
-    for (int J = 0; J < L2; J++) v += s2[J * k01 + j01] * __ldg(t2 + J * TG_KB + j2);
-    out[o] = v;
+  // stage 3: one lane per (j0,j1): out[(j2*K1 + j1)*K0 + j0] = sum_J s2[J*K0*K1 + j01] t2[J][j2]
+  const int k01 = K0 * K1;
+  for (int j01 = lane; j01 < k01; j01 += 32) {
+    double sv[KE];
+#pragma unroll
+    for (int J = 0; J < KE; J++) sv[J] = (J < L2) ? s2[J * k01 + j01] : 0.0;
+    for (int j2 = 0; j2 < K2; j2++) {
+      double v = 0.0;
+#pragma unroll
+      for (int J = 0; J < KE; J++) v += sv[J] * t2[J * TG_KB + j2];
+      out[j2 * k01 + j01] = v;
+    }
   }
 }
 
@@ -230,17 +254,35 @@ extern "C" int tg_ptap_kron_ap(const tg_win* h_wA, const double* Avals,
   TG_REQUIRE(h_wA->w0max <= TG_KB && h_wP->w0max <= TG_KB, "window wider than the 1-D block");
   TG_REQUIRE(h_wA->maxrow > 0 && h_wP->maxrow > 0, "window descriptors lack maxrow");
   TG_REQUIRE(box >= h_wA->maxrow && box >= h_wP->maxrow, "box smaller than a row");
-  size_t smem = (size_t)TG_KAP_WARPS * 3 * box * sizeof(double);
+  size_t smem = (size_t)TG_KAP_WARPS * (3 * box + 3 * TG_KB * TG_KB) * sizeof(double);
   TG_REQUIRE(smem <= 200 * 1024, "row box too large for the shared-memory tile");
   int64_t nrows = tg_win_nrows(h_wA);
   if (nrows == 0) return 0;
-  TG_CHECK(cudaFuncSetAttribute(k_ptap_kron_ap, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
   TgKronTabs T;
   for (int d = 0; d < 3; d++) T.tab[d] = (d < h_wA->dim) ? h_tabs[d] : nullptr;
-  k_ptap_kron_ap<<<(unsigned)tg_cdiv(nrows, TG_KAP_WARPS), TG_KAP_WARPS * 32, smem,
-                   tg_stream(stream)>>>(tg_win_dev(h_wA), Avals, T, tg_win_dev(h_wP), APvals,
-                                        nrows, box);
+  // widest FE-side window over all directions bounds the contraction length
+  int wmax = h_wA->w0max;
+  if (h_wA->maxrow > 0) {
+    // maxrow = prod of per-direction maxima; the host passes box >= that, and every
+    // per-direction length is <= TG_KB; use the conservative TG_KB unless the first
+    // direction's width (equal in all directions for isotropic degrees) says less
+    int iso = 1;
+    for (int d = 0; d < h_wA->dim; d++) iso *= h_wA->w0max;
+    if (iso != h_wA->maxrow) wmax = TG_KB;
+  }
+#define TG_KAP_LAUNCH(KE)                                                                      \
+  {                                                                                            \
+    TG_CHECK(cudaFuncSetAttribute(k_ptap_kron_ap<KE>,                                          \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    k_ptap_kron_ap<KE><<<(unsigned)tg_cdiv(nrows, TG_KAP_WARPS), TG_KAP_WARPS * 32, smem,      \
+                         tg_stream(stream)>>>(tg_win_dev(h_wA), Avals, T, tg_win_dev(h_wP),    \
+                                              APvals, nrows, box);                             \
+  }
+  if (wmax <= 4) TG_KAP_LAUNCH(4)
+  else if (wmax <= 6) TG_KAP_LAUNCH(6)
+  else if (wmax <= 8) TG_KAP_LAUNCH(8)
+  else TG_KAP_LAUNCH(10)
+#undef TG_KAP_LAUNCH
   TG_LAUNCH_CHECK();
   return 0;
 }
@@ -254,7 +296,12 @@ struct TgRowComb {
   const int32_t* shi;
 };
 
-// one warp per output row; lanes over the output window
+// one warp per output row; lanes over the output window.  The loop over the
+// (<= p(p+1)+1) contributing input rows is OUTSIDE the loop over output
+// entries: per input row the weight, window and base pointer are computed once
+// (warp-uniform), per output entry only a range test, one gather and one FMA
+// remain.  Accumulators live in registers (TG_RC_SLOTS entries per lane).
+#define TG_RC_SLOTS 12
 __global__ void __launch_bounds__(256)
 k_win_rowcombine(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __restrict__ Yv,
                  TgRowComb R, int64_t nrowsY) {
@@ -269,7 +316,76 @@ k_win_rowcombine(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __re
   const int Ilo = R.slo[i], Ihi = R.shi[i];
   const int tot = ry.len[0] * ry.len[1] * ry.len[2];
   double* out = Yv + wY.rowptr[row];
-  // strides of the X row grid
+  const int64_t sx[3] = {1, wX.nr[0], (int64_t)wX.nr[0] * wX.nr[1]};
+  int xc[3] = {rc[0], rc[1], rc[2]};
+  xc[d] = 0;
+  const int64_t xrow0 = xc[0] * sx[0] + xc[1] * sx[1] + xc[2] * sx[2];
+  // strides of the X row's window: only the transformed direction's length varies
+  const int ylen_d = ry.len[d];
+  // decompose each of this lane's output positions once: (pd = offset in direction d,
+  // prest = offset contribution of the other directions, expressed with len_d factored out)
+  // X position = A*pd' + B  where the split depends on d:
+  //   d=0: pos = (p2*len1 + p1)*lenX0 + pd'      -> hi = (p2*len1+p1), lo part = pd'
+  //   d=1: pos = (p2*lenX1 + pd')*len0 + p0
+  //   d=2: pos = (pd'*len1 + p1)*len0 + p0
+  double acc[TG_RC_SLOTS];
+  int pd[TG_RC_SLOTS], pa[TG_RC_SLOTS], pb[TG_RC_SLOTS];
+#pragma unroll
+  for (int s = 0; s < TG_RC_SLOTS; s++) {
+    acc[s] = 0.0;
+    const int pos = lane + 32 * s;
+    int p0 = 0, p1 = 0, p2 = 0;
+    if (pos < tot) {
+      p0 = pos % ry.len[0];
+      const int t = pos / ry.len[0];
+      p1 = t % ry.len[1];
+      p2 = t / ry.len[1];
+    }
+    if (d == 0) { pd[s] = p0 + ry.lo[0]; pa[s] = p2 * ry.len[1] + p1; pb[s] = 0; }
+    else if (d == 1) { pd[s] = p1 + ry.lo[1]; pa[s] = p2; pb[s] = p0; }
+    else { pd[s] = p2 + ry.lo[2]; pa[s] = 0; pb[s] = p1 * ry.len[0] + p0; }
+    if (pos >= tot) pd[s] = -(1 << 30);
+  }
+  (void)ylen_d;
+  for (int I = Ilo; I <= Ihi; I++) {
+    const int k = i - R.mfirst[I];
+    if (k < 0 || k >= R.np1) continue;                       // warp-uniform
+    const double wgt = R.mvals[I * R.np1 + k];
+    const int lod = wX.lo[d][I], lend = wX.hi[d][I] - lod + 1;
+    const double* __restrict__ xr = Xv + wX.rowptr[xrow0 + I * sx[d]];
+    // pos_X = pa*mulA + cd*mulD + pb
+    int mulA, mulD;
+    if (d == 0) { mulA = lend; mulD = 1; }
+    else if (d == 1) { mulA = lend * ry.len[0]; mulD = ry.len[0]; }
+    else { mulA = 0; mulD = ry.len[1] * ry.len[0]; }
+#pragma unroll
+    for (int s = 0; s < TG_RC_SLOTS; s++) {
+      const int cd = pd[s] - lod;
+      if (cd >= 0 && cd < lend) acc[s] += wgt * xr[pa[s] * mulA + cd * mulD + pb[s]];
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < TG_RC_SLOTS; s++) {
+    const int pos = lane + 32 * s;
+    if (pos < tot) out[pos] = acc[s];
+  }
+}
+
+// generic variant for rows longer than 32*TG_RC_SLOTS entries
+__global__ void __launch_bounds__(256)
+k_win_rowcombine_big(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __restrict__ Yv,
+                     TgRowComb R, int64_t nrowsY) {
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= nrowsY) return;
+  int rc[3];
+  tg_decode(row, wY.nr, wY.dim, rc);
+  const TgRowWin ry = tg_row_window(wY, rc);
+  const int d = R.d;
+  const int i = rc[d];
+  const int Ilo = R.slo[i], Ihi = R.shi[i];
+  const int tot = ry.len[0] * ry.len[1] * ry.len[2];
+  double* out = Yv + wY.rowptr[row];
   const int64_t sx[3] = {1, wX.nr[0], (int64_t)wX.nr[0] * wX.nr[1]};
   int xc[3] = {rc[0], rc[1], rc[2]};
   xc[d] = 0;
@@ -285,7 +401,6 @@ k_win_rowcombine(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __re
       const int k = i - R.mfirst[I];
       if (k < 0 || k >= R.np1) continue;
       const double wgt = R.mvals[I * R.np1 + k];
-      // window of X row (.., I, ..) in direction d; other directions equal Y's
       const int lod = wX.lo[d][I], lend = wX.hi[d][I] - lod + 1;
       const int cd = c[d] - lod;
       if (cd < 0 || cd >= lend) continue;
@@ -315,8 +430,12 @@ extern "C" int tg_win_rowcombine(const tg_win* h_wX, const double* Xvals, const 
   R.np1 = np1;
   R.slo = supp_lo;
   R.shi = supp_hi;
-  k_win_rowcombine<<<(unsigned)tg_cdiv(nrows * 32, 256), 256, 0, tg_stream(stream)>>>(
-      tg_win_dev(h_wX), Xvals, tg_win_dev(h_wY), Yvals, R, nrows);
+  if (h_wY->maxrow > 0 && h_wY->maxrow <= 32 * TG_RC_SLOTS)
+    k_win_rowcombine<<<(unsigned)tg_cdiv(nrows * 32, 256), 256, 0, tg_stream(stream)>>>(
+        tg_win_dev(h_wX), Xvals, tg_win_dev(h_wY), Yvals, R, nrows);
+  else
+    k_win_rowcombine_big<<<(unsigned)tg_cdiv(nrows * 32, 256), 256, 0, tg_stream(stream)>>>(
+        tg_win_dev(h_wX), Xvals, tg_win_dev(h_wY), Yvals, R, nrows);
   TG_LAUNCH_CHECK();
   return 0;
 }

@@ -264,13 +264,38 @@ def _diff(n, j):
         al = list(al)
         al[j] += 1
         return jet(f, c, al)
+    return _diff_rule(n, lambda c: diff(c, j))
+
+
+def diff_leaf(n, leaf, _memo=None):
+    """Partial derivative of ``n`` with respect to the leaf node ``leaf`` (a jet),
+    every other leaf held fixed: the building block of the Gateaux derivative
+    (UFL ``derivative``)."""
+    if _memo is None:
+        _memo = {}
+    r = _memo.get(n.uid)
+    if r is None:
+        if n is leaf:
+            r = ONE
+        elif n.op in ("const", "wq", "xi", "jet"):
+            r = ZERO
+        else:
+            r = _diff_rule(n, lambda c: diff_leaf(c, leaf, _memo))
+        _memo[n.uid] = r
+    return r
+
+
+def _diff_rule(n, d):
+    """Differentiation rules of the interior nodes; ``d(child)`` differentiates
+    a child."""
+    op = n.op
     a = n.args[0]
-    da = diff(a, j)
+    da = d(a)
     if op == "neg":
         return neg(da)
     if op in ("add", "sub", "mul", "div", "pow", "max", "min", "gt"):
         b = n.args[1]
-        db = diff(b, j)
+        db = d(b)
         if op == "add":
             return add(da, db)
         if op == "sub":

@@ -504,3 +504,24 @@ def lhs(form):
 
 def rhs(form):
     return -form.part(1)
+
+
+def gateaux(form, fid):
+    """d/d(eps) form(u + eps*du) at eps=0 for the coefficient function with id
+    ``fid``; du is the trial function (UFL ``derivative(form, u)``).  Every term
+    must be free of trial functions."""
+    out = []
+    for sc, owner in form.integrals:
+        acc = Scalar()
+        for (t, tr), coef in sc.terms.items():
+            if tr is not None:
+                raise ValueError("derivative() of a form that already has a trial function")
+            for jn in S.jets_of([coef]):
+                if jn.args[0] != fid:
+                    continue
+                dc = S.diff_leaf(coef, jn)
+                if dc is not S.ZERO:
+                    acc = acc.add(Scalar({(t, tuple(jn.args[2])): dc}))
+        if acc.terms:
+            out.append((acc, owner))
+    return Form(out)
