@@ -1,0 +1,77 @@
+"""Parity at BASELINE.json's full size (3-D cubic Poisson, 256^3 cells, 17.4 M
+DoFs, element-fused path) through size-independent properties, since the
+oracle cannot hold that problem: constants are in the kernel of the stiffness
+matrix (partition of unity of the extracted basis), symmetry, the load vector
+sums to the integral of f, the CG residual recomputed independently, and the
+manufactured-solution error is at the O(h^4) level."""
+import math
+
+import numpy as np
+import pytest
+
+from gpu_util import make_pair, uk
+
+pytestmark = pytest.mark.gpu
+PI = math.pi
+
+
+@pytest.mark.parametrize("nel", [96, 256])
+def test_full_size_properties(nel):
+    import torch
+    from tIGAr import TrialFunction, TestFunction, Function, inner, sin, assemble
+    from tigar_b200 import dev
+    free, _ = torch.cuda.mem_get_info()
+    if nel == 256 and free < 90e9:
+        pytest.skip("needs ~80 GB of free HBM")
+    from tIGAr import EqualOrderSpline, ExtractedSpline
+    from tIGAr.BSplines import ExplicitBSplineControlMesh
+    p = 3
+    kv = [uk(p, nel)] * 3
+    gen = EqualOrderSpline(1, ExplicitBSplineControlMesh([p] * 3, kv))
+    sp = gen.getScalarSpline(0)
+    for d in range(3):
+        for side in (0, 1):
+            gen.addZeroDofs(0, sp.getSideDofs(d, side))
+    spline = ExtractedSpline(gen, 2 * p, mode="fused")
+    u, v = TrialFunction(spline.V), TestFunction(spline.V)
+    x = spline.spatialCoordinates()
+    soln = sin(PI * x[0]) * sin(PI * x[1]) * sin(PI * x[2])
+    f = 3 * PI ** 2 * soln
+    a = inner(spline.grad(u), spline.grad(v)) * spline.dx
+    L = inner(f, v) * spline.dx
+    n = spline.patch().n_iga
+    assert n == (nel + p) ** 3
+    # --- without BCs
+    C0 = spline.assembleMatrix(a, applyBCs=False)
+    b0 = spline.assembleVector(L, applyBCs=False).t
+    ones = torch.ones(n, dtype=torch.float64, device=b0.device)
+    y = C0.matvec(ones)
+    scale = float(C0.vals.abs().max())
+    assert float(y.abs().max()) < 1e-11 * scale * 343          # C 1 = 0
+    g = torch.Generator(device=b0.device).manual_seed(1)
+    r1 = torch.rand(n, dtype=torch.float64, device=b0.device, generator=g)
+    r2 = torch.rand(n, dtype=torch.float64, device=b0.device, generator=g)
+    s12 = float(torch.dot(r1, C0.matvec(r2)))
+    s21 = float(torch.dot(r2, C0.matvec(r1)))
+    assert abs(s12 - s21) < 1e-11 * abs(s12)                    # symmetry
+    # sum of the load vector = int f = 3 pi^2 (2/pi)^3 (Gauss rule is near-exact for sin)
+    assert abs(float(b0.sum()) - 24.0 / PI) < 1e-6
+    del C0, y, r1, r2
+    # --- with BCs: solve and verify the residual with an independent product
+    C, b = spline.assembleLinearSystem(a, L)
+    uh = Function(spline.V)
+    from tIGAr import KrylovSolver
+    ks = KrylovSolver("cg", "jacobi")
+    ks.parameters["relative_tolerance"] = 1e-12
+    spline.setSolverOptions(linearSolver=ks)
+    U = spline.solveLinearSystem(C, b, uh)
+    res = b.t - C.matvec(U.t)
+    relres = float(res.norm() / b.t.norm())
+    assert relres < 5e-12, relres
+    z = torch.from_numpy(np.unique(spline.zeroDofs)).to(b.t.device)
+    assert float(U.t[z].abs().max()) == 0.0                     # homogeneous Dirichlet rows
+    del C, res
+    err = math.sqrt(assemble(((uh - soln) ** 2) * spline.dx))
+    h = 1.0 / nel
+    assert err < 0.2 * h ** 4, (err, h ** 4)                    # optimal order for p=3
+    assert err > 1e-4 * h ** 4
