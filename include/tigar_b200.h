@@ -257,6 +257,32 @@ int tg_win_rowcombine(const tg_win* h_wX, const double* Xvals, const tg_win* h_w
                       int32_t np1, const int32_t* supp_lo, const int32_t* supp_hi,
                       void* stream);
 
+/* One two-sided pass of the Kronecker-structured M^T A M (MatPtAP,
+ * common.py:1194-1195): direction d of both the row and the column grid goes
+ * from FE nodes to IGA functions,
+ *   Y[(..i..),(..j..)] = sum_{I,J} M_d[I,i] X[(..I..),(..J..)] M_d[J,j];
+ * applied for d = 0,1,2 it turns A_FE into C = M^T A M reading A once (the
+ * global M is never formed).  h_wX / h_wY differ only in direction d (FE-FE
+ * window -> IGA-IGA window, which must lie inside [i-p, i+p]).  Device arrays:
+ *   first[n_fe_d], mrow[n_fe_d][p+1]   1-D extraction rows (eps-filtered),
+ *   tabc[n_fe_d][KA][TWP]              M_d[loX_d(I)+q, first(I)+m], TWP = (p+3)&~1,
+ *   slo/shi[n_cp_d]                    FE support of function i,
+ *   ga[nga+1], gb[ngb+1]               groups of consecutive row coordinates of the
+ *                                      two other directions handled by one CTA
+ *                                      (sum of window lengths a x b <= 256),
+ *   seg[nseg+1]                        output-row boundaries of the march segments.
+ * stage_doubles (even) / out_doubles / maxlines: shared-memory sizing, maxima
+ * over the CTAs of  sum_l ((KAmax*L_l + 3) & ~1),  sum_l (2p+1)*L_l  and the
+ * number of lines, L_l = product of the line's other-direction window lengths.
+ * Rows are staged by 1-D bulk async copies (TMA); the value array of X must be
+ * readable up to the next 16-byte boundary past its end.                      */
+int tg_ptap_march(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY, double* Yvals,
+                  int32_t d, int32_t p, int32_t KA, int32_t KAmax, const int32_t* first,
+                  const double* mrow, const double* tabc, const int32_t* slo,
+                  const int32_t* shi, const int32_t* ga, int32_t nga, const int32_t* gb,
+                  int32_t ngb, const int32_t* seg, int32_t nseg, int32_t stage_doubles,
+                  int32_t out_doubles, int32_t maxlines, void* stream);
+
 /* ---- windowed-CSR operators (no column array: 8 B per non-zero) ---------- */
 /* y = C x  (MatMult inside KSP, common.py:1255-1258; M*U, common.py:379,1259) */
 int tg_win_spmv(const tg_win* h_w, const double* vals, const double* x, double* y,

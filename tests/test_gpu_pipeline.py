@@ -286,6 +286,48 @@ def test_kronecker_ptap_equals_generic_ptap_and_scipy(deg, nels):
     assert relm(AP.to_scipy(), (As @ Ms).tocsr()) < 1e-13
 
 
+@pytest.mark.parametrize("deg,nels", [([3, 2], [4, 5]), ([3, 3, 3], [3, 4, 3]), ([4, 4], [4, 3]),
+                                      ([2, 3, 2], [3, 3, 4]), ([3, 3, 3], [9, 7, 8]),
+                                      ([2, 2], [40, 37]), ([1, 1, 1], [5, 4, 6]),
+                                      ([4, 4, 4], [3, 2, 3]), ([3, 3], [70, 3])])
+def test_march_ptap_equals_scipy(deg, nels):
+    """tg_ptap_march (two-sided per-direction passes, TMA-staged rows, sliding
+    register accumulators) against scipy's M^T A M on a random windowed A, on
+    non-uniform knot spacing, and against the row-wise Kronecker kernels."""
+    from tigar_b200.engine import TensorPatch, WinMatrix
+    from tigar_b200 import dev
+    rng = np.random.RandomState(7)
+    kv = []
+    for p, n in zip(deg, nels):
+        k = np.array(uk(p, n, -1.0, 2.0))
+        inner = k[p + 1:-(p + 1)]
+        if len(inner):
+            k[p + 1:-(p + 1)] = inner + 0.3 * (3.0 / n) * (rng.rand(len(inner)) - 0.5)
+        kv.append(list(k))
+    patch = TensorPatch(deg, kv)
+    assert patch._march_setup() is not None
+    A = WinMatrix(patch.window("A"))
+    A.vals.copy_(dev.from_np(rng.randn(A.window.nnz)))
+    M = patch.build_M()
+    Cm, stages = patch.ptap_march(A, keep=True)
+    As, Ms = A.to_scipy(), M.to_scipy()
+    ref = (Ms.T @ As @ Ms).tocsr()
+    assert relm(Cm.to_scipy(), ref) < 1e-13
+    assert relm(patch.ptap_kron(A).to_scipy(), ref) < 1e-13
+    # segments along the march direction give the same rows
+    dirs, passes = patch._march
+    saved = [(P_["nseg"], P_["seg"]) for P_ in passes]
+    for P_ in passes:
+        n = patch.ncp[P_["d"]]
+        P_["nseg"] = min(3, n)
+        P_["seg"] = dev.from_np(np.array([(n * k) // P_["nseg"] for k in range(P_["nseg"] + 1)],
+                                         dtype=np.int32))
+    C3 = patch.ptap_march(A)
+    assert relm(C3.to_scipy(), ref) < 1e-13
+    for P_, (ns, sg) in zip(passes, saved):
+        P_["nseg"], P_["seg"] = ns, sg
+
+
 def test_jit_kernel_equals_interpreter():
     """NVRTC-compiled Gauss-point kernel vs the register-machine interpreter
     (tg_qp_eval) on the same forms: identical systems to rounding (the JIT may

@@ -766,10 +766,130 @@ class TensorPatch(object):
         out = WinMatrix.from_csr_values(self.window("C"), Cw.vals)
         return (out, [s for s in stages if s is not None]) if keep else out
 
+    # ---- two-sided march passes (tg_ptap_march) --------------------------------
+    MARCH_THREADS = 256
+
+    def _march_setup(self):
+        """Per-direction tables, intermediate windows and CTA tilings of the
+        march PtAP; None when the patch does not have the structure the kernel
+        assumes (then ptap() uses the row-wise Kronecker kernels)."""
+        if getattr(self, "_march", 0) != 0:
+            return self._march
+        self._march = None
+        if self.dim < 2:
+            return None
+        wA, wC, wMT = (self._global_window(k) for k in ("A", "C", "MT"))
+        dirs = []
+        for d, D in enumerate(self.dirs):
+            p = D.p
+            if p > 4:
+                return None
+            TW, TWP = p + 2, (p + 3) & ~1
+            first = dev.to_np(D.m_first).astype(np.int64)
+            vals = dev.to_np(D.m_vals)
+            j = first[:, None] + np.arange(p + 1)[None, :]
+            keep = (j >= D.m_lo[:, None]) & (j <= D.m_hi[:, None])
+            mrow = np.where(keep, vals, 0.0)
+            KA = int(wA.len[d].max())
+            tabc = np.zeros((D.nfe, KA, TWP))
+            for I in range(D.nfe):
+                for q, J in enumerate(range(wA.lo[d][I], wA.hi[d][I] + 1)):
+                    m = first[J] - first[I] + np.arange(p + 1)
+                    k = np.nonzero(mrow[J])[0]
+                    if k.size == 0:
+                        continue
+                    if m[k].min() < 0 or m[k].max() >= TW:
+                        return None
+                    tabc[I, q, m[k]] = mrow[J, k]
+            # (k = 0, m = p+1) would fall outside the 2p+1 band: must vanish
+            if np.any((np.abs(tabc[:, :, p + 1]).sum(axis=1) > 0) & (mrow[:, 0] != 0)):
+                return None
+            i = np.arange(D.ncp)
+            if np.any(wC.lo[d] < i - p) or np.any(wC.hi[d] > i + p):
+                return None
+            if np.any(np.diff(first) < 0):
+                return None
+            dirs.append(dict(p=p, KA=KA, first=dev.from_np(first.astype(np.int32)),
+                             mrow=dev.from_np(mrow), tabc=dev.from_np(tabc),
+                             slo=dev.from_np(wMT.lo[d].astype(np.int32)),
+                             shi=dev.from_np(wMT.hi[d].astype(np.int32))))
+
+        def groups(lens, cap):
+            g, tot = [0], 0
+            for r, L in enumerate(lens):
+                if tot + L > cap and tot > 0:
+                    g.append(r)
+                    tot = 0
+                tot += int(L)
+            g.append(len(lens))
+            return g
+
+        passes = []
+        wX = wA
+        for d in range(self.dim):
+            nr = [self.ncp[k] if k <= d else self.nfe[k] for k in range(self.dim)]
+            lo = [wC.lo[k] if k <= d else wA.lo[k] for k in range(self.dim)]
+            hi = [wC.hi[k] if k <= d else wA.hi[k] for k in range(self.dim)]
+            wY = Window(nr, nr, lo, hi)
+            others = [k for k in range(self.dim) if k != d]
+            cap = 16 if self.dim == 3 else self.MARCH_THREADS
+            ga = groups(wX.len[others[0]], cap)
+            gb = groups(wX.len[others[1]], cap) if self.dim == 3 else [0, 1]
+
+            def gmax(g, lens):
+                return (max(int(lens[g[k]:g[k + 1]].sum()) for k in range(len(g) - 1)),
+                        max(g[k + 1] - g[k] for k in range(len(g) - 1)))
+            Fa, na = gmax(ga, wX.len[others[0]])
+            Fb, nb = gmax(gb, wX.len[others[1]]) if self.dim == 3 else (1, 1)
+            assert Fa * Fb <= self.MARCH_THREADS
+            KAmax = int(wX.len[d].max())
+            CW = 2 * dirs[d]["p"] + 1
+            maxlines = na * nb
+            stage = (KAmax * Fa * Fb + 3 * maxlines + 1) & ~1
+            outd = CW * Fa * Fb
+            nseg = int(min(max(1, self.ncp[d] // 16),
+                           max(1, -(-4 * 148 // ((len(ga) - 1) * (len(gb) - 1))))))
+            seg = [(self.ncp[d] * k) // nseg for k in range(nseg + 1)]
+            passes.append(dict(wX=wX, wY=wY, d=d, KAmax=KAmax, maxlines=maxlines, stage=stage,
+                               outd=outd, nga=len(ga) - 1, ngb=len(gb) - 1, nseg=nseg,
+                               ga=dev.from_np(np.array(ga, dtype=np.int32)),
+                               gb=dev.from_np(np.array(gb, dtype=np.int32)),
+                               seg=dev.from_np(np.array(seg, dtype=np.int32))))
+            wX = wY
+        assert passes[-1]["wY"].nnz == wC.nnz
+        self._march = (dirs, passes)
+        return self._march
+
+    def ptap_march(self, A, keep=False):
+        """C = M^T A M by one two-sided march pass per direction (A read once,
+        two shrinking intermediates, M never formed)."""
+        dirs, passes = self._march_setup()
+        X = A.vals
+        stages = []
+        for P_ in passes:
+            D = dirs[P_["d"]]
+            Y = dev.empty(P_["wY"].nnz)
+            check(lib.tg_ptap_march(P_["wX"].ref(), dev.ptr(X), P_["wY"].ref(), dev.ptr(Y),
+                                    P_["d"], D["p"], D["KA"], P_["KAmax"], dev.ptr(D["first"]),
+                                    dev.ptr(D["mrow"]), dev.ptr(D["tabc"]), dev.ptr(D["slo"]),
+                                    dev.ptr(D["shi"]), dev.ptr(P_["ga"]), P_["nga"],
+                                    dev.ptr(P_["gb"]), P_["ngb"], dev.ptr(P_["seg"]),
+                                    P_["nseg"], P_["stage"], P_["outd"], P_["maxlines"],
+                                    dev.stream()))
+            X = Y
+            if keep:
+                stages.append(WinMatrix(P_["wY"], Y))
+        out = WinMatrix.from_csr_values(self.window("C"), X)
+        return (out, stages) if keep else out
+
     def ptap(self, A, M=None, keep_AP=False):
         """C = M^T A M on windowed operands (MatPtAP, common.py:1194-1195)."""
-        if not keep_AP and self.kron_supported() and not os.environ.get("TIGAR_B200_PTAP_GENERIC"):
-            return self.ptap_kron(A)
+        if not keep_AP and not os.environ.get("TIGAR_B200_PTAP_GENERIC"):
+            if os.environ.get("TIGAR_B200_PTAP", "march") == "march" \
+                    and self._march_setup() is not None:
+                return self.ptap_march(A)
+            if self.kron_supported():
+                return self.ptap_kron(A)
         if M is None:
             M = self.build_M()
         wA, wM, wMT = self.window("A"), self.window("M"), self.window("MT")
