@@ -274,14 +274,35 @@ int tg_win_rowcombine(const tg_win* h_wX, const double* Xvals, const tg_win* h_w
  * stage_doubles (even) / out_doubles / maxlines: shared-memory sizing, maxima
  * over the CTAs of  sum_l ((KAmax*L_l + 3) & ~1),  sum_l (2p+1)*L_l  and the
  * number of lines, L_l = product of the line's other-direction window lengths.
- * Rows are staged by 1-D bulk async copies (TMA); the value array of X must be
- * readable up to the next 16-byte boundary past its end.                      */
+ * variant 0: rows staged by 8-byte cp.async (LDGSTS) from all warps; variant 1:
+ * by 1-D bulk async copies (TMA) -- then the value array of X must be readable
+ * up to the next 16-byte boundary past its end.                               */
 int tg_ptap_march(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY, double* Yvals,
                   int32_t d, int32_t p, int32_t KA, int32_t KAmax, const int32_t* first,
                   const double* mrow, const double* tabc, const int32_t* slo,
                   const int32_t* shi, const int32_t* ga, int32_t nga, const int32_t* gb,
                   int32_t ngb, const int32_t* seg, int32_t nseg, int32_t stage_doubles,
-                  int32_t out_doubles, int32_t maxlines, void* stream);
+                  int32_t out_doubles, int32_t maxlines, int32_t variant, void* stream);
+
+/* Same pass, warp-independent variant (the default): every warp owns a task --
+ * up to 8 pieces, each a contiguous range of fibres of one line -- and runs its
+ * own cp.async ring in a private shared-memory slice (no CTA barriers inside the
+ * march); the per-node tables of a CTA's march segment live in shared memory.
+ *   irec[n_fe_d] int32x4 {len_d(I) | lo_d(I) << 8 of X, first(I), sbits, 0};
+ *        sbits: 2 bits per column q of the row's window, first(lo+q) - first(I) + 1
+ *   Sx[n_fe_d]   int64   S_d[I] of X (exclusive prefix sum of the window lengths)
+ *   jrec[n_cp_d] int32x4 {lo_d(i) of Y - (i-p), len_d(i) of Y, S_d[i] lo32, hi32}
+ *   cpad[n_fe_d][p+4]    {0, M_d[I, first(I)+k] (k = 0..p, eps-filtered), 0, 0}
+ *   tasks[ntask][36] int32 {npieces,0,0,0, {ra, rb, cb0, ncb} x npieces}: piece =
+ *        fibres (all ca, cb0 <= cb < cb0+ncb) of line (ra, rb); <= 32 fibres/task
+ *   seg[nseg+1]  output-row boundaries of the march segments (grid.y); maxnodes /
+ *        maxrows: most FE nodes (lo_d(slo[i0]) .. hi_d(shi[i1-1])) / rows of a segment. */
+int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY, double* Yvals,
+                    int32_t d, int32_t p, int32_t KAmax, const void* irec, const void* Sx,
+                    const void* jrec, const double* cpad, const int32_t* slo,
+                    const int32_t* shi, const int32_t* tasks, int32_t ntask,
+                    const int32_t* seg, int32_t nseg, int32_t maxnodes, int32_t maxrows,
+                    void* stream);
 
 /* ---- windowed-CSR operators (no column array: 8 B per non-zero) ---------- */
 /* y = C x  (MatMult inside KSP, common.py:1255-1258; M*U, common.py:379,1259) */

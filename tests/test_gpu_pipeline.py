@@ -316,16 +316,24 @@ def test_march_ptap_equals_scipy(deg, nels):
     assert relm(patch.ptap_kron(A).to_scipy(), ref) < 1e-13
     # segments along the march direction give the same rows
     dirs, passes = patch._march
-    saved = [(P_["nseg"], P_["seg"]) for P_ in passes]
+    saved = [(P_["nseg"], P_["seg"], P_["nsegw"], P_["segw"]) for P_ in passes]
     for P_ in passes:
         n = patch.ncp[P_["d"]]
-        P_["nseg"] = min(3, n)
-        P_["seg"] = dev.from_np(np.array([(n * k) // P_["nseg"] for k in range(P_["nseg"] + 1)],
-                                         dtype=np.int32))
+        P_["nseg"] = P_["nsegw"] = max(min(3, n), P_["nsegw"])
+        P_["seg"] = P_["segw"] = dev.from_np(
+            np.array([(n * k) // P_["nseg"] for k in range(P_["nseg"] + 1)], dtype=np.int32))
     C3 = patch.ptap_march(A)
     assert relm(C3.to_scipy(), ref) < 1e-13
-    for P_, (ns, sg) in zip(passes, saved):
-        P_["nseg"], P_["seg"] = ns, sg
+    for P_, sv in zip(passes, saved):
+        P_["nseg"], P_["seg"], P_["nsegw"], P_["segw"] = sv
+    # the CTA-tiled variants (cp.async and TMA-staged rows) stay in the tree: same result
+    old = patch.MARCH_VARIANT
+    try:
+        for v in (0, 1, 2):
+            patch.MARCH_VARIANT = v
+            assert relm(patch.ptap_march(A).to_scipy(), ref) < 1e-13
+    finally:
+        patch.MARCH_VARIANT = old
 
 
 def test_jit_kernel_equals_interpreter():

@@ -66,7 +66,17 @@ __device__ inline void tgm_line_consts(const TgWin& w, int d, int a, int b, int 
   (void)b;
 }
 
-template <int P, int NS>
+__device__ __forceinline__ void tgm_cp_async8(uint32_t dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tgm_cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tg_smem_u32(bar))
+               : "memory");
+}
+
+// TMA = true: rows staged by cp.async.bulk (one copy per line per step, issued by
+// warp 0); false: by 8-byte cp.async (LDGSTS) issued by all warps, one line per warp.
+template <int P, int NS, bool TMA>
 __global__ void __launch_bounds__(TGM_THREADS, 2)
 k_ptap_march(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __restrict__ Yv,
              TgMarch R) {
@@ -122,7 +132,7 @@ k_ptap_march(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __restri
     li[3 * l] = lla * llb;
   }
   if (tid == 0) {
-    for (int s = 0; s < NS; s++) tg_mbar_init(&full[s], (uint32_t)nlines);
+    for (int s = 0; s < NS; s++) tg_mbar_init(&full[s], TMA ? (uint32_t)nlines : TGM_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -149,6 +159,18 @@ k_ptap_march(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __restri
     const int I = I_start + t;
     const int lenI = tgm_len(wX, d, I);
     const long long Sd = tgm_S(wX, d, I);
+    if (!TMA) {
+      for (int l = wid; l < nlines; l += TGM_THREADS / 32) {
+        const long long addr = lc[6 * l] + lc[6 * l + 1] * lenI + lc[6 * l + 2] * Sd;
+        const int n = lenI * li[3 * l];
+        const double* src = Xv + addr;
+        const uint32_t dst = tg_smem_u32(stg + (size_t)s * R.stage_doubles + li[3 * l + 1]);
+        for (int o = lane; o < n; o += 32) tgm_cp_async8(dst + 8u * o, src + o);
+      }
+      tgm_cp_async_arrive(&full[s]);
+      return;
+    }
+    if (wid != 0) return;
     for (int l = lane; l < nlines; l += 32) {
       const long long addr = lc[6 * l] + lc[6 * l + 1] * lenI + lc[6 * l + 2] * Sd;
       const int n = lenI * li[3 * l];
@@ -160,8 +182,7 @@ k_ptap_march(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __restri
                   &full[s]);
     }
   };
-  if (wid == 0)
-    for (int t = 0; t < NS && t < nsteps; t++) issue(t);
+  for (int t = 0; t < NS && t < nsteps; t++) issue(t);
 
   double acc[P + 1][CW];
 #pragma unroll
@@ -212,8 +233,8 @@ k_ptap_march(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __restri
 #pragma unroll
     for (int m = 0; m < TWP; m++) tv[m] = 0.0;
     if (active) {
-      const double* xs = stg + (size_t)s * R.stage_doubles + slotX + par[s * R.maxlines + line] +
-                         u + v * lenI;
+      const double* xs = stg + (size_t)s * R.stage_doubles + slotX +
+                         (TMA ? par[s * R.maxlines + line] : 0) + u + v * lenI;
       const double2* mc = (const double2*)(R.tabc + (size_t)I * R.KA * TWP);
       for (int q = 0; q < lenI; q++) {
         const double x = xs[q * stride];
@@ -226,7 +247,7 @@ k_ptap_march(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __restri
       }
     }
     __syncthreads();                                   // stage s consumed by every thread
-    if (wid == 0 && t + NS < nsteps) issue(t + NS);
+    if (t + NS < nsteps) issue(t + NS);
     const int f = __ldg(R.first + I);
     while (ib < f) emit_shift();
     const double* mrp = R.mrow + (size_t)I * (P + 1);
@@ -251,7 +272,7 @@ extern "C" int tg_ptap_march(const tg_win* h_wX, const double* Xvals, const tg_w
                              const int32_t* slo, const int32_t* shi, const int32_t* ga,
                              int32_t nga, const int32_t* gb, int32_t ngb, const int32_t* seg,
                              int32_t nseg, int32_t stage_doubles, int32_t out_doubles,
-                             int32_t maxlines, void* stream) {
+                             int32_t maxlines, int32_t variant, void* stream) {
   TG_REQUIRE(h_wX->dim >= 2 && h_wX->dim <= 3, "march PtAP needs a 2-D or 3-D patch");
   TG_REQUIRE(d >= 0 && d < h_wX->dim, "direction");
   TG_REQUIRE(p >= 1 && p <= 4, "degree 1..4");
@@ -278,12 +299,16 @@ extern "C" int tg_ptap_march(const tg_win* h_wX, const double* Xvals, const tg_w
                 NS * 8 + (size_t)maxlines * 3 * 4 + (size_t)NS * maxlines * 4 + 16;
   TG_REQUIRE(smem <= 220 * 1024, "line tile too large for shared memory");
   dim3 grid((unsigned)nga, (unsigned)ngb, (unsigned)nseg);
+#define TGM_LAUNCH2(PP, TT)                                                                     \
+  {                                                                                             \
+    TG_CHECK(cudaFuncSetAttribute(k_ptap_march<PP, NS, TT>,                                     \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    k_ptap_march<PP, NS, TT><<<grid, TGM_THREADS, smem, tg_stream(stream)>>>(                   \
+        tg_win_dev(h_wX), Xvals, tg_win_dev(h_wY), Yvals, R);                                   \
+  }
 #define TGM_LAUNCH(PP)                                                                          \
   {                                                                                             \
-    TG_CHECK(cudaFuncSetAttribute(k_ptap_march<PP, NS>,                                         \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    k_ptap_march<PP, NS><<<grid, TGM_THREADS, smem, tg_stream(stream)>>>(                       \
-        tg_win_dev(h_wX), Xvals, tg_win_dev(h_wY), Yvals, R);                                   \
+    if (variant == 1) TGM_LAUNCH2(PP, true) else TGM_LAUNCH2(PP, false)                         \
   }
   switch (p) {
     case 1: TGM_LAUNCH(1) break;
@@ -292,6 +317,320 @@ extern "C" int tg_ptap_march(const tg_win* h_wX, const double* Xvals, const tg_w
     default: TGM_LAUNCH(4) break;
   }
 #undef TGM_LAUNCH
+#undef TGM_LAUNCH2
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ===========================================================================
+// Warp-independent march (the default).  ncu on the CTA-tiled kernel above showed
+// ~370 instructions per warp and step for ~43 DFMAs, CTA barriers on the critical
+// path and the per-step table loads missing L1 (36 % issue utilisation, 43-60 %
+// long-scoreboard stalls): not the copies.  Here
+//  * every warp owns a "task" -- up to TGW_MAXSUB pieces, each a contiguous range
+//    of fibres of one line -- and runs its own NS-deep cp.async (LDGSTS) ring in a
+//    private shared-memory slice: no CTA-level synchronisation inside the march;
+//  * all per-node tables of the CTA's march segment live in shared memory: the
+//    1-D extraction row of every FE node as a zero-padded vector
+//    cpad[J] = [0, M_d[J,first(J)..first(J)+p], 0, 0], so that the column-side
+//    contraction reads p+2 consecutive entries at offset 1 - (first(J)-first(I))
+//    (static register indices, dynamic shared-memory address), and the row-side
+//    weights are cpad[I][1..p+1];
+//  * the (p+1) x (2p+1) accumulator block rotates by code specialisation
+//    (switch over p+1 copies of the step) instead of register moves;
+//  * each lane copies exactly len_d(I) values per step (its piece's sub-row,
+//    strided by the piece's lane count: contiguous global reads per piece);
+//    finished rows leave through a per-warp transpose tile (d = 0,1) or directly
+//    (d = 2, already coalesced).
+#include <type_traits>
+#include <stdlib.h>
+#define TGW_MAXSUB 8
+#define TGW_TSTRIDE (4 * TGW_MAXSUB + 4)
+
+struct TgMarchW {
+  int KAmax, ntask, maxnodes, maxrows, dbg;
+  const int4* irec;        // [n_fe_d] {len_d(I) | lo_d(I) << 8 (X window), first(I), sbits, 0}
+  const long long* Sx;     // [n_fe_d] S_d[I] of the X window
+  const int4* jrec;        // [n_cp_d] {lo_d(i) of Y - (i-p), len_d(i) of Y, S_d[i] lo, hi}
+  const double* cpad;      // [n_fe_d][p+4]
+  const int32_t* slo;
+  const int32_t* shi;
+  const int32_t* tasks;    // [ntask][TGW_TSTRIDE]: npieces, -, -, -, then {ra, rb, cb0, ncb} each
+  const int32_t* seg;
+};
+
+__device__ __forceinline__ void tgm_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tgm_cp_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int P, int D, int NS, int WPC, int MINB>
+__global__ void __launch_bounds__(WPC * 32, MINB)
+k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __restrict__ Yv,
+               TgMarchW R) {
+  constexpr int CW = 2 * P + 1, TW = P + 2, CPS = P + 4, NR = P + 1;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int STG = 32 * R.KAmax;
+  const int WSM = NS * STG + 32 * CW + 6 * 32;                        // doubles per warp
+  double* ring0 = (double*)smraw;                                     // [WPC][WSM]
+  int4* irec_s = (int4*)(ring0 + (size_t)WPC * WSM);                  // [maxnodes]
+  int4* jrec_s = irec_s + R.maxnodes;                                 // [maxrows]
+  long long* S_s = (long long*)(jrec_s + R.maxrows);                  // [maxnodes]
+  double* cpad_s = (double*)(S_s + R.maxnodes);                       // [maxnodes][CPS]
+
+  // ---- march segment and its tables ------------------------------------------------
+  const int i_lo = __ldg(R.seg + blockIdx.y), i_hi = __ldg(R.seg + blockIdx.y + 1);
+  const int I_start = __ldg(R.slo + i_lo), I_end = __ldg(R.shi + i_hi - 1);
+  const int nsteps = I_end - I_start + 1;
+  const int J0 = __ldg(R.irec + I_start).x >> 8;
+  {
+    const int xe = __ldg(R.irec + I_end).x;
+    const int nn = (xe >> 8) + (xe & 255) - J0;                       // nodes J0 .. hi_d(I_end)
+    for (int e = tid; e < nn * CPS; e += WPC * 32) cpad_s[e] = __ldg(R.cpad + (size_t)J0 * CPS + e);
+    for (int e = tid; e < nn; e += WPC * 32) {
+      irec_s[e] = __ldg(R.irec + J0 + e);
+      S_s[e] = __ldg(R.Sx + J0 + e);
+    }
+    for (int e = tid; e < i_hi - i_lo; e += WPC * 32) jrec_s[e] = __ldg(R.jrec + i_lo + e);
+  }
+  __syncthreads();                                   // the only CTA barrier
+  const int task = blockIdx.x * WPC + wid;
+  if (task >= R.ntask) return;
+  double* stg = ring0 + (size_t)wid * WSM;
+  double* osm = stg + NS * STG;
+  long long* lcs = (long long*)(osm + 32 * CW) + lane;               // [6][32] per-lane constants
+  constexpr int a = (D == 0) ? 1 : 0, b = (D == 2) ? 1 : 2;
+
+  // ---- this lane's piece and fibre ---------------------------------------------------
+  const int32_t* T = R.tasks + (size_t)task * TGW_TSTRIDE;
+  const int npieces = __ldg(T);
+  int f = lane, pre = 0, ra = 0, rb = 0, cb0 = 0, la = 1, np = 1;
+  bool active = false;
+  for (int k = 0; k < npieces; k++) {
+    const int ra_ = __ldg(T + 4 + 4 * k), rb_ = __ldg(T + 5 + 4 * k);
+    const int cb0_ = __ldg(T + 6 + 4 * k), ncb_ = __ldg(T + 7 + 4 * k);
+    const int la_ = tgm_len(wX, a, ra_);
+    const int np_ = la_ * ncb_;
+    if (!active) {
+      ra = ra_; rb = rb_; cb0 = cb0_; la = la_; np = np_;
+      if (f < np_) active = true;
+      else { f -= np_; pre += np_; }
+    }
+  }
+  const int lb = tgm_len(wX, b, rb);
+  const int ca = f % la, cbl = f / la, cb = cb0 + cbl;
+  long long cX[3], cY[3];
+  tgm_line_consts(wX, D, a, b, ra, rb, la, lb, cX);
+  tgm_line_consts(wY, D, a, b, ra, rb, la, lb, cY);
+  // fibre value q of a staged row: xa + xb*len + q*XS (piece-relative);
+  // copy k of a step: row + sA + sL*len + k*sB  ->  slot + f + k*np
+  int xa, xb, sB;
+  if (D == 0) { xa = 0; xb = f; sB = np; cX[0] += f; cX[1] += cb0 * la; cY[0] += f; cY[1] += cb0 * la; }
+  else if (D == 1) { xa = ca; xb = cbl * la; sB = np; cX[0] += f; cX[1] += cb0 * la; cY[0] += f; cY[1] += cb0 * la; }
+  else { xa = f; xb = 0; sB = la * lb; cX[0] += cb * la + ca; cY[0] += cb * la + ca; }
+  const int XS = (D == 0) ? 1 : (D == 1 ? la : np);
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    lcs[j * 32] = cX[j];
+    lcs[(3 + j) * 32] = cY[j];
+  }
+  const uint32_t slot_u32 = tg_smem_u32(stg + pre * R.KAmax + f);
+  const double* xslot = stg + pre * R.KAmax + xa;
+  double* oslot = osm + pre * CW;
+  const int nbase = I_start - J0;                    // table index of the first step
+
+  int istage = 0;                                    // stage the next issue() fills
+  auto issue = [&](int t) {
+    if (t < nsteps && active && !(R.dbg & 1)) {
+      const int lenI = irec_s[nbase + t].x & 255;
+      const double* src = Xv + (lcs[0] + lcs[32] * lenI + lcs[64] * S_s[nbase + t]);
+      uint32_t dst = slot_u32 + (uint32_t)(istage * STG * 8);
+      for (int k = 0; k < lenI; k++) {
+        tgm_cp_async8(dst, src);
+        dst += (uint32_t)(np * 8);
+        src += sB;
+      }
+    }
+    tgm_cp_commit();
+    istage = (istage + 1 == NS) ? 0 : istage + 1;
+  };
+  for (int t = 0; t < NS - 1; t++) issue(t);
+
+  double acc[NR][CW];
+#pragma unroll
+  for (int k = 0; k < NR; k++)
+#pragma unroll
+    for (int c = 0; c < CW; c++) acc[k][c] = 0.0;
+  int ib = irec_s[nbase].y;
+  int cstage = 0;                                    // stage the next step consumes
+
+  // emit the finished IGA row ib held in physical accumulator row ROT, then clear it
+  auto emit = [&](auto rc) {
+    constexpr int ROT = decltype(rc)::value;
+    if (ib >= i_lo && ib < i_hi && !(R.dbg & 4)) {   // warp-uniform
+      const int4 jr = jrec_s[ib - i_lo];
+      const int clo = jr.x, lenC = jr.y;
+      const long long SdY = ((long long)(unsigned)jr.z) | ((long long)jr.w << 32);
+      double* yrow = Yv + (lcs[96] + lcs[128] * lenC + lcs[160] * SdY);
+      if (D == 2) {
+        if (active) {
+#pragma unroll
+          for (int c = 0; c < CW; c++) {
+            const int jj = c - clo;
+            if (jj >= 0 && jj < lenC) yrow[(size_t)jj * sB] = acc[ROT][c];
+          }
+        }
+      } else {
+        __syncwarp();                                // previous tile fully copied out
+        if (active) {
+          double* o = oslot + xa + xb * lenC;
+          if (lenC == CW) {
+#pragma unroll
+            for (int c = 0; c < CW; c++) o[c * XS] = acc[ROT][c];
+          } else {
+#pragma unroll
+            for (int c = 0; c < CW; c++) {
+              const int jj = c - clo;
+              if (jj >= 0 && jj < lenC) o[jj * XS] = acc[ROT][c];
+            }
+          }
+        }
+        __syncwarp();
+        if (active) {
+          const double* src = oslot + f;
+          for (int k = 0; k < lenC; k++) {
+            *yrow = *src;
+            yrow += np;
+            src += np;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CW; c++) acc[ROT][c] = 0.0;
+  };
+
+  auto step = [&](auto rc, int t, const int4 ir) {
+    constexpr int ROT = decltype(rc)::value;
+    tgm_cp_wait<NS - 2>();
+    __syncwarp();
+    issue(t + NS - 1);
+    if (active && !(R.dbg & 2)) {
+      const int lenI = ir.x & 255;
+      const double* xs_ = xslot + cstage * STG + xb * lenI;
+      const double* cp = cpad_s + ((ir.x >> 8) - J0) * CPS + 2;
+      unsigned sb = (unsigned)ir.z;
+      double tv[TW];
+#pragma unroll
+      for (int m = 0; m < TW; m++) tv[m] = 0.0;
+      for (int q = 0; q < lenI; q++) {
+        const double x = xs_[q * XS];
+        const double* c = cp - (int)(sb & 3u);
+        sb >>= 2;
+        cp += CPS;
+#pragma unroll
+        for (int m = 0; m < TW; m++) tv[m] += x * c[m];
+      }
+      const double* mrp = cpad_s + (nbase + t) * CPS + 1;
+#pragma unroll
+      for (int k = 0; k < NR; k++) {
+        const double mr = mrp[k];
+#pragma unroll
+        for (int m = 0; m < TW; m++) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int c = m - k + P;
+          if (c >= 0 && c < CW) acc[(k + ROT) % NR][c] += mr * tv[m];
+        }
+      }
+    }
+    cstage = (cstage + 1 == NS) ? 0 : cstage + 1;
+  };
+
+  int rot = 0;
+#define TGW_DISPATCH(fn, ...)                                                  \
+  switch (rot) {                                                               \
+    case 0: fn(std::integral_constant<int, 0>{}, ##__VA_ARGS__); break;        \
+    case 1: fn(std::integral_constant<int, (1 < NR ? 1 : 0)>{}, ##__VA_ARGS__); break; \
+    case 2: fn(std::integral_constant<int, (2 < NR ? 2 : 0)>{}, ##__VA_ARGS__); break; \
+    case 3: fn(std::integral_constant<int, (3 < NR ? 3 : 0)>{}, ##__VA_ARGS__); break; \
+    default: fn(std::integral_constant<int, (4 < NR ? 4 : 0)>{}, ##__VA_ARGS__); break; \
+  }
+  for (int t = 0; t < nsteps; t++) {
+    const int4 ir = irec_s[nbase + t];
+    while (ib < ir.y) {
+      TGW_DISPATCH(emit)
+      rot = (rot + 1 == NR) ? 0 : rot + 1;
+      ib++;
+    }
+    TGW_DISPATCH(step, t, ir)
+  }
+  for (int k = 0; k < NR; k++) {
+    TGW_DISPATCH(emit)
+    rot = (rot + 1 == NR) ? 0 : rot + 1;
+    ib++;
+  }
+#undef TGW_DISPATCH
+  tgm_cp_wait<0>();
+}
+
+extern "C" int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY,
+                               double* Yvals, int32_t d, int32_t p, int32_t KAmax,
+                               const void* irec, const void* Sx, const void* jrec,
+                               const double* cpad, const int32_t* slo, const int32_t* shi,
+                               const int32_t* tasks, int32_t ntask, const int32_t* seg,
+                               int32_t nseg, int32_t maxnodes, int32_t maxrows, void* stream) {
+  TG_REQUIRE(h_wX->dim >= 2 && h_wX->dim <= 3, "march PtAP needs a 2-D or 3-D patch");
+  TG_REQUIRE(d >= 0 && d < h_wX->dim, "direction");
+  TG_REQUIRE(p >= 1 && p <= 4, "degree 1..4");
+  TG_REQUIRE(h_wX->layout == 0 && h_wY->layout == 0, "row-major windows only");
+  TG_REQUIRE(ntask >= 1 && nseg >= 1 && nseg <= 65535, "grid");
+  TgMarchW R;
+  R.KAmax = KAmax;
+  R.ntask = ntask;
+  R.maxnodes = maxnodes;
+  R.maxrows = maxrows;
+  {
+    const char* e = getenv("TIGAR_B200_MARCH_DBG");   // profiling experiments only
+    R.dbg = e ? atoi(e) : 0;
+  }
+  R.irec = (const int4*)irec;
+  R.Sx = (const long long*)Sx;
+  R.jrec = (const int4*)jrec;
+  R.cpad = cpad;
+  R.slo = slo;
+  R.shi = shi;
+  R.tasks = tasks;
+  R.seg = seg;
+  constexpr int NS = 4;
+  const int WPC = (p >= 4) ? 4 : 8;
+  const int CW = 2 * p + 1;
+  size_t smem = (size_t)WPC * (NS * 32 * KAmax + 32 * CW + 6 * 32) * 8 +
+                (size_t)maxnodes * ((p + 4) * 8 + 8 + 16) + (size_t)maxrows * 16;
+  TG_REQUIRE(smem <= 220 * 1024, "stage ring + tables too large for shared memory");
+  dim3 grid((unsigned)tg_cdiv(ntask, WPC), (unsigned)nseg, 1);
+#define TGW_LAUNCH2(PP, DD)                                                                     \
+  {                                                                                             \
+    constexpr int W_ = (PP >= 4) ? 4 : 8, MB_ = (PP >= 4) ? 3 : 2;                              \
+    TG_CHECK(cudaFuncSetAttribute(k_ptap_march_w<PP, DD, NS, W_, MB_>,                          \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    k_ptap_march_w<PP, DD, NS, W_, MB_><<<grid, W_ * 32, smem, tg_stream(stream)>>>(            \
+        tg_win_dev(h_wX), Xvals, tg_win_dev(h_wY), Yvals, R);                                   \
+  }
+#define TGW_LAUNCH(PP)                                                                          \
+  {                                                                                             \
+    if (d == 0) TGW_LAUNCH2(PP, 0) else if (d == 1) TGW_LAUNCH2(PP, 1) else TGW_LAUNCH2(PP, 2)  \
+  }
+  switch (p) {
+    case 1: TGW_LAUNCH(1) break;
+    case 2: TGW_LAUNCH(2) break;
+    case 3: TGW_LAUNCH(3) break;
+    default: TGW_LAUNCH(4) break;
+  }
+#undef TGW_LAUNCH
+#undef TGW_LAUNCH2
   TG_LAUNCH_CHECK();
   return 0;
 }

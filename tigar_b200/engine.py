@@ -768,6 +768,7 @@ class TensorPatch(object):
 
     # ---- two-sided march passes (tg_ptap_march) --------------------------------
     MARCH_THREADS = 256
+    MARCH_VARIANT = int(os.environ.get("TIGAR_B200_MARCH_VARIANT", "2"))
 
     def _march_setup(self):
         """Per-direction tables, intermediate windows and CTA tilings of the
@@ -809,7 +810,32 @@ class TensorPatch(object):
                 return None
             if np.any(np.diff(first) < 0):
                 return None
+            # tables of the warp-task kernel (tg_ptap_march_w)
+            SX = np.concatenate([[0], np.cumsum(wA.len[d])]).astype(np.int64)
+            SY = np.concatenate([[0], np.cumsum(wC.len[d])]).astype(np.int64)
+            sbits = np.zeros(D.nfe, dtype=np.int64)
+            for I in range(D.nfe):
+                for q, J in enumerate(range(wA.lo[d][I], wA.hi[d][I] + 1)):
+                    sh = first[J] - first[I] + 1
+                    if not np.any(mrow[J]):
+                        sh = 1
+                    if sh < 0 or sh > 2:
+                        return None
+                    sbits[I] |= int(sh) << (2 * q)
+            if KA > 15 or D.nfe >= (1 << 23):
+                return None
+            irec = np.stack([wA.len[d] | (wA.lo[d].astype(np.int64) << 8), first, sbits,
+                             np.zeros(D.nfe, dtype=np.int64)], axis=1)
+            jrec = np.stack([wC.lo[d] - (i - p), wC.len[d], SY[:-1] & 0xffffffff, SY[:-1] >> 32],
+                            axis=1)
+            cpad = np.zeros((D.nfe, p + 4))
+            cpad[:, 1:p + 2] = mrow
             dirs.append(dict(p=p, KA=KA, first=dev.from_np(first.astype(np.int32)),
+                             irec=dev.from_np(irec.astype(np.uint32).view(np.int32)),
+                             jrec=dev.from_np(jrec.astype(np.uint32).view(np.int32)),
+                             Sx=dev.from_np(SX[:-1].copy()), cpad=dev.from_np(cpad),
+                             loX=wA.lo[d].astype(np.int64), hiX=wA.hi[d].astype(np.int64),
+                             h_slo=wMT.lo[d].astype(np.int64), h_shi=wMT.hi[d].astype(np.int64),
                              mrow=dev.from_np(mrow), tabc=dev.from_np(tabc),
                              slo=dev.from_np(wMT.lo[d].astype(np.int32)),
                              shi=dev.from_np(wMT.hi[d].astype(np.int32))))
@@ -850,7 +876,24 @@ class TensorPatch(object):
             nseg = int(min(max(1, self.ncp[d] // 16),
                            max(1, -(-4 * 148 // ((len(ga) - 1) * (len(gb) - 1))))))
             seg = [(self.ncp[d] * k) // nseg for k in range(nseg + 1)]
+            tasks = self._march_tasks(wX.len[others[0]],
+                                      wX.len[others[1]] if self.dim == 3 else np.ones(1, np.int64))
+            nsegw = int(min(max(1, self.ncp[d] // 16),
+                            max(1, -(-16 * 148 * 2 // len(tasks)))))
+            Dd = dirs[d]
+            while True:        # bound the per-segment tables held in shared memory
+                segw = [(self.ncp[d] * k) // nsegw for k in range(nsegw + 1)]
+                nodes = [int(Dd["hiX"][Dd["h_shi"][segw[k + 1] - 1]]
+                             - Dd["loX"][Dd["h_slo"][segw[k]]] + 1) for k in range(nsegw)]
+                if max(nodes) <= self.MARCH_NODEMAX or nsegw >= self.ncp[d]:
+                    break
+                nsegw += 1
+            maxnodes = max(nodes)
+            maxrows = max(segw[k + 1] - segw[k] for k in range(nsegw))
             passes.append(dict(wX=wX, wY=wY, d=d, KAmax=KAmax, maxlines=maxlines, stage=stage,
+                               tasks=dev.from_np(tasks.ravel()), ntask=len(tasks), nsegw=nsegw,
+                               maxnodes=maxnodes, maxrows=maxrows,
+                               segw=dev.from_np(np.array(segw, dtype=np.int32)),
                                outd=outd, nga=len(ga) - 1, ngb=len(gb) - 1, nseg=nseg,
                                ga=dev.from_np(np.array(ga, dtype=np.int32)),
                                gb=dev.from_np(np.array(gb, dtype=np.int32)),
@@ -859,6 +902,49 @@ class TensorPatch(object):
         assert passes[-1]["wY"].nnz == wC.nnz
         self._march = (dirs, passes)
         return self._march
+
+    MARCH_MAXSUB = 8
+    MARCH_NODEMAX = 200       # FE nodes of one march segment whose tables sit in shared memory
+
+    @classmethod
+    def _march_tasks(cls, lena, lenb):
+        """Warp tasks of tg_ptap_march_w: every line (ra, rb) of the two
+        non-march directions has la*lb fibres; lines wider than a warp are cut
+        along the second direction, narrow ones are packed up to MARCH_MAXSUB to a
+        warp.  Returns int32 [ntask][4*MAXSUB+4]: npieces,0,0,0, {ra,rb,cb0,ncb}*."""
+        MS = cls.MARCH_MAXSUB
+        tasks, open_ = [], []          # open_: [lanes used, [pieces]]
+        minp = int(min(lena.min() * 1, 32))
+        for rb, lb in enumerate(lenb):
+            for ra, la in enumerate(lena):
+                la, lb = int(la), int(lb)
+                assert la <= 32
+                ncbmax = max(1, 32 // la)
+                nsplit = -(-lb // ncbmax)
+                cuts = [(lb * k) // nsplit for k in range(nsplit + 1)]
+                for k in range(nsplit):
+                    cb0, ncb = cuts[k], cuts[k + 1] - cuts[k]
+                    n = la * ncb
+                    for T in open_:
+                        if T[0] + n <= 32 and len(T[1]) < MS:
+                            T[0] += n
+                            T[1].append((ra, rb, cb0, ncb))
+                            break
+                    else:
+                        T = [n, [(ra, rb, cb0, ncb)]]
+                        open_.append(T)
+                    if T[0] + minp > 32 or len(T[1]) == MS:
+                        open_.remove(T)
+                        tasks.append(T[1])
+                    elif len(open_) > 4:
+                        tasks.append(open_.pop(0)[1])
+        tasks += [T[1] for T in open_]
+        out = np.zeros((len(tasks), 4 * MS + 4), dtype=np.int32)
+        for t, pcs in enumerate(tasks):
+            out[t, 0] = len(pcs)
+            for k, pc in enumerate(pcs):
+                out[t, 4 + 4 * k:8 + 4 * k] = pc
+        return out
 
     def ptap_march(self, A, keep=False):
         """C = M^T A M by one two-sided march pass per direction (A read once,
@@ -869,13 +955,25 @@ class TensorPatch(object):
         for P_ in passes:
             D = dirs[P_["d"]]
             Y = dev.empty(P_["wY"].nnz)
+            if self.MARCH_VARIANT == 2:
+                check(lib.tg_ptap_march_w(P_["wX"].ref(), dev.ptr(X), P_["wY"].ref(), dev.ptr(Y),
+                                          P_["d"], D["p"], P_["KAmax"], dev.ptr(D["irec"]),
+                                          dev.ptr(D["Sx"]), dev.ptr(D["jrec"]),
+                                          dev.ptr(D["cpad"]), dev.ptr(D["slo"]),
+                                          dev.ptr(D["shi"]), dev.ptr(P_["tasks"]), P_["ntask"],
+                                          dev.ptr(P_["segw"]), P_["nsegw"], P_["maxnodes"],
+                                          P_["maxrows"], dev.stream()))
+                X = Y
+                if keep:
+                    stages.append(WinMatrix(P_["wY"], Y))
+                continue
             check(lib.tg_ptap_march(P_["wX"].ref(), dev.ptr(X), P_["wY"].ref(), dev.ptr(Y),
                                     P_["d"], D["p"], D["KA"], P_["KAmax"], dev.ptr(D["first"]),
                                     dev.ptr(D["mrow"]), dev.ptr(D["tabc"]), dev.ptr(D["slo"]),
                                     dev.ptr(D["shi"]), dev.ptr(P_["ga"]), P_["nga"],
                                     dev.ptr(P_["gb"]), P_["ngb"], dev.ptr(P_["seg"]),
                                     P_["nseg"], P_["stage"], P_["outd"], P_["maxlines"],
-                                    dev.stream()))
+                                    self.MARCH_VARIANT, dev.stream()))
             X = Y
             if keep:
                 stages.append(WinMatrix(P_["wY"], Y))
