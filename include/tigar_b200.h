@@ -287,22 +287,26 @@ int tg_ptap_march(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY, d
 /* Same pass, warp-independent variant (the default): every warp owns a task --
  * up to 8 pieces, each a contiguous range of fibres of one line -- and runs its
  * own cp.async ring in a private shared-memory slice (no CTA barriers inside the
- * march); the per-node tables of a CTA's march segment live in shared memory.
- *   irec[n_fe_d] int32x4 {len_d(I) | lo_d(I) << 8 of X, first(I), sbits, 0};
+ * march); the march advances by groups of <= 4 consecutive FE rows sharing
+ * first(I); the per-node tables of a CTA's march segment live in shared memory.
+ *   irec[n_fe_d] int32x4 {len_d(I) | lo_d(I) << 8 of X, first(I), sbits, group(I)};
  *        sbits: 2 bits per column q of the row's window, first(lo+q) - first(I) + 1
  *   Sx[n_fe_d]   int64   S_d[I] of X (exclusive prefix sum of the window lengths)
  *   jrec[n_cp_d] int32x4 {lo_d(i) of Y - (i-p), len_d(i) of Y, S_d[i] lo32, hi32}
  *   cpad[n_fe_d][p+4]    {0, M_d[I, first(I)+k] (k = 0..p, eps-filtered), 0, 0}
+ *   grp[ngroups+1]       first FE row of every group
  *   tasks[ntask][36] int32 {npieces,0,0,0, {ra, rb, cb0, ncb} x npieces}: piece =
  *        fibres (all ca, cb0 <= cb < cb0+ncb) of line (ra, rb); <= 32 fibres/task
- *   seg[nseg+1]  output-row boundaries of the march segments (grid.y); maxnodes /
- *        maxrows: most FE nodes (lo_d(slo[i0]) .. hi_d(shi[i1-1])) / rows of a segment. */
+ *   seg[nseg+1]  output-row boundaries of the march segments (grid.y)
+ * GMAX: most window entries (sum of len_d) of one group, >= 2p+1; maxnodes /
+ * maxrows / maxgroups: most FE nodes, output rows and groups of one segment
+ * (a segment marches over the whole groups covering its rows' FE support).   */
 int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY, double* Yvals,
-                    int32_t d, int32_t p, int32_t KAmax, const void* irec, const void* Sx,
-                    const void* jrec, const double* cpad, const int32_t* slo,
-                    const int32_t* shi, const int32_t* tasks, int32_t ntask,
-                    const int32_t* seg, int32_t nseg, int32_t maxnodes, int32_t maxrows,
-                    void* stream);
+                    int32_t d, int32_t p, int32_t GMAX, const void* irec, const void* Sx,
+                    const void* jrec, const double* cpad, const int32_t* grp,
+                    const int32_t* slo, const int32_t* shi, const int32_t* tasks,
+                    int32_t ntask, const int32_t* seg, int32_t nseg, int32_t maxnodes,
+                    int32_t maxrows, int32_t maxgroups, void* stream);
 
 /* ---- windowed-CSR operators (no column array: 8 B per non-zero) ---------- */
 /* y = C x  (MatMult inside KSP, common.py:1255-1258; M*U, common.py:379,1259) */

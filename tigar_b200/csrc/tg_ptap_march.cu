@@ -325,34 +325,40 @@ extern "C" int tg_ptap_march(const tg_win* h_wX, const double* Xvals, const tg_w
 // ===========================================================================
 // Warp-independent march (the default).  ncu on the CTA-tiled kernel above showed
 // ~370 instructions per warp and step for ~43 DFMAs, CTA barriers on the critical
-// path and the per-step table loads missing L1 (36 % issue utilisation, 43-60 %
-// long-scoreboard stalls): not the copies.  Here
+// path and per-step table loads missing L1 (36 % issue utilisation, 43-60 %
+// long-scoreboard stalls); an ablation of a first warp-level version showed the
+// load, compute and store parts adding up instead of overlapping (in-order issue,
+// 16 warps/SM at 128 registers).  Hence:
 //  * every warp owns a "task" -- up to TGW_MAXSUB pieces, each a contiguous range
 //    of fibres of one line -- and runs its own NS-deep cp.async (LDGSTS) ring in a
 //    private shared-memory slice: no CTA-level synchronisation inside the march;
+//  * the march advances by GROUPS of consecutive FE rows that share first(I)
+//    (one knot span: <= TGW_RMAX rows).  One wait / warp-sync / prefetch issue and
+//    (usually) one finished IGA row per group; the group's rows are straight-line
+//    code with static register indices, so the loads of one row overlap the
+//    DFMAs of the previous one;
 //  * all per-node tables of the CTA's march segment live in shared memory: the
 //    1-D extraction row of every FE node as a zero-padded vector
 //    cpad[J] = [0, M_d[J,first(J)..first(J)+p], 0, 0], so that the column-side
 //    contraction reads p+2 consecutive entries at offset 1 - (first(J)-first(I))
-//    (static register indices, dynamic shared-memory address), and the row-side
+//    (static register indices, dynamic shared-memory address); the row-side
 //    weights are cpad[I][1..p+1];
-//  * the (p+1) x (2p+1) accumulator block rotates by code specialisation
-//    (switch over p+1 copies of the step) instead of register moves;
-//  * each lane copies exactly len_d(I) values per step (its piece's sub-row,
+//  * each lane copies exactly len_d(I) values per row (its piece's sub-row,
 //    strided by the piece's lane count: contiguous global reads per piece);
-//    finished rows leave through a per-warp transpose tile (d = 0,1) or directly
-//    (d = 2, already coalesced).
-#include <type_traits>
+//    finished rows leave through a transpose tile that aliases the ring stage
+//    about to be refilled (d = 0,1) or directly (d = 2, already coalesced).
 #include <stdlib.h>
 #define TGW_MAXSUB 8
 #define TGW_TSTRIDE (4 * TGW_MAXSUB + 4)
+#define TGW_RMAX 4
 
 struct TgMarchW {
-  int KAmax, ntask, maxnodes, maxrows, dbg;
-  const int4* irec;        // [n_fe_d] {len_d(I) | lo_d(I) << 8 (X window), first(I), sbits, 0}
+  int GMAX, ntask, maxnodes, maxrows, maxgroups, dbg;
+  const int4* irec;        // [n_fe_d] {len_d(I) | lo_d(I) << 8 (X window), first(I), sbits, group(I)}
   const long long* Sx;     // [n_fe_d] S_d[I] of the X window
   const int4* jrec;        // [n_cp_d] {lo_d(i) of Y - (i-p), len_d(i) of Y, S_d[i] lo, hi}
   const double* cpad;      // [n_fe_d][p+4]
+  const int32_t* grp;      // [ngroups+1] first FE row of every group
   const int32_t* slo;
   const int32_t* shi;
   const int32_t* tasks;    // [ntask][TGW_TSTRIDE]: npieces, -, -, -, then {ra, rb, cb0, ncb} each
@@ -372,35 +378,38 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
   constexpr int CW = 2 * P + 1, TW = P + 2, CPS = P + 4, NR = P + 1;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int STG = 32 * R.KAmax;
-  const int WSM = NS * STG + 32 * CW + 6 * 32;                        // doubles per warp
+  const int STG = 32 * R.GMAX;                                        // doubles per stage
+  const int WSM = NS * STG + 2 * 32;                                  // doubles per warp
   double* ring0 = (double*)smraw;                                     // [WPC][WSM]
   int4* irec_s = (int4*)(ring0 + (size_t)WPC * WSM);                  // [maxnodes]
   int4* jrec_s = irec_s + R.maxnodes;                                 // [maxrows]
   long long* S_s = (long long*)(jrec_s + R.maxrows);                  // [maxnodes]
   double* cpad_s = (double*)(S_s + R.maxnodes);                       // [maxnodes][CPS]
+  int* gb_s = (int*)(cpad_s + (size_t)R.maxnodes * CPS);              // [maxgroups+1]
 
-  // ---- march segment and its tables ------------------------------------------------
+  // ---- march segment: whole groups covering the FE support of rows [i_lo, i_hi) -----
   const int i_lo = __ldg(R.seg + blockIdx.y), i_hi = __ldg(R.seg + blockIdx.y + 1);
-  const int I_start = __ldg(R.slo + i_lo), I_end = __ldg(R.shi + i_hi - 1);
-  const int nsteps = I_end - I_start + 1;
-  const int J0 = __ldg(R.irec + I_start).x >> 8;
+  const int g0 = __ldg(R.irec + __ldg(R.slo + i_lo)).w;
+  const int g1 = __ldg(R.irec + __ldg(R.shi + i_hi - 1)).w;
+  const int ngroups = g1 - g0 + 1;
+  const int rowA = __ldg(R.grp + g0), rowB = __ldg(R.grp + g1 + 1) - 1;
+  const int J0 = __ldg(R.irec + rowA).x >> 8;
   {
-    const int xe = __ldg(R.irec + I_end).x;
-    const int nn = (xe >> 8) + (xe & 255) - J0;                       // nodes J0 .. hi_d(I_end)
+    const int xe = __ldg(R.irec + rowB).x;
+    const int nn = (xe >> 8) + (xe & 255) - J0;                       // nodes J0 .. hi_d(rowB)
     for (int e = tid; e < nn * CPS; e += WPC * 32) cpad_s[e] = __ldg(R.cpad + (size_t)J0 * CPS + e);
     for (int e = tid; e < nn; e += WPC * 32) {
       irec_s[e] = __ldg(R.irec + J0 + e);
       S_s[e] = __ldg(R.Sx + J0 + e);
     }
     for (int e = tid; e < i_hi - i_lo; e += WPC * 32) jrec_s[e] = __ldg(R.jrec + i_lo + e);
+    for (int e = tid; e <= ngroups; e += WPC * 32) gb_s[e] = __ldg(R.grp + g0 + e) - J0;
   }
   __syncthreads();                                   // the only CTA barrier
   const int task = blockIdx.x * WPC + wid;
   if (task >= R.ntask) return;
   double* stg = ring0 + (size_t)wid * WSM;
-  double* osm = stg + NS * STG;
-  long long* lcs = (long long*)(osm + 32 * CW) + lane;               // [6][32] per-lane constants
+  long long* lcs = (long long*)(stg + NS * STG) + lane;               // [2][32]: 64-bit row bases
   constexpr int a = (D == 0) ? 1 : 0, b = (D == 2) ? 1 : 2;
 
   // ---- this lane's piece and fibre ---------------------------------------------------
@@ -421,79 +430,84 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
   }
   const int lb = tgm_len(wX, b, rb);
   const int ca = f % la, cbl = f / la, cb = cb0 + cbl;
-  long long cX[3], cY[3];
-  tgm_line_consts(wX, D, a, b, ra, rb, la, lb, cX);
-  tgm_line_consts(wY, D, a, b, ra, rb, la, lb, cY);
   // fibre value q of a staged row: xa + xb*len + q*XS (piece-relative);
-  // copy k of a step: row + sA + sL*len + k*sB  ->  slot + f + k*np
+  // copy k of a row: row + sL*len + k*sB  ->  piece slot + f + k*np
   int xa, xb, sB;
-  if (D == 0) { xa = 0; xb = f; sB = np; cX[0] += f; cX[1] += cb0 * la; cY[0] += f; cY[1] += cb0 * la; }
-  else if (D == 1) { xa = ca; xb = cbl * la; sB = np; cX[0] += f; cX[1] += cb0 * la; cY[0] += f; cY[1] += cb0 * la; }
-  else { xa = f; xb = 0; sB = la * lb; cX[0] += cb * la + ca; cY[0] += cb * la + ca; }
-  const int XS = (D == 0) ? 1 : (D == 1 ? la : np);
-#pragma unroll
-  for (int j = 0; j < 3; j++) {
-    lcs[j * 32] = cX[j];
-    lcs[(3 + j) * 32] = cY[j];
+  long long c1x, c2x, c1y, c2y;
+  {
+    long long cX[3], cY[3];
+    tgm_line_consts(wX, D, a, b, ra, rb, la, lb, cX);
+    tgm_line_consts(wY, D, a, b, ra, rb, la, lb, cY);
+    if (D == 0) { xa = 0; xb = f; sB = np; cX[0] += f; cX[1] += cb0 * la; cY[0] += f; cY[1] += cb0 * la; }
+    else if (D == 1) { xa = ca; xb = cbl * la; sB = np; cX[0] += f; cX[1] += cb0 * la; cY[0] += f; cY[1] += cb0 * la; }
+    else { xa = f; xb = 0; sB = la * lb; cX[0] += cb * la + ca; cY[0] += cb * la + ca; }
+    lcs[0] = cX[0];
+    lcs[32] = cY[0];
+    c1x = cX[1]; c2x = cX[2]; c1y = cY[1]; c2y = cY[2];
   }
-  const uint32_t slot_u32 = tg_smem_u32(stg + pre * R.KAmax + f);
-  const double* xslot = stg + pre * R.KAmax + xa;
-  double* oslot = osm + pre * CW;
-  const int nbase = I_start - J0;                    // table index of the first step
+  const int XS = (D == 0) ? 1 : (D == 1 ? la : np);
+  const int pslot = pre * R.GMAX;                    // this piece's region of a stage
+  const uint32_t slot_u32 = tg_smem_u32(stg + pslot + f);
+  const double* xslot = stg + pslot + xa;
 
   int istage = 0;                                    // stage the next issue() fills
-  auto issue = [&](int t) {
-    if (t < nsteps && active && !(R.dbg & 1)) {
-      const int lenI = irec_s[nbase + t].x & 255;
-      const double* src = Xv + (lcs[0] + lcs[32] * lenI + lcs[64] * S_s[nbase + t]);
+  auto issue = [&](int gk) {
+    if (gk < ngroups && active && !(R.dbg & 1)) {
       uint32_t dst = slot_u32 + (uint32_t)(istage * STG * 8);
-      for (int k = 0; k < lenI; k++) {
-        tgm_cp_async8(dst, src);
-        dst += (uint32_t)(np * 8);
-        src += sB;
+      const int n1 = gb_s[gk + 1];
+      const long long base = lcs[0];
+      for (int n = gb_s[gk]; n < n1; n++) {
+        const int lenI = irec_s[n].x & 255;
+        const double* src = Xv + (base + c1x * lenI + c2x * S_s[n]);
+        for (int k = 0; k < lenI; k++) {
+          tgm_cp_async8(dst, src);
+          dst += (uint32_t)(np * 8);
+          src += sB;
+        }
       }
     }
     tgm_cp_commit();
     istage = (istage + 1 == NS) ? 0 : istage + 1;
   };
-  for (int t = 0; t < NS - 1; t++) issue(t);
+  for (int g = 0; g < NS - 1; g++) issue(g);
 
   double acc[NR][CW];
 #pragma unroll
   for (int k = 0; k < NR; k++)
 #pragma unroll
     for (int c = 0; c < CW; c++) acc[k][c] = 0.0;
-  int ib = irec_s[nbase].y;
-  int cstage = 0;                                    // stage the next step consumes
+  int ib = irec_s[gb_s[0]].y;
+  int cstage = 0;                                    // stage the next group consumes
 
-  // emit the finished IGA row ib held in physical accumulator row ROT, then clear it
-  auto emit = [&](auto rc) {
-    constexpr int ROT = decltype(rc)::value;
+  // emit the finished IGA row ib (accumulator row 0) and shift the block up; `tile` is
+  // a ring stage nobody is reading (the one the next issue() refills)
+  auto emit_shift = [&](double* tile) {
     if (ib >= i_lo && ib < i_hi && !(R.dbg & 4)) {   // warp-uniform
       const int4 jr = jrec_s[ib - i_lo];
       const int clo = jr.x, lenC = jr.y;
       const long long SdY = ((long long)(unsigned)jr.z) | ((long long)jr.w << 32);
-      double* yrow = Yv + (lcs[96] + lcs[128] * lenC + lcs[160] * SdY);
+      double* yrow = Yv + (lcs[32] + c1y * lenC + c2y * SdY);
       if (D == 2) {
         if (active) {
 #pragma unroll
           for (int c = 0; c < CW; c++) {
             const int jj = c - clo;
-            if (jj >= 0 && jj < lenC) yrow[(size_t)jj * sB] = acc[ROT][c];
+            if (jj >= 0 && jj < lenC) yrow[(size_t)jj * sB] = acc[0][c];
           }
         }
       } else {
-        __syncwarp();                                // previous tile fully copied out
+        double* oslot = tile + pslot;
+        __syncwarp();                                // tile free: its readers are done
         if (active) {
           double* o = oslot + xa + xb * lenC;
           if (lenC == CW) {
 #pragma unroll
-            for (int c = 0; c < CW; c++) o[c * XS] = acc[ROT][c];
+            for (int c = 0; c < CW; c++) o[c * XS] = acc[0][c];
           } else {
 #pragma unroll
             for (int c = 0; c < CW; c++) {
               const int jj = c - clo;
-              if (jj >= 0 && jj < lenC) o[jj * XS] = acc[ROT][c];
+              if (jj >= 0 && jj < lenC) o[jj * XS] = acc[0][c];
             }
           }
         }
@@ -509,89 +523,81 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
       }
     }
 #pragma unroll
-    for (int c = 0; c < CW; c++) acc[ROT][c] = 0.0;
+    for (int k = 0; k < NR - 1; k++)
+#pragma unroll
+      for (int c = 0; c < CW; c++) acc[k][c] = acc[k + 1][c];
+#pragma unroll
+    for (int c = 0; c < CW; c++) acc[NR - 1][c] = 0.0;
+    ib++;
   };
 
-  auto step = [&](auto rc, int t, const int4 ir) {
-    constexpr int ROT = decltype(rc)::value;
+  for (int gk = 0; gk < ngroups; gk++) {
+    const int n0 = gb_s[gk], n1 = gb_s[gk + 1];
+    const int F = irec_s[n0].y;
+    while (ib < F) emit_shift(stg + istage * STG);
     tgm_cp_wait<NS - 2>();
     __syncwarp();
-    issue(t + NS - 1);
+    issue(gk + NS - 1);
     if (active && !(R.dbg & 2)) {
-      const int lenI = ir.x & 255;
-      const double* xs_ = xslot + cstage * STG + xb * lenI;
-      const double* cp = cpad_s + ((ir.x >> 8) - J0) * CPS + 2;
-      unsigned sb = (unsigned)ir.z;
-      double tv[TW];
+      const double* xrow = xslot + cstage * STG;
 #pragma unroll
-      for (int m = 0; m < TW; m++) tv[m] = 0.0;
-      for (int q = 0; q < lenI; q++) {
-        const double x = xs_[q * XS];
-        const double* c = cp - (int)(sb & 3u);
-        sb >>= 2;
-        cp += CPS;
+      for (int r = 0; r < TGW_RMAX; r++) {
+        if (n0 + r < n1) {
+          const int4 ir = irec_s[n0 + r];
+          const int lenI = ir.x & 255;
+          const double* xs_ = xrow + xb * lenI;
+          xrow += np * lenI;
+          const double* cp = cpad_s + ((ir.x >> 8) - J0) * CPS + 2;
+          unsigned sb = (unsigned)ir.z;
+          double tv[TW];
 #pragma unroll
-        for (int m = 0; m < TW; m++) tv[m] += x * c[m];
-      }
-      const double* mrp = cpad_s + (nbase + t) * CPS + 1;
+          for (int m = 0; m < TW; m++) tv[m] = 0.0;
+          for (int q = 0; q < lenI; q++) {
+            const double x = xs_[q * XS];
+            const double* c = cp - (int)(sb & 3u);
+            sb >>= 2;
+            cp += CPS;
 #pragma unroll
-      for (int k = 0; k < NR; k++) {
-        const double mr = mrp[k];
+            for (int m = 0; m < TW; m++) tv[m] += x * c[m];
+          }
+          const double* mrp = cpad_s + (n0 + r) * CPS + 1;
 #pragma unroll
-        for (int m = 0; m < TW; m++) {
-          constexpr int dummy = 0;
-          (void)dummy;
-          const int c = m - k + P;
-          if (c >= 0 && c < CW) acc[(k + ROT) % NR][c] += mr * tv[m];
+          for (int k = 0; k < NR; k++) {
+            const double mr = mrp[k];
+#pragma unroll
+            for (int m = 0; m < TW; m++) {
+              const int c = m - k + P;
+              if (c >= 0 && c < CW) acc[k][c] += mr * tv[m];
+            }
+          }
         }
       }
     }
     cstage = (cstage + 1 == NS) ? 0 : cstage + 1;
-  };
-
-  int rot = 0;
-#define TGW_DISPATCH(fn, ...)                                                  \
-  switch (rot) {                                                               \
-    case 0: fn(std::integral_constant<int, 0>{}, ##__VA_ARGS__); break;        \
-    case 1: fn(std::integral_constant<int, (1 < NR ? 1 : 0)>{}, ##__VA_ARGS__); break; \
-    case 2: fn(std::integral_constant<int, (2 < NR ? 2 : 0)>{}, ##__VA_ARGS__); break; \
-    case 3: fn(std::integral_constant<int, (3 < NR ? 3 : 0)>{}, ##__VA_ARGS__); break; \
-    default: fn(std::integral_constant<int, (4 < NR ? 4 : 0)>{}, ##__VA_ARGS__); break; \
   }
-  for (int t = 0; t < nsteps; t++) {
-    const int4 ir = irec_s[nbase + t];
-    while (ib < ir.y) {
-      TGW_DISPATCH(emit)
-      rot = (rot + 1 == NR) ? 0 : rot + 1;
-      ib++;
-    }
-    TGW_DISPATCH(step, t, ir)
-  }
-  for (int k = 0; k < NR; k++) {
-    TGW_DISPATCH(emit)
-    rot = (rot + 1 == NR) ? 0 : rot + 1;
-    ib++;
-  }
-#undef TGW_DISPATCH
   tgm_cp_wait<0>();
+  for (int k = 0; k < NR; k++) emit_shift(stg);
 }
 
 extern "C" int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY,
-                               double* Yvals, int32_t d, int32_t p, int32_t KAmax,
+                               double* Yvals, int32_t d, int32_t p, int32_t GMAX,
                                const void* irec, const void* Sx, const void* jrec,
-                               const double* cpad, const int32_t* slo, const int32_t* shi,
-                               const int32_t* tasks, int32_t ntask, const int32_t* seg,
-                               int32_t nseg, int32_t maxnodes, int32_t maxrows, void* stream) {
+                               const double* cpad, const int32_t* grp, const int32_t* slo,
+                               const int32_t* shi, const int32_t* tasks, int32_t ntask,
+                               const int32_t* seg, int32_t nseg, int32_t maxnodes,
+                               int32_t maxrows, int32_t maxgroups, void* stream) {
   TG_REQUIRE(h_wX->dim >= 2 && h_wX->dim <= 3, "march PtAP needs a 2-D or 3-D patch");
   TG_REQUIRE(d >= 0 && d < h_wX->dim, "direction");
   TG_REQUIRE(p >= 1 && p <= 4, "degree 1..4");
   TG_REQUIRE(h_wX->layout == 0 && h_wY->layout == 0, "row-major windows only");
   TG_REQUIRE(ntask >= 1 && nseg >= 1 && nseg <= 65535, "grid");
+  TG_REQUIRE(GMAX >= 2 * p + 1, "stage must hold one output row");
   TgMarchW R;
-  R.KAmax = KAmax;
+  R.GMAX = GMAX;
   R.ntask = ntask;
   R.maxnodes = maxnodes;
   R.maxrows = maxrows;
+  R.maxgroups = maxgroups;
   {
     const char* e = getenv("TIGAR_B200_MARCH_DBG");   // profiling experiments only
     R.dbg = e ? atoi(e) : 0;
@@ -600,15 +606,16 @@ extern "C" int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg
   R.Sx = (const long long*)Sx;
   R.jrec = (const int4*)jrec;
   R.cpad = cpad;
+  R.grp = grp;
   R.slo = slo;
   R.shi = shi;
   R.tasks = tasks;
   R.seg = seg;
-  constexpr int NS = 4;
+  constexpr int NS = 3;
   const int WPC = (p >= 4) ? 4 : 8;
-  const int CW = 2 * p + 1;
-  size_t smem = (size_t)WPC * (NS * 32 * KAmax + 32 * CW + 6 * 32) * 8 +
-                (size_t)maxnodes * ((p + 4) * 8 + 8 + 16) + (size_t)maxrows * 16;
+  size_t smem = (size_t)WPC * (NS * 32 * GMAX + 2 * 32) * 8 +
+                (size_t)maxnodes * ((p + 4) * 8 + 8 + 16) + (size_t)maxrows * 16 +
+                (size_t)(maxgroups + 1) * 4 + 16;
   TG_REQUIRE(smem <= 220 * 1024, "stage ring + tables too large for shared memory");
   dim3 grid((unsigned)tg_cdiv(ntask, WPC), (unsigned)nseg, 1);
 #define TGW_LAUNCH2(PP, DD)                                                                     \

@@ -824,8 +824,18 @@ class TensorPatch(object):
                     sbits[I] |= int(sh) << (2 * q)
             if KA > 15 or D.nfe >= (1 << 23):
                 return None
-            irec = np.stack([wA.len[d] | (wA.lo[d].astype(np.int64) << 8), first, sbits,
-                             np.zeros(D.nfe, dtype=np.int64)], axis=1)
+            # groups: runs of FE rows sharing first(I), at most MARCH_RMAX rows each
+            grp, gidx = [0], np.zeros(D.nfe, dtype=np.int64)
+            for I in range(1, D.nfe):
+                if first[I] != first[I - 1] or I - grp[-1] >= min(self.MARCH_RMAX, D.pf):
+                    grp.append(I)
+                gidx[I] = len(grp) - 1
+            grp.append(D.nfe)
+            grp = np.array(grp, dtype=np.int64)
+            gsum = np.add.reduceat(wA.len[d], grp[:-1])
+            GMAX = int(max(gsum.max(), 2 * p + 1))
+            irec = np.stack([wA.len[d] | (wA.lo[d].astype(np.int64) << 8), first, sbits, gidx],
+                            axis=1)
             jrec = np.stack([wC.lo[d] - (i - p), wC.len[d], SY[:-1] & 0xffffffff, SY[:-1] >> 32],
                             axis=1)
             cpad = np.zeros((D.nfe, p + 4))
@@ -834,6 +844,8 @@ class TensorPatch(object):
                              irec=dev.from_np(irec.astype(np.uint32).view(np.int32)),
                              jrec=dev.from_np(jrec.astype(np.uint32).view(np.int32)),
                              Sx=dev.from_np(SX[:-1].copy()), cpad=dev.from_np(cpad),
+                             grp=dev.from_np(grp.astype(np.int32)), h_grp=grp, h_gidx=gidx,
+                             GMAX=GMAX,
                              loX=wA.lo[d].astype(np.int64), hiX=wA.hi[d].astype(np.int64),
                              h_slo=wMT.lo[d].astype(np.int64), h_shi=wMT.hi[d].astype(np.int64),
                              mrow=dev.from_np(mrow), tabc=dev.from_np(tabc),
@@ -883,16 +895,19 @@ class TensorPatch(object):
             Dd = dirs[d]
             while True:        # bound the per-segment tables held in shared memory
                 segw = [(self.ncp[d] * k) // nsegw for k in range(nsegw + 1)]
-                nodes = [int(Dd["hiX"][Dd["h_shi"][segw[k + 1] - 1]]
-                             - Dd["loX"][Dd["h_slo"][segw[k]]] + 1) for k in range(nsegw)]
+                gA = [int(Dd["h_gidx"][Dd["h_slo"][segw[k]]]) for k in range(nsegw)]
+                gB = [int(Dd["h_gidx"][Dd["h_shi"][segw[k + 1] - 1]]) for k in range(nsegw)]
+                nodes = [int(Dd["hiX"][Dd["h_grp"][b_ + 1] - 1] - Dd["loX"][Dd["h_grp"][a_]] + 1)
+                         for a_, b_ in zip(gA, gB)]
                 if max(nodes) <= self.MARCH_NODEMAX or nsegw >= self.ncp[d]:
                     break
                 nsegw += 1
             maxnodes = max(nodes)
+            maxgroups = max(b_ - a_ + 1 for a_, b_ in zip(gA, gB))
             maxrows = max(segw[k + 1] - segw[k] for k in range(nsegw))
             passes.append(dict(wX=wX, wY=wY, d=d, KAmax=KAmax, maxlines=maxlines, stage=stage,
                                tasks=dev.from_np(tasks.ravel()), ntask=len(tasks), nsegw=nsegw,
-                               maxnodes=maxnodes, maxrows=maxrows,
+                               maxnodes=maxnodes, maxrows=maxrows, maxgroups=maxgroups,
                                segw=dev.from_np(np.array(segw, dtype=np.int32)),
                                outd=outd, nga=len(ga) - 1, ngb=len(gb) - 1, nseg=nseg,
                                ga=dev.from_np(np.array(ga, dtype=np.int32)),
@@ -904,7 +919,8 @@ class TensorPatch(object):
         return self._march
 
     MARCH_MAXSUB = 8
-    MARCH_NODEMAX = 200       # FE nodes of one march segment whose tables sit in shared memory
+    MARCH_NODEMAX = 110       # FE nodes of one march segment whose tables sit in shared memory
+    MARCH_RMAX = 4            # rows per march group (TGW_RMAX)
 
     @classmethod
     def _march_tasks(cls, lena, lenb):
@@ -957,12 +973,12 @@ class TensorPatch(object):
             Y = dev.empty(P_["wY"].nnz)
             if self.MARCH_VARIANT == 2:
                 check(lib.tg_ptap_march_w(P_["wX"].ref(), dev.ptr(X), P_["wY"].ref(), dev.ptr(Y),
-                                          P_["d"], D["p"], P_["KAmax"], dev.ptr(D["irec"]),
+                                          P_["d"], D["p"], D["GMAX"], dev.ptr(D["irec"]),
                                           dev.ptr(D["Sx"]), dev.ptr(D["jrec"]),
-                                          dev.ptr(D["cpad"]), dev.ptr(D["slo"]),
+                                          dev.ptr(D["cpad"]), dev.ptr(D["grp"]), dev.ptr(D["slo"]),
                                           dev.ptr(D["shi"]), dev.ptr(P_["tasks"]), P_["ntask"],
                                           dev.ptr(P_["segw"]), P_["nsegw"], P_["maxnodes"],
-                                          P_["maxrows"], dev.stream()))
+                                          P_["maxrows"], P_["maxgroups"], dev.stream()))
                 X = Y
                 if keep:
                     stages.append(WinMatrix(P_["wY"], Y))

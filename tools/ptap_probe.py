@@ -27,12 +27,12 @@ for rep in range(4):
         Y = dev.empty(P_["wY"].nnz)
         if VARIANT == 2:
             check(lib.tg_ptap_march_w(P_["wX"].ref(), dev.ptr(X), P_["wY"].ref(), dev.ptr(Y),
-                                      P_["d"], D["p"], P_["KAmax"], dev.ptr(D["irec"]),
+                                      P_["d"], D["p"], D["GMAX"], dev.ptr(D["irec"]),
                                       dev.ptr(D["Sx"]), dev.ptr(D["jrec"]),
-                                      dev.ptr(D["cpad"]), dev.ptr(D["slo"]),
+                                      dev.ptr(D["cpad"]), dev.ptr(D["grp"]), dev.ptr(D["slo"]),
                                       dev.ptr(D["shi"]), dev.ptr(P_["tasks"]), P_["ntask"],
                                       dev.ptr(P_["segw"]), P_["nsegw"], P_["maxnodes"],
-                                      P_["maxrows"], dev.stream()))
+                                      P_["maxrows"], P_["maxgroups"], dev.stream()))
         else:
           check(lib.tg_ptap_march(P_["wX"].ref(), dev.ptr(X), P_["wY"].ref(), dev.ptr(Y),
                                 P_["d"], D["p"], D["KA"], P_["KAmax"], dev.ptr(D["first"]),
