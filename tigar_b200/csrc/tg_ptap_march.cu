@@ -348,6 +348,7 @@ extern "C" int tg_ptap_march(const tg_win* h_wX, const double* Xvals, const tg_w
 //    finished rows leave through a transpose tile that aliases the ring stage
 //    about to be refilled (d = 0,1) or directly (d = 2, already coalesced).
 #include <stdlib.h>
+#include <type_traits>
 #define TGW_MAXSUB 8
 #define TGW_TSTRIDE (4 * TGW_MAXSUB + 4)
 #define TGW_RMAX 4
@@ -383,9 +384,9 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
   double* ring0 = (double*)smraw;                                     // [WPC][WSM]
   int4* irec_s = (int4*)(ring0 + (size_t)WPC * WSM);                  // [maxnodes]
   int4* jrec_s = irec_s + R.maxnodes;                                 // [maxrows]
-  long long* S_s = (long long*)(jrec_s + R.maxrows);                  // [maxnodes]
-  double* cpad_s = (double*)(S_s + R.maxnodes);                       // [maxnodes][CPS]
-  int* gb_s = (int*)(cpad_s + (size_t)R.maxnodes * CPS);              // [maxgroups+1]
+  double* cpad_s = (double*)(jrec_s + R.maxrows);                     // [maxnodes][CPS]
+  unsigned* S_s = (unsigned*)(cpad_s + (size_t)R.maxnodes * CPS);     // [maxnodes] (fits 32 bits)
+  int* gb_s = (int*)(S_s + R.maxnodes);                               // [maxgroups+1]
 
   // ---- march segment: whole groups covering the FE support of rows [i_lo, i_hi) -----
   const int i_lo = __ldg(R.seg + blockIdx.y), i_hi = __ldg(R.seg + blockIdx.y + 1);
@@ -400,7 +401,7 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
     for (int e = tid; e < nn * CPS; e += WPC * 32) cpad_s[e] = __ldg(R.cpad + (size_t)J0 * CPS + e);
     for (int e = tid; e < nn; e += WPC * 32) {
       irec_s[e] = __ldg(R.irec + J0 + e);
-      S_s[e] = __ldg(R.Sx + J0 + e);
+      S_s[e] = (unsigned)__ldg(R.Sx + J0 + e);
     }
     for (int e = tid; e < i_hi - i_lo; e += WPC * 32) jrec_s[e] = __ldg(R.jrec + i_lo + e);
     for (int e = tid; e <= ngroups; e += WPC * 32) gb_s[e] = __ldg(R.grp + g0 + e) - J0;
@@ -433,7 +434,7 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
   // fibre value q of a staged row: xa + xb*len + q*XS (piece-relative);
   // copy k of a row: row + sL*len + k*sB  ->  piece slot + f + k*np
   int xa, xb, sB;
-  long long c1x, c2x, c1y, c2y;
+  unsigned c1x, c2x, c1y, c2y;                       // < 2^32 (checked by the host)
   {
     long long cX[3], cY[3];
     tgm_line_consts(wX, D, a, b, ra, rb, la, lb, cX);
@@ -443,13 +444,14 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
     else { xa = f; xb = 0; sB = la * lb; cX[0] += cb * la + ca; cY[0] += cb * la + ca; }
     lcs[0] = cX[0];
     lcs[32] = cY[0];
-    c1x = cX[1]; c2x = cX[2]; c1y = cY[1]; c2y = cY[2];
+    c1x = (unsigned)cX[1]; c2x = (unsigned)cX[2]; c1y = (unsigned)cY[1]; c2y = (unsigned)cY[2];
   }
   const int XS = (D == 0) ? 1 : (D == 1 ? la : np);
   const int pslot = pre * R.GMAX;                    // this piece's region of a stage
   const uint32_t slot_u32 = tg_smem_u32(stg + pslot + f);
   const double* xslot = stg + pslot + xa;
 
+  const int np8 = np * 8;
   int istage = 0;                                    // stage the next issue() fills
   auto issue = [&](int gk) {
     if (gk < ngroups && active && !(R.dbg & 1)) {
@@ -457,13 +459,15 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
       const int n1 = gb_s[gk + 1];
       const long long base = lcs[0];
       for (int n = gb_s[gk]; n < n1; n++) {
-        const int lenI = irec_s[n].x & 255;
-        const double* src = Xv + (base + c1x * lenI + c2x * S_s[n]);
-        for (int k = 0; k < lenI; k++) {
-          tgm_cp_async8(dst, src);
-          dst += (uint32_t)(np * 8);
-          src += sB;
-        }
+        const unsigned lenI = (unsigned)irec_s[n].x & 255u;
+        const double* src = Xv + (base + (unsigned long long)c1x * lenI +
+                                  (unsigned long long)c2x * S_s[n]);
+#pragma unroll
+        for (int k = 0; k < 2 * P + 1; k++)
+          if (k < (int)lenI) tgm_cp_async8(dst + (uint32_t)(k * np8), src + (unsigned)(k * sB));
+        for (int k = 2 * P + 1; k < (int)lenI; k++)      // FE degree above the spline degree
+          tgm_cp_async8(dst + (uint32_t)(k * np8), src + (unsigned)(k * sB));
+        dst += lenI * (unsigned)np8;
       }
     }
     tgm_cp_commit();
@@ -479,20 +483,22 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
   int ib = irec_s[gb_s[0]].y;
   int cstage = 0;                                    // stage the next group consumes
 
-  // emit the finished IGA row ib (accumulator row 0) and shift the block up; `tile` is
-  // a ring stage nobody is reading (the one the next issue() refills)
-  auto emit_shift = [&](double* tile) {
+  // emit the finished IGA row ib, held in physical accumulator row ROT, and clear it (it
+  // becomes the newest row of the sliding block); `tile` is a ring stage nobody is
+  // reading (the one the next issue() refills)
+  auto emit = [&](auto rc, double* tile) {
+    constexpr int ROT = decltype(rc)::value;
     if (ib >= i_lo && ib < i_hi && !(R.dbg & 4)) {   // warp-uniform
       const int4 jr = jrec_s[ib - i_lo];
       const int clo = jr.x, lenC = jr.y;
       const long long SdY = ((long long)(unsigned)jr.z) | ((long long)jr.w << 32);
-      double* yrow = Yv + (lcs[32] + c1y * lenC + c2y * SdY);
+      double* yrow = Yv + (lcs[32] + (unsigned long long)c1y * (unsigned)lenC + c2y * SdY);
       if (D == 2) {
         if (active) {
 #pragma unroll
           for (int c = 0; c < CW; c++) {
             const int jj = c - clo;
-            if (jj >= 0 && jj < lenC) yrow[(size_t)jj * sB] = acc[0][c];
+            if (jj >= 0 && jj < lenC) yrow[(size_t)jj * sB] = acc[ROT][c];
           }
         }
       } else {
@@ -502,81 +508,100 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
           double* o = oslot + xa + xb * lenC;
           if (lenC == CW) {
 #pragma unroll
-            for (int c = 0; c < CW; c++) o[c * XS] = acc[0][c];
+            for (int c = 0; c < CW; c++) o[c * XS] = acc[ROT][c];
           } else {
 #pragma unroll
             for (int c = 0; c < CW; c++) {
               const int jj = c - clo;
-              if (jj >= 0 && jj < lenC) o[jj * XS] = acc[0][c];
+              if (jj >= 0 && jj < lenC) o[jj * XS] = acc[ROT][c];
             }
           }
         }
         __syncwarp();
         if (active) {
           const double* src = oslot + f;
-          for (int k = 0; k < lenC; k++) {
-            *yrow = *src;
-            yrow += np;
-            src += np;
-          }
+#pragma unroll
+          for (int k = 0; k < CW; k++)
+            if (k < lenC) yrow[(unsigned)(k * np)] = src[k * np];
         }
       }
     }
+    // slide the block up (register moves: rotating the block by code specialisation
+    // -- NR copies of the group code -- was measured 2x SLOWER, instruction cache)
 #pragma unroll
     for (int k = 0; k < NR - 1; k++)
 #pragma unroll
       for (int c = 0; c < CW; c++) acc[k][c] = acc[k + 1][c];
 #pragma unroll
     for (int c = 0; c < CW; c++) acc[NR - 1][c] = 0.0;
-    ib++;
   };
 
-  for (int gk = 0; gk < ngroups; gk++) {
-    const int n0 = gb_s[gk], n1 = gb_s[gk + 1];
-    const int F = irec_s[n0].y;
-    while (ib < F) emit_shift(stg + istage * STG);
-    tgm_cp_wait<NS - 2>();
-    __syncwarp();
-    issue(gk + NS - 1);
-    if (active && !(R.dbg & 2)) {
-      const double* xrow = xslot + cstage * STG;
+  // the rows of one group: column-side contraction then the sliding row-side update;
+  // ROT = physical accumulator row of IGA row `ib`
+  auto rows = [&](auto rc, int n0, int n1) {
+    constexpr int ROT = decltype(rc)::value;
+    const double* xrow = xslot + cstage * STG;
 #pragma unroll
-      for (int r = 0; r < TGW_RMAX; r++) {
-        if (n0 + r < n1) {
-          const int4 ir = irec_s[n0 + r];
-          const int lenI = ir.x & 255;
-          const double* xs_ = xrow + xb * lenI;
-          xrow += np * lenI;
-          const double* cp = cpad_s + ((ir.x >> 8) - J0) * CPS + 2;
-          unsigned sb = (unsigned)ir.z;
-          double tv[TW];
+    for (int r = 0; r < TGW_RMAX; r++) {
+      if (n0 + r < n1) {
+        const int4 ir = irec_s[n0 + r];
+        const int lenI = ir.x & 255;
+        const double* xs_ = xrow + xb * lenI;
+        xrow += np * lenI;
+        const double* cp = cpad_s + ((ir.x >> 8) - J0) * CPS + 2;
+        const unsigned sb = (unsigned)ir.z;
+        double tv[TW];
+        auto col = [&](int q, bool first_) {
+          const double x = xs_[q * XS];
+          const double* c = cp + q * CPS - (int)((sb >> (2 * q)) & 3u);
 #pragma unroll
-          for (int m = 0; m < TW; m++) tv[m] = 0.0;
-          for (int q = 0; q < lenI; q++) {
-            const double x = xs_[q * XS];
-            const double* c = cp - (int)(sb & 3u);
-            sb >>= 2;
-            cp += CPS;
+          for (int m = 0; m < TW; m++) tv[m] = first_ ? x * c[m] : fma(x, c[m], tv[m]);
+        };
+        col(0, true);
+        if (lenI == P + 1) {
 #pragma unroll
-            for (int m = 0; m < TW; m++) tv[m] += x * c[m];
-          }
-          const double* mrp = cpad_s + (n0 + r) * CPS + 1;
+          for (int q = 1; q < P + 1; q++) col(q, false);
+        } else if (lenI == 2 * P + 1) {
 #pragma unroll
-          for (int k = 0; k < NR; k++) {
-            const double mr = mrp[k];
+          for (int q = 1; q < 2 * P + 1; q++) col(q, false);
+        } else {
+          for (int q = 1; q < lenI; q++) col(q, false);
+        }
+        const double* mrp = cpad_s + (n0 + r) * CPS + 1;
 #pragma unroll
-            for (int m = 0; m < TW; m++) {
-              const int c = m - k + P;
-              if (c >= 0 && c < CW) acc[k][c] += mr * tv[m];
-            }
+        for (int k = 0; k < NR; k++) {
+          const double mr = mrp[k];
+#pragma unroll
+          for (int m = 0; m < TW; m++) {
+            const int c = m - k + P;
+            if (c >= 0 && c < CW) acc[(k + ROT) % NR][c] += mr * tv[m];
           }
         }
       }
     }
+  };
+
+  const std::integral_constant<int, 0> rot0{};
+  for (int gk = 0; gk < ngroups; gk++) {
+    const int n0 = gb_s[gk], n1 = gb_s[gk + 1];
+    const int F = irec_s[n0].y;
+    while (ib < F) {
+      emit(rot0, stg + istage * STG);
+      ib++;
+    }
+    tgm_cp_wait<NS - 2>();
+    __syncwarp();
+    issue(gk + NS - 1);
+    if (active && !(R.dbg & 2)) {
+      rows(rot0, n0, n1);
+    }
     cstage = (cstage + 1 == NS) ? 0 : cstage + 1;
   }
   tgm_cp_wait<0>();
-  for (int k = 0; k < NR; k++) emit_shift(stg);
+  for (int k = 0; k < NR; k++) {
+    emit(rot0, stg);
+    ib++;
+  }
 }
 
 extern "C" int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY,
@@ -614,7 +639,7 @@ extern "C" int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg
   constexpr int NS = 3;
   const int WPC = (p >= 4) ? 4 : 8;
   size_t smem = (size_t)WPC * (NS * 32 * GMAX + 2 * 32) * 8 +
-                (size_t)maxnodes * ((p + 4) * 8 + 8 + 16) + (size_t)maxrows * 16 +
+                (size_t)maxnodes * ((p + 4) * 8 + 4 + 16) + (size_t)maxrows * 16 +
                 (size_t)(maxgroups + 1) * 4 + 16;
   TG_REQUIRE(smem <= 220 * 1024, "stage ring + tables too large for shared memory");
   dim3 grid((unsigned)tg_cdiv(ntask, WPC), (unsigned)nseg, 1);

@@ -888,6 +888,10 @@ class TensorPatch(object):
             nseg = int(min(max(1, self.ncp[d] // 16),
                            max(1, -(-4 * 148 // ((len(ga) - 1) * (len(gb) - 1))))))
             seg = [(self.ncp[d] * k) // nseg for k in range(nseg + 1)]
+            for w_ in (wX, wY):     # 32-bit line constants of tg_ptap_march_w
+                tot = [int(l.sum()) for l in w_.len]
+                if 16 * tot[0] * (tot[1] if self.dim > 1 else 1) >= 2 ** 32 or max(tot) >= 2 ** 31:
+                    return None
             tasks = self._march_tasks(wX.len[others[0]],
                                       wX.len[others[1]] if self.dim == 3 else np.ones(1, np.int64))
             nsegw = int(min(max(1, self.ncp[d] // 16),
@@ -899,7 +903,12 @@ class TensorPatch(object):
                 gB = [int(Dd["h_gidx"][Dd["h_shi"][segw[k + 1] - 1]]) for k in range(nsegw)]
                 nodes = [int(Dd["hiX"][Dd["h_grp"][b_ + 1] - 1] - Dd["loX"][Dd["h_grp"][a_]] + 1)
                          for a_, b_ in zip(gA, gB)]
-                if max(nodes) <= self.MARCH_NODEMAX or nsegw >= self.ncp[d]:
+                # shared-memory budget of two resident CTAs (tg_ptap_march_w: NS = 3 ring
+                # stages of 32*GMAX doubles per warp, 8 warps -- 4 for p = 4)
+                wpc = 4 if Dd["p"] >= 4 else 8
+                budget = 115712 - wpc * (3 * 32 * Dd["GMAX"] + 64) * 8 - 2048
+                nodemax = max(32, min(self.MARCH_NODEMAX, budget // ((Dd["p"] + 4) * 8 + 20)))
+                if max(nodes) <= nodemax or nsegw >= self.ncp[d]:
                     break
                 nsegw += 1
             maxnodes = max(nodes)
@@ -919,7 +928,7 @@ class TensorPatch(object):
         return self._march
 
     MARCH_MAXSUB = 8
-    MARCH_NODEMAX = 110       # FE nodes of one march segment whose tables sit in shared memory
+    MARCH_NODEMAX = 400       # FE nodes of one march segment whose tables sit in shared memory
     MARCH_RMAX = 4            # rows per march group (TGW_RMAX)
 
     @classmethod
