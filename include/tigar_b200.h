@@ -300,13 +300,16 @@ int tg_ptap_march(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY, d
  *   seg[nseg+1]  output-row boundaries of the march segments (grid.y)
  * GMAX: most window entries (sum of len_d) of one group, >= 2p+1; maxnodes /
  * maxrows / maxgroups: most FE nodes, output rows and groups of one segment
- * (a segment marches over the whole groups covering its rows' FE support).   */
+ * (a segment marches over the whole groups covering its rows' FE support);
+ * maxpieces: most pieces of one task.  For d = 0,1 the rows are staged by 1-D
+ * bulk async copies (TMA): the value array of X must then be readable up to the
+ * next 16-byte boundary past its end.                                        */
 int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY, double* Yvals,
                     int32_t d, int32_t p, int32_t GMAX, const void* irec, const void* Sx,
                     const void* jrec, const double* cpad, const int32_t* grp,
                     const int32_t* slo, const int32_t* shi, const int32_t* tasks,
                     int32_t ntask, const int32_t* seg, int32_t nseg, int32_t maxnodes,
-                    int32_t maxrows, int32_t maxgroups, void* stream);
+                    int32_t maxrows, int32_t maxgroups, int32_t maxpieces, void* stream);
 
 /* ---- windowed-CSR operators (no column array: 8 B per non-zero) ---------- */
 /* y = C x  (MatMult inside KSP, common.py:1255-1258; M*U, common.py:379,1259) */

@@ -354,7 +354,7 @@ extern "C" int tg_ptap_march(const tg_win* h_wX, const double* Xvals, const tg_w
 #define TGW_RMAX 4
 
 struct TgMarchW {
-  int GMAX, ntask, maxnodes, maxrows, maxgroups, dbg;
+  int GMAX, ntask, maxnodes, maxrows, maxgroups, stgpad, dbg;
   const int4* irec;        // [n_fe_d] {len_d(I) | lo_d(I) << 8 (X window), first(I), sbits, group(I)}
   const long long* Sx;     // [n_fe_d] S_d[I] of the X window
   const int4* jrec;        // [n_cp_d] {lo_d(i) of Y - (i-p), len_d(i) of Y, S_d[i] lo, hi}
@@ -379,8 +379,9 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
   constexpr int CW = 2 * P + 1, TW = P + 2, CPS = P + 4, NR = P + 1;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int STG = 32 * R.GMAX;                                        // doubles per stage
-  const int WSM = NS * STG + 2 * 32;                                  // doubles per warp
+  constexpr bool TMA = (D != 2);                     // rows staged by bulk async copies
+  const int STG = 32 * R.GMAX + R.stgpad;                             // doubles per stage (even)
+  const int WSM = (NS * STG + 2 * 32 + NS + NS * 16 + 1) & ~1;        // doubles per warp (even)
   double* ring0 = (double*)smraw;                                     // [WPC][WSM]
   int4* irec_s = (int4*)(ring0 + (size_t)WPC * WSM);                  // [maxnodes]
   int4* jrec_s = irec_s + R.maxnodes;                                 // [maxrows]
@@ -411,12 +412,14 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
   if (task >= R.ntask) return;
   double* stg = ring0 + (size_t)wid * WSM;
   long long* lcs = (long long*)(stg + NS * STG) + lane;               // [2][32]: 64-bit row bases
+  uint64_t* full = (uint64_t*)(stg + NS * STG + 64);                  // [NS] (TMA variant)
+  int* par_s = (int*)(full + NS);                                     // [NS][TGW_MAXSUB][TGW_RMAX]
   constexpr int a = (D == 0) ? 1 : 0, b = (D == 2) ? 1 : 2;
 
   // ---- this lane's piece and fibre ---------------------------------------------------
   const int32_t* T = R.tasks + (size_t)task * TGW_TSTRIDE;
   const int npieces = __ldg(T);
-  int f = lane, pre = 0, ra = 0, rb = 0, cb0 = 0, la = 1, np = 1;
+  int f = lane, pre = 0, ra = 0, rb = 0, cb0 = 0, la = 1, np = 1, pidx = 0;
   bool active = false;
   for (int k = 0; k < npieces; k++) {
     const int ra_ = __ldg(T + 4 + 4 * k), rb_ = __ldg(T + 5 + 4 * k);
@@ -426,7 +429,7 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
     if (!active) {
       ra = ra_; rb = rb_; cb0 = cb0_; la = la_; np = np_;
       if (f < np_) active = true;
-      else { f -= np_; pre += np_; }
+      else { f -= np_; pre += np_; pidx++; }
     }
   }
   const int lb = tgm_len(wX, b, rb);
@@ -447,30 +450,72 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
     c1x = (unsigned)cX[1]; c2x = (unsigned)cX[2]; c1y = (unsigned)cY[1]; c2y = (unsigned)cY[2];
   }
   const int XS = (D == 0) ? 1 : (D == 1 ? la : np);
-  const int pslot = pre * R.GMAX;                    // this piece's region of a stage
+  // this piece's region of a stage; the TMA variant needs 16-byte aligned row slots
+  // with room for one leading and one trailing element per row
+  const int pslot = TMA ? (((pre * R.GMAX + 1) & ~1) + (2 * TGW_RMAX + 2) * pidx) : pre * R.GMAX;
+  const bool leader = active && f == 0;
+  if (TMA) {
+    if (lane == 0) {
+      for (int s_ = 0; s_ < NS; s_++) tg_mbar_init(&full[s_], (uint32_t)npieces);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
   const uint32_t slot_u32 = tg_smem_u32(stg + pslot + f);
   const double* xslot = stg + pslot + xa;
 
   const int np8 = np * 8;
   int istage = 0;                                    // stage the next issue() fills
   auto issue = [&](int gk) {
-    if (gk < ngroups && active && !(R.dbg & 1)) {
-      uint32_t dst = slot_u32 + (uint32_t)(istage * STG * 8);
-      const int n1 = gb_s[gk + 1];
-      const long long base = lcs[0];
-      for (int n = gb_s[gk]; n < n1; n++) {
-        const unsigned lenI = (unsigned)irec_s[n].x & 255u;
-        const double* src = Xv + (base + (unsigned long long)c1x * lenI +
-                                  (unsigned long long)c2x * S_s[n]);
+    if (TMA) {
+      if (gk < ngroups && leader && !(R.dbg & 1)) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const int n0 = gb_s[gk], n1 = gb_s[gk + 1];
+        const long long base = lcs[0];
+        long long addr[TGW_RMAX];
+        int cnt[TGW_RMAX];
+        int tot = 0;
 #pragma unroll
-        for (int k = 0; k < 2 * P + 1; k++)
-          if (k < (int)lenI) tgm_cp_async8(dst + (uint32_t)(k * np8), src + (unsigned)(k * sB));
-        for (int k = 2 * P + 1; k < (int)lenI; k++)      // FE degree above the spline degree
-          tgm_cp_async8(dst + (uint32_t)(k * np8), src + (unsigned)(k * sB));
-        dst += lenI * (unsigned)np8;
+        for (int r = 0; r < TGW_RMAX; r++) {
+          cnt[r] = 0;
+          if (n0 + r < n1) {
+            const unsigned lenI = (unsigned)irec_s[n0 + r].x & 255u;
+            addr[r] = base + (unsigned long long)c1x * lenI + (unsigned long long)c2x * S_s[n0 + r];
+            const int off = (int)(addr[r] & 1);
+            cnt[r] = ((int)lenI * np + off + 1) & ~1;
+            par_s[(istage * TGW_MAXSUB + pidx) * TGW_RMAX + r] = tot + off;
+            tot += cnt[r];
+          }
+        }
+        tg_mbar_expect_tx(&full[istage], (uint32_t)(tot * 8));
+        double* dst = stg + istage * STG + pslot;
+#pragma unroll
+        for (int r = 0; r < TGW_RMAX; r++) {
+          if (n0 + r < n1) {
+            tg_bulk_g2s(dst, Xv + (addr[r] & ~1LL), (uint32_t)(cnt[r] * 8), &full[istage]);
+            dst += cnt[r];
+          }
+        }
       }
+    } else {
+      if (gk < ngroups && active && !(R.dbg & 1)) {
+        uint32_t dst = slot_u32 + (uint32_t)(istage * STG * 8);
+        const int n1 = gb_s[gk + 1];
+        const long long base = lcs[0];
+        for (int n = gb_s[gk]; n < n1; n++) {
+          const unsigned lenI = (unsigned)irec_s[n].x & 255u;
+          const double* src = Xv + (base + (unsigned long long)c1x * lenI +
+                                    (unsigned long long)c2x * S_s[n]);
+#pragma unroll
+          for (int k = 0; k < 2 * P + 1; k++)
+            if (k < (int)lenI) tgm_cp_async8(dst + (uint32_t)(k * np8), src + (unsigned)(k * sB));
+          for (int k = 2 * P + 1; k < (int)lenI; k++)      // FE degree above the spline degree
+            tgm_cp_async8(dst + (uint32_t)(k * np8), src + (unsigned)(k * sB));
+          dst += lenI * (unsigned)np8;
+        }
+      }
+      tgm_cp_commit();
     }
-    tgm_cp_commit();
     istage = (istage + 1 == NS) ? 0 : istage + 1;
   };
   for (int g = 0; g < NS - 1; g++) issue(g);
@@ -482,6 +527,7 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
     for (int c = 0; c < CW; c++) acc[k][c] = 0.0;
   int ib = irec_s[gb_s[0]].y;
   int cstage = 0;                                    // stage the next group consumes
+  uint32_t cphase = 0;
 
   // emit the finished IGA row ib, held in physical accumulator row ROT, and clear it (it
   // becomes the newest row of the sliding block); `tile` is a ring stage nobody is
@@ -541,12 +587,13 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
   auto rows = [&](auto rc, int n0, int n1) {
     constexpr int ROT = decltype(rc)::value;
     const double* xrow = xslot + cstage * STG;
+    const int* pr = par_s + (cstage * TGW_MAXSUB + pidx) * TGW_RMAX;
 #pragma unroll
     for (int r = 0; r < TGW_RMAX; r++) {
       if (n0 + r < n1) {
         const int4 ir = irec_s[n0 + r];
         const int lenI = ir.x & 255;
-        const double* xs_ = xrow + xb * lenI;
+        const double* xs_ = (TMA ? xslot + cstage * STG + pr[r] : xrow) + xb * lenI;
         xrow += np * lenI;
         const double* cp = cpad_s + ((ir.x >> 8) - J0) * CPS + 2;
         const unsigned sb = (unsigned)ir.z;
@@ -589,15 +636,22 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
       emit(rot0, stg + istage * STG);
       ib++;
     }
-    tgm_cp_wait<NS - 2>();
+    if (TMA) {
+      if (!(R.dbg & 1)) tg_mbar_wait(&full[cstage], cphase);
+    } else {
+      tgm_cp_wait<NS - 2>();
+    }
     __syncwarp();
     issue(gk + NS - 1);
     if (active && !(R.dbg & 2)) {
       rows(rot0, n0, n1);
     }
-    cstage = (cstage + 1 == NS) ? 0 : cstage + 1;
+    if (++cstage == NS) {
+      cstage = 0;
+      cphase ^= 1u;
+    }
   }
-  tgm_cp_wait<0>();
+  if (!TMA) tgm_cp_wait<0>();
   for (int k = 0; k < NR; k++) {
     emit(rot0, stg);
     ib++;
@@ -610,7 +664,8 @@ extern "C" int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg
                                const double* cpad, const int32_t* grp, const int32_t* slo,
                                const int32_t* shi, const int32_t* tasks, int32_t ntask,
                                const int32_t* seg, int32_t nseg, int32_t maxnodes,
-                               int32_t maxrows, int32_t maxgroups, void* stream) {
+                               int32_t maxrows, int32_t maxgroups, int32_t maxpieces,
+                               void* stream) {
   TG_REQUIRE(h_wX->dim >= 2 && h_wX->dim <= 3, "march PtAP needs a 2-D or 3-D patch");
   TG_REQUIRE(d >= 0 && d < h_wX->dim, "direction");
   TG_REQUIRE(p >= 1 && p <= 4, "degree 1..4");
@@ -623,6 +678,9 @@ extern "C" int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg
   R.maxnodes = maxnodes;
   R.maxrows = maxrows;
   R.maxgroups = maxgroups;
+  TG_REQUIRE(maxpieces >= 1 && maxpieces <= TGW_MAXSUB, "pieces per task");
+  R.stgpad = (d != 2) ? (2 * TGW_RMAX + 2) * maxpieces + 2 : (GMAX & 1) * 0;
+  if ((32 * GMAX + R.stgpad) & 1) R.stgpad++;
   {
     const char* e = getenv("TIGAR_B200_MARCH_DBG");   // profiling experiments only
     R.dbg = e ? atoi(e) : 0;
@@ -638,7 +696,7 @@ extern "C" int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg
   R.seg = seg;
   constexpr int NS = 3;
   const int WPC = (p >= 4) ? 4 : 8;
-  size_t smem = (size_t)WPC * (NS * 32 * GMAX + 2 * 32) * 8 +
+  size_t smem = (size_t)WPC * ((NS * (32 * GMAX + R.stgpad) + 2 * 32 + NS + NS * 16 + 1) & ~1) * 8 +
                 (size_t)maxnodes * ((p + 4) * 8 + 4 + 16) + (size_t)maxrows * 16 +
                 (size_t)(maxgroups + 1) * 4 + 16;
   TG_REQUIRE(smem <= 220 * 1024, "stage ring + tables too large for shared memory");

@@ -906,7 +906,8 @@ class TensorPatch(object):
                 # shared-memory budget of two resident CTAs (tg_ptap_march_w: NS = 3 ring
                 # stages of 32*GMAX doubles per warp, 8 warps -- 4 for p = 4)
                 wpc = 4 if Dd["p"] >= 4 else 8
-                budget = 115712 - wpc * (3 * 32 * Dd["GMAX"] + 64) * 8 - 2048
+                stgd = 32 * Dd["GMAX"] + 10 * int(tasks[:, 0].max()) + 4
+                budget = 115712 - wpc * (3 * stgd + 64 + 3 + 48) * 8 - 2048
                 nodemax = max(32, min(self.MARCH_NODEMAX, budget // ((Dd["p"] + 4) * 8 + 20)))
                 if max(nodes) <= nodemax or nsegw >= self.ncp[d]:
                     break
@@ -917,6 +918,7 @@ class TensorPatch(object):
             passes.append(dict(wX=wX, wY=wY, d=d, KAmax=KAmax, maxlines=maxlines, stage=stage,
                                tasks=dev.from_np(tasks.ravel()), ntask=len(tasks), nsegw=nsegw,
                                maxnodes=maxnodes, maxrows=maxrows, maxgroups=maxgroups,
+                               maxpieces=int(tasks[:, 0].max()),
                                segw=dev.from_np(np.array(segw, dtype=np.int32)),
                                outd=outd, nga=len(ga) - 1, ngb=len(gb) - 1, nseg=nseg,
                                ga=dev.from_np(np.array(ga, dtype=np.int32)),
@@ -987,7 +989,7 @@ class TensorPatch(object):
                                           dev.ptr(D["cpad"]), dev.ptr(D["grp"]), dev.ptr(D["slo"]),
                                           dev.ptr(D["shi"]), dev.ptr(P_["tasks"]), P_["ntask"],
                                           dev.ptr(P_["segw"]), P_["nsegw"], P_["maxnodes"],
-                                          P_["maxrows"], P_["maxgroups"], dev.stream()))
+                                          P_["maxrows"], P_["maxgroups"], P_["maxpieces"], dev.stream()))
                 X = Y
                 if keep:
                     stages.append(WinMatrix(P_["wY"], Y))
