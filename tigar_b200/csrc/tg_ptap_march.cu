@@ -380,14 +380,19 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
   extern __shared__ __align__(128) unsigned char smraw[];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   constexpr bool TMA = (D != 2);                     // rows staged by bulk async copies
+  // per-node tables of the segment in shared memory.  TS = false (read them through
+  // L1 with ld.global.nc, no segment length limit) was measured 1.6x SLOWER on the
+  // TMA-staged passes, where nothing else competes for L1: the ~90 warp-uniform
+  // coefficient loads per group want the shared-memory broadcast path.
+  constexpr bool TS = true;
   const int STG = 32 * R.GMAX + R.stgpad;                             // doubles per stage (even)
   const int WSM = (NS * STG + 2 * 32 + NS + NS * 16 + 1) & ~1;        // doubles per warp (even)
   double* ring0 = (double*)smraw;                                     // [WPC][WSM]
-  int4* irec_s = (int4*)(ring0 + (size_t)WPC * WSM);                  // [maxnodes]
-  int4* jrec_s = irec_s + R.maxnodes;                                 // [maxrows]
-  double* cpad_s = (double*)(jrec_s + R.maxrows);                     // [maxnodes][CPS]
-  unsigned* S_s = (unsigned*)(cpad_s + (size_t)R.maxnodes * CPS);     // [maxnodes] (fits 32 bits)
-  int* gb_s = (int*)(S_s + R.maxnodes);                               // [maxgroups+1]
+  int4* irec_sm = (int4*)(ring0 + (size_t)WPC * WSM);                 // [maxnodes]
+  int4* jrec_sm = irec_sm + R.maxnodes;                               // [maxrows]
+  double* cpad_sm = (double*)(jrec_sm + R.maxrows);                   // [maxnodes][CPS]
+  unsigned* S_sm = (unsigned*)(cpad_sm + (size_t)R.maxnodes * CPS);   // [maxnodes] (fits 32 bits)
+  int* gb_sm = (int*)(S_sm + R.maxnodes);                             // [maxgroups+1]
 
   // ---- march segment: whole groups covering the FE support of rows [i_lo, i_hi) -----
   const int i_lo = __ldg(R.seg + blockIdx.y), i_hi = __ldg(R.seg + blockIdx.y + 1);
@@ -396,17 +401,28 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
   const int ngroups = g1 - g0 + 1;
   const int rowA = __ldg(R.grp + g0), rowB = __ldg(R.grp + g1 + 1) - 1;
   const int J0 = __ldg(R.irec + rowA).x >> 8;
-  {
+  if (TS) {
     const int xe = __ldg(R.irec + rowB).x;
     const int nn = (xe >> 8) + (xe & 255) - J0;                       // nodes J0 .. hi_d(rowB)
-    for (int e = tid; e < nn * CPS; e += WPC * 32) cpad_s[e] = __ldg(R.cpad + (size_t)J0 * CPS + e);
+    for (int e = tid; e < nn * CPS; e += WPC * 32) cpad_sm[e] = __ldg(R.cpad + (size_t)J0 * CPS + e);
     for (int e = tid; e < nn; e += WPC * 32) {
-      irec_s[e] = __ldg(R.irec + J0 + e);
-      S_s[e] = (unsigned)__ldg(R.Sx + J0 + e);
+      irec_sm[e] = __ldg(R.irec + J0 + e);
+      S_sm[e] = (unsigned)__ldg(R.Sx + J0 + e);
     }
-    for (int e = tid; e < i_hi - i_lo; e += WPC * 32) jrec_s[e] = __ldg(R.jrec + i_lo + e);
-    for (int e = tid; e <= ngroups; e += WPC * 32) gb_s[e] = __ldg(R.grp + g0 + e) - J0;
+    for (int e = tid; e < i_hi - i_lo; e += WPC * 32) jrec_sm[e] = __ldg(R.jrec + i_lo + e);
+    for (int e = tid; e <= ngroups; e += WPC * 32) gb_sm[e] = __ldg(R.grp + g0 + e) - J0;
   }
+  // table accessors, indices relative to node J0 / row i_lo / group g0
+  const int4* irec_g = R.irec + J0;
+  const long long* S_g = R.Sx + J0;
+  const int4* jrec_g = R.jrec + i_lo;
+  const double* cpad_s = TS ? cpad_sm : R.cpad + (size_t)J0 * CPS;
+  const int32_t* grp_g = R.grp + g0;
+  auto ld_irec = [&](int n) -> int4 { return TS ? irec_sm[n] : __ldg(irec_g + n); };
+  auto ld_S = [&](int n) -> unsigned { return TS ? S_sm[n] : (unsigned)__ldg(S_g + n); };
+  auto ld_jrec = [&](int i) -> int4 { return TS ? jrec_sm[i] : __ldg(jrec_g + i); };
+  auto ld_gb = [&](int k) -> int { return TS ? gb_sm[k] : __ldg(grp_g + k) - J0; };
+  auto ld_c = [&](const double* q) -> double { return TS ? *q : __ldg(q); };
   __syncthreads();                                   // the only CTA barrier
   const int task = blockIdx.x * WPC + wid;
   if (task >= R.ntask) return;
@@ -470,7 +486,7 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
     if (TMA) {
       if (gk < ngroups && leader && !(R.dbg & 1)) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const int n0 = gb_s[gk], n1 = gb_s[gk + 1];
+        const int n0 = ld_gb(gk), n1 = ld_gb(gk + 1);
         const long long base = lcs[0];
         long long addr[TGW_RMAX];
         int cnt[TGW_RMAX];
@@ -479,8 +495,8 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
         for (int r = 0; r < TGW_RMAX; r++) {
           cnt[r] = 0;
           if (n0 + r < n1) {
-            const unsigned lenI = (unsigned)irec_s[n0 + r].x & 255u;
-            addr[r] = base + (unsigned long long)c1x * lenI + (unsigned long long)c2x * S_s[n0 + r];
+            const unsigned lenI = (unsigned)ld_irec(n0 + r).x & 255u;
+            addr[r] = base + (unsigned long long)c1x * lenI + (unsigned long long)c2x * ld_S(n0 + r);
             const int off = (int)(addr[r] & 1);
             cnt[r] = ((int)lenI * np + off + 1) & ~1;
             par_s[(istage * TGW_MAXSUB + pidx) * TGW_RMAX + r] = tot + off;
@@ -500,12 +516,12 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
     } else {
       if (gk < ngroups && active && !(R.dbg & 1)) {
         uint32_t dst = slot_u32 + (uint32_t)(istage * STG * 8);
-        const int n1 = gb_s[gk + 1];
+        const int n1 = ld_gb(gk + 1);
         const long long base = lcs[0];
-        for (int n = gb_s[gk]; n < n1; n++) {
-          const unsigned lenI = (unsigned)irec_s[n].x & 255u;
+        for (int n = ld_gb(gk); n < n1; n++) {
+          const unsigned lenI = (unsigned)ld_irec(n).x & 255u;
           const double* src = Xv + (base + (unsigned long long)c1x * lenI +
-                                    (unsigned long long)c2x * S_s[n]);
+                                    (unsigned long long)c2x * ld_S(n));
 #pragma unroll
           for (int k = 0; k < 2 * P + 1; k++)
             if (k < (int)lenI) tgm_cp_async8(dst + (uint32_t)(k * np8), src + (unsigned)(k * sB));
@@ -525,7 +541,7 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
   for (int k = 0; k < NR; k++)
 #pragma unroll
     for (int c = 0; c < CW; c++) acc[k][c] = 0.0;
-  int ib = irec_s[gb_s[0]].y;
+  int ib = ld_irec(ld_gb(0)).y;
   int cstage = 0;                                    // stage the next group consumes
   uint32_t cphase = 0;
 
@@ -535,7 +551,7 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
   auto emit = [&](auto rc, double* tile) {
     constexpr int ROT = decltype(rc)::value;
     if (ib >= i_lo && ib < i_hi && !(R.dbg & 4)) {   // warp-uniform
-      const int4 jr = jrec_s[ib - i_lo];
+      const int4 jr = ld_jrec(ib - i_lo);
       const int clo = jr.x, lenC = jr.y;
       const long long SdY = ((long long)(unsigned)jr.z) | ((long long)jr.w << 32);
       double* yrow = Yv + (lcs[32] + (unsigned long long)c1y * (unsigned)lenC + c2y * SdY);
@@ -591,7 +607,7 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
 #pragma unroll
     for (int r = 0; r < TGW_RMAX; r++) {
       if (n0 + r < n1) {
-        const int4 ir = irec_s[n0 + r];
+        const int4 ir = ld_irec(n0 + r);
         const int lenI = ir.x & 255;
         const double* xs_ = (TMA ? xslot + cstage * STG + pr[r] : xrow) + xb * lenI;
         xrow += np * lenI;
@@ -602,7 +618,7 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
           const double x = xs_[q * XS];
           const double* c = cp + q * CPS - (int)((sb >> (2 * q)) & 3u);
 #pragma unroll
-          for (int m = 0; m < TW; m++) tv[m] = first_ ? x * c[m] : fma(x, c[m], tv[m]);
+          for (int m = 0; m < TW; m++) tv[m] = first_ ? x * ld_c(c + m) : fma(x, ld_c(c + m), tv[m]);
         };
         col(0, true);
         if (lenI == P + 1) {
@@ -617,7 +633,7 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
         const double* mrp = cpad_s + (n0 + r) * CPS + 1;
 #pragma unroll
         for (int k = 0; k < NR; k++) {
-          const double mr = mrp[k];
+          const double mr = ld_c(mrp + k);
 #pragma unroll
           for (int m = 0; m < TW; m++) {
             const int c = m - k + P;
@@ -630,8 +646,8 @@ k_ptap_march_w(TgWin wX, const double* __restrict__ Xv, TgWin wY, double* __rest
 
   const std::integral_constant<int, 0> rot0{};
   for (int gk = 0; gk < ngroups; gk++) {
-    const int n0 = gb_s[gk], n1 = gb_s[gk + 1];
-    const int F = irec_s[n0].y;
+    const int n0 = ld_gb(gk), n1 = ld_gb(gk + 1);
+    const int F = ld_irec(n0).y;
     while (ib < F) {
       emit(rot0, stg + istage * STG);
       ib++;
