@@ -301,7 +301,9 @@ int tg_ptap_march(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY, d
  * GMAX: most window entries (sum of len_d) of one group, >= 2p+1; maxnodes /
  * maxrows / maxgroups: most FE nodes, output rows and groups of one segment
  * (a segment marches over the whole groups covering its rows' FE support);
- * maxpieces: most pieces of one task.  For d = 0,1 the rows are staged by 1-D
+ * maxpieces: most pieces of one task; wpc: warps (tasks) per CTA -- 8 (two CTAs
+ * per SM), 16 (one CTA per SM, the segment tables are shared by twice as many
+ * warps: longer segments) or 4 (required for p = 4).  For d = 0,1 the rows are staged by 1-D
  * bulk async copies (TMA): the value array of X must then be readable up to the
  * next 16-byte boundary past its end.                                        */
 int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY, double* Yvals,
@@ -309,7 +311,8 @@ int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY,
                     const void* jrec, const double* cpad, const int32_t* grp,
                     const int32_t* slo, const int32_t* shi, const int32_t* tasks,
                     int32_t ntask, const int32_t* seg, int32_t nseg, int32_t maxnodes,
-                    int32_t maxrows, int32_t maxgroups, int32_t maxpieces, void* stream);
+                    int32_t maxrows, int32_t maxgroups, int32_t maxpieces, int32_t wpc,
+                    void* stream);
 
 /* ---- windowed-CSR operators (no column array: 8 B per non-zero) ---------- */
 /* y = C x  (MatMult inside KSP, common.py:1255-1258; M*U, common.py:379,1259) */

@@ -89,7 +89,7 @@ SIGNATURES = {
     "tg_ptap_march": [PW, c_vp, PW, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
                       c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
     "tg_ptap_march_w": [PW, c_vp, PW, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
-                        c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
+                        c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
     "tg_win_export_vals": [PW, c_vp, c_vp, c_vp],
     "tg_win_import_vals": [PW, c_vp, c_vp, c_vp],
     "tg_win_storage": [PW, C.POINTER(c_i64)],

@@ -681,7 +681,7 @@ extern "C" int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg
                                const int32_t* shi, const int32_t* tasks, int32_t ntask,
                                const int32_t* seg, int32_t nseg, int32_t maxnodes,
                                int32_t maxrows, int32_t maxgroups, int32_t maxpieces,
-                               void* stream) {
+                               int32_t wpc, void* stream) {
   TG_REQUIRE(h_wX->dim >= 2 && h_wX->dim <= 3, "march PtAP needs a 2-D or 3-D patch");
   TG_REQUIRE(d >= 0 && d < h_wX->dim, "direction");
   TG_REQUIRE(p >= 1 && p <= 4, "degree 1..4");
@@ -711,19 +711,28 @@ extern "C" int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg
   R.tasks = tasks;
   R.seg = seg;
   constexpr int NS = 3;
-  const int WPC = (p >= 4) ? 4 : 8;
+  // warps per CTA: 8 (two CTAs per SM) or 16 (one CTA per SM: the segment tables are
+  // shared by twice as many warps, so segments can be about twice as long)
+  TG_REQUIRE(p >= 4 ? wpc == 4 : (wpc == 8 || wpc == 16), "warps per CTA: 4 (p = 4), 8 or 16");
+  const bool wide = wpc == 16;
+  const int WPC = wpc;
   size_t smem = (size_t)WPC * ((NS * (32 * GMAX + R.stgpad) + 2 * 32 + NS + NS * 16 + 1) & ~1) * 8 +
                 (size_t)maxnodes * ((p + 4) * 8 + 4 + 16) + (size_t)maxrows * 16 +
                 (size_t)(maxgroups + 1) * 4 + 16;
   TG_REQUIRE(smem <= 220 * 1024, "stage ring + tables too large for shared memory");
   dim3 grid((unsigned)tg_cdiv(ntask, WPC), (unsigned)nseg, 1);
-#define TGW_LAUNCH2(PP, DD)                                                                     \
+#define TGW_LAUNCH3(PP, DD, W_, MB_)                                                            \
   {                                                                                             \
-    constexpr int W_ = (PP >= 4) ? 4 : 8, MB_ = (PP >= 4) ? 3 : 2;                              \
     TG_CHECK(cudaFuncSetAttribute(k_ptap_march_w<PP, DD, NS, W_, MB_>,                          \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
     k_ptap_march_w<PP, DD, NS, W_, MB_><<<grid, W_ * 32, smem, tg_stream(stream)>>>(            \
         tg_win_dev(h_wX), Xvals, tg_win_dev(h_wY), Yvals, R);                                   \
+  }
+#define TGW_LAUNCH2(PP, DD)                                                                     \
+  {                                                                                             \
+    if (PP >= 4) TGW_LAUNCH3(PP, DD, 4, 3)                                                      \
+    else if (wide) TGW_LAUNCH3(PP, DD, 16, 1)                                                   \
+    else TGW_LAUNCH3(PP, DD, 8, 2)                                                              \
   }
 #define TGW_LAUNCH(PP)                                                                          \
   {                                                                                             \
@@ -737,6 +746,7 @@ extern "C" int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg
   }
 #undef TGW_LAUNCH
 #undef TGW_LAUNCH2
+#undef TGW_LAUNCH3
   TG_LAUNCH_CHECK();
   return 0;
 }

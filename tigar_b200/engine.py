@@ -905,10 +905,16 @@ class TensorPatch(object):
                          for a_, b_ in zip(gA, gB)]
                 # shared-memory budget of two resident CTAs (tg_ptap_march_w: NS = 3 ring
                 # stages of 32*GMAX doubles per warp, 8 warps -- 4 for p = 4)
-                wpc = 4 if Dd["p"] >= 4 else 8
                 stgd = 32 * Dd["GMAX"] + 10 * int(tasks[:, 0].max()) + 4
-                budget = 115712 - wpc * (3 * stgd + 64 + 3 + 48) * 8 - 2048
-                nodemax = max(32, min(self.MARCH_NODEMAX, budget // ((Dd["p"] + 4) * 8 + 20)))
+                warpb = (3 * stgd + 64 + 3 + 48 + 1) * 8
+                pernode = (Dd["p"] + 4) * 8 + 20
+                # 16 warps per CTA (one CTA per SM) share one table copy: longer segments;
+                # needs room for the ring of 16 warps plus a useful table
+                wide = (Dd["p"] <= 3 and os.environ.get("TIGAR_B200_MARCH_WPC", "16") != "8"
+                        and 16 * warpb + 100 * pernode + 4096 <= 220 * 1024)
+                wpc, ncta = (4, 2) if Dd["p"] >= 4 else ((16, 1) if wide else (8, 2))
+                budget = min(220 * 1024, (233472 - 1024 * ncta) // ncta) - wpc * warpb - 2048
+                nodemax = max(32, min(self.MARCH_NODEMAX, budget // pernode))
                 if max(nodes) <= nodemax or nsegw >= self.ncp[d]:
                     break
                 nsegw += 1
@@ -918,7 +924,7 @@ class TensorPatch(object):
             passes.append(dict(wX=wX, wY=wY, d=d, KAmax=KAmax, maxlines=maxlines, stage=stage,
                                tasks=dev.from_np(tasks.ravel()), ntask=len(tasks), nsegw=nsegw,
                                maxnodes=maxnodes, maxrows=maxrows, maxgroups=maxgroups,
-                               maxpieces=int(tasks[:, 0].max()),
+                               maxpieces=int(tasks[:, 0].max()), wpc=wpc,
                                segw=dev.from_np(np.array(segw, dtype=np.int32)),
                                outd=outd, nga=len(ga) - 1, ngb=len(gb) - 1, nseg=nseg,
                                ga=dev.from_np(np.array(ga, dtype=np.int32)),
@@ -989,7 +995,7 @@ class TensorPatch(object):
                                           dev.ptr(D["cpad"]), dev.ptr(D["grp"]), dev.ptr(D["slo"]),
                                           dev.ptr(D["shi"]), dev.ptr(P_["tasks"]), P_["ntask"],
                                           dev.ptr(P_["segw"]), P_["nsegw"], P_["maxnodes"],
-                                          P_["maxrows"], P_["maxgroups"], P_["maxpieces"], dev.stream()))
+                                          P_["maxrows"], P_["maxgroups"], P_["maxpieces"], P_["wpc"], dev.stream()))
                 X = Y
                 if keep:
                     stages.append(WinMatrix(P_["wY"], Y))

@@ -32,7 +32,7 @@ for rep in range(4):
                                       dev.ptr(D["cpad"]), dev.ptr(D["grp"]), dev.ptr(D["slo"]),
                                       dev.ptr(D["shi"]), dev.ptr(P_["tasks"]), P_["ntask"],
                                       dev.ptr(P_["segw"]), P_["nsegw"], P_["maxnodes"],
-                                      P_["maxrows"], P_["maxgroups"], P_["maxpieces"], dev.stream()))
+                                      P_["maxrows"], P_["maxgroups"], P_["maxpieces"], P_["wpc"], dev.stream()))
         else:
           check(lib.tg_ptap_march(P_["wX"].ref(), dev.ptr(X), P_["wY"].ref(), dev.ptr(Y),
                                 P_["d"], D["p"], D["KA"], P_["KAmax"], dev.ptr(D["first"]),
