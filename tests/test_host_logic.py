@@ -220,3 +220,40 @@ def test_gateaux_derivative_matches_finite_difference():
     assert abs(ev(J.terms[((0, 0, 0), (0, 0, 0))], vals) - math.cos(0.3) * 1.7) < 1e-14
     with pytest.raises(ValueError):
         U.gateaux(U.Form([((U.Tensor(U.Scalar({(None, U.ZERO3): S.ONE})) * v).a[()], None)]), 11)
+
+
+def test_march_task_packing_covers_every_fibre_once():
+    """Warp tasks of tg_ptap_march_w (engine.TensorPatch._march_tasks is pure
+    numpy): every fibre (line, column offset) belongs to exactly one piece, no
+    task exceeds a warp or MARCH_MAXSUB pieces, pieces wider than a warp are cut
+    along the second direction only."""
+    import importlib.util
+    import os
+    import re
+    import textwrap
+    import numpy as np
+    src = open(os.path.join(os.path.dirname(__file__), "..", "tigar_b200", "engine.py")).read()
+    i = src.index("    @classmethod\n    def _march_tasks")
+    j = src.index("    def ptap_march(self, A, keep=False):")
+    ns = {"np": np}
+    exec("class X(object):\n    MARCH_MAXSUB = 8\n" + src[i:j], ns)
+    X = ns["X"]
+    for lena, lenb in [(np.array([4, 4, 4, 7, 4, 4, 7, 4, 4, 4]), np.array([4, 5, 6, 7, 7, 6, 5, 4])),
+                       (np.array([5, 5, 5, 9] * 6 + [5]), np.ones(1, np.int64)),
+                       (np.array([3, 5, 3, 5, 3]), np.array([9, 5, 5, 5, 9])),
+                       (np.array([7] * 5), np.array([7] * 5))]:
+        T = X._march_tasks(lena, lenb)
+        seen = {}
+        for row in T:
+            npc = row[0]
+            assert 1 <= npc <= 8
+            lanes = 0
+            for k in range(npc):
+                ra, rb, cb0, ncb = row[4 + 4 * k:8 + 4 * k]
+                assert ncb >= 1 and cb0 + ncb <= lenb[rb]
+                lanes += lena[ra] * ncb
+                for cb in range(cb0, cb0 + ncb):
+                    assert (ra, rb, cb) not in seen
+                    seen[(ra, rb, cb)] = 1
+            assert lanes <= 32
+        assert len(seen) == len(lena) * int(lenb.sum())
