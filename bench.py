@@ -288,8 +288,9 @@ def run_ours(args):
     bytes_per_launch = spmv_bytes(W)
     avg_ms = spmv_ms.value / max(spmv_n.value, 1)
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": ("k_sell_spmv<7,true>" if W.layout == 1 else "k_win_spmv<true>")
-                + " (CG matvec + p.Ap partials)",
+    kname = {0: "k_win_spmv<true>", 1: "k_win_spmv_tma<true>", 2: "k_sell_spmv<7,true>", 3: "k_win_spmv_pf<true>"}[
+        int(lib.tg_last_spmv_kind())]
+    roofline = {"bound": "hbm", "kernel": kname + " (CG matvec + p.Ap partials)",
                 "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None,
                 "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,

@@ -318,6 +318,10 @@ int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY,
 /* y = C x  (MatMult inside KSP, common.py:1255-1258; M*U, common.py:379,1259) */
 int tg_win_spmv(const tg_win* h_w, const double* vals, const double* x, double* y,
                 void* stream);
+/* which kernel the last windowed SpMV used: 0 direct-load (k_win_spmv), 1 TMA-staged
+ * rows + shared-memory x tiles (k_win_spmv_tma), 2 SELL layout (k_sell_spmv),
+ * 3 direct-load with per-warp cp.async row prefetch (k_win_spmv_pf, the default)  */
+int tg_last_spmv_kind(void);
 /* y = C x and out1[0] = sum_r x[xoff+r] y[r]; scratch: tg_cg_scratch_len()   */
 int tg_win_spmv_dot(const tg_win* h_w, const double* vals, const double* x, int64_t xoff,
                     double* y, double* scratch, double* out1, void* stream);
@@ -348,6 +352,9 @@ int tg_zero_rows_cols(const int64_t* rowptr, const int32_t* cols, double* vals,
                       int64_t nrows, const uint8_t* mask, double diag, void* stream);
 /* b[zeroDofs] = 0 (common.py:1154-1158) */
 int tg_zero_entries(double* b, const uint8_t* mask, int64_t n, void* stream);
+/* mask[idx[k]] = 1 for the zeroDofs list (device int64 indices, duplicates allowed;
+ * mask must be zero-initialised): the row/column masks of the calls above        */
+int tg_mask_set(uint8_t* mask, const int64_t* idx, int64_t nidx, int64_t n, void* stream);
 
 /* dinv[i] = 1/C[i,i] */
 int tg_diag_inv(const int64_t* rowptr, const int32_t* cols, const double* vals,

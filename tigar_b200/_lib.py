@@ -46,6 +46,7 @@ SIGNATURES = {
     "tg_version": [],
     "tg_device_sm_count": [],
     "tg_launch_count": [],
+    "tg_last_spmv_kind": [],
     "tg_bspline_eval_batch": [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32,
                               c_vp, c_i64, c_vp, c_vp, c_vp, c_vp],
     "tg_fe_nodes_1d": [c_vp, c_i32, c_i32, c_vp, c_vp],
@@ -95,6 +96,7 @@ SIGNATURES = {
     "tg_win_storage": [PW, C.POINTER(c_i64)],
     "tg_zero_rows_cols": [c_vp, c_vp, c_vp, c_i64, c_vp, c_dbl, c_vp],
     "tg_zero_entries": [c_vp, c_vp, c_i64, c_vp],
+    "tg_mask_set": [c_vp, c_vp, c_i64, c_i64, c_vp],
     "tg_diag_inv": [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp],
     "tg_cg_scratch_len": [],
     "tg_solve_cg": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_i32, c_i32,

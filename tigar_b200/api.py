@@ -524,6 +524,18 @@ class FieldListSpline(AbstractMultiFieldSpline):
 
 
 # ---------------------------------------------------------------- analysis
+def _sorted_unique(z):
+    """np.unique for an int64 index list (sort + adjacent compare; numpy's hash
+    based path costs 30 ms on the 4e5 side DoFs of a 256^3 patch)."""
+    z = np.sort(np.asarray(z, dtype=np.int64).ravel())
+    if z.size == 0:
+        return z
+    keep = np.empty(z.size, dtype=bool)
+    keep[0] = True
+    np.not_equal(z[1:], z[:-1], out=keep[1:])
+    return z[keep]
+
+
 class ExtractedSpline(object):
     """common.py:667-1433."""
 
@@ -567,7 +579,7 @@ class ExtractedSpline(object):
         self.VE, self.VE_control = generator.VE, generator.VE_control
         P = self._controlNetArg if self._controlNetArg is not None else generator.controlNet()
         self._set_control_net(P)
-        self.zeroDofs = np.unique(np.array(generator.zeroDofs, dtype=np.int64))
+        self.zeroDofs = _sorted_unique(np.array(generator.zeroDofs, dtype=np.int64))
         self._M = None
 
     def initFromFilesystem(self, dirname, quadDeg, comm, mesh=None):
@@ -595,7 +607,7 @@ class ExtractedSpline(object):
         self.V_control = FunctionSpace(self, 1, control=True)
         self.VE = self.VE_control = ("Lagrange", self.p_control)
         self._set_control_net(data["P"])
-        self.zeroDofs = np.unique(data["zeroDofs"].astype(np.int64))
+        self.zeroDofs = _sorted_unique(data["zeroDofs"].astype(np.int64))
         self._M = None
 
     def _set_control_net(self, P):

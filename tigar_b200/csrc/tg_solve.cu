@@ -81,6 +81,26 @@ extern "C" int tg_zero_entries(double* b, const uint8_t* mask, int64_t n, void* 
   return 0;
 }
 
+// zeroDofs list -> 0/1 mask over the IGA DoFs (the list is what the reference
+// hands to zeroRowsColumns / setValues, common.py:1154-1158,1199-1200; duplicates
+// are harmless)
+__global__ void k_mask_set(uint8_t* __restrict__ mask, const int64_t* __restrict__ idx,
+                           int64_t nidx, int64_t n) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < nidx) {
+    const int64_t i = idx[t];
+    if (i >= 0 && i < n) mask[i] = 1;
+  }
+}
+
+extern "C" int tg_mask_set(uint8_t* mask, const int64_t* idx, int64_t nidx, int64_t n,
+                           void* stream) {
+  if (nidx == 0) return 0;
+  k_mask_set<<<(unsigned)tg_cdiv(nidx, 256), 256, 0, tg_stream(stream)>>>(mask, idx, nidx, n);
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
 // local row r is global row row0+r (column indices are global/extended)
 __global__ void k_diag_inv(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ cols,
                            const double* __restrict__ vals, int64_t nrows, int64_t row0,

@@ -163,39 +163,288 @@ k_win_spmv(TgWin w, const double* __restrict__ vals, const double* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------
-// TMA-staged variant: the value array of a windowed matrix is one contiguous
-// stream in row order, so each CTA owns a contiguous range of rows and a
-// producer warp pulls it through a ring of shared-memory stages with 1-D bulk
-// async copies (cp.async.bulk, SASS UBLKCP) completing on mbarriers; eight
-// consumer warps each reduce one row per stage out of shared memory while x is
-// gathered through L1/L2.  Keeps NS x 22 KB per CTA in flight, independent of
-// occupancy.
+// Direct kernel with a per-warp row prefetch: while a warp reduces row r out of
+// its private shared-memory buffer, the NEXT row it will process (r+8, or its
+// first row of the CTA's next item) is already streaming in by 8-byte cp.async
+// (LDGSTS).  Bytes in flight per SM go from 32 warps x 1 KB (U=4 chunk loads) to
+// 32 warps x 2.7 KB, with no cross-warp synchronisation.
+__device__ __forceinline__ void tg_cp8(uint32_t dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <bool DOT>
+__global__ void __launch_bounds__(TG_WS_BLOCK, 4)
+k_win_spmv_pf(TgWin w, const double* __restrict__ vals, const double* __restrict__ x,
+              int64_t xoff, double* __restrict__ y, int nchunk, int nitems, int w0max, int RB,
+              double* __restrict__ part) {
+  extern __shared__ __align__(16) double rowbuf[];            // [8 warps][2][RB]
+  __shared__ double sh[32];
+  __shared__ int xtab[TG_WS_MAXTAB];
+  __shared__ int tab_len1, tab_len2;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nr0 = w.nr[0], nr1 = w.nr[1];
+  const int nc0 = w.nc[0];
+  const int64_t pl = (int64_t)nc0 * w.nc[1];
+  double* mybuf = rowbuf + (size_t)wid * 2 * RB;
+  const uint32_t mybuf_u32 = tg_smem_u32(mybuf);
+  if (threadIdx.x == 0) {
+    tab_len1 = -1;
+    tab_len2 = -1;
+  }
+  __syncthreads();
+
+  // value-array address and length of row r0 of item `item`; false if the item has no such row
+  auto locate = [&](int item, int r0, const double*& av, int& n) -> bool {
+    const int line = item / nchunk;
+    const int ch = item - line * nchunk;
+    const int rend = min(nr0, ch * TG_WS_ROWS + TG_WS_ROWS);
+    r0 += ch * TG_WS_ROWS;
+    if (r0 >= rend) return false;
+    const int r2 = line / nr1, r1 = line - r2 * nr1;
+    int len1 = 1, len2 = 1;
+    int64_t linebase = 0;
+    if (w.dim > 1) len1 = __ldg(w.hi[1] + r1) - __ldg(w.lo[1] + r1) + 1;
+    if (w.dim > 2) len2 = __ldg(w.hi[2] + r2) - __ldg(w.lo[2] + r2) + 1;
+    if (w.dim > 1) {
+      const int64_t T0 = __ldg(w.S[0] + nr0);
+      int64_t inner = __ldg(w.S[1] + r1) * len2;
+      if (w.dim > 2) inner += __ldg(w.S[1] + nr1) * __ldg(w.S[2] + r2);
+      linebase = T0 * inner;
+    }
+    const int tile = len1 * len2;
+    av = vals + linebase + __ldg(w.S[0] + r0) * tile;
+    n = (__ldg(w.hi[0] + r0) - __ldg(w.lo[0] + r0) + 1) * tile;
+    return true;
+  };
+  // the row this warp processes after (item, local row k): (item, k+8) or the first row
+  // it owns in a later item of this CTA
+  auto advance = [&](int& item, int& k, const double*& av, int& n) -> bool {
+    k += TG_WS_BLOCK / 32;
+    if (k < TG_WS_ROWS && locate(item, k, av, n)) return true;
+    for (item += gridDim.x; item < nitems; item += gridDim.x) {
+      k = wid;
+      if (locate(item, k, av, n)) return true;
+    }
+    return false;
+  };
+  auto prefetch = [&](const double* av, int n, int buf) {
+    const uint32_t dst = mybuf_u32 + (uint32_t)(buf * RB * 8);
+    for (int p = lane; p < n; p += 32) tg_cp8(dst + 8u * p, av + p);
+  };
+
+  // prime the pipeline with this warp's first row
+  int pitem = blockIdx.x - gridDim.x, pk = TG_WS_ROWS;        // "before the first item"
+  const double* pav = nullptr;
+  int pn = 0;
+  bool pvalid = advance(pitem, pk, pav, pn);
+  if (pvalid) prefetch(pav, pn, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  int cbuf = 0;
+
+  double dot = 0.0;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int line = item / nchunk;
+    const int ch = item - line * nchunk;
+    const int r2 = line / nr1;
+    const int r1 = line - r2 * nr1;
+    int lo1 = 0, len1 = 1, lo2 = 0, len2 = 1;
+    if (w.dim > 1) {
+      lo1 = __ldg(w.lo[1] + r1);
+      len1 = __ldg(w.hi[1] + r1) - lo1 + 1;
+    }
+    if (w.dim > 2) {
+      lo2 = __ldg(w.lo[2] + r2);
+      len2 = __ldg(w.hi[2] + r2) - lo2 + 1;
+    }
+    const int tile = len1 * len2;
+    const int ntab = w0max * tile;
+    const bool usetab = ntab <= TG_WS_MAXTAB;
+    if (usetab && (tab_len1 != len1 || tab_len2 != len2)) {      // uniform branch
+      __syncthreads();
+      for (int p = threadIdx.x; p < ntab; p += TG_WS_BLOCK) {
+        int c0 = p % w0max, t = p / w0max, c1 = t % len1, c2 = t / len1;
+        xtab[p] = c0 + nc0 * c1 + (int)pl * c2;
+      }
+      if (threadIdx.x == 0) {
+        tab_len1 = len1;
+        tab_len2 = len2;
+      }
+      __syncthreads();
+    }
+    const int rend = min(nr0, ch * TG_WS_ROWS + TG_WS_ROWS);
+    const double* xb = x + (int64_t)nc0 * lo1 + pl * lo2;
+    for (int r0 = ch * TG_WS_ROWS + wid; r0 < rend; r0 += TG_WS_BLOCK / 32) {
+      // (item, r0) is the row primed in buffer cbuf; start the following one
+      pvalid = advance(pitem, pk, pav, pn);
+      __syncwarp();                                   // everyone done with buffer cbuf^1
+      if (pvalid) prefetch(pav, pn, cbuf ^ 1);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      __syncwarp();
+      const double* sv = mybuf + cbuf * RB;
+      const int64_t row = r0 + (int64_t)nr0 * line;
+      const int lo0 = __ldg(w.lo[0] + r0);
+      const int len0 = __ldg(w.hi[0] + r0) - lo0 + 1;
+      const double* xr = xb + lo0;
+      const int n = len0 * tile;
+      double acc = 0.0;
+      if (usetab && len0 == w0max) {
+        double acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        int p = lane;
+        for (; p + 96 < n; p += 128) {
+          const double x0 = xr[xtab[p]], x1 = xr[xtab[p + 32]], x2 = xr[xtab[p + 64]],
+                       x3 = xr[xtab[p + 96]];
+          acc += sv[p] * x0;
+          acc1 += sv[p + 32] * x1;
+          acc2 += sv[p + 64] * x2;
+          acc3 += sv[p + 96] * x3;
+        }
+        {
+          const bool b0 = p < n, b1 = p + 32 < n, b2 = p + 64 < n;
+          const double x0 = b0 ? xr[xtab[p]] : 0.0, x1 = b1 ? xr[xtab[p + 32]] : 0.0,
+                       x2 = b2 ? xr[xtab[p + 64]] : 0.0;
+          if (b0) acc += sv[p] * x0;
+          if (b1) acc1 += sv[p + 32] * x1;
+          if (b2) acc2 += sv[p + 64] * x2;
+        }
+        acc += (acc1 + acc2) + acc3;
+      } else {
+        for (int p = lane; p < n; p += 32) {
+          int c0 = p % len0, t = p / len0, c1 = t % len1, c2 = t / len1;
+          acc += sv[p] * xr[c0 + nc0 * c1 + pl * c2];
+        }
+      }
+      cbuf ^= 1;
+      acc = tg_warp_sum(acc);
+      if (lane == 0) {
+        y[row] = acc;
+        if (DOT) dot += x[xoff + row] * acc;
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (DOT) {
+    dot = tg_block_sum_ws(dot, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = dot;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// TMA-staged variant (the default for row-major windows that fit): the rows of
+// one (r1,r2) line are one contiguous run of the value array, so a producer warp
+// pulls stages of TG_TMA_ROWS consecutive rows through a ring of shared-memory
+// buffers with 1-D bulk async copies (cp.async.bulk, SASS UBLKCP) completing on
+// mbarriers, and eight consumer warps each reduce one row per stage.  The x
+// entries a stage touches -- the union of its rows' column boxes, (rows+w0-1) x
+// len1 x len2 values -- are staged in shared memory too (register-prefetched
+// one stage ahead, double buffered), so the consumers never wait on a global
+// load: the first TMA version gathered x through L1/L2 and was latency-bound
+// there (0.34 of HBM peak, profiles/r1_ncu_spmv_tma.txt).  NS x 22 KB per CTA in
+// flight, independent of occupancy.
 #define TG_TMA_ROWS 8
 #define TG_TMA_CONSUMERS (TG_TMA_ROWS * 32)
 #define TG_TMA_THREADS (TG_TMA_CONSUMERS + 32)
+#define TG_TMA_XW 16          // stride of the x tile's first direction (>= rows + w0max - 1)
+#define TG_TMA_XPT 4          // x-tile elements prefetched per consumer thread
+
+struct TgStage {              // one stage = rows [r0a, r0b) of line (r1, r2)
+  int ch, r1, r2, r0a, r0b, len1, len2, tile, c0lo, cw;
+  long long line, xline, linebase, start, end;
+};
+
+// line-dependent part (recomputed only when the stage sequence enters a new line)
+__device__ __forceinline__ void tg_stage_line(const TgWin& w, TgStage& d, long long pl) {
+  const int nr0 = w.nr[0], nr1 = w.nr[1];
+  int lo1 = 0, lo2 = 0;
+  d.len1 = 1;
+  d.len2 = 1;
+  d.linebase = 0;
+  if (w.dim > 1) {
+    lo1 = __ldg(w.lo[1] + d.r1);
+    d.len1 = __ldg(w.hi[1] + d.r1) - lo1 + 1;
+  }
+  if (w.dim > 2) {
+    lo2 = __ldg(w.lo[2] + d.r2);
+    d.len2 = __ldg(w.hi[2] + d.r2) - lo2 + 1;
+  }
+  d.tile = d.len1 * d.len2;
+  if (w.dim > 1) {
+    const long long T0 = __ldg(w.S[0] + nr0);
+    long long inner = __ldg(w.S[1] + d.r1) * d.len2;
+    if (w.dim > 2) inner += __ldg(w.S[1] + nr1) * __ldg(w.S[2] + d.r2);
+    d.linebase = T0 * inner;
+  }
+  d.xline = (long long)w.nc[0] * lo1 + pl * lo2;
+}
+// first-direction window data of every row of a line, staged in shared memory once
+struct TgDir0 {
+  const int* lo;            // [nr0]
+  const int* len;           // [nr0]
+  const long long* S;       // [nr0 + 1]
+};
+// chunk-dependent part
+__device__ __forceinline__ void tg_stage_chunk(const TgWin& w, TgStage& d, const TgDir0& z) {
+  d.r0a = d.ch * TG_TMA_ROWS;
+  d.r0b = min(w.nr[0], d.r0a + TG_TMA_ROWS);
+  d.c0lo = z.lo[d.r0a];
+  d.cw = z.lo[d.r0b - 1] + z.len[d.r0b - 1] - d.c0lo;
+  d.start = d.linebase + z.S[d.r0a] * d.tile;
+  d.end = d.linebase + z.S[d.r0b] * d.tile;
+}
+__device__ __forceinline__ TgStage tg_stage_first(const TgWin& w, long long g, int spl,
+                                                  long long pl, const TgDir0& z) {
+  TgStage d;
+  d.line = g / spl;
+  d.ch = (int)(g - d.line * spl);
+  d.r2 = (int)(d.line / w.nr[1]);
+  d.r1 = (int)(d.line - (long long)d.r2 * w.nr[1]);
+  tg_stage_line(w, d, pl);
+  tg_stage_chunk(w, d, z);
+  return d;
+}
+// returns true if the line changed
+__device__ __forceinline__ bool tg_stage_next(const TgWin& w, TgStage& d, int spl, long long pl,
+                                              const TgDir0& z) {
+  bool newline = false;
+  if (++d.ch == spl) {
+    d.ch = 0;
+    d.line++;
+    if (++d.r1 == w.nr[1]) {
+      d.r1 = 0;
+      d.r2++;
+    }
+    tg_stage_line(w, d, pl);
+    newline = true;
+  }
+  tg_stage_chunk(w, d, z);
+  return newline;
+}
 
 template <bool DOT>
 __global__ void __launch_bounds__(TG_TMA_THREADS)
 k_win_spmv_tma(TgWin w, const double* __restrict__ vals, const double* __restrict__ x,
-               int64_t xoff, double* __restrict__ y, int64_t nrows, int w0max, int NS,
-               int stage_doubles, double* __restrict__ part) {
+               int64_t xoff, double* __restrict__ y, long long nstage_tot, int spl, int w0max,
+               int maxtile, int NS, int stage_doubles, double* __restrict__ part) {
   extern __shared__ __align__(128) unsigned char tsm[];
   double* bufs = (double*)tsm;                                       // [NS][stage_doubles]
-  long long* offs = (long long*)(bufs + (size_t)NS * stage_doubles);  // [NS][TG_TMA_ROWS + 2]
-  uint64_t* full = (uint64_t*)(offs + (size_t)NS * (TG_TMA_ROWS + 2));
+  const int XT = TG_TMA_XW * TG_TMA_XPT * 16;                        // 64 groups x 16 columns
+  double* xs = bufs + (size_t)NS * stage_doubles;                    // [2][XT]
+  uint64_t* full = (uint64_t*)(xs + 2 * XT);
   uint64_t* empty = full + NS;
-  int* xtab = (int*)(empty + NS);                                    // [TG_WS_MAXTAB]
+  long long* gtab = (long long*)(empty + NS);                        // [2][64] x offset of group g
+  long long* S0s = gtab + 2 * 64;                                    // [nr0 + 1]
+  int* lo0s = (int*)(S0s + w.nr[0] + 1);                             // [nr0]
+  int* len0s = lo0s + w.nr[0];                                       // [nr0]
+  int* xtab = len0s + w.nr[0];                                       // [w0max * maxtile]
   __shared__ double sh[32];
-  __shared__ int tab_len1, tab_len2;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int nr0 = w.nr[0], nr1 = w.nr[1];
+  const int nr0 = w.nr[0];
   const int nc0 = w.nc[0];
-  const int64_t pl = (int64_t)nc0 * w.nc[1];
-  // contiguous row range of this CTA, in whole stages
-  const int64_t nstage_tot = (nrows + TG_TMA_ROWS - 1) / TG_TMA_ROWS;
-  const int64_t st0 = nstage_tot * blockIdx.x / gridDim.x;
-  const int64_t st1 = nstage_tot * (blockIdx.x + 1) / gridDim.x;
+  const long long pl = (long long)nc0 * w.nc[1];
+  // contiguous range of stages of this CTA
+  const long long st0 = nstage_tot * blockIdx.x / gridDim.x;
+  const long long st1 = nstage_tot * (blockIdx.x + 1) / gridDim.x;
   const int nst = (int)(st1 - st0);
 
   if (tid == 0) {
@@ -203,125 +452,118 @@ k_win_spmv_tma(TgWin w, const double* __restrict__ vals, const double* __restric
       tg_mbar_init(&full[s], 1);
       tg_mbar_init(&empty[s], TG_TMA_ROWS);
     }
-    tab_len1 = -1;
-    tab_len2 = -1;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // x-tile offset of window position p of a full-width row (relative to the row's lo0)
+  for (int p = tid; p < w0max * maxtile; p += TG_TMA_THREADS)
+    xtab[p] = (p / w0max) * TG_TMA_XW + p % w0max;
+  for (int r = tid; r <= w.nr[0]; r += TG_TMA_THREADS) {
+    S0s[r] = __ldg(w.S[0] + r);
+    if (r < w.nr[0]) {
+      const int l = __ldg(w.lo[0] + r);
+      lo0s[r] = l;
+      len0s[r] = __ldg(w.hi[0] + r) - l + 1;
+    }
+  }
   __syncthreads();
+  TgDir0 z;
+  z.lo = lo0s;
+  z.len = len0s;
+  z.S = S0s;
 
   double dot = 0.0;
   if (wid == TG_TMA_ROWS) {
-    // ---------------- producer warp ----------------
-    const long long T0 = __ldg(w.S[0] + nr0);
-    const long long T1 = (w.dim > 1) ? __ldg(w.S[1] + nr1) : 1;
-    const long long T2 = (w.dim > 2) ? __ldg(w.S[2] + w.nr[2]) : 1;
-    const long long nnz_total = T0 * T1 * T2;
-    for (int t = 0; t < nst; t++) {
-      const int s = t % NS;
-      const int k = t / NS;
-      if (k > 0) tg_mbar_wait(&empty[s], (uint32_t)((k - 1) & 1));
-      const int64_t rb = (st0 + t) * TG_TMA_ROWS;
-      const int64_t re = min(rb + (int64_t)TG_TMA_ROWS, nrows);
-      long long* o = offs + (size_t)s * (TG_TMA_ROWS + 2);
-      // row offsets in closed form from the 1-D prefix sums (L1-resident):
-      // S0[r0]*len1*len2 + T0*(S1[r1]*len2 + T1*S2[r2]); no DRAM round trip.
-      long long v = 0;
-      if (lane <= (int)(re - rb)) {
-        const int64_t row = rb + lane;
-        if (row >= nrows) {
-          v = nnz_total;
-        } else {
-          const unsigned line = (unsigned)(row / nr0);
-          const int r0 = (int)(row - (int64_t)line * nr0);
-          const int r2 = (int)(line / (unsigned)nr1), r1 = (int)(line - (unsigned)r2 * nr1);
-          long long len1 = 1, len2 = 1, inner = 0;
-          if (w.dim > 2) len2 = __ldg(w.hi[2] + r2) - __ldg(w.lo[2] + r2) + 1;
-          if (w.dim > 1) {
-            len1 = __ldg(w.hi[1] + r1) - __ldg(w.lo[1] + r1) + 1;
-            inner = __ldg(w.S[1] + r1) * len2;
-            if (w.dim > 2) inner += T1 * __ldg(w.S[2] + r2);
-          }
-          v = __ldg(w.S[0] + r0) * len1 * len2 + T0 * inner;
-        }
-      }
-      const long long start = __shfl_sync(0xffffffffu, v, 0);
-      const long long end = __shfl_sync(0xffffffffu, v, (int)(re - rb));
-      const long long astart = start & ~1LL;                    // 16-byte aligned
-      if (lane <= TG_TMA_ROWS) o[lane] = v - astart;
-      __syncwarp();
-      if (lane == 0) {
-        const uint32_t bytes = (uint32_t)((((end - astart) * 8) + 15) & ~15LL);
+    // ---------------- producer warp (one lane) ----------------
+    if (lane == 0 && nst > 0) {
+      TgStage d = tg_stage_first(w, st0, spl, pl, z);
+      for (int t = 0; t < nst; t++) {
+        const int s = t % NS;
+        const int k = t / NS;
+        if (k > 0) tg_mbar_wait(&empty[s], (uint32_t)((k - 1) & 1));
+        const long long astart = d.start & ~1LL;                  // 16-byte aligned
+        const uint32_t bytes = (uint32_t)((((d.end - astart) * 8) + 15) & ~15LL);
         tg_mbar_expect_tx(&full[s], bytes);
         tg_bulk_g2s(bufs + (size_t)s * stage_doubles, vals + astart, bytes, &full[s]);
+        if (t + 1 < nst) tg_stage_next(w, d, spl, pl, z);
       }
     }
-  } else {
+  } else if (nst > 0) {
     // ---------------- consumer warps: one row per stage each ----------------
+    // x tile: thread tid owns tile slots tid + 256 j = (group tid/16 + 16 j, column tid%16)
+    const int xg = tid >> 4, xc = tid & 15;
+    double xr_[TG_TMA_XPT];
+    // gtab[g] = x offset of group g = (c1, c2) of the line's column box
+    auto build_gtab = [&](const TgStage& d, long long* gt) {
+      if (tid < 64) {
+        const int c2 = tid / d.len1, c1 = tid - c2 * d.len1;
+        gt[tid] = (tid < d.tile) ? (long long)nc0 * c1 + pl * c2 : -1;
+      }
+    };
+    auto xload = [&](const TgStage& d, const long long* gt) {
+      const double* xb = x + d.xline + d.c0lo + xc;
+#pragma unroll
+      for (int j = 0; j < TG_TMA_XPT; j++) {
+        const long long go = gt[xg + 16 * j];
+        xr_[j] = (go >= 0 && xc < d.cw) ? xb[go] : 0.0;
+      }
+    };
+    TgStage cur = tg_stage_first(w, st0, spl, pl, z), nxt;
+    int gsel = 0;                                  // gtab buffer of the current line
+    build_gtab(cur, gtab);
+    asm volatile("bar.sync 1, %0;" ::"n"(TG_TMA_CONSUMERS) : "memory");
+    xload(cur, gtab);
+#pragma unroll
+    for (int j = 0; j < TG_TMA_XPT; j++) xs[tid + TG_TMA_CONSUMERS * j] = xr_[j];
+    asm volatile("bar.sync 1, %0;" ::"n"(TG_TMA_CONSUMERS) : "memory");
     for (int t = 0; t < nst; t++) {
       const int s = t % NS;
       const int k = t / NS;
-      const int64_t rb = (st0 + t) * TG_TMA_ROWS;
-      const int64_t re = min(rb + (int64_t)TG_TMA_ROWS, nrows);
-      // window shape of the stage's first row decides the shared x-offset table
-      {
-        const unsigned line = (unsigned)(rb / nr0);
-        const int r2 = (int)(line / (unsigned)nr1), r1 = (int)(line - (unsigned)r2 * nr1);
-        int len1 = 1, len2 = 1;
-        if (w.dim > 1) len1 = __ldg(w.hi[1] + r1) - __ldg(w.lo[1] + r1) + 1;
-        if (w.dim > 2) len2 = __ldg(w.hi[2] + r2) - __ldg(w.lo[2] + r2) + 1;
-        const int ntab = w0max * len1 * len2;
-        if (ntab <= TG_WS_MAXTAB && (tab_len1 != len1 || tab_len2 != len2)) {
-          asm volatile("bar.sync 1, %0;" ::"n"(TG_TMA_CONSUMERS) : "memory");
-          for (int p = tid; p < ntab; p += TG_TMA_CONSUMERS) {
-            int c0 = p % w0max, tt = p / w0max, c1 = tt % len1, c2 = tt / len1;
-            xtab[p] = c0 + nc0 * c1 + (int)pl * c2;
-          }
-          if (tid == 0) {
-            tab_len1 = len1;
-            tab_len2 = len2;
-          }
+      const double* xt = xs + (t & 1) * XT;
+      const bool more = t + 1 < nst;
+      if (more) {
+        nxt = cur;
+        if (tg_stage_next(w, nxt, spl, pl, z)) {   // new line: its group table (other buffer)
+          gsel ^= 1;
+          build_gtab(nxt, gtab + 64 * gsel);
           asm volatile("bar.sync 1, %0;" ::"n"(TG_TMA_CONSUMERS) : "memory");
         }
+        xload(nxt, gtab + 64 * gsel);
       }
       tg_mbar_wait(&full[s], (uint32_t)(k & 1));
-      const int64_t row = rb + wid;
-      if (row < re) {
-        const long long* o = offs + (size_t)s * (TG_TMA_ROWS + 2);
-        const double* sv = bufs + (size_t)s * stage_doubles + o[wid];
-        const unsigned line = (unsigned)(row / nr0);
-        const int r0 = (int)(row - (int64_t)line * nr0);
-        const int r2 = (int)(line / (unsigned)nr1), r1 = (int)(line - (unsigned)r2 * nr1);
-        int lo1 = 0, len1 = 1, lo2 = 0, len2 = 1;
-        if (w.dim > 1) {
-          lo1 = __ldg(w.lo[1] + r1);
-          len1 = __ldg(w.hi[1] + r1) - lo1 + 1;
-        }
-        if (w.dim > 2) {
-          lo2 = __ldg(w.lo[2] + r2);
-          len2 = __ldg(w.hi[2] + r2) - lo2 + 1;
-        }
-        const int lo0 = __ldg(w.lo[0] + r0);
-        const int len0 = __ldg(w.hi[0] + r0) - lo0 + 1;
-        const double* xr = x + lo0 + (int64_t)nc0 * lo1 + pl * lo2;
-        const int n = len0 * len1 * len2;
+      const int r0 = cur.r0a + wid;
+      if (r0 < cur.r0b) {
+        const int lo0 = lo0s[r0];
+        const int len0 = len0s[r0];
+        const long long rstart = cur.start + (S0s[r0] - S0s[cur.r0a]) * cur.tile;
+        const double* sv = bufs + (size_t)s * stage_doubles + (rstart - (cur.start & ~1LL));
+        const int n = len0 * cur.tile;
+        const long long row = r0 + (long long)nr0 * cur.line;
         double acc = 0.0;
-        if (len0 == w0max && len1 == tab_len1 && len2 == tab_len2) {
-          double acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-          int p = lane;
-          for (; p + 96 < n; p += 128) {
-            double x0 = xr[xtab[p]], x1 = xr[xtab[p + 32]], x2 = xr[xtab[p + 64]],
-                   x3 = xr[xtab[p + 96]];
-            acc += sv[p] * x0;
-            acc1 += sv[p + 32] * x1;
-            acc2 += sv[p + 64] * x2;
-            acc3 += sv[p + 96] * x3;
+        if (cur.cw <= TG_TMA_XW) {
+          const double* xq = xt + (lo0 - cur.c0lo);
+          if (len0 == w0max) {
+            double acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+            int p = lane;
+            for (; p + 96 < n; p += 128) {
+              acc += sv[p] * xq[xtab[p]];
+              acc1 += sv[p + 32] * xq[xtab[p + 32]];
+              acc2 += sv[p + 64] * xq[xtab[p + 64]];
+              acc3 += sv[p + 96] * xq[xtab[p + 96]];
+            }
+            for (; p < n; p += 32) acc += sv[p] * xq[xtab[p]];
+            acc += (acc1 + acc2) + acc3;
+          } else {
+            for (int p = lane; p < n; p += 32) {
+              const int g = p / len0, c0 = p - g * len0;
+              acc += sv[p] * xq[g * TG_TMA_XW + c0];
+            }
           }
-          for (; p < n; p += 32) acc += sv[p] * xr[xtab[p]];
-          acc += (acc1 + acc2) + acc3;
-        } else {
+        } else {                       // window union wider than the tile: gather from global
+          const double* xg_ = x + cur.xline + lo0;
           for (int p = lane; p < n; p += 32) {
-            int c0 = p % len0, tt = p / len0, c1 = tt % len1, c2 = tt / len1;
-            acc += sv[p] * xr[c0 + nc0 * c1 + pl * c2];
+            const int g = p / len0, c0 = p - g * len0;
+            const int c2 = g / cur.len1, c1 = g - c2 * cur.len1;
+            acc += sv[p] * xg_[c0 + (long long)nc0 * c1 + pl * c2];
           }
         }
         acc = tg_warp_sum(acc);
@@ -332,6 +574,13 @@ k_win_spmv_tma(TgWin w, const double* __restrict__ vals, const double* __restric
       }
       __syncwarp();
       if (lane == 0) tg_mbar_arrive(&empty[s]);
+      if (more) {
+        double* dst = xs + ((t + 1) & 1) * XT;
+#pragma unroll
+        for (int j = 0; j < TG_TMA_XPT; j++) dst[tid + TG_TMA_CONSUMERS * j] = xr_[j];
+        cur = nxt;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TG_TMA_CONSUMERS) : "memory");
     }
   }
   if (DOT) {
@@ -341,51 +590,62 @@ k_win_spmv_tma(TgWin w, const double* __restrict__ vals, const double* __restric
 }
 
 static int g_tma_smem_ok = -1;
+static int g_last_spmv_kind = 0;      // 0 direct-load, 1 TMA-staged, 2 SELL
+extern "C" int tg_last_spmv_kind(void) { return g_last_spmv_kind; }
 
-// returns 1 if launched, 0 if the shape does not fit the staged kernel
+// returns 0; *launched = 1 if the staged kernel took the call
 static int tg_win_spmv_tma_try(const tg_win* h_w, const double* vals, const double* x,
                                int64_t xoff, double* y, double* part, cudaStream_t st,
                                int* launched) {
   *launched = 0;
-  // Opt-in: on B200 the staged kernel reaches ~34 % of HBM peak (consumer warps
-  // are latency-bound on the x gathers at 16 warps/SM, profiles/r1_ncu_spmv_tma.txt)
-  // against ~63 % for the direct-load kernel below, so the latter is the default.
-  if (!getenv("TIGAR_B200_TMA_SPMV")) return 0;
-  // largest row: w0max * max len1 * max len2 is not known on the host without the
-  // lo/hi arrays; S totals bound it: use nnz/nrows-free bound passed by the caller
-  if (h_w->maxrow <= 0 || (((uintptr_t)vals) & 15) != 0) return 0;
-  const int64_t nrows = tg_win_nrows(h_w);
-  if (nrows >= (int64_t)1 << 31) return 0;
+  // Opt-in (TIGAR_B200_TMA_SPMV=1): 0.39-0.41 of HBM peak on B200 against 0.70 for the
+  // direct-load kernel -- with 2 CTAs/SM in lock step the per-stage chain (x-tile
+  // loads, mbarrier wait, reduction, CTA barrier) is not hidden (profiles/r1_spmv_variants.txt)
+  const char* e = getenv("TIGAR_B200_TMA_SPMV");
+  if (!e || atoi(e) == 0) return 0;
+  if (h_w->layout != 0 || h_w->maxrow <= 0 || h_w->w0max <= 0) return 0;
+  if ((((uintptr_t)vals) & 15) != 0) return 0;
+  const int w0max = h_w->w0max;
+  const int maxtile = h_w->maxrow / w0max;
+  if (TG_TMA_ROWS + w0max - 1 > TG_TMA_XW) return 0;
+  if (maxtile > 16 * TG_TMA_XPT) return 0;             // x tile: 64 groups x 16 columns
+  const int64_t nlines = tg_win_nrows(h_w) / h_w->nr[0];
+  const int spl = (int)tg_cdiv(h_w->nr[0], TG_TMA_ROWS);
+  const long long nstage_tot = (long long)nlines * spl;
+  if (nstage_tot < 1) return 0;
   int stage_doubles = (int)(((int64_t)TG_TMA_ROWS * h_w->maxrow + 2 + 15) & ~15);
   size_t stage_bytes = (size_t)stage_doubles * 8;
-  const size_t budget = 100 * 1024;
-  int NS = (int)(budget / stage_bytes);
-  if (NS < 2) return 0;
+  if (h_w->nr[0] > 1024) return 0;                     // first-direction tables in smem
+  const size_t fixed = (size_t)2 * TG_TMA_XW * TG_TMA_XPT * 16 * 8 + 2 * 64 * 8 +
+                       (size_t)w0max * maxtile * 4 + 2 * 8 * 8 + 16 * (size_t)h_w->nr[0] + 8 + 256;
+  const size_t budget = 112 * 1024;
+  if (fixed + 2 * stage_bytes > budget) return 0;
+  int NS = (int)((budget - fixed) / stage_bytes);
   if (NS > 6) NS = 6;
-  if ((int64_t)h_w->w0max * (h_w->maxrow / h_w->w0max) > TG_WS_MAXTAB) return 0;
-  size_t smem = (size_t)NS * stage_bytes + (size_t)NS * (TG_TMA_ROWS + 2) * 8 + 2 * NS * 8 +
-                TG_WS_MAXTAB * 4 + 128;
+  size_t smem = (size_t)NS * stage_bytes + fixed;
   if (g_tma_smem_ok < 0) {
     cudaError_t e1 = cudaFuncSetAttribute(k_win_spmv_tma<true>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
     cudaError_t e2 = cudaFuncSetAttribute(k_win_spmv_tma<false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
     g_tma_smem_ok = (e1 == cudaSuccess && e2 == cudaSuccess) ? 1 : 0;
   }
   if (!g_tma_smem_ok) return 0;
-  int g = tg_ws_grid_size() / 2;          // 2 CTAs per SM
+  long long g = tg_ws_grid_size() / 2;          // 2 CTAs per SM
+  if (g > nstage_tot) g = nstage_tot;
   TgWin w = tg_win_dev(h_w);
   if (part) {
     // unused partial sums of the wider reduction grid must be zero
     TG_CHECK(cudaMemsetAsync(part, 0, sizeof(double) * tg_ws_grid_size(), st));
-    k_win_spmv_tma<true><<<g, TG_TMA_THREADS, smem, st>>>(w, vals, x, xoff, y, nrows, h_w->w0max,
-                                                          NS, stage_doubles, part);
+    k_win_spmv_tma<true><<<(unsigned)g, TG_TMA_THREADS, smem, st>>>(
+        w, vals, x, xoff, y, nstage_tot, spl, w0max, maxtile, NS, stage_doubles, part);
   } else {
-    k_win_spmv_tma<false><<<g, TG_TMA_THREADS, smem, st>>>(w, vals, x, xoff, y, nrows,
-                                                           h_w->w0max, NS, stage_doubles, nullptr);
+    k_win_spmv_tma<false><<<(unsigned)g, TG_TMA_THREADS, smem, st>>>(
+        w, vals, x, xoff, y, nstage_tot, spl, w0max, maxtile, NS, stage_doubles, nullptr);
   }
   TG_LAUNCH_CHECK();
   *launched = 1;
+  g_last_spmv_kind = 1;
   return 0;
 }
 
@@ -547,6 +807,7 @@ int tg_win_spmv_launch(const tg_win* h_w, const double* vals, const double* x, i
       tg_sell_launch<false>(h_w->w0max, g, st, w, vals, x, xoff, y, nchunk, nitems, nullptr);
     }
     TG_LAUNCH_CHECK();
+    g_last_spmv_kind = 2;
     return 0;
   }
   {
@@ -567,6 +828,36 @@ int tg_win_spmv_launch(const tg_win* h_w, const double* vals, const double* x, i
     U = e ? atoi(e) : 4;
     if (U != 4 && U != 6 && U != 8) U = 4;
   }
+  static int PF = -1;
+  if (PF < 0) {
+    // opt-in: measured 0.46-0.50 of HBM peak against 0.70 without the prefetch (8-byte
+    // cp.async has no evict-first / no-allocate form, so the streamed rows evict the x
+    // entries the gathers want from L1; profiles/r1_spmv_variants.txt)
+    const char* e = getenv("TIGAR_B200_SPMV_PF");
+    PF = e ? atoi(e) : 0;
+  }
+  if (PF && h_w->maxrow > 0 && h_w->maxrow <= 704) {
+    // per-warp double-buffered row prefetch: 8 warps x 2 x RB doubles per CTA, 4 CTAs/SM
+    const int RB = (h_w->maxrow + 1) & ~1;
+    const size_t smem = (size_t)(TG_WS_BLOCK / 32) * 2 * RB * 8;
+    static int attr_ok = 0;
+    if (!attr_ok) {
+      TG_CHECK(cudaFuncSetAttribute(k_win_spmv_pf<true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      TG_CHECK(cudaFuncSetAttribute(k_win_spmv_pf<false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_ok = 1;
+    }
+    if (part)
+      k_win_spmv_pf<true><<<g, TG_WS_BLOCK, smem, st>>>(w, vals, x, xoff, y, nchunk, (int)nitems,
+                                                        h_w->w0max, RB, part);
+    else
+      k_win_spmv_pf<false><<<g, TG_WS_BLOCK, smem, st>>>(w, vals, x, xoff, y, nchunk,
+                                                         (int)nitems, h_w->w0max, RB, nullptr);
+    TG_LAUNCH_CHECK();
+    g_last_spmv_kind = 3;
+    return 0;
+  }
   if (U > 4) {                       // 3 resident CTAs per SM: keep it one wave
     g = (g / 4) * 3;
     if (part) TG_CHECK(cudaMemsetAsync(part, 0, sizeof(double) * tg_ws_grid_size(), st));
@@ -583,6 +874,7 @@ int tg_win_spmv_launch(const tg_win* h_w, const double* vals, const double* x, i
   else { TG_SPMV_LAUNCH(8) }
 #undef TG_SPMV_LAUNCH
   TG_LAUNCH_CHECK();
+  g_last_spmv_kind = 0;
   return 0;
 }
 

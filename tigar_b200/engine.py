@@ -1037,11 +1037,15 @@ class TensorPatch(object):
         return Cm
 
     def bc_mask(self, zeroDofs):
-        m = np.zeros(self.n_iga, dtype=np.uint8)
-        z = np.asarray(zeroDofs, dtype=np.int64)
+        """0/1 mask over the IGA DoFs, built on the device from the zeroDofs list."""
+        m = dev.zeros(self.n_iga, dev.U8)
+        z = np.ascontiguousarray(zeroDofs, dtype=np.int64).ravel()
         if z.size:
-            m[z] = 1
-        return dev.from_np(m)
+            if z.min() < 0 or z.max() >= self.n_iga:
+                raise IndexError("zero DoF outside [0, %d)" % self.n_iga)
+            dz = dev.from_np(z)
+            check(lib.tg_mask_set(dev.ptr(m), dev.ptr(dz), z.size, self.n_iga, dev.stream()))
+        return m
 
     def apply_bcs_matrix(self, Cm, mask, diag=1.0):
         if self.part is not None:
