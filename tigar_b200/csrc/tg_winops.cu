@@ -52,7 +52,21 @@ __device__ inline double tg_block_sum_ws(double v, double* sh) {
 // Rows whose first-direction window is clipped by the patch boundary take the
 // generic path.
 #define TG_WS_MAXTAB 1024
-template <bool DOT, int U>
+// streaming load of a matrix value: LD = 0 ld.global.cs (evict-first), 1 L1::no_allocate,
+// 2 L1::no_allocate + 256-byte L2 prefetch
+template <int LD>
+__device__ __forceinline__ double tg_ld_stream(const double* p) {
+  double v;
+  if (LD == 1)
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  else if (LD == 2)
+    asm volatile("ld.global.L1::no_allocate.L2::256B.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  else
+    v = __ldcs(p);
+  return v;
+}
+
+template <bool DOT, int U, int LD = 0>
 __global__ void __launch_bounds__(TG_WS_BLOCK, (U <= 4) ? 4 : 3)
 k_win_spmv(TgWin w, const double* __restrict__ vals, const double* __restrict__ x,
            int64_t xoff, double* __restrict__ y, int nchunk, int nitems, int w0max,
@@ -126,7 +140,7 @@ k_win_spmv(TgWin w, const double* __restrict__ vals, const double* __restrict__ 
         for (; p + 32 * (U - 1) < n; p += 32 * U) {
           double a[U], xv[U];
 #pragma unroll
-          for (int u = 0; u < U; u++) a[u] = __ldcs(av + p + 32 * u);
+          for (int u = 0; u < U; u++) a[u] = tg_ld_stream<LD>(av + p + 32 * u);
 #pragma unroll
           for (int u = 0; u < U; u++) xv[u] = xr[xtab[p + 32 * u]];
 #pragma unroll
@@ -135,7 +149,8 @@ k_win_spmv(TgWin w, const double* __restrict__ vals, const double* __restrict__ 
         {   // remainder (< U chunks): predicated, still issued together
           double a[U], xv[U];
 #pragma unroll
-          for (int u = 0; u < U - 1; u++) a[u] = (p + 32 * u < n) ? __ldcs(av + p + 32 * u) : 0.0;
+          for (int u = 0; u < U - 1; u++)
+            a[u] = (p + 32 * u < n) ? tg_ld_stream<LD>(av + p + 32 * u) : 0.0;
 #pragma unroll
           for (int u = 0; u < U - 1; u++) xv[u] = (p + 32 * u < n) ? xr[xtab[p + 32 * u]] : 0.0;
 #pragma unroll
@@ -869,7 +884,26 @@ int tg_win_spmv_launch(const tg_win* h_w, const double* vals, const double* x, i
   else                                                                                        \
     k_win_spmv<false, UU><<<g, TG_WS_BLOCK, 0, st>>>(w, vals, x, xoff, y, nchunk,             \
                                                      (int)nitems, h_w->w0max, nullptr);
-  if (U == 4) { TG_SPMV_LAUNCH(4) }
+  static int LDM = -1;
+  if (LDM < 0) {
+    const char* e = getenv("TIGAR_B200_SPMV_LD");
+    LDM = e ? atoi(e) : 0;
+  }
+  if (U == 4 && LDM == 1) {
+    if (part)
+      k_win_spmv<true, 4, 1><<<g, TG_WS_BLOCK, 0, st>>>(w, vals, x, xoff, y, nchunk, (int)nitems,
+                                                       h_w->w0max, part);
+    else
+      k_win_spmv<false, 4, 1><<<g, TG_WS_BLOCK, 0, st>>>(w, vals, x, xoff, y, nchunk,
+                                                        (int)nitems, h_w->w0max, nullptr);
+  } else if (U == 4 && LDM == 2) {
+    if (part)
+      k_win_spmv<true, 4, 2><<<g, TG_WS_BLOCK, 0, st>>>(w, vals, x, xoff, y, nchunk, (int)nitems,
+                                                       h_w->w0max, part);
+    else
+      k_win_spmv<false, 4, 2><<<g, TG_WS_BLOCK, 0, st>>>(w, vals, x, xoff, y, nchunk,
+                                                        (int)nitems, h_w->w0max, nullptr);
+  } else if (U == 4) { TG_SPMV_LAUNCH(4) }
   else if (U == 6) { TG_SPMV_LAUNCH(6) }
   else { TG_SPMV_LAUNCH(8) }
 #undef TG_SPMV_LAUNCH

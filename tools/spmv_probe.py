@@ -26,6 +26,8 @@ if len(sys.argv) > 2:      # child: one variant
 for name, env in [("rowmajor + cp.async row prefetch", {"TIGAR_B200_SPMV_PF": "1"}),
                   ("tma rows + smem x tiles", {"TIGAR_B200_TMA_SPMV": "1"}),
                   ("rowmajor U=4 (default)", {"TIGAR_B200_SPMV_U": "4"}),
+                  ("rowmajor U=4 L1::no_allocate", {"TIGAR_B200_SPMV_LD": "1"}),
+                  ("rowmajor U=4 no_alloc+L2::256B", {"TIGAR_B200_SPMV_LD": "2"}),
                   ("sell G=4", {"TIGAR_B200_LAYOUT": "1", "TIGAR_B200_SELL_G": "4"})]:
     e = dict(os.environ); e.update(env)
     subprocess.run([sys.executable, __file__, str(nel), name], env=e)
