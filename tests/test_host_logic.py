@@ -257,3 +257,100 @@ def test_march_task_packing_covers_every_fibre_once():
                     seen[(ra, rb, cb)] = 1
             assert lanes <= 32
         assert len(seen) == len(lena) * int(lenb.sum())
+
+
+@pytest.mark.parametrize("p,pf,nel,uniform", [(1, 1, 7, True), (2, 2, 9, False), (3, 3, 8, True),
+                                              (3, 3, 11, False), (4, 4, 6, False), (2, 3, 7, False)])
+def test_march_tables_drive_a_correct_1d_ptap(p, pf, nel, uniform):
+    """tigar_b200.march_tables.dir_tables (pure numpy) + a numpy emulation of what one
+    lane of k_ptap_march_w does with them (groups of rows sharing first(I), zero-padded
+    coefficient vectors addressed through the 2-bit shifts, sliding (p+1)x(2p+1)
+    accumulator block, emit through jrec) reproduce the dense M^T A M of a banded
+    1-D A on its window -- for every segment split."""
+    import numpy as np
+    from oracle import bsplines as OB
+    from tigar_b200 import march_tables
+    from tigar_b200.engine import Window
+    rng = np.random.RandomState(11)
+    kn = np.array(OB.uniform_knots(p, 0.0, 1.0, nel))
+    if not uniform:
+        inner = kn[p + 1:-(p + 1)]
+        kn[p + 1:-(p + 1)] = inner + 0.35 / nel * (rng.rand(len(inner)) - 0.5)
+    s1 = OB.Spline1(p, list(kn))
+    uk_ = np.asarray(s1.uniqueKnots)
+    x = np.concatenate([uk_[e] + (uk_[e + 1] - uk_[e]) * np.arange(pf) / pf for e in range(nel)]
+                       + [uk_[-1:]])
+    nfe, ncp = len(x), s1.ncp
+    span = np.array([s1.getKnotSpan(u) for u in x])
+    vals = np.array([s1.basisFuncs(sp, u) for sp, u in zip(span, x)])
+    first = span - p
+    keep = np.abs(vals) > 1e-15
+    m_lo = first + keep.argmax(axis=1)
+    m_hi = first + p - keep[:, ::-1].argmax(axis=1)
+    M = np.zeros((nfe, ncp))
+    for I in range(nfe):
+        for k in range(p + 1):
+            if keep[I, k]:
+                M[I, first[I] + k] = vals[I, k]
+    g = np.arange(nfe)
+    loA = np.maximum((g - 1) // pf, 0) * pf
+    hiA = (np.minimum(g // pf, nel - 1) + 1) * pf
+    wM = Window([nfe], [ncp], [m_lo], [m_hi])
+    wA = Window([nfe], [nfe], [loA], [hiA])
+    wMT = wM.transpose()
+    wC = wMT.compose(wA.compose(wM))
+    loC, hiC = wC.lo[0].astype(np.int64), wC.hi[0].astype(np.int64)
+    slo, shi = wMT.lo[0], wMT.hi[0]
+    T = march_tables.dir_tables(p, pf, first, vals, m_lo, m_hi, loA, hiA, loC, hiC, 4)
+    assert T is not None
+    irec, jrec, cpad, grp, gidx = T["irec"], T["jrec"], T["cpad"], T["grp"], T["gidx"]
+    assert T["GMAX"] >= 2 * p + 1 and np.all(np.diff(grp) <= min(4, pf))
+    A = np.zeros((nfe, nfe))
+    for I in range(nfe):
+        A[I, loA[I]:hiA[I] + 1] = rng.randn(hiA[I] - loA[I] + 1)
+    ref = M.T @ A @ M
+    inwin = np.zeros_like(ref, dtype=bool)
+    for i in range(ncp):
+        inwin[i, loC[i]:hiC[i] + 1] = True
+    assert np.abs(ref[~inwin]).max() < 1e-14               # the window holds the pattern
+    CW, TW = 2 * p + 1, p + 2
+    for nseg in (1, 3):
+        seg = [(ncp * k) // nseg for k in range(nseg + 1)]
+        C = np.full((ncp, ncp), np.nan)
+        for sgi in range(nseg):
+            i_lo, i_hi = seg[sgi], seg[sgi + 1]
+            g0, g1 = gidx[slo[i_lo]], gidx[shi[i_hi - 1]]
+            acc = np.zeros((p + 1, CW))
+            ib = first[grp[g0]]
+
+            def emit_shift():
+                nonlocal acc, ib
+                if i_lo <= ib < i_hi:
+                    clo, lenC = jrec[ib, 0], jrec[ib, 1]
+                    for c in range(CW):
+                        jj = c - clo
+                        if 0 <= jj < lenC:
+                            C[ib, loC[ib] + jj] = acc[0, c]
+                acc[:-1] = acc[1:]
+                acc[-1] = 0.0
+                ib += 1
+            for gk in range(g0, g1 + 1):
+                n0, n1 = grp[gk], grp[gk + 1]
+                while ib < irec[n0, 1]:
+                    emit_shift()
+                for I in range(n0, n1):
+                    lenI, lo, sb = irec[I, 0] & 255, irec[I, 0] >> 8, irec[I, 2]
+                    assert irec[I, 1] == irec[n0, 1]              # one first(I) per group
+                    tv = np.zeros(TW)
+                    for q in range(lenI):
+                        e = (sb >> (2 * q)) & 3
+                        tv += A[I, lo + q] * cpad[lo + q, 2 - e:2 - e + TW]
+                    for k in range(p + 1):
+                        for m in range(TW):
+                            c = m - k + p
+                            if 0 <= c < CW:
+                                acc[k, c] += cpad[I, 1 + k] * tv[m]
+            for k in range(p + 1):
+                emit_shift()
+        assert not np.isnan(C[inwin]).any()                   # every window entry written once
+        assert np.abs(C[inwin] - ref[inwin]).max() < 1e-13 * max(1.0, np.abs(ref).max())

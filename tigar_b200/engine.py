@@ -21,6 +21,7 @@ import numpy as np
 
 from . import dev
 from . import symbolic as S
+from . import march_tables
 from ._lib import lib, check, tg_basis, tg_win, i32arr, vparr, c_vp
 from .bsplines import BSpline1
 
@@ -783,63 +784,15 @@ class TensorPatch(object):
         dirs = []
         for d, D in enumerate(self.dirs):
             p = D.p
-            if p > 4:
-                return None
-            TW, TWP = p + 2, (p + 3) & ~1
             first = dev.to_np(D.m_first).astype(np.int64)
-            vals = dev.to_np(D.m_vals)
-            j = first[:, None] + np.arange(p + 1)[None, :]
-            keep = (j >= D.m_lo[:, None]) & (j <= D.m_hi[:, None])
-            mrow = np.where(keep, vals, 0.0)
-            KA = int(wA.len[d].max())
-            tabc = np.zeros((D.nfe, KA, TWP))
-            for I in range(D.nfe):
-                for q, J in enumerate(range(wA.lo[d][I], wA.hi[d][I] + 1)):
-                    m = first[J] - first[I] + np.arange(p + 1)
-                    k = np.nonzero(mrow[J])[0]
-                    if k.size == 0:
-                        continue
-                    if m[k].min() < 0 or m[k].max() >= TW:
-                        return None
-                    tabc[I, q, m[k]] = mrow[J, k]
-            # (k = 0, m = p+1) would fall outside the 2p+1 band: must vanish
-            if np.any((np.abs(tabc[:, :, p + 1]).sum(axis=1) > 0) & (mrow[:, 0] != 0)):
+            T = march_tables.dir_tables(p, D.pf, first, dev.to_np(D.m_vals), D.m_lo, D.m_hi,
+                                        wA.lo[d], wA.hi[d], wC.lo[d], wC.hi[d],
+                                        self.MARCH_RMAX)
+            if T is None:
                 return None
-            i = np.arange(D.ncp)
-            if np.any(wC.lo[d] < i - p) or np.any(wC.hi[d] > i + p):
-                return None
-            if np.any(np.diff(first) < 0):
-                return None
-            # tables of the warp-task kernel (tg_ptap_march_w)
-            SX = np.concatenate([[0], np.cumsum(wA.len[d])]).astype(np.int64)
-            SY = np.concatenate([[0], np.cumsum(wC.len[d])]).astype(np.int64)
-            sbits = np.zeros(D.nfe, dtype=np.int64)
-            for I in range(D.nfe):
-                for q, J in enumerate(range(wA.lo[d][I], wA.hi[d][I] + 1)):
-                    sh = first[J] - first[I] + 1
-                    if not np.any(mrow[J]):
-                        sh = 1
-                    if sh < 0 or sh > 2:
-                        return None
-                    sbits[I] |= int(sh) << (2 * q)
-            if KA > 15 or D.nfe >= (1 << 23):
-                return None
-            # groups: runs of FE rows sharing first(I), at most MARCH_RMAX rows each
-            grp, gidx = [0], np.zeros(D.nfe, dtype=np.int64)
-            for I in range(1, D.nfe):
-                if first[I] != first[I - 1] or I - grp[-1] >= min(self.MARCH_RMAX, D.pf):
-                    grp.append(I)
-                gidx[I] = len(grp) - 1
-            grp.append(D.nfe)
-            grp = np.array(grp, dtype=np.int64)
-            gsum = np.add.reduceat(wA.len[d], grp[:-1])
-            GMAX = int(max(gsum.max(), 2 * p + 1))
-            irec = np.stack([wA.len[d] | (wA.lo[d].astype(np.int64) << 8), first, sbits, gidx],
-                            axis=1)
-            jrec = np.stack([wC.lo[d] - (i - p), wC.len[d], SY[:-1] & 0xffffffff, SY[:-1] >> 32],
-                            axis=1)
-            cpad = np.zeros((D.nfe, p + 4))
-            cpad[:, 1:p + 2] = mrow
+            mrow, tabc, KA, SX = T["mrow"], T["tabc"], T["KA"], T["SX"]
+            irec, jrec, cpad = T["irec"], T["jrec"], T["cpad"]
+            grp, gidx, GMAX = T["grp"], T["gidx"], T["GMAX"]
             dirs.append(dict(p=p, KA=KA, first=dev.from_np(first.astype(np.int32)),
                              irec=dev.from_np(irec.astype(np.uint32).view(np.int32)),
                              jrec=dev.from_np(jrec.astype(np.uint32).view(np.int32)),
