@@ -354,3 +354,85 @@ def test_march_tables_drive_a_correct_1d_ptap(p, pf, nel, uniform):
                 emit_shift()
         assert not np.isnan(C[inwin]).any()                   # every window entry written once
         assert np.abs(C[inwin] - ref[inwin]).max() < 1e-13 * max(1.0, np.abs(ref).max())
+
+
+def _eval_coef(t, X):
+    """Value of a coefficient-only ufl_lite scalar at parametric point X."""
+    sc = U.as_tensor(t).a[()]
+    assert sc.is_coef()
+    prog = S.compile_program([sc.node()], len(X))
+    return run_program(prog, list(X), 1.0, {})[0]
+
+
+def test_curl_and_parametric_expression_symbolics():
+    """curl_from_grad (cartesianCurl, calculusUtils.py:278-302) and
+    expression_from_string (parametricExpression, common.py:1111-1117) on the
+    identity geometry, against closed forms."""
+    X3 = (0.3, 0.7, 0.2)
+    x = [U.Tensor(U.Scalar.coef(S.xi(d))) for d in range(3)]
+    f = U.as_vector([x[1] * x[2] * x[2], U.sin(x[0]) * x[2], x[0] * x[0] * x[1]])
+    c = U.curl_from_grad(f, U.parametric_grad(f, 3))
+    ref = [X3[0] ** 2 - math.sin(X3[0]), 2 * X3[1] * X3[2] - 2 * X3[0] * X3[1],
+           math.cos(X3[0]) * X3[2] - X3[2] ** 2]
+    for i in range(3):
+        assert abs(_eval_coef(c[i], X3) - ref[i]) < 1e-14
+    X2 = (0.4, 0.9)
+    y = x[:2]
+    g = U.as_vector([y[0] * y[1] * y[1], U.exp(y[0]) * y[1]])
+    c2 = U.curl_from_grad(g, U.parametric_grad(g, 2))
+    assert abs(_eval_coef(c2, X2) - (math.exp(X2[0]) * X2[1] - 2 * X2[0] * X2[1])) < 1e-14
+    s = y[0] * y[0] * U.cos(y[1])
+    c3 = U.curl_from_grad(s, U.parametric_grad(s, 2))
+    assert abs(_eval_coef(c3[0], X2) - X2[0] ** 2 * math.sin(X2[1])) < 1e-14
+    assert abs(_eval_coef(c3[1], X2) - 2 * X2[0] * math.cos(X2[1])) < 1e-14
+    with pytest.raises(ValueError):
+        U.curl_from_grad(U.as_matrix([[1.0, 0.0], [0.0, 1.0]]), U.as_matrix([[1.0, 0.0], [0.0, 1.0]]))
+    e = U.expression_from_string("sin(pi*x[0])*pow(x[1],2) + sqrt(x[0]+1.0)/exp(x[1])", y)
+    assert abs(_eval_coef(e, X2) - (math.sin(math.pi * X2[0]) * X2[1] ** 2
+                                    + math.sqrt(X2[0] + 1.0) / math.exp(X2[1]))) < 1e-14
+    v = U.expression_from_string(("x[0]", "2.0*x[1]"), y)
+    assert abs(_eval_coef(v[1], X2) - 2 * X2[1]) < 1e-15
+
+
+def test_calculus_utils_on_a_polar_map():
+    """tigar_b200.calculus (the reference's calculusUtils.py:18-24, 56-69, 255-302,
+    412-470) on the polar map F(r, t) = (r cos t, r sin t): metric diag(1, r^2), volume
+    element r, Cartesian gradient / divergence / curl of fields given in the
+    parametric coordinates, and the Gauss rules against the reference's constants."""
+    from tigar_b200 import calculus as CU
+    import tIGAr.calculusUtils as TCU
+    assert TCU.cartesianGrad is CU.cartesianGrad
+    old = U.DEFAULT_DIM[0]
+    U.DEFAULT_DIM[0] = 2
+    try:
+        r, t = (U.Tensor(U.Scalar.coef(S.xi(d))) for d in range(2))
+        F = U.as_vector([r * U.cos(t), r * U.sin(t)])
+        X = (1.7, 0.6)
+        x_, y_ = X[0] * math.cos(X[1]), X[0] * math.sin(X[1])
+        g = CU.getMetric(F)
+        assert abs(_eval_coef(g[0, 0], X) - 1.0) < 1e-14 and abs(_eval_coef(g[1, 1], X) - X[0] ** 2) < 1e-13
+        assert abs(_eval_coef(g[0, 1], X)) < 1e-14
+        assert abs(_eval_coef(CU.volumeJacobian(g), X) - X[0]) < 1e-14
+        P = CU.pinvD(F)
+        DF = U.grad(F)
+        I2 = U.dot(P, DF)                                   # pinv(DF) DF = I for a square map
+        for i in range(2):
+            for j in range(2):
+                assert abs(_eval_coef(I2[i, j], X) - (1.0 if i == j else 0.0)) < 1e-13
+        f = r * r                                            # x^2 + y^2
+        gf = CU.cartesianGrad(f, F)
+        assert abs(_eval_coef(gf[0], X) - 2 * x_) < 1e-13 and abs(_eval_coef(gf[1], X) - 2 * y_) < 1e-13
+        v = U.as_vector([r * U.cos(t) * r * U.sin(t), r * r])   # (x y, x^2 + y^2)
+        assert abs(_eval_coef(CU.cartesianDiv(v, F), X) - (y_ + 2 * y_)) < 1e-13
+        assert abs(_eval_coef(CU.cartesianCurl(v, F), X) - (2 * x_ - x_)) < 1e-13
+        lap = CU.cartesianDiv(CU.cartesianGrad(f, F), F)
+        assert abs(_eval_coef(lap, X) - 4.0) < 1e-12
+    finally:
+        U.DEFAULT_DIM[0] = old
+    xs, ws = CU.getQuadRule(3)
+    vals = [c.a[()].node().args[0] for c in xs], [c.a[()].node().args[0] for c in ws]
+    assert vals[0][1] == 0.0 and abs(vals[0][2] - 0.77459666924148337703585308) < 1e-15
+    assert abs(vals[1][0] - 0.55555555555555555555555556) < 1e-15
+    x4, w4 = CU.getQuadRuleInterval(4, 0.2)
+    assert abs(x4[3].a[()].node().args[0] - 0.1 * 0.86113631159405257524) < 1e-16
+    assert abs(sum(c.a[()].node().args[0] for c in w4) - 0.2) < 1e-15

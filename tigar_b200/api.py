@@ -696,7 +696,14 @@ class ExtractedSpline(object):
         return U.Tensor(out) if out.shape else U.Tensor(out[()])
 
     def curl(self, f, F=None):
-        raise NotImplementedError("curl is outside the built hot path")
+        """Physical curl (calculusUtils.py:278-302): vector in 3-D, scalar for a
+        2-D vector, vector for a 2-D scalar."""
+        return U.curl_from_grad(f, self.grad(f, F))
+
+    def parametricExpression(self, expr):
+        """``Expression`` in the parametric coordinates (common.py:1111-1117); the
+        formula is evaluated exactly at the Gauss points, not interpolated."""
+        return U.expression_from_string(expr, self.parametricCoordinates())
 
     def parametricGrad(self, f):
         return U.parametric_grad(f, self._patch.dim)

@@ -415,6 +415,45 @@ def parametric_grad(f, dim):
     return Tensor(out)
 
 
+def curl_from_grad(f, gradf):
+    """``cartesianCurl`` (calculusUtils.py:278-302) given ``gradf[a, j] = d f_a / d x_j``
+    (or ``gradf[j]`` for a scalar ``f``): rank 1 in 3-D -> vector
+    ``eps_ijk gradf[k, j]``; rank 1 in 2-D -> scalar ``gradf[1,0] - gradf[0,1]``;
+    scalar in 2-D -> vector ``(-gradf[1], gradf[0])``."""
+    f, g = as_tensor(f), as_tensor(gradf)
+    if f.a.ndim == 1:
+        m = f.a.shape[0]
+        if g.a.shape != (m, m):
+            raise ValueError("curl: gradient of shape %r for a %d-vector" % (g.a.shape, m))
+        if m == 3:
+            return as_vector([Tensor(g.a[2, 1].add(g.a[1, 2], -1.0)),
+                              Tensor(g.a[0, 2].add(g.a[2, 0], -1.0)),
+                              Tensor(g.a[1, 0].add(g.a[0, 1], -1.0))])
+        if m == 2:
+            return Tensor(g.a[1, 0].add(g.a[0, 1], -1.0))
+        raise ValueError("Unsupported dimension of argument to curl.")
+    if f.a.ndim == 0:
+        if g.a.shape != (2,):
+            raise ValueError("curl of a scalar is defined in 2-D only")
+        return as_vector([Tensor(g.a[1].neg()), Tensor(g.a[0])])
+    raise ValueError("Unsupported rank of argument to curl.")
+
+
+def expression_from_string(expr, coords):
+    """``Expression(expr, degree=...)`` of the reference (common.py:1111-1117) for the
+    C++-style scalar expressions the demos use: ``x[i]`` are the given coordinate
+    tensors, ``pi`` / ``DOLFIN_PI``, ``pow``, ``sqrt``, ``exp``, ``log``, ``sin``,
+    ``cos``, ``tan``, ``fabs``/``abs`` are available.  A tuple/list of strings gives
+    a vector."""
+    import math
+    if isinstance(expr, (tuple, list)):
+        return as_vector([expression_from_string(e, coords) for e in expr])
+    ns = {"x": list(coords), "pi": math.pi, "DOLFIN_PI": math.pi, "pow": lambda a, b: a ** b,
+          "sqrt": sqrt, "exp": exp, "log": ln, "sin": sin, "cos": cos, "tan": tan,
+          "fabs": abs_, "abs": abs_, "__builtins__": {}}
+    return as_tensor(eval(str(expr), ns))     # noqa: S307 (user-supplied formula, as in the reference)
+
+
 # ------------------------------------------------------------ forms
 class Measure(object):
     """Weighted volume measure (tIGArMeasure, calculusUtils.py:351-410):
