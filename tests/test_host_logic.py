@@ -436,3 +436,70 @@ def test_calculus_utils_on_a_polar_map():
     x4, w4 = CU.getQuadRuleInterval(4, 0.2)
     assert abs(x4[3].a[()].node().args[0] - 0.1 * 0.86113631159405257524) < 1e-16
     assert abs(sum(c.a[()].node().args[0] for c in w4) - 0.2) < 1e-15
+
+
+def test_window_algebra_matches_sparse_patterns():
+    """engine.Window (pure numpy part): nnz, transpose and compose of tensor-product row
+    windows against explicit scipy patterns, and the closed-form row pointer
+    rowptr(r) = S0[r0] l1 l2 + T0 (S1[r1] l2 + T1 S2[r2]) the kernels use."""
+    import scipy.sparse as sp
+    from tigar_b200.engine import Window
+    rng = np.random.RandomState(3)
+
+    def rand_win(nr, nc):
+        lo, hi = [], []
+        for a, b in zip(nr, nc):
+            l = np.sort(rng.randint(0, b, size=a))
+            h = np.minimum(b - 1, l + rng.randint(0, 3, size=a))
+            h = np.maximum.accumulate(h)
+            lo.append(l)
+            hi.append(h)
+        return Window(nr, nc, lo, hi)
+
+    def pattern(w):
+        mats = []
+        for d in range(w.dim):
+            m = np.zeros((w.nr[d], w.nc[d]))
+            for r in range(w.nr[d]):
+                m[r, w.lo[d][r]:w.hi[d][r] + 1] = 1.0
+            mats.append(sp.csr_matrix(m))
+        out = mats[0]
+        for m in mats[1:]:
+            out = sp.kron(m, out, format="csr")          # first direction fastest
+        return out
+
+    for nr, nm, nc in [([5, 4], [6, 3], [4, 5]), ([3, 4, 2], [4, 3, 3], [2, 5, 3]), ([7], [5], [6])]:
+        A, B = rand_win(nr, nm), rand_win(nm, nc)
+        PA, PB = pattern(A), pattern(B)
+        assert A.nnz == PA.nnz and A.nrows == PA.shape[0] and A.ncols == PA.shape[1]
+        # closed-form row pointer
+        S = [np.concatenate([[0], np.cumsum(l)]) for l in A.len] + [np.array([0, 1])] * (3 - A.dim)
+        ln = list(A.len) + [np.array([1])] * (3 - A.dim)
+        n3 = list(A.nr) + [1] * (3 - A.dim)
+        T0, T1 = S[0][-1], S[1][-1]
+        row = 0
+        for r2 in range(n3[2]):
+            for r1 in range(n3[1]):
+                for r0 in range(n3[0]):
+                    rp = S[0][r0] * ln[1][r1] * ln[2][r2] + T0 * (S[1][r1] * ln[2][r2] + T1 * S[2][r2])
+                    assert rp == PA.indptr[row]
+                    row += 1
+        # transpose: smallest window containing the transposed pattern
+        AT = A.transpose() if all((PA.sum(axis=0) > 0).A1) else None
+        if AT is not None:
+            PT = pattern(AT)
+            assert (PT.multiply(PA.T) - PA.T).nnz == 0        # contains A^T
+            for d in range(A.dim):
+                for c in range(A.nc[d]):
+                    rows = [r for r in range(A.nr[d]) if A.lo[d][r] <= c <= A.hi[d][r]]
+                    assert AT.lo[d][c] == min(rows) and AT.hi[d][c] == max(rows)
+        # compose: window of the product pattern, tight per direction
+        AB = A.compose(B)
+        PAB = ((PA @ PB) > 0).astype(float)
+        PW = pattern(AB)
+        assert (PW.multiply(PAB) - PAB).nnz == 0              # contains the product
+        for d in range(A.dim):
+            for r in range(A.nr[d]):
+                cols = np.concatenate([np.arange(B.lo[d][k], B.hi[d][k] + 1)
+                                       for k in range(A.lo[d][r], A.hi[d][r] + 1)])
+                assert AB.lo[d][r] == cols.min() and AB.hi[d][r] == cols.max()
