@@ -320,7 +320,10 @@ def run_ours(args):
         "roofline": roofline}
 
     if not args.no_ptap:
-        out["ptap"] = ptap_roofline(args.ptap_nel, peak)
+        try:
+            out["ptap"] = ptap_roofline(args.ptap_nel, peak)
+        except Exception as e:                  # keep the headline line if the extra fails
+            out["ptap"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if not args.no_cpu:
         nd, dt, its = cpu_port_step(args.cpu_nel)
         out["cpu_baseline"] = {
