@@ -503,3 +503,93 @@ def test_window_algebra_matches_sparse_patterns():
                 cols = np.concatenate([np.arange(B.lo[d][k], B.hi[d][k] + 1)
                                        for k in range(A.lo[d][r], A.hi[d][r] + 1)])
                 assert AB.lo[d][r] == cols.min() and AB.hi[d][r] == cols.max()
+
+
+def _eval_with_functions(expr, values):
+    """Value of a coefficient-only expression given {Function.fid: number}."""
+    sc = U.as_tensor(expr).a[()]
+    prog = S.compile_program([sc.node()], 2)
+    jv = {j: values[j[0]] for j in prog.jets}
+    return run_program(prog, [0.0, 0.0], 1.0, jv)[0]
+
+
+class _DummyOwner(object):
+    pass
+
+
+def test_linear_combination_assign_and_time_integrators():
+    """api.linear_combination / Function.assign of linear combinations and the
+    integrators of tigar_b200.time_integration (timeIntegration.py:13-247) against
+    the Newmark / generalized-alpha update formulas solved independently here."""
+    import torch
+    from tigar_b200 import api as A
+    from tigar_b200 import time_integration as TI
+    import tIGAr.timeIntegration as TTI
+    assert TTI.GeneralizedAlphaIntegrator is TI.GeneralizedAlphaIntegrator
+    V = A.FunctionSpace(_DummyOwner())
+    u, v, w = A.Function(V), A.Function(V), A.Function(V)
+    e = 2.0 * u - U.Constant(0.5) * v + (u + v) * 3.0
+    assert sorted(A.linear_combination(e)) == sorted([(u.fid, 5.0), (v.fid, 2.5)])
+    for bad in (u * u, u + 1.0, u.dx(0), U.sin(u)):
+        with pytest.raises(ValueError):
+            A.linear_combination(bad)
+    rng = np.random.RandomState(0)
+    for f in (u, v, w):
+        f.set_iga(torch.from_numpy(rng.rand(7)))
+    t = A.Function(V)
+    t.assign(e)
+    assert torch.allclose(t.iga, 5.0 * u.iga + 2.5 * v.iga, rtol=0, atol=1e-15)
+
+    dt, rho = 0.1, 0.4
+    x, x0, v0, a0 = (A.Function(V) for _ in range(4))
+    vals = {x.fid: 1.3, x0.fid: 0.9, v0.fid: -0.7, a0.fid: 2.1}
+    F_ = {f.fid: f for f in (x, x0, v0, a0)}
+    # ---- second order: Newmark relations solved for a1, v1 given x1
+    gi = TI.GeneralizedAlphaIntegrator(rho, dt, x, [x0, v0, a0], t=1.0)
+    am, af = (2 - rho) / (1 + rho), 1 / (1 + rho)
+    g, b = 0.5 + am - af, 0.25 * (1 + am - af) ** 2
+    assert abs(gi.ALPHA_M - am) < 1e-15 and abs(gi.GAMMA - g) < 1e-15 and abs(gi.BETA - b) < 1e-15
+    a1 = (vals[x.fid] - vals[x0.fid] - dt * vals[v0.fid] - 0.5 * dt * dt * (1 - 2 * b) * vals[a0.fid]) / (b * dt * dt)
+    v1 = vals[v0.fid] + dt * ((1 - g) * vals[a0.fid] + g * a1)
+    assert abs(_eval_with_functions(gi.xddot(), vals) - a1) < 1e-11
+    assert abs(_eval_with_functions(gi.xdot(), vals) - v1) < 1e-12
+    assert abs(_eval_with_functions(gi.x_alpha(), vals) - (af * vals[x.fid] + (1 - af) * vals[x0.fid])) < 1e-14
+    assert abs(_eval_with_functions(gi.xdot_alpha(), vals) - (af * v1 + (1 - af) * vals[v0.fid])) < 1e-12
+    assert abs(_eval_with_functions(gi.xddot_alpha(), vals) - (am * a1 + (1 - am) * vals[a0.fid])) < 1e-11
+    # same-velocity predictor: x1 such that v1 == v0
+    xp = _eval_with_functions(gi.sameVelocityPredictor(), vals)
+    ap = (xp - vals[x0.fid] - dt * vals[v0.fid] - 0.5 * dt * dt * (1 - 2 * b) * vals[a0.fid]) / (b * dt * dt)
+    assert abs(vals[v0.fid] + dt * ((1 - g) * vals[a0.fid] + g * ap) - vals[v0.fid]) < 1e-12
+    # advance(): data moves with the OLD values on the right-hand sides
+    for fid, val in vals.items():
+        F_[fid].set_iga(torch.full((3,), val, dtype=torch.float64))
+    gi.advance()
+    assert np.allclose(x0.iga.numpy(), 1.3) and np.allclose(v0.iga.numpy(), v1, atol=1e-12)
+    assert np.allclose(a0.iga.numpy(), a1, atol=1e-10)
+    assert abs(gi.t - 1.2) < 1e-15
+    # ---- first order
+    y, y0, yd0 = (A.Function(V) for _ in range(3))
+    vv = {y.fid: 0.3, y0.fid: 0.5, yd0.fid: 1.1}
+    g1 = TI.GeneralizedAlphaIntegrator(rho, dt, y, [y0, yd0])
+    am1 = 0.5 * (3 - rho) / (1 + rho)
+    gm = 0.5 + am1 - af
+    yd1 = ((vv[y.fid] - vv[y0.fid]) / dt - (1 - gm) * vv[yd0.fid]) / gm
+    assert abs(_eval_with_functions(g1.xdot(), vv) - yd1) < 1e-12
+    assert abs(_eval_with_functions(g1.xdot_alpha(), vv) - (am1 * yd1 + (1 - am1) * vv[yd0.fid])) < 1e-12
+    assert g1.sameVelocityPredictor() is y0
+    with pytest.raises(ValueError):
+        g1.xddot()
+    # ---- backward Euler, second order
+    be = TI.BackwardEulerIntegrator(dt, x, [x0, v0])
+    for fid, val in vals.items():
+        F_[fid].set_iga(torch.full((2,), val, dtype=torch.float64))
+    bv = (vals[x.fid] - vals[x0.fid]) / dt
+    assert abs(_eval_with_functions(be.xdot(), vals) - bv) < 1e-12
+    assert abs(_eval_with_functions(be.xddot(), vals) - (bv - vals[v0.fid]) / dt) < 1e-11
+    be.advance()
+    assert np.allclose(x0.iga.numpy(), vals[x.fid]) and np.allclose(v0.iga.numpy(), bv, atol=1e-12)
+    ls = TI.LoadStepper(0.25)
+    ls.advance()
+    assert abs(ls.t - 0.5) < 1e-15
+    with pytest.raises(NotImplementedError):
+        TI.LinearDGSpaceTimeIntegrator(dt, x, x0)

@@ -193,17 +193,61 @@ class Function(U.Tensor):
         return DeviceVector(self.fe_tensor())
 
     def assign(self, other):
+        """``u.assign(v)`` or ``u.assign(c1*v1 + c2*v2 + ...)`` (dolfin accepts linear
+        combinations of Functions of the same space; timeIntegration.py uses them)."""
         if isinstance(other, Function):
             self.iga = None if other.iga is None else other.iga.clone()
             self._fe = None if other._fe is None else other._fe.clone()
             return
-        raise NotImplementedError("Function.assign of a general expression")
+        combo = linear_combination(other)
+        funcs = [(c, _functions[fid]) for fid, c in combo]
+        if all(f.iga is not None for _, f in funcs):
+            acc = None
+            for c, f in funcs:
+                acc = f.iga * c if acc is None else acc + f.iga * c
+            self.set_iga(acc)
+            return
+        acc = None
+        for c, f in funcs:
+            acc = f.fe_tensor() * c if acc is None else acc + f.fe_tensor() * c
+        self.iga = None
+        self._fe = acc
 
     def rename(self, *a):
         pass
 
     def function_space(self):
         return self.V
+
+
+def linear_combination(expr):
+    """[(fid, coefficient)] of an expression that is a linear combination, with
+    constant coefficients, of (undifferentiated) Functions; ValueError otherwise."""
+    sc = U.as_tensor(expr)
+    if sc.a.ndim != 0:
+        raise ValueError("assign: scalar expressions only")
+    sc = sc.a[()]
+    if not sc.is_coef():
+        raise ValueError("assign: the expression contains trial/test functions")
+    n = sc.node()
+    leaves = S.jets_of([n])
+    out = []
+    for leaf in leaves:
+        fid, comp, al = leaf.args
+        if comp != 0 or any(al):
+            raise ValueError("assign: derivatives of Functions are not a nodal combination")
+        c = S.diff_leaf(n, leaf)
+        if not c.is_const():
+            raise ValueError("assign: the expression is not linear in its Functions")
+        if fid not in _functions:
+            raise ValueError("assign: unknown Function in the expression")
+        out.append((fid, float(c.args[0])))
+    rest = S.substitute(n, {leaf: S.ZERO for leaf in leaves})
+    if not (rest.is_const() and float(rest.args[0]) == 0.0):
+        raise ValueError("assign: the expression has a part that is not a Function")
+    if not out:
+        raise ValueError("assign: no Function in the expression")
+    return out
 
 
 def TrialFunction(V):
