@@ -593,3 +593,61 @@ def test_linear_combination_assign_and_time_integrators():
     assert abs(ls.t - 0.5) < 1e-15
     with pytest.raises(NotImplementedError):
         TI.LinearDGSpaceTimeIntegrator(dt, x, x0)
+
+
+def test_nurbs_shim_refine_elevate_preserve_geometry_and_annulus_is_exact():
+    """tigar_b200.nurbs (the igakit stand-in of SURVEY 8f n2): knot insertion and
+    Bezier degree elevation leave the rational map unchanged, the quarter annulus
+    of BASELINE configs[3] is an exact circular arc with a linear radius, and the
+    NURBSControlMesh net is flattened first-direction-fastest (NURBS.py:43-77)."""
+    from oracle import bsplines as OB
+    from tigar_b200.nurbs import NURBS, NURBSControlMesh, quarter_annulus
+
+    def evaluate(nrb, pts):
+        sp = [OB.Spline1(int(p), list(k)) for p, k in zip(nrb.degree, nrb.knots)]
+        out = []
+        for xi in pts:
+            acc = np.zeros(nrb.control.shape[-1])
+            spans = [s.getKnotSpan(u) for s, u in zip(sp, xi)]
+            vals = [s.basisFuncs(k, u) for s, k, u in zip(sp, spans, xi)]
+            idx = [range(k - s.p, k + 1) for s, k in zip(sp, spans)]
+            for loc in np.ndindex(*[len(r) for r in idx]):
+                w = np.prod([vals[d][loc[d]] for d in range(len(sp))])
+                acc += w * nrb.control[tuple(idx[d][loc[d]] for d in range(len(sp)))]
+            out.append(acc[:-1] / acc[-1])
+        return np.array(out)
+
+    rng = np.random.RandomState(5)
+    s = 1.0 / math.sqrt(2.0)
+    arc = np.array([[1.0, 0.0, 1.0], [s, s, s], [0.0, 1.0, 1.0]])
+    net = np.zeros((2, 3, 3))                               # (radial, angular) quadratic arc
+    for i, r in enumerate((1.0, 2.0)):
+        net[i, :, 0], net[i, :, 1], net[i, :, 2] = r * arc[:, 0], r * arc[:, 1], arc[:, 2]
+    base = NURBS([[0, 0, 1, 1], [0, 0, 0, 1, 1, 1]], net, homogeneous=True)
+    pts = rng.rand(12, 2) * 0.98 + 0.01
+    ref = evaluate(base, pts)
+    assert np.allclose(np.hypot(ref[:, 0], ref[:, 1]), 1.0 + pts[:, 0], atol=1e-14)
+    mod = NURBS([k.copy() for k in base.knots], base.control.copy(), homogeneous=True)
+    mod.elevate(0, 2).elevate(1, 1)
+    assert mod.degree == [3, 3]
+    assert np.allclose(evaluate(mod, pts), ref, atol=1e-14)
+    mod.refine(0, [0.25, 0.5, 0.5001]).refine(1, [0.3, 0.9])
+    assert mod.control.shape[:2] == (7, 6)
+    assert np.allclose(evaluate(mod, pts), ref, atol=1e-13)
+
+    ann = quarter_annulus(3, [5, 4], 2)
+    assert ann.degree == [3, 3] and ann.control.shape == (8, 7, 3)
+    X = evaluate(ann, pts)
+    assert np.allclose(np.hypot(X[:, 0], X[:, 1]), 1.0 + pts[:, 0], atol=1e-13)   # r linear in xi_0
+    assert np.all(X >= -1e-14)                                                     # first quadrant
+    ann3 = quarter_annulus(3, [3, 4, 2], 3, height=0.5)
+    p3 = rng.rand(6, 3) * 0.98 + 0.01
+    X3 = evaluate(ann3, p3)
+    assert np.allclose(np.hypot(X3[:, 0], X3[:, 1]), 1.0 + p3[:, 0], atol=1e-13)
+    assert np.allclose(X3[:, 2], 0.5 * p3[:, 2], atol=1e-14)
+    cm = NURBSControlMesh(ann3)
+    n0, n1, n2 = ann3.control.shape[:3]
+    assert cm.getNsd() == 3 and cm.controlNet().shape == (n0 * n1 * n2, 4)
+    i, j, k = 2, 3, 1
+    assert np.array_equal(cm.controlNet()[i + n0 * (j + n1 * k)], ann3.control[i, j, k])
+    assert cm.getHomogeneousCoordinate(i + n0 * (j + n1 * k), 3) == ann3.control[i, j, k, 3]
