@@ -16,7 +16,8 @@ from tigar_b200.bsplines import (                               # noqa: F401
     AbstractScalarBasis, AbstractControlMesh, DOLFIN_EPS, USE_RECT_ELEM_DEFAULT, near)
 from tigar_b200.ufl_lite import (                               # noqa: F401
     pi, inner, dot, outer, tr, det, inv, transpose, grad, sqrt, sin, cos, tan, exp, ln, tanh,
-    sinh, cosh, atan, as_vector, as_matrix, as_tensor, Constant, lhs, rhs, Form, Equation)
+    sinh, cosh, atan, as_vector, as_matrix, as_tensor, Constant, Parameter, lhs, rhs, Form,
+    Equation)
 from tigar_b200.calculus import (                               # noqa: F401
     getMetric, pinvD, volumeJacobian, cartesianGrad, cartesianDiv, cartesianCurl, getQuadRule,
     getQuadRuleInterval)

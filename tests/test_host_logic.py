@@ -590,7 +590,7 @@ def test_linear_combination_assign_and_time_integrators():
     assert np.allclose(x0.iga.numpy(), vals[x.fid]) and np.allclose(v0.iga.numpy(), bv, atol=1e-12)
     ls = TI.LoadStepper(0.25)
     ls.advance()
-    assert abs(ls.t - 0.5) < 1e-15
+    assert abs(float(ls.t) - 0.5) < 1e-15
     with pytest.raises(NotImplementedError):
         TI.LinearDGSpaceTimeIntegrator(dt, x, x0)
 
@@ -651,3 +651,30 @@ def test_nurbs_shim_refine_elevate_preserve_geometry_and_annulus_is_exact():
     i, j, k = 2, 3, 1
     assert np.array_equal(cm.controlNet()[i + n0 * (j + n1 * k)], ann3.control[i, j, k])
     assert cm.getHomogeneousCoordinate(i + n0 * (j + n1 * k), 3) == ann3.control[i, j, k, 3]
+
+
+def test_mutable_parameter_is_baked_at_compile_time():
+    """ufl_lite.Parameter / symbolic.param: a leaf with zero derivative whose current
+    value enters the program each time it is compiled (dolfin Constant.assign /
+    Expression parameters between solves)."""
+    from tigar_b200 import api as A
+    x = U.Tensor(U.Scalar.coef(S.xi(0)))
+    t = U.Parameter(0.25)
+    e = U.sin(t * x) + t * t
+    node = U.as_tensor(e).a[()].node()
+    dnode = S.diff(node, 0)
+    X = 0.7
+    for val in (0.25, 1.5):
+        t.assign(val)
+        prog = S.compile_program([node, dnode], 1)
+        got = run_program(prog, [X], 1.0, {})
+        assert abs(got[0] - (math.sin(val * X) + val * val)) < 1e-15
+        assert abs(got[1] - val * math.cos(val * X)) < 1e-15
+        assert val in prog.consts
+    assert float(t) == 1.5 and S.jets_of([node]) == []
+    frozen = S.freeze_params(S.mul(S.param(t.pid), S.const(2.0)))
+    assert frozen.is_const() and frozen.args[0] == 3.0
+    # a linear combination with a parameter coefficient uses the current value
+    V = A.FunctionSpace(_DummyOwner())
+    u = A.Function(V)
+    assert A.linear_combination(t * u) == [(u.fid, 1.5)]

@@ -229,7 +229,7 @@ def linear_combination(expr):
     sc = sc.a[()]
     if not sc.is_coef():
         raise ValueError("assign: the expression contains trial/test functions")
-    n = sc.node()
+    n = S.freeze_params(sc.node())
     leaves = S.jets_of([n])
     out = []
     for leaf in leaves:

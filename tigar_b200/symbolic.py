@@ -54,7 +54,7 @@ class Node(object):
     def __repr__(self):
         if self.op == "const":
             return repr(self.args[0])
-        if self.op in ("xi", "wq", "jet"):
+        if self.op in ("xi", "wq", "jet", "param"):
             return "%s%r" % (self.op, self.args)
         return "%s(%s)" % (self.op, ",".join(repr(a) for a in self.args))
 
@@ -91,6 +91,37 @@ def xi(d):
 
 def wq():
     return _mk("wq")
+
+
+PARAMS = {}          # pid -> current value of a mutable scalar parameter
+
+
+def param(pid, value=None):
+    """Mutable scalar parameter (a dolfin ``Constant`` / ``Expression`` parameter that is
+    re-assigned between solves, e.g. the load-stepping time, timeIntegration.py:84-93):
+    a leaf whose CURRENT value is baked into the program each time it is compiled."""
+    pid = int(pid)
+    if value is not None:
+        PARAMS[pid] = float(value)
+    return _mk("param", pid)
+
+
+def freeze_params(n):
+    """``n`` with every parameter leaf replaced by its current value."""
+    leaves = []
+    seen, stack = set(), [n]
+    while stack:
+        m = stack.pop()
+        if m.uid in seen:
+            continue
+        seen.add(m.uid)
+        if m.op == "param":
+            leaves.append(m)
+        elif m.op not in ("const", "xi", "wq", "jet"):
+            stack.extend(m.args)
+    if not leaves:
+        return n
+    return substitute(n, {m: const(PARAMS[m.args[0]]) for m in leaves})
 
 
 def jet(fid, comp, alpha):
@@ -255,7 +286,7 @@ def diff(n, j):
 
 def _diff(n, j):
     op = n.op
-    if op in ("const", "wq"):
+    if op in ("const", "wq", "param"):
         return ZERO
     if op == "xi":
         return ONE if n.args[0] == j else ZERO
@@ -277,7 +308,7 @@ def diff_leaf(n, leaf, _memo=None):
     if r is None:
         if n is leaf:
             r = ONE
-        elif n.op in ("const", "wq", "xi", "jet"):
+        elif n.op in ("const", "wq", "xi", "jet", "param"):
             r = ZERO
         else:
             r = _diff_rule(n, lambda c: diff_leaf(c, leaf, _memo))
@@ -351,7 +382,7 @@ def substitute(n, mapping, _memo=None):
         return r
     if n in mapping:
         r = mapping[n]
-    elif n.op in ("const", "xi", "wq", "jet"):
+    elif n.op in ("const", "xi", "wq", "jet", "param"):
         r = n
     else:
         args = [substitute(a, mapping, _memo) for a in n.args]
@@ -373,7 +404,7 @@ def jets_of(nodes):
         seen.add(n.uid)
         if n.op == "jet":
             out.append(n)
-        elif n.op not in ("const", "xi", "wq"):
+        elif n.op not in ("const", "xi", "wq", "param"):
             stack.extend(n.args)
     out.sort(key=lambda n: n.args)
     return out
@@ -414,7 +445,7 @@ def compile_program(outputs, dim):
             n, i = stack.pop()
             if n.uid in seen:
                 continue
-            kids = n.args if n.op not in ("const", "xi", "wq", "jet") else ()
+            kids = n.args if n.op not in ("const", "xi", "wq", "jet", "param") else ()
             if i < len(kids):
                 stack.append((n, i + 1))
                 if kids[i].uid not in seen:
@@ -438,7 +469,7 @@ def compile_program(outputs, dim):
     # last use of each node
     last = {}
     for pos, n in enumerate(order):
-        if n.op in ("const", "xi", "wq", "jet"):
+        if n.op in ("const", "xi", "wq", "jet", "param"):
             continue
         for a in n.args:
             last[a.uid] = pos
@@ -448,14 +479,15 @@ def compile_program(outputs, dim):
     for pos, n in enumerate(order):
         if n.op in ("xi", "wq", "jet"):
             continue
-        if n.op == "const":
-            v = n.args[0]
+        isc = n.op in ("const", "param")          # a parameter is a constant of THIS program
+        if isc:
+            v = n.args[0] if n.op == "const" else float(PARAMS[n.args[0]])
             if v not in cidx:
                 cidx[v] = len(consts)
                 consts.append(v)
         # release operands whose last use is here (their registers may be the dst)
-        ops = [] if n.op == "const" else [reg[a.uid] for a in n.args]
-        if n.op != "const":
+        ops = [] if isc else [reg[a.uid] for a in n.args]
+        if not isc:
             for a in n.args:
                 if (last.get(a.uid) == pos and a.uid not in outset
                         and reg[a.uid] >= nfixed and reg[a.uid] not in free):
@@ -466,8 +498,8 @@ def compile_program(outputs, dim):
             dst = nreg
             nreg += 1
         reg[n.uid] = dst
-        if n.op == "const":
-            prog.append((OPCODES["const"], dst, cidx[n.args[0]], 0))
+        if isc:
+            prog.append((OPCODES["const"], dst, cidx[v], 0))
         elif len(ops) == 1:
             prog.append((OPCODES[n.op], dst, ops[0], ops[0]))
         else:

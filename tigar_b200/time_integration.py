@@ -8,9 +8,9 @@ form-language expression on demand; ``advance()`` moves the data with
 ``Function.assign`` of those combinations (api.linear_combination).
 
 Not built: ``LinearDGSpaceTimeIntegrator`` (needs mixed function spaces, SURVEY
-8f n1).  ``LoadStepper.t`` is a plain float here: forms that depend on it have
-to be rebuilt after ``advance()`` (the reference mutates a DOLFIN ``Expression``
-parameter in place, timeIntegration.py:74-93).
+8f n1).  ``LoadStepper.t`` is a ``ufl_lite.Parameter``: forms written with it see
+the new value at their next assembly, like the DOLFIN ``Expression`` parameter the
+reference mutates in place (timeIntegration.py:74-93).
 """
 from . import ufl_lite as U
 
@@ -104,11 +104,12 @@ class LoadStepper(object):
     def __init__(self, DELTA_T, t=0.0):
         self.DELTA_T = DELTA_T
         self.tval = t
+        self.t = U.Parameter(t)
         self.advance()
 
     def advance(self):
         self.tval += float(self.DELTA_T)
-        self.t = self.tval
+        self.t.assign(self.tval)
 
 
 class GeneralizedAlphaIntegrator(_Integrator):

@@ -274,6 +274,30 @@ def Constant(v):
     return as_tensor(np.asarray(v, dtype=float)) if np.ndim(v) else as_tensor(float(v))
 
 
+_param_counter = [0]
+
+
+class Parameter(Tensor):
+    """Mutable scalar: what a dolfin ``Constant`` that is later ``assign``-ed, or an
+    ``Expression("t", t=...)`` whose parameter is updated between solves, is in the
+    reference's demos (timeIntegration.py:84-93).  Forms keep a symbolic leaf; the
+    CURRENT value is baked in each time a form is compiled for assembly."""
+
+    def __init__(self, value=0.0):
+        _param_counter[0] += 1
+        self.pid = _param_counter[0]
+        Tensor.__init__(self, Scalar.coef(S.param(self.pid, float(value))))
+
+    def assign(self, value):
+        S.PARAMS[self.pid] = float(value)
+
+    def __float__(self):
+        return S.PARAMS[self.pid]
+
+    def values(self):
+        return np.array([S.PARAMS[self.pid]])
+
+
 # ---------------------------------------------------------------- algebra
 def inner(a, b):
     a, b = as_tensor(a), as_tensor(b)
