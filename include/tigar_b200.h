@@ -286,8 +286,10 @@ int tg_ptap_march(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY, d
 
 /* Same pass, warp-independent variant (the default): every warp owns a task --
  * up to 8 pieces, each a contiguous range of fibres of one line -- and runs its
- * own cp.async ring in a private shared-memory slice (no CTA barriers inside the
- * march); the march advances by groups of <= 4 consecutive FE rows sharing
+ * own 3-stage ring in a private shared-memory slice (1-D bulk async copies = TMA
+ * with per-warp mbarriers for d = 0,1; 8-byte cp.async for d = 2, whose sub-rows
+ * are strided; no CTA barriers inside the march); the march advances by groups
+ * of <= 4 consecutive FE rows sharing
  * first(I); the per-node tables of a CTA's march segment live in shared memory.
  *   irec[n_fe_d] int32x4 {len_d(I) | lo_d(I) << 8 of X, first(I), sbits, group(I)};
  *        sbits: 2 bits per column q of the row's window, first(lo+q) - first(I) + 1
@@ -303,9 +305,8 @@ int tg_ptap_march(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY, d
  * (a segment marches over the whole groups covering its rows' FE support);
  * maxpieces: most pieces of one task; wpc: warps (tasks) per CTA -- 8 (two CTAs
  * per SM), 16 (one CTA per SM, the segment tables are shared by twice as many
- * warps: longer segments) or 4 (required for p = 4).  For d = 0,1 the rows are staged by 1-D
- * bulk async copies (TMA): the value array of X must then be readable up to the
- * next 16-byte boundary past its end.                                        */
+ * warps: longer segments) or 4 (required for p = 4).  For d = 0,1 the value
+ * array of X must be readable up to the next 16-byte boundary past its end.   */
 int tg_ptap_march_w(const tg_win* h_wX, const double* Xvals, const tg_win* h_wY, double* Yvals,
                     int32_t d, int32_t p, int32_t GMAX, const void* irec, const void* Sx,
                     const void* jrec, const double* cpad, const int32_t* grp,
@@ -320,7 +321,8 @@ int tg_win_spmv(const tg_win* h_w, const double* vals, const double* x, double* 
                 void* stream);
 /* which kernel the last windowed SpMV used: 0 direct-load (k_win_spmv), 1 TMA-staged
  * rows + shared-memory x tiles (k_win_spmv_tma), 2 SELL layout (k_sell_spmv),
- * 3 direct-load with per-warp cp.async row prefetch (k_win_spmv_pf, the default)  */
+ * 3 direct-load with per-warp cp.async row prefetch (k_win_spmv_pf).  0 is the
+ * default; 1 and 3 are opt-in (TIGAR_B200_TMA_SPMV=1, TIGAR_B200_SPMV_PF=1)       */
 int tg_last_spmv_kind(void);
 /* y = C x and out1[0] = sum_r x[xoff+r] y[r]; scratch: tg_cg_scratch_len()   */
 int tg_win_spmv_dot(const tg_win* h_w, const double* vals, const double* x, int64_t xoff,
