@@ -20,4 +20,6 @@ from tigar_b200.ufl_lite import (                               # noqa: F401
     Equation)
 from tigar_b200.calculus import (                               # noqa: F401
     getMetric, pinvD, volumeJacobian, cartesianGrad, cartesianDiv, cartesianCurl, getQuadRule,
-    getQuadRuleInterval)
+    getQuadRuleInterval, getChristoffel, CurvilinearTensor, curvilinearInner, covariantDerivative,
+    curvilinearGrad, curvilinearDiv, mappedNormal, surfaceJacobian, cartesianPushforwardN,
+    cartesianPushforwardRT, cartesianPushforwardW)

@@ -678,3 +678,68 @@ def test_mutable_parameter_is_baked_at_compile_time():
     V = A.FunctionSpace(_DummyOwner())
     u = A.Function(V)
     assert A.linear_combination(t * u) == [(u.fid, 1.5)]
+
+
+def test_curvilinear_calculus_in_polar_coordinates():
+    """tigar_b200.calculus curvilinear part (calculusUtils.py:26-54, 71-250, 307-346) in
+    the polar chart g = diag(1, r^2): Christoffel symbols, metric compatibility,
+    gradient / divergence / Laplace-Beltrami against the textbook formulas, index
+    gymnastics, mapped normal, surface element and the three pushforwards."""
+    from tigar_b200 import calculus as CU
+    old = U.DEFAULT_DIM[0]
+    U.DEFAULT_DIM[0] = 2
+    try:
+        r, t = (U.Tensor(U.Scalar.coef(S.xi(d))) for d in range(2))
+        F = U.as_vector([r * U.cos(t), r * U.sin(t)])
+        g = CU.getMetric(F)
+        X = (1.3, 0.8)
+        R, T_ = X
+        ev = lambda e: _eval_coef(e, X)
+        gam = CU.getChristoffel(g)
+        ref = np.zeros((2, 2, 2))
+        ref[0, 1, 1] = -R
+        ref[1, 0, 1] = ref[1, 1, 0] = 1.0 / R
+        for idx in np.ndindex(2, 2, 2):
+            assert abs(ev(gam[idx]) - ref[idx]) < 1e-12, idx
+        # metric compatibility: the covariant derivative of g vanishes
+        Dg = CU.covariantDerivative(CU.CurvilinearTensor(g, g))
+        assert Dg.lowered == [True, True, True]
+        for idx in np.ndindex(2, 2, 2):
+            assert abs(ev(Dg.T[idx])) < 1e-12
+        # scalar: GRAD raises the derivative index, DIV GRAD = Laplace-Beltrami
+        f = r * r * U.cos(2.0 * t)                   # x^2 - y^2: harmonic
+        G = CU.curvilinearGrad(CU.CurvilinearTensor(f, g))
+        assert G.lowered == [False]
+        assert abs(ev(G.T[0]) - 2 * R * math.cos(2 * T_)) < 1e-12
+        assert abs(ev(G.T[1]) - (-2 * R * R * math.sin(2 * T_)) / R ** 2) < 1e-12
+        assert abs(ev(CU.curvilinearDiv(G).T)) < 1e-11
+        lap = CU.curvilinearDiv(CU.curvilinearGrad(CU.CurvilinearTensor(r * r * r, g)))
+        assert abs(ev(lap.T) - 9 * R) < 1e-11         # (1/r)(r f')' with f = r^3
+        # contravariant vector: div v = d_r v^r + d_t v^t + v^r / r
+        v = U.as_vector([r * r * U.sin(t), U.cos(t) / r])
+        dv = CU.curvilinearDiv(CU.CurvilinearTensor(v, g, [False]))
+        assert dv.rank() == 0
+        assert abs(ev(dv.T) - (2 * R * math.sin(T_) - math.sin(T_) / R + R * math.sin(T_))) < 1e-12
+        # index gymnastics and the inner product
+        a = CU.CurvilinearTensor(U.as_vector([r * t, r + t]), g)            # covector
+        up = a.sharp()
+        assert up.lowered == [False] and abs(ev(up.T[1]) - (R + T_) / R ** 2) < 1e-13
+        assert abs(ev(up.flat().T[1]) - (R + T_)) < 1e-13
+        assert abs(ev(CU.curvilinearInner(a, a)) - ((R * T_) ** 2 + (R + T_) ** 2 / R ** 2)) < 1e-12
+        s2 = 2.0 * a - a
+        assert abs(ev(s2.T[0]) - R * T_) < 1e-14
+        # geometry of the circle r = const and the pushforwards
+        n = CU.mappedNormal(U.as_vector([1.0, 0.0]), F)
+        assert abs(ev(n[0]) - math.cos(T_)) < 1e-13 and abs(ev(n[1]) - math.sin(T_)) < 1e-13
+        assert abs(ev(CU.surfaceJacobian(g, U.as_vector([1.0, 0.0]))) - R) < 1e-13
+        w = U.as_vector([r, t])
+        rt = CU.cartesianPushforwardRT(w, F)         # DF w / J
+        DFn = np.array([[math.cos(T_), -R * math.sin(T_)], [math.sin(T_), R * math.cos(T_)]])
+        exp_rt = DFn @ np.array([R, T_]) / R
+        exp_n = np.linalg.inv(DFn.T) @ np.array([R, T_])
+        pn = CU.cartesianPushforwardN(w, F)
+        for i in range(2):
+            assert abs(ev(rt[i]) - exp_rt[i]) < 1e-13 and abs(ev(pn[i]) - exp_n[i]) < 1e-13
+        assert abs(ev(CU.cartesianPushforwardW(r * t, F)) - T_) < 1e-13
+    finally:
+        U.DEFAULT_DIM[0] = old

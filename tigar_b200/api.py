@@ -744,6 +744,20 @@ class ExtractedSpline(object):
         2-D vector, vector for a 2-D scalar."""
         return U.curl_from_grad(f, self.grad(f, F))
 
+    def GRAD(self, f):
+        """Covariant derivative w.r.t. the parametric chart with the new index raised
+        (common.py:1068-1080); a plain tensor is taken with all indices lowered."""
+        from . import calculus as CU
+        ff = f if isinstance(f, CU.CurvilinearTensor) else CU.CurvilinearTensor(f, self.g)
+        return CU.curvilinearGrad(ff)
+
+    def DIV(self, f):
+        """Curvilinear divergence matching GRAD (common.py:1081-1093); a plain tensor
+        is taken with all indices raised."""
+        from . import calculus as CU
+        ff = f if isinstance(f, CU.CurvilinearTensor) else CU.CurvilinearTensor(f, self.g).sharp()
+        return CU.curvilinearDiv(ff)
+
     def parametricExpression(self, expr):
         """``Expression`` in the parametric coordinates (common.py:1111-1117); the
         formula is evaluated exactly at the Gauss points, not interpolated."""
