@@ -378,6 +378,11 @@ int tg_solve_cg(const int64_t* rowptr, const int32_t* cols, const double* vals,
 void tg_prof_enable(int on);
 void tg_prof_get(double* spmv_ms, int64_t* spmv_launches);
 
+/* y += a x.  Block-row accumulation y_i = sum_j C_ij x_j of an equal-order
+ * multi-field system (field blocks of common.py:337-351, 1546-1573): one
+ * windowed SpMV per block, summed with this.                                */
+int tg_axpy(double* y, double a, const double* x, int64_t n, void* stream);
+
 /* CG building blocks for the row-distributed multi-GPU solver (the host
  * interleaves torch.distributed halo exchange / all-reduce between them).
  * scratch: tg_cg_scratch_len() doubles.

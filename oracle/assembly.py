@@ -307,6 +307,55 @@ def assemble(tabs, coef, form, f=None, rationalize=False, chunk=2048):
     return A, b
 
 
+def assemble_elasticity(tabs, coef, mu, lam, f=None, chunk=2048):
+    """Equal-order multi-field system (MixedElement with one sub-element per field,
+    common.py:337-351; field-major IGA numbering ``globalDof``, common.py:254-262):
+    plane / 3-D linear elasticity on the mapped patch,
+
+        a(u, v) = int [ 2 mu eps(u):eps(v) + lam div(u) div(v) ] J dxi ,
+        L(v) = int f . v J dxi ,    eps = sym(grad_x) ,
+
+    with grad_x as in calculusUtils.py:255-261.  Block (i, k) of the matrix couples
+    test field i with trial field k; all blocks share the scalar pattern.  Returns
+    (A [nf*n, nf*n] CSR, b [nf*n]) in the basis described by ``tabs``."""
+    dim = len(tabs)
+    nsd = coef.shape[1] - 1
+    ncell = int(np.prod([tb.T.shape[0] for tb in tabs]))
+    n = int(np.prod([tb.n for tb in tabs]))
+    rows, cols, vals = [], [], []
+    b = np.zeros(nsd * n)
+    for c0 in range(0, ncell, chunk):
+        cells = np.arange(c0, min(ncell, c0 + chunk))
+        blk = CellBlock(tabs, cells, 1)
+        geo = Geometry(blk, coef, 1)
+        G = operators("poisson", blk, geo, blk.jets)        # G[i][c,q,a] = d psi_a / d x_i
+        W = blk.wq * geo.J
+        gg = sum(np.einsum("cq,cqa,cqb->cab", W, G[j], G[j], optimize=True) for j in range(nsd))
+        nen = blk.gidx.shape[1]
+        r0 = np.repeat(blk.gidx, nen, axis=1).ravel()
+        c0_ = np.tile(blk.gidx, (1, nen)).ravel()
+        for i in range(nsd):
+            for k in range(nsd):
+                # 2 mu eps(u):eps(v) = mu (grad u : grad v + grad u : grad v^T)
+                Ke = mu * np.einsum("cq,cqa,cqb->cab", W, G[k], G[i], optimize=True) \
+                    + lam * np.einsum("cq,cqa,cqb->cab", W, G[i], G[k], optimize=True)
+                if i == k:
+                    Ke = Ke + mu * gg
+                rows.append(r0 + i * n)
+                cols.append(c0_ + k * n)
+                vals.append(Ke.ravel())
+        if f is not None:
+            fv = f(geo.F)                                     # [c,q,nsd]
+            z = (0,) * dim
+            for i in range(nsd):
+                fe = np.einsum("cq,cqa->ca", W * fv[..., i], blk.jets[z])
+                np.add.at(b, blk.gidx.ravel() + i * n, fe.ravel())
+    A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                      shape=(nsd * n, nsd * n)).tocsr()
+    A.sort_indices()
+    return A, b
+
+
 def functional(tabs, coef, U, kind, exact, rationalize=False, chunk=2048):
     """int (u_h - exact)^2 J  (kind='l2', poisson.py:132) or
     int (lap(u_h) - exact)^2 J (kind='energy', biharmonic.py:127), with

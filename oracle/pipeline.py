@@ -167,3 +167,42 @@ class Problem(object):
         tabs = [A.tab_iga(s, self.nq, nder) for s in self.ts.splines]
         return np.sqrt(A.functional(tabs, self.P, U, kind, exact,
                                     rationalize=self.rationalize))
+
+
+class ElasticityProblem(object):
+    """Equal-order multi-field patch problem: nsd displacement fields
+    on the control mesh's spline (EqualOrderSpline, common.py:1891-1945).  The
+    multi-field extraction operator (generateM, common.py:1546-1573) is block
+    diagonal, ``I_nf (x) M_scalar``; IGA DoFs are field-major (globalDof,
+    common.py:254-262); homogeneous BCs on the listed global DoFs
+    (common.py:1154-1158, 1199-1200)."""
+
+    def __init__(self, degrees, kvecs, P, mu, lam, zeroDofs, quadDeg=None):
+        self.ts = B.TensorSpline(degrees, kvecs)
+        self.P = np.asarray(P, float)
+        self.nf = self.P.shape[1] - 1
+        self.mu, self.lam = mu, lam
+        self.quadDeg = 2 * max(degrees) if quadDeg is None else quadDeg
+        self.nq = self.quadDeg // 2 + 1
+        self.zeroDofs = np.unique(np.asarray(zeroDofs, dtype=np.int64))
+
+    def fe_path(self, f):
+        """Reference-faithful: A_FE, b_FE on the Lagrange mesh, then M^T A M, M^T b."""
+        Ms = X.build_M_kron(self.ts)
+        M = sp.kron(sp.identity(self.nf), Ms, format="csr")
+        cpn = X.control_funcs(Ms, self.P)
+        pf = self.ts.getDegree()
+        tabs = [A.tab_fe(s, pf, self.nq, 1) for s in self.ts.splines]
+        Afe, bfe = A.assemble_elasticity(tabs, cpn, self.mu, self.lam, f)
+        return ptap(Afe, M), M.T @ bfe
+
+    def direct_iga(self, f):
+        tabs = [A.tab_iga(s, self.nq, 1) for s in self.ts.splines]
+        return A.assemble_elasticity(tabs, self.P, self.mu, self.lam, f)
+
+    def solve(self, f, direct=True):
+        C0, b0 = self.direct_iga(f) if direct else self.fe_path(f)
+        self.C = apply_bcs_matrix_fast(C0, self.zeroDofs, 1.0)
+        self.b = apply_bcs_vector(b0, self.zeroDofs)
+        self.U = spla.spsolve(self.C.tocsc(), self.b)
+        return self.U

@@ -108,6 +108,7 @@ SIGNATURES = {
     "tg_cg_axpy_dot": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp],
     "tg_cg_xpby": [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
     "tg_dot": [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
+    "tg_axpy": [c_vp, c_dbl, c_vp, c_i64, c_vp],
 }
 _RESTYPES = {"tg_last_error": C.c_char_p, "tg_prof_enable": None, "tg_prof_get": None, "tg_launch_count": c_i64, "tg_win_storage": c_i64}
 

@@ -156,6 +156,19 @@ class FunctionSpace(object):
     def mesh(self):
         return self.owner.mesh
 
+    def num_sub_spaces(self):
+        return 0 if self.nfields == 1 else self.nfields
+
+    def sub(self, i):
+        """Scalar space of field ``i`` (all fields share the control mesh's spline)."""
+        if not 0 <= i < self.nfields:
+            raise IndexError("field %d of a %d-field space" % (i, self.nfields))
+        if self.nfields == 1:
+            return self
+        if getattr(self, "_subs", None) is None:
+            self._subs = [FunctionSpace(self.owner, 1) for _ in range(self.nfields)]
+        return self._subs[i]
+
 
 _fid_counter = [0]
 _functions = weakref.WeakValueDictionary()
@@ -165,14 +178,17 @@ class Function(U.Tensor):
     """FE function on the extraction mesh.  Holds FE nodal coefficients
     (``fe``) and, when it was produced from IGA DoFs, those too (``iga``)."""
 
+    def __new__(cls, V):
+        if cls is Function and V.nfields != 1:
+            return object.__new__(VectorFunction)
+        return object.__new__(cls)
+
     def __init__(self, V):
         _fid_counter[0] += 1
         self.fid = _fid_counter[0]
         self.V = V
         self._fe = None
         self.iga = None
-        if V.nfields != 1:
-            raise NotImplementedError("multi-field function spaces (next row n1)")
         U.Tensor.__init__(self, U.Scalar.coef(S.jet(self.fid, 0, (0, 0, 0))))
         _functions[self.fid] = self
 
@@ -220,6 +236,70 @@ class Function(U.Tensor):
         return self.V
 
 
+class VectorFunction(Function):
+    """Function on a multi-field space (``Function(V)`` with ``V.nfields > 1``): a
+    vector of scalar component Functions, one per field, all on the control mesh's
+    spline.  IGA DoFs are field-major (``globalDof``, common.py:254-262)."""
+
+    def __init__(self, V):
+        self.V = V
+        self.fid = None
+        self.comps = [Function(V.sub(i)) for i in range(V.nfields)]
+        arr = np.empty((V.nfields,), dtype=object)
+        for i, c in enumerate(self.comps):
+            arr[i] = c.a[()]
+        U.Tensor.__init__(self, arr)
+
+    def sub(self, i):
+        return self.comps[i]
+
+    def split(self):
+        return tuple(self.comps)
+
+    def fid_fields(self):
+        return {c.fid: i for i, c in enumerate(self.comps)}
+
+    @property
+    def iga(self):
+        import torch
+        if any(c.iga is None for c in self.comps):
+            return None
+        return torch.cat([c.iga for c in self.comps])
+
+    @property
+    def _fe(self):
+        import torch
+        return torch.cat([c.fe_tensor() for c in self.comps])
+
+    def fe_tensor(self):
+        return self._fe
+
+    def set_iga(self, t):
+        n = t.numel() // len(self.comps)
+        if n * len(self.comps) != t.numel():
+            raise ValueError("IGA vector length is not a multiple of the field count")
+        for i, c in enumerate(self.comps):
+            c.set_iga(t[i * n:(i + 1) * n])
+
+    def assign(self, other):
+        other = U.as_tensor(other)
+        if other.a.shape != (len(self.comps),):
+            raise ValueError("assign: expected a %d-vector" % len(self.comps))
+        for i, c in enumerate(self.comps):
+            o = other[i]
+            src = None
+            if isinstance(other, VectorFunction):
+                src = other.comps[i]
+            c.assign(src if src is not None else o)
+
+
+def split(u):
+    """dolfin ``split``: the field components of a multi-field Function / argument."""
+    if isinstance(u, VectorFunction):
+        return u.split()
+    return tuple(u[i] for i in range(len(u)))
+
+
 def linear_combination(expr):
     """[(fid, coefficient)] of an expression that is a linear combination, with
     constant coefficients, of (undifferentiated) Functions; ValueError otherwise."""
@@ -250,16 +330,24 @@ def linear_combination(expr):
     return out
 
 
+def _argument(V, test):
+    if V.nfields == 1:
+        return U.Tensor(U.Scalar({((U.ZERO3, None) if test else (None, U.ZERO3)): S.ONE}))
+    arr = np.empty((V.nfields,), dtype=object)
+    for f in range(V.nfields):
+        part = U.ZERO3 + (f,)                    # (a0, a1, a2, field)
+        arr[f] = U.Scalar({((part, None) if test else (None, part)): S.ONE})
+    return U.Tensor(arr)
+
+
 def TrialFunction(V):
-    if V.nfields != 1:
-        raise NotImplementedError("multi-field function spaces (next row n1)")
-    return U.Tensor(U.Scalar({(None, U.ZERO3): S.ONE}))
+    """Scalar for a one-field space, a vector with one component per field otherwise
+    (the MixedElement of common.py:337-351)."""
+    return _argument(V, False)
 
 
 def TestFunction(V):
-    if V.nfields != 1:
-        raise NotImplementedError("multi-field function spaces (next row n1)")
-    return U.Tensor(U.Scalar({(U.ZERO3, None): S.ONE}))
+    return _argument(V, True)
 
 
 def derivative(form, u, du=None):
@@ -267,6 +355,8 @@ def derivative(form, u, du=None):
     Function ``u`` in the direction of a trial function (poisson-nonzero-bc.py:103)."""
     if not isinstance(u, Function):
         raise TypeError("derivative() is taken with respect to a Function")
+    if isinstance(u, VectorFunction):
+        return U.gateaux(form, u.fid_fields())
     return U.gateaux(form, u.fid)
 
 
@@ -478,10 +568,30 @@ class AbstractCoordinateChartSpline(AbstractExtractionGenerator):
     def generateM_control(self):
         return self.patch().build_M()
 
+    def equalOrder(self):
+        """True if every field uses the control mesh's scalar spline (same degrees and
+        knot vectors): the multi-field ``M`` (common.py:1546-1573) is then block
+        diagonal with ``M_control`` in every block."""
+        ctl = self.getScalarSpline(-1)
+        for i in range(self.getNFields()):
+            sp = self.getScalarSpline(i)
+            if sp is ctl:
+                continue
+            if not (isinstance(sp, BSpline) and isinstance(ctl, BSpline)
+                    and len(sp.splines) == len(ctl.splines)
+                    and all(a.p == b.p and len(a.knots) == len(b.knots)
+                            and np.array_equal(a.knots, b.knots)
+                            for a, b in zip(sp.splines, ctl.splines))):
+                return False
+        return True
+
     def generateM(self):
-        if self.getNFields() == 1 and self.getScalarSpline(0) is self.getScalarSpline(-1):
+        """Scalar extraction operator of one field block; the multi-field ``M`` of an
+        equal-order spline is ``I_nFields (x) M_control`` and is never formed."""
+        if self.equalOrder():
             return self.M_control
-        raise NotImplementedError("multi-field extraction (next row n1)")
+        raise NotImplementedError("fields of different order (FieldListSpline with "
+                                  "unequal bases) are not built")
 
     def controlNet(self):
         cm = self.getControlMesh() if hasattr(self, "getControlMesh") else None
@@ -615,7 +725,12 @@ class ExtractedSpline(object):
         self.mesh = generator.mesh
         self.comm = generator.getComm()
         sp = generator._tensor_spline(-1)
+        if self.nFields > 1 and not generator.equalOrder():
+            raise NotImplementedError("multi-field splines are built for equal-order "
+                                      "fields (every field on the control mesh's spline)")
         part = (self.comm.rank, self.comm.size) if self.comm.size > 1 else None
+        if self.nFields > 1 and part is not None:
+            raise NotImplementedError("multi-field systems run on one GPU")
         self._patch = TensorPatch([s.p for s in sp.splines], None, quadDeg=quadDeg,
                                   splines=sp.splines, eps=generator.getIgnoreEps(), part=part)
         self.V = FunctionSpace(self, self.nFields)
@@ -793,11 +908,36 @@ class ExtractedSpline(object):
         w = S.wq()
         return {k: S.mul(v, w) for k, v in scalar.terms.items()}
 
+    def n_total(self):
+        """Number of IGA DoFs of all fields."""
+        return self._patch.n_iga * self.nFields
+
+    def _assemble_blocks(self, terms, ar, kind):
+        """Multi-field: one scalar assembly per (test field, trial field) block."""
+        from . import multifield as MF
+        p, nf = self._patch, self.nFields
+        funcs = self._funcs(kind)
+        if ar == 2:
+            blocks = {}
+            for fg, bt in sorted(MF.split_matrix_terms(terms, nf).items()):
+                blocks[fg] = p.assemble_matrix(bt, funcs, kind)
+            W = p.window("A" if kind == "fe" else "C")
+            return MF.BlockMatrix(nf, blocks, W.nrows)
+        import torch
+        parts = MF.split_vector_terms(terms, nf)
+        n = p.n_fe if kind == "fe" else p.n_iga
+        out = dev.zeros(nf * n)
+        for f, vt in sorted(parts.items()):
+            p.assemble_vector(vt, funcs, kind, out=out[f * n:(f + 1) * n])
+        return out
+
     def _assemble_kind(self, form, kind):
         sc = form.scalar()
         ar = sc.arity()
         terms = self._weighted(sc)
         p = self._patch
+        if self.nFields > 1 and ar > 0:
+            return self._assemble_blocks(terms, ar, kind)
         if ar == 2:
             return p.assemble_matrix({(k[0], k[1]): v for k, v in terms.items()},
                                      self._funcs(kind), kind)
@@ -816,14 +956,47 @@ class ExtractedSpline(object):
         return DeviceVector(r) if ar == 1 else r
 
     def _bc_mask(self):
+        """Device 0/1 mask over the IGA DoFs of all fields (field-major)."""
         if self._mask is None:
-            self._mask = self._patch.bc_mask(self.zeroDofs)
+            if self.nFields == 1:
+                self._mask = self._patch.bc_mask(self.zeroDofs)
+            else:
+                from . import multifield as MF
+                import torch
+                per = MF.split_zero_dofs(self.zeroDofs, self.nFields, self._patch.n_iga)
+                self._mask = torch.cat([self._patch.bc_mask(z) for z in per])
         return self._mask
+
+    def _field_mask(self, f):
+        n = self._patch.n_iga
+        return self._bc_mask()[f * n:(f + 1) * n]
+
+    def _apply_bcs_blocks(self, Cm, diag):
+        """zeroRowsColumns(zeroDofs, diag) (common.py:1199-1200) on the block grid: rows
+        of the test field's zero DoFs, columns of the trial field's, ``diag`` on the
+        diagonal of the diagonal blocks (which must exist to carry it)."""
+        p = self._patch
+        for f in range(self.nFields):
+            if Cm.block(f, f) is None:
+                Cm.blocks[(f, f)] = WinMatrix(p.window("C"))
+        for (f, g), B in Cm.blocks.items():
+            check(lib.tg_win_zero_rows_cols(B.window.ref(), dev.ptr(B.vals),
+                                            dev.ptr(self._field_mask(f)),
+                                            dev.ptr(self._field_mask(g)),
+                                            float(diag) if f == g else 0.0, 0, dev.stream()))
+        return Cm
 
     def extractVector(self, b, applyBCs=True):
         """M^T b (+ zero BC entries), common.py:1142-1160."""
         t = b.t if isinstance(b, DeviceVector) else b
-        MTb = self._patch.mt_vec(self.M_matrix(), t)
+        if self.nFields > 1:
+            nfe, n = self._patch.n_fe, self._patch.n_iga
+            MTb = dev.empty(self.nFields * n)
+            for f in range(self.nFields):
+                MTb[f * n:(f + 1) * n].copy_(
+                    self._patch.mt_vec(self.M_matrix(), t[f * nfe:(f + 1) * nfe].contiguous()))
+        else:
+            MTb = self._patch.mt_vec(self.M_matrix(), t)
         if applyBCs:
             self._patch.apply_bcs_vector(MTb, self._bc_mask())
         return DeviceVector(MTb)
@@ -838,6 +1011,12 @@ class ExtractedSpline(object):
 
     def extractMatrix(self, A, applyBCs=True, diag=1):
         """M^T A M then zeroRowsColumns, common.py:1176-1204."""
+        if self.nFields > 1:
+            from . import multifield as MF
+            MTAM = MF.BlockMatrix(self.nFields,
+                                  {fg: self._patch.ptap(B, self.M_matrix())
+                                   for fg, B in sorted(A.blocks.items())}, self._patch.n_iga)
+            return self._apply_bcs_blocks(MTAM, diag) if applyBCs else MTAM
         MTAM = self._patch.ptap(A, self.M_matrix())
         if applyBCs:
             self._patch.apply_bcs_matrix(MTAM, self._bc_mask(), diag)
@@ -848,6 +1027,8 @@ class ExtractedSpline(object):
             return self.extractMatrix(self._assemble_kind(form, "fe"), applyBCs, diag)
         MTAM = self._assemble_kind(form, "iga")
         if applyBCs:
+            if self.nFields > 1:
+                return self._apply_bcs_blocks(MTAM, diag)
             self._patch.apply_bcs_matrix(MTAM, self._bc_mask(), diag)
         return MTAM
 
@@ -855,7 +1036,8 @@ class ExtractedSpline(object):
         """common.py:1223-1234.  Matrix and vector share one Gauss-point pass."""
         kind = "fe" if self.mode == "csr" else "iga"
         ms, vs = lhsForm.scalar(), rhsForm.scalar()
-        if ms.arity() != 2 or vs.arity() != 1 or any(k[0] is None for k in vs.terms):
+        if (self.nFields > 1 or ms.arity() != 2 or vs.arity() != 1
+                or any(k[0] is None for k in vs.terms)):
             return (self.assembleMatrix(lhsForm, applyBCs),
                     self.assembleVector(rhsForm, applyBCs))
         mt = {(k[0], k[1]): n for k, n in self._weighted(ms).items()}
@@ -875,6 +1057,12 @@ class ExtractedSpline(object):
         rtol = prm.get("relative_tolerance", self.cgRelativeTolerance)
         atol = prm.get("absolute_tolerance", 0.0)
         maxit = prm.get("maximum_iterations", 200000)
+        if self.nFields > 1:
+            from . import multifield as MF
+            x, its, rel = MF.solve_block_cg(MTAM, MTb.t, rtol, atol, maxit)
+            self.lastSolve = dict(iterations=its, relative_residual=rel)
+            u.set_iga(x)
+            return DeviceVector(x)
         x0 = None if u.iga is None else u.iga.clone()
         x, its, rel = self._patch.solve_cg(MTAM, MTb.t, x0, rtol, atol, maxit)
         self.lastSolve = dict(iterations=its, relative_residual=rel)
@@ -891,7 +1079,7 @@ class ExtractedSpline(object):
             lhsForm, rhsForm = U.lhs(residualForm), U.rhs(residualForm)
         if rhsForm.empty():          # common.py:1285-1287: zero right-hand side
             MTAM = self.assembleMatrix(lhsForm, applyBCs)
-            MTb = DeviceVector(dev.zeros(self._patch.n_iga))
+            MTb = DeviceVector(dev.zeros(self.n_total()))
         else:
             MTAM, MTb = self.assembleLinearSystem(lhsForm, rhsForm, applyBCs)
         return self.solveLinearSystem(MTAM, MTb, u)
@@ -925,7 +1113,7 @@ class ExtractedSpline(object):
                 break
             du = Function(self.V)
             inc = self.solveLinearSystem(MTAM, MTb, du)
-            base = u.iga if u.iga is not None else dev.zeros(self._patch.n_iga)
+            base = u.iga if u.iga is not None else dev.zeros(self.n_total())
             u.set_iga(base - inc.t)
             if igaDoFs is not None:
                 igaDoFs.t.copy_(u.iga)

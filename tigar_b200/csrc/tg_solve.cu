@@ -217,6 +217,22 @@ extern "C" int tg_cg_xpby(double* p, const double* r, const double* dinv, int64_
   return 0;
 }
 
+// y += a x  (block-row accumulation y_i = sum_j C_ij x_j of a multi-field system)
+__global__ void k_axpy(double* __restrict__ y, double a, const double* __restrict__ x,
+                       int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = __fma_rn(a, x[i], y[i]);
+}
+
+extern "C" int tg_axpy(double* y, double a, const double* x, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  int g = tg_cg_grid_size();
+  k_axpy<<<g, TG_CG_BLOCK, 0, tg_stream(stream)>>>(y, a, x, n);
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
 // r = b - y ; p = dinv*r ; part0 = r*dinv*r ; part1 = r*r ; part2.. not used
 __global__ void __launch_bounds__(TG_CG_BLOCK)
 k_cg_init(const double* __restrict__ b, const double* __restrict__ y,

@@ -35,7 +35,9 @@ def _inc(al, j):
 
 class Scalar(object):
     """sum over keys (test, trial) of Node * D^test v * D^trial u; a key part is
-    None (absent) or a 3-multi-index of parametric derivatives."""
+    None (absent), a 3-multi-index of parametric derivatives (single-field space)
+    or ``(a0, a1, a2, field)`` for a basis function of one field of a multi-field
+    space (tigar_b200.multifield)."""
     __slots__ = ("terms",)
 
     def __init__(self, terms=None):
@@ -572,7 +574,10 @@ def rhs(form):
 def gateaux(form, fid):
     """d/d(eps) form(u + eps*du) at eps=0 for the coefficient function with id
     ``fid``; du is the trial function (UFL ``derivative(form, u)``).  Every term
-    must be free of trial functions."""
+    must be free of trial functions.  For a multi-field Function ``fid`` is a dict
+    {component fid: field}: the trial key then carries the field,
+    ``(a0, a1, a2, field)``."""
+    fields = fid if isinstance(fid, dict) else {fid: None}
     out = []
     for sc, owner in form.integrals:
         acc = Scalar()
@@ -580,11 +585,13 @@ def gateaux(form, fid):
             if tr is not None:
                 raise ValueError("derivative() of a form that already has a trial function")
             for jn in S.jets_of([coef]):
-                if jn.args[0] != fid:
+                if jn.args[0] not in fields:
                     continue
                 dc = S.diff_leaf(coef, jn)
                 if dc is not S.ZERO:
-                    acc = acc.add(Scalar({(t, tuple(jn.args[2])): dc}))
+                    fld = fields[jn.args[0]]
+                    key = tuple(jn.args[2]) if fld is None else tuple(jn.args[2]) + (fld,)
+                    acc = acc.add(Scalar({(t, key): dc}))
         if acc.terms:
             out.append((acc, owner))
     return Form(out)
