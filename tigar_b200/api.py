@@ -923,7 +923,6 @@ class ExtractedSpline(object):
                 blocks[fg] = p.assemble_matrix(bt, funcs, kind)
             W = p.window("A" if kind == "fe" else "C")
             return MF.BlockMatrix(nf, blocks, W.nrows)
-        import torch
         parts = MF.split_vector_terms(terms, nf)
         n = p.n_fe if kind == "fe" else p.n_iga
         out = dev.zeros(nf * n)
@@ -1098,6 +1097,11 @@ class ExtractedSpline(object):
         """Newton iteration of common.py:1304-1348."""
         if igaDoFs is not None:
             u.set_iga(igaDoFs.t.clone())
+        # a Function that was never assigned is zero (dolfin); give it IGA data so the
+        # element-fused path can read it
+        for c in (u.comps if isinstance(u, VectorFunction) else [u]):
+            if c.iga is None and c._fe is None:
+                c.set_iga(dev.zeros(self._patch.n_iga))
         converged = False
         for i in range(self.maxIters):
             MTAM, MTb = self.assembleLinearSystem(J, residualForm)
