@@ -4,4 +4,5 @@ igakit is not required: any object with ``degree``, ``knots``, ``control``
 minimal stand-in with ``refine`` / ``elevate``."""
 from tIGAr.common import *                                      # noqa: F401,F403
 from tIGAr.BSplines import *                                    # noqa: F401,F403
-from tigar_b200.nurbs import NURBSControlMesh, NURBS, quarter_annulus   # noqa: F401
+from tigar_b200.nurbs import (NURBSControlMesh, NURBS, quarter_annulus,     # noqa: F401
+                               cylindrical_roof)

@@ -7,6 +7,7 @@ Tolerances as for the scalar path: matrix / vector 1e-12 relative, IGA DoF vecto
 relative (BASELINE.json north_star).  (File name sorts last on purpose: this widening was
 written after the round's GPU budget was spent)"""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -113,3 +114,46 @@ def test_elasticity_3d_three_fields_fused_and_newton():
     R = forms(spline, un, v)[0] - L
     spline.solveNonlinearVariationalProblem(R, derivative(R, un), un)
     assert rel(un.iga.cpu().numpy(), Uo) < 1e-8
+
+
+@pytest.mark.skipif(os.environ.get("TIGAR_B200_UNVERIFIED") != "1",
+                    reason="written after the round's GPU budget was spent; never run on a "
+                           "device yet -- opt in with TIGAR_B200_UNVERIFIED=1")
+def test_kl_shell_scordelis_lo_roof_on_the_device():
+    """BASELINE configs[4] in small: the SVK Kirchhoff-Love shell residual of the
+    reference's kl-shell-svk demo (tests/test_kl_shell_cpu.shell_forms, CPU-checked) on the
+    cubic NURBS Scordelis-Lo roof, three fields, Newton with J = derivative(R, y) through
+    ExtractedSpline.solveNonlinearVariationalProblem.  Checks the device tangent against
+    the host-integrated one and the textbook mid-side displacement (0.3006)."""
+    from tIGAr import (EqualOrderSpline, ExtractedSpline, Function, TestFunction, KrylovSolver)
+    from tIGAr.NURBS import NURBSControlMesh, cylindrical_roof
+    from test_kl_shell_cpu import shell_forms, Roof
+    from oracle import assembly as OA
+    scale, nel = 1e-3, [6, 6]
+    host = Roof(nel, -90.0 * scale)
+    gen = EqualOrderSpline(3, NURBSControlMesh(cylindrical_roof(3, nel)))
+    sp = gen.getScalarSpline(0)
+    for side in (0, 1):                                   # rigid diaphragms: u_x = u_z = 0
+        gen.addZeroDofs(0, sp.getSideDofs(1, side))
+        gen.addZeroDofs(2, sp.getSideDofs(1, side))
+    n0 = sp.splines[0].ncp
+    gen.addZeroDofs(1, [n0 // 2])                         # axial rigid-body translation
+    spline = ExtractedSpline(gen, 6, mode="fused")
+    n = host.n
+    y = Function(spline.V)
+    z = TestFunction(spline.V)
+    W, res, dres = shell_forms(spline, y, z, -90.0 * scale)
+    K = spline.assembleMatrix(dres, applyBCs=False)
+    Kh = host.tangent(np.zeros(3 * n))
+    assert relm(K.to_scipy(), Kh) < 1e-10
+    ks = KrylovSolver("cg", "jacobi")
+    ks.parameters["relative_tolerance"] = 1e-11
+    spline.setSolverOptions(maxIters=6, relativeTolerance=1e-6, linearSolver=ks)
+    spline.solveNonlinearVariationalProblem(res, dres, y)
+    Uv = y.iga.cpu().numpy()
+    s1 = host.ts.splines[1]
+    span = int(s1.getKnotSpan(0.5))
+    N = OA.bspline_ders(s1.ghostKnots, s1.p, span + s1.nGhost, 0.5, 0)[0]
+    idx = (span - s1.p + np.arange(s1.p + 1)) * n0
+    uz = (N * Uv[2 * n + idx]).sum() / (N * host.P[idx, 3]).sum()
+    assert abs(abs(uz) / scale - 0.3006) < 0.02 * 0.3006

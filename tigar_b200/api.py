@@ -351,13 +351,23 @@ def TestFunction(V):
 
 
 def derivative(form, u, du=None):
-    """UFL ``derivative``: Gateaux derivative of ``form`` with respect to the
-    Function ``u`` in the direction of a trial function (poisson-nonzero-bc.py:103)."""
+    """UFL ``derivative``: Gateaux derivative of ``form`` with respect to the Function
+    ``u`` in the direction ``du`` -- a trial function by default
+    (poisson-nonzero-bc.py:103), or the given TestFunction (first variation of an energy,
+    kl-shell-svk/dynamic-tspline.py:232)."""
     if not isinstance(u, Function):
         raise TypeError("derivative() is taken with respect to a Function")
+    test = False
+    if du is not None:
+        parts = [k for sc in U.as_tensor(du).a.ravel() for k in sc.terms]
+        if not parts or any((k[0] is None) == (k[1] is None) for k in parts):
+            raise ValueError("derivative(): du must be a TestFunction or a TrialFunction")
+        test = parts[0][0] is not None
+        if any((k[0] is not None) != test for k in parts):
+            raise ValueError("derivative(): du mixes test and trial functions")
     if isinstance(u, VectorFunction):
-        return U.gateaux(form, u.fid_fields())
-    return U.gateaux(form, u.fid)
+        return U.gateaux(form, u.fid_fields(), test)
+    return U.gateaux(form, u.fid, test)
 
 
 def assemble(form, tensor=None):
@@ -899,6 +909,8 @@ class ExtractedSpline(object):
             if kind == "iga":
                 if f.iga is not None:
                     out[fid] = f.iga
+                elif f._fe is None and not f.V.control:
+                    out[fid] = _LazyZero(f, self._patch.n_iga)   # never assigned: zero (dolfin)
             else:
                 out[fid] = _LazyFE(f)
         return _FuncTable(out)
@@ -1152,10 +1164,23 @@ class _LazyFE(object):
         return self.f.fe_tensor()
 
 
+class _LazyZero(object):
+    """A Function that was never assigned reads as zero; its IGA data is created the first
+    time a kernel needs it."""
+
+    def __init__(self, f, n):
+        self.f, self.n = f, n
+
+    def resolve(self):
+        if self.f.iga is None:
+            self.f.set_iga(dev.zeros(self.n))
+        return self.f.iga
+
+
 class _FuncTable(dict):
     def __getitem__(self, k):
         v = dict.__getitem__(self, k)
-        if isinstance(v, _LazyFE):
+        if isinstance(v, (_LazyFE, _LazyZero)):
             v = v.resolve()
             dict.__setitem__(self, k, v)
         return v

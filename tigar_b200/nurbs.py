@@ -163,3 +163,31 @@ def quarter_annulus(p, nel, dim=2, r_in=1.0, r_out=2.0, height=1.0):
     net[..., 2] = z[None, None, :] * ca[None, :, None, 2]
     net[..., 3] = ca[None, :, None, 2]
     return NURBS([kr, ka, kz], net, homogeneous=True)
+
+
+def cylindrical_roof(p, nel, R=25.0, L=50.0, half_angle_deg=40.0):
+    """Cylindrical roof of BASELINE configs[4] (Scordelis-Lo data: R = 25, L = 50, 80
+    degree arc; textbook benchmark, not in the reference): axis along y, crown at
+    (0, *, R).  Exact quadratic-rational arc, degree elevated to ``p`` and uniformly
+    h-refined to ``nel`` elements per direction.  Parametric directions: (angular,
+    axial); control points homogeneous (wx, wy, wz, w) as igakit stores them
+    (NURBS.py:43-77)."""
+    if isinstance(nel, int):
+        nel = [nel, nel]
+    phi = math.radians(half_angle_deg)
+    s, c = math.sin(phi), math.cos(phi)
+    # arc in the (x, z) plane, homogeneous (wx, wz, w); middle weight cos(phi)
+    arc = np.array([[-R * s, R * c, 1.0], [0.0, R, c], [R * s, R * c, 1.0]])
+    lin = np.array([[0.0, 1.0], [1.0, 1.0]])
+
+    def inner(n):
+        return np.arange(1, n) / float(n)
+    ka, ca = _curve_1d([0, 0, 0, 1, 1, 1], arc, p, inner(nel[0]))
+    kl, cl = _curve_1d([0, 0, 1, 1], lin, p, inner(nel[1]))
+    y = L * cl[:, 0] / cl[:, 1]
+    net = np.zeros((ca.shape[0], len(y), 4))
+    net[..., 0] = ca[:, None, 0]
+    net[..., 1] = ca[:, None, 2] * y[None, :]
+    net[..., 2] = ca[:, None, 1]
+    net[..., 3] = ca[:, None, 2]
+    return NURBS([ka, kl], net, homogeneous=True)

@@ -199,6 +199,8 @@ class Tensor(object):
     def __mul__(self, o):
         if isinstance(o, Measure):
             return o.__rmul__(self)
+        if isinstance(o, Form):
+            return o.__rmul__(self)
         o = as_tensor(o)
         if self.a.ndim == 0:
             s = self.a[()]
@@ -336,6 +338,46 @@ def outer(a, b):
         for j in np.ndindex(*b.a.shape):
             out[i + j] = a.a[i].mul(b.a[j])
     return Tensor(out)
+
+
+def cross(a, b):
+    """UFL ``cross`` of two 3-vectors (kl-shell-svk/dynamic-tspline.py:146)."""
+    a, b = as_tensor(a), as_tensor(b)
+    if a.a.shape != (3,) or b.a.shape != (3,):
+        raise ValueError("cross: two 3-vectors expected")
+    out = np.empty((3,), dtype=object)
+    for i in range(3):
+        j, k = (i + 1) % 3, (i + 2) % 3
+        out[i] = a.a[j].mul(b.a[k]).add(a.a[k].mul(b.a[j]), -1.0)
+    return Tensor(out)
+
+
+def _compare(kind):
+    def f(a, b):
+        na, nb = _as_scalar(a).node(), _as_scalar(b).node()
+        if kind == "gt":
+            c = S.binary("gt", na, nb)
+        elif kind == "lt":
+            c = S.binary("gt", nb, na)
+        elif kind == "ge":
+            c = S.sub(S.ONE, S.binary("gt", nb, na))
+        else:
+            c = S.sub(S.ONE, S.binary("gt", na, nb))
+        return Tensor(Scalar.coef(c))
+    f.__name__ = kind
+    return f
+
+
+gt, lt, ge, le = _compare("gt"), _compare("lt"), _compare("ge"), _compare("le")
+
+
+def conditional(cond, a, b):
+    """UFL ``conditional``: ``cond`` is a 0/1 coefficient expression (gt/lt/ge/le); the
+    branches may contain test/trial functions."""
+    c = _as_scalar(cond)
+    a, b = as_tensor(a), as_tensor(b)
+    one_minus = Scalar.coef(S.ONE).add(c, -1.0)
+    return a._zip(b, lambda x, y: c.mul(x).add(one_minus.mul(y)))
 
 
 def tr(a):
@@ -571,19 +613,22 @@ def rhs(form):
     return -form.part(1)
 
 
-def gateaux(form, fid):
+def gateaux(form, fid, test=False):
     """d/d(eps) form(u + eps*du) at eps=0 for the coefficient function with id
-    ``fid``; du is the trial function (UFL ``derivative(form, u)``).  Every term
-    must be free of trial functions.  For a multi-field Function ``fid`` is a dict
-    {component fid: field}: the trial key then carries the field,
+    ``fid`` (UFL ``derivative(form, u, du)``).  ``du`` is the trial function, or, with
+    ``test=True``, the test function (first variation of an energy functional,
+    kl-shell-svk/dynamic-tspline.py:232); the differentiated terms must not already
+    contain that argument.  For a multi-field Function ``fid`` is a dict
+    {component fid: field}: the new key part then carries the field,
     ``(a0, a1, a2, field)``."""
     fields = fid if isinstance(fid, dict) else {fid: None}
     out = []
     for sc, owner in form.integrals:
         acc = Scalar()
         for (t, tr), coef in sc.terms.items():
-            if tr is not None:
-                raise ValueError("derivative() of a form that already has a trial function")
+            if (t if test else tr) is not None:
+                raise ValueError("derivative() of a form that already has a %s function"
+                                 % ("test" if test else "trial"))
             for jn in S.jets_of([coef]):
                 if jn.args[0] not in fields:
                     continue
@@ -591,7 +636,7 @@ def gateaux(form, fid):
                 if dc is not S.ZERO:
                     fld = fields[jn.args[0]]
                     key = tuple(jn.args[2]) if fld is None else tuple(jn.args[2]) + (fld,)
-                    acc = acc.add(Scalar({(t, key): dc}))
+                    acc = acc.add(Scalar({((key, tr) if test else (t, key)): dc}))
         if acc.terms:
             out.append((acc, owner))
     return Form(out)
