@@ -287,3 +287,59 @@ def test_missing_diagonal_block_is_created_for_the_bc_diagonal(cpu_backend):
     D = Cm.block(1, 1).dense()
     zl = spl.zeroDofs[spl.zeroDofs >= n] - n
     assert np.count_nonzero(D) == len(zl) and np.all(D[zl, zl] == 7.0)
+
+
+def test_multifield_generalized_alpha_elastodynamics(cpu_backend):
+    """The time loop of the reference's dynamic demos (dynamic-tspline.py:100-128, 247-293)
+    on a two-field linear elastodynamics problem: generalized-alpha integrator on
+    multi-field Functions, residual at the alpha levels, tangent by derivative(), Newton per
+    step -- against the same recurrence written in numpy on the oracle's matrices."""
+    from tigar_b200 import api as A
+    from tigar_b200 import ufl_lite as U
+    from tigar_b200.time_integration import GeneralizedAlphaIntegrator
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    spl, prob, n = build("fused", cpu_backend)
+    rho_inf, dt, dens = 0.5, 0.05, 3.0
+    y, y0, v0, a0 = (A.Function(spl.V) for _ in range(4))
+    rng = np.random.RandomState(5)
+    free = np.ones(2 * n, bool)
+    free[spl.zeroDofs] = False
+    V0 = rng.rand(2 * n) * free
+    for f_, val in ((y, np.zeros(2 * n)), (y0, np.zeros(2 * n)), (v0, V0), (a0, np.zeros(2 * n))):
+        f_.set_iga(torch.from_numpy(val.copy()))
+    ti = GeneralizedAlphaIntegrator(rho_inf, dt, y, (y0, v0, a0))
+    z = A.TestFunction(spl.V)
+    a_alpha, L = elasticity_forms(spl, ti.x_alpha(), z)
+    res = dens * U.inner(ti.xddot_alpha(), z) * spl.dx + a_alpha - L
+    dres = A.derivative(res, y)
+    ks = A.KrylovSolver("cg", "jacobi")
+    ks.parameters["relative_tolerance"] = 1e-14
+    spl.setSolverOptions(maxIters=5, relativeTolerance=1e-8, linearSolver=ks)
+
+    # the same scheme in numpy on the oracle's matrices
+    K, b = prob.direct_iga(body_force)
+    tabs = [OA.tab_iga(s, 3, 1) for s in prob.ts.splines]
+    Ms = OA.assemble(tabs, prob.P, "mass")[0]
+    M = dens * sp.kron(sp.identity(2), Ms, format="csr")
+    am, af = (2 - rho_inf) / (1 + rho_inf), 1 / (1 + rho_inf)
+    g = 0.5 + am - af
+    be = 0.25 * (1 + am - af) ** 2
+    x0, vv, aa = np.zeros(2 * n), V0.copy(), np.zeros(2 * n)
+    Aeff = (am / (be * dt * dt)) * M + af * K
+    fr = np.nonzero(free)[0]
+    lu = spla.splu(Aeff[fr][:, fr].tocsc())
+    for step in range(3):
+        spl.solveNonlinearVariationalProblem(res, dres, y)
+        pred = x0 + dt * vv + 0.5 * dt * dt * (1 - 2 * be) * aa
+        rhs = b - M @ ((1 - am) * aa - am * pred / (be * dt * dt)) - (1 - af) * (K @ x0)
+        x1 = np.zeros(2 * n)
+        x1[fr] = lu.solve(rhs[fr])
+        a1 = (x1 - pred) / (be * dt * dt)
+        v1 = vv + dt * ((1 - g) * aa + g * a1)
+        assert np.linalg.norm(y.iga.numpy() - x1) < 1e-9 * np.linalg.norm(x1), step
+        ti.advance()
+        x0, vv, aa = x1, v1, a1
+        assert np.linalg.norm(v0.iga.numpy() - vv) < 1e-8 * np.linalg.norm(vv)
+        assert np.linalg.norm(a0.iga.numpy() - aa) < 1e-7 * np.linalg.norm(aa)
+    assert abs(ti.t - (dt + 3 * dt)) < 1e-14
