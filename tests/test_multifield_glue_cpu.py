@@ -181,6 +181,9 @@ class FakePatch(object):
         self.lib.tg_zero_entries(b.data_ptr(), mask.data_ptr(), b.numel(), None)
         return b
 
+    def solve_cg(self, Cm, b, x=None, rtol=1e-12, atol=0.0, maxit=100000, check_every=5):
+        return torch.from_numpy(np.linalg.solve(Cm.dense(), b.numpy())), 1, 0.0
+
 
 @pytest.fixture
 def cpu_backend(monkeypatch):
@@ -343,3 +346,25 @@ def test_multifield_generalized_alpha_elastodynamics(cpu_backend):
         assert np.linalg.norm(v0.iga.numpy() - vv) < 1e-8 * np.linalg.norm(vv)
         assert np.linalg.norm(a0.iga.numpy() - aa) < 1e-7 * np.linalg.norm(aa)
     assert abs(ti.t - (dt + 3 * dt)) < 1e-14
+
+
+def test_fe_to_iga_round_trip(cpu_backend):
+    """SURVEY 8c KAT 5: FEtoIGA(M U) = U (common.py:968-993), scalar and multi-field."""
+    from tigar_b200 import api as A
+    spl, prob, n = build("csr", cpu_backend)
+    spl.cgRelativeTolerance = 1e-13
+    rng = np.random.RandomState(2)
+    Uv = rng.rand(2 * n)
+    w = A.Function(spl.V)
+    w.set_iga(torch.from_numpy(Uv.copy()))
+    back = spl.FEtoIGA(w).get_local()
+    assert np.abs(back - Uv).max() < 1e-10
+    # an FE function that is NOT in the spline space comes back as its least-squares fit
+    Ms = spl._patch.Ms
+    fe = rng.rand(Ms.shape[0])
+    g = A.Function(spl.V.sub(0))
+    g._fe = torch.from_numpy(fe.copy())
+    spl.nFields = 1
+    ls = spl.FEtoIGA(g).get_local()
+    ref = np.linalg.lstsq(Ms.toarray(), fe, rcond=None)[0]
+    assert np.abs(ls - ref).max() < 1e-9

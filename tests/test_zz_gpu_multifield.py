@@ -157,3 +157,17 @@ def test_kl_shell_scordelis_lo_roof_on_the_device():
     idx = (span - s1.p + np.arange(s1.p + 1)) * n0
     uz = (N * Uv[2 * n + idx]).sum() / (N * host.P[idx, 3]).sum()
     assert abs(abs(uz) / scale - 0.3006) < 0.02 * 0.3006
+
+
+@pytest.mark.skipif(os.environ.get("TIGAR_B200_UNVERIFIED") != "1",
+                    reason="never run on a device yet -- opt in with TIGAR_B200_UNVERIFIED=1")
+def test_fe_to_iga_round_trip_on_the_device():
+    """SURVEY 8c KAT 5: FEtoIGA(M U) = U (common.py:968-993)."""
+    from tIGAr import Function
+    from tigar_b200 import dev
+    spline, prob, n = build([2, 2], [6, 5], "csr")
+    rng = np.random.RandomState(2)
+    Uv = rng.rand(2 * n)
+    w = Function(spline.V)
+    w.set_iga(dev.from_np(Uv))
+    assert np.abs(spline.FEtoIGA(w).get_local() - Uv).max() < 1e-9

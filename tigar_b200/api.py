@@ -1149,9 +1149,25 @@ class ExtractedSpline(object):
         return self.rationalize(retval) if rationalize else retval
 
     def FEtoIGA(self, u):
-        """Testing helper of the reference (common.py:968-993), not on the hot
-        path: solves (M^T M) U = M^T u."""
-        raise NotImplementedError("FEtoIGA is not built (reference marks it testing-only)")
+        """Testing helper of the reference (common.py:968-993): IGA DoFs from the FE
+        coefficients of ``u`` by the pseudo-inverse problem (M^T M) U = M^T u, with
+        M^T M formed as the triple product M^T I M on the FE pattern (as inefficient as
+        the reference says it is) and solved by the device CG.  Returns the IGA vector."""
+        p, M = self._patch, self.M_matrix()
+        n_fe, n = p.n_fe, p.n_iga
+        ident = WinMatrix(p.window("A"))
+        ones = dev.zeros(n_fe, dev.U8) + 1
+        check(lib.tg_win_zero_rows_cols(ident.window.ref(), dev.ptr(ident.vals), dev.ptr(ones),
+                                        dev.ptr(ones), 1.0, 0, dev.stream()))
+        MTM = p.ptap(ident, M)
+        del ident
+        fe = u.fe_tensor()
+        out = dev.empty(self.nFields * n)
+        for f in range(self.nFields):
+            rhs = p.mt_vec(M, fe[f * n_fe:(f + 1) * n_fe].contiguous())
+            x, its, rel = p.solve_cg(MTM, rhs, None, self.cgRelativeTolerance, 0.0, 200000)
+            out[f * n:(f + 1) * n].copy_(x)
+        return DeviceVector(out)
 
 
 class _LazyFE(object):
