@@ -244,6 +244,12 @@ def rationalized_jets(blk, geo, order):
     return out
 
 
+def wdot(W, La, Lb):
+    """K[c,a,b] = sum_q W[c,q] La[c,q,a] Lb[c,q,b] as one batched GEMM per chunk (BLAS;
+    the same contraction written as an einsum runs ~6x slower)."""
+    return np.matmul((La * W[..., None]).transpose(0, 2, 1), Lb)
+
+
 def operators(form, blk, geo, jets):
     """Return list of per-basis operator arrays L_s[c,q,a] such that the
     bilinear form is sum_s int L_s(u) L_s(v) J dxi."""
@@ -293,7 +299,7 @@ def assemble(tabs, coef, form, f=None, rationalize=False, chunk=2048):
         W = blk.wq * geo.J
         Ke = 0.0
         for Ls in operators(form, blk, geo, jets):
-            Ke = Ke + np.einsum("cq,cqa,cqb->cab", W, Ls, Ls, optimize=True)
+            Ke = Ke + wdot(W, Ls, Ls)
         nen = blk.gidx.shape[1]
         rows.append(np.repeat(blk.gidx, nen, axis=1).ravel())
         cols.append(np.tile(blk.gidx, (1, nen)).ravel())
@@ -330,15 +336,14 @@ def assemble_elasticity(tabs, coef, mu, lam, f=None, chunk=2048):
         geo = Geometry(blk, coef, 1)
         G = operators("poisson", blk, geo, blk.jets)        # G[i][c,q,a] = d psi_a / d x_i
         W = blk.wq * geo.J
-        gg = sum(np.einsum("cq,cqa,cqb->cab", W, G[j], G[j], optimize=True) for j in range(nsd))
+        gg = sum(wdot(W, G[j], G[j]) for j in range(nsd))
         nen = blk.gidx.shape[1]
         r0 = np.repeat(blk.gidx, nen, axis=1).ravel()
         c0_ = np.tile(blk.gidx, (1, nen)).ravel()
         for i in range(nsd):
             for k in range(nsd):
                 # 2 mu eps(u):eps(v) = mu (grad u : grad v + grad u : grad v^T)
-                Ke = mu * np.einsum("cq,cqa,cqb->cab", W, G[k], G[i], optimize=True) \
-                    + lam * np.einsum("cq,cqa,cqb->cab", W, G[i], G[k], optimize=True)
+                Ke = mu * wdot(W, G[k], G[i]) + lam * wdot(W, G[i], G[k])
                 if i == k:
                     Ke = Ke + mu * gg
                 rows.append(r0 + i * n)

@@ -191,3 +191,25 @@ def test_scordelis_lo_midside_displacement():
     w = r.P[idx, 3]
     uz = (N * Uv[2 * n + idx]).sum() / (N * w).sum()
     assert abs(abs(uz) / scale - 0.3006) < 0.02 * 0.3006, uz / scale
+
+
+def test_shell_tangent_block_kernel_compiles_for_sm100a(roof):
+    """The Gauss-point program of one tangent block (36 coefficient outputs, ~4 300
+    operations, 335 registers, second-derivative jets of 7 functions) goes through the form
+    compiler's CUDA generator and NVRTC for sm_100a (no GPU needed to compile)."""
+    from tigar_b200 import symbolic as S
+    from tigar_b200 import jit
+    bt = roof.jterms[(2, 0)]
+    alS = sorted(set(k[0] for k in bt))
+    alT = sorted(set(k[1] for k in bt))
+    grid = [[S.ZERO] * len(alT) for _ in alS]
+    for (a, b), node in bt.items():
+        grid[alS.index(a)][alT.index(b)] = node
+    prog = S.compile_program([grid[s][t] for s in range(len(alS)) for t in range(len(alT))], 2)
+    assert len(prog.outregs) == 36 and prog.nreg <= 2048       # interpreter limit (tg_qp.cu)
+    fids = sorted(set(j[0] for j in prog.jets))
+    assert len(fids) == 7 <= jit.MAXFUN
+    assert max(max(al) for (_, _, al) in prog.jets) == 2
+    jets = [(fids.index(f), c, al) for (f, c, al) in prog.jets]
+    src, nth = jit.generate(prog, 2, [4, 4, 1], [4, 4, 1], 3, jets, len(fids))
+    assert nth == 32 and jit.check_source(src) > 1000
