@@ -743,3 +743,41 @@ def test_curvilinear_calculus_in_polar_coordinates():
         assert abs(ev(CU.cartesianPushforwardW(r * t, F)) - T_) < 1e-13
     finally:
         U.DEFAULT_DIM[0] = old
+
+
+def test_dof_list_is_a_list_that_remembers_its_arrays():
+    """getSideDofs returns a real Python list (reference API, BSplines.py:599-649) whose
+    numpy form is kept through ``+=`` / ``+`` and dropped by any other edit."""
+    from tigar_b200.bsplines import DofList, BSpline, uniformKnots
+    sp = BSpline([2, 3], [uniformKnots(2, 0.0, 1.0, 4), uniformKnots(3, 0.0, 1.0, 3)])
+    a = sp.getSideDofs(0, 0)
+    b = sp.getSideDofs(1, 1, nLayers=2)
+    assert isinstance(a, list) and isinstance(a, DofList) and a == [0, 6, 12, 18, 24, 30]
+    assert b == list(range(30, 36)) + list(range(24, 30))
+    z = DofList()
+    z += a
+    z += b
+    z += [99, 98]                                     # plain lists are fine
+    assert z == a + b + [99, 98] and len(z._chunks) == 3
+    assert z.asarray().tolist() == list(z) and z.asarray().dtype == np.int64
+    c = a + b
+    assert isinstance(c, DofList) and c.asarray().tolist() == list(a) + list(b)
+    assert a.asarray().tolist() == list(a)            # operands untouched
+    z.append(7)
+    assert z._chunks is None and z.asarray().tolist() == list(z)
+    z2 = DofList([5, 4])
+    z2 += a
+    assert z2.asarray().tolist() == [5, 4] + list(a)
+    z2[0] = 1
+    z2 += b
+    assert z2.asarray().tolist() == list(z2)
+    # generator bookkeeping: field offsets, duplicates at corners kept
+    from tigar_b200 import api as A
+    from tigar_b200.bsplines import ExplicitBSplineControlMesh
+    cm = ExplicitBSplineControlMesh([2, 3], [uniformKnots(2, 0.0, 1.0, 4), uniformKnots(3, 0.0, 1.0, 3)])
+    gen = A.EqualOrderSpline(2, cm)
+    gen.addZeroDofs(0, a)
+    gen.addZeroDofs(1, a)
+    gen.addZeroDofs(1, [3, 4])
+    assert list(gen.zeroDofs) == list(a) + [d + 36 for d in a] + [39, 40]
+    assert gen.zeroDofs.asarray().tolist() == list(gen.zeroDofs)

@@ -14,14 +14,12 @@ Checked: residual = dW/dU and tangent = dR/dU by central differences, symmetry o
 tangent, and the textbook mid-side displacement of the roof (0.3006 for Kirchhoff-Love
 theory; load scaled into the linear regime).
 """
-import math
 
 import numpy as np
 import pytest
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
-from tigar_b200 import ufl_lite as U
 from tigar_b200 import multifield as MF
 from oracle import bsplines as OB
 from test_multifield_cpu import HostIntegrator, symbolic_spline

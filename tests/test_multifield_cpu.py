@@ -13,7 +13,6 @@ import math
 import numpy as np
 import pytest
 import scipy.sparse as sp
-import scipy.sparse.linalg as spla
 
 from tigar_b200 import symbolic as S
 from tigar_b200 import ufl_lite as U

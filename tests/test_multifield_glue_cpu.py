@@ -189,7 +189,6 @@ class FakePatch(object):
 def cpu_backend(monkeypatch):
     from tigar_b200 import api as A
     from tigar_b200 import dev, _lib
-    from tigar_b200 import engine
     fake = FakeLib()
     monkeypatch.setattr(dev, "device", lambda: torch.device("cpu"))
     monkeypatch.setattr(dev, "stream", lambda: None)

@@ -24,7 +24,7 @@ import numpy as np
 from . import dev
 from . import symbolic as S
 from . import ufl_lite as U
-from .bsplines import (AbstractScalarBasis, AbstractControlMesh, BSpline, DOLFIN_EPS,
+from .bsplines import (AbstractScalarBasis, AbstractControlMesh, BSpline, DofList, DOLFIN_EPS,
                        USE_RECT_ELEM_DEFAULT, near)
 from .engine import TensorPatch, WinMatrix, IGNORE_EPS
 from ._lib import lib, check
@@ -471,7 +471,12 @@ class AbstractExtractionGenerator(object):
 
     def addZeroDofs(self, field, newDofs):
         off = self.globalDof(field, 0)
-        self.addZeroDofsGlobal(list(newDofs) if off == 0 else [d + off for d in newDofs])
+        if off == 0:
+            self.addZeroDofsGlobal(newDofs if isinstance(newDofs, DofList) else list(newDofs))
+        elif isinstance(newDofs, DofList):
+            self.addZeroDofsGlobal(DofList.from_array(newDofs.asarray() + off))
+        else:
+            self.addZeroDofsGlobal([d + off for d in newDofs])
 
     def getPrealloc(self, control):
         return DEFAULT_PREALLOC
@@ -495,7 +500,7 @@ class AbstractExtractionGenerator(object):
         self._M = None
         self._M_control = None
         self._cpFuncs = None
-        self.zeroDofs = []
+        self.zeroDofs = DofList()
 
     # lazily built heavy objects ------------------------------------------
     def patch(self):
@@ -748,7 +753,11 @@ class ExtractedSpline(object):
         self.VE, self.VE_control = generator.VE, generator.VE_control
         P = self._controlNetArg if self._controlNetArg is not None else generator.controlNet()
         self._set_control_net(P)
-        self.zeroDofs = _sorted_unique(np.array(generator.zeroDofs, dtype=np.int64))
+        z = generator.zeroDofs
+        # raw list (duplicates allowed, e.g. patch corners): the device mask does not need
+        # it sorted; the public ``zeroDofs`` attribute is sorted and unique, made on demand
+        self._zeroDofsRaw = z.asarray() if isinstance(z, DofList) else np.array(z, dtype=np.int64)
+        self._zeroDofs = None
         self._M = None
 
     def initFromFilesystem(self, dirname, quadDeg, comm, mesh=None):
@@ -776,8 +785,21 @@ class ExtractedSpline(object):
         self.V_control = FunctionSpace(self, 1, control=True)
         self.VE = self.VE_control = ("Lagrange", self.p_control)
         self._set_control_net(data["P"])
-        self.zeroDofs = _sorted_unique(data["zeroDofs"].astype(np.int64))
+        self.zeroDofs = data["zeroDofs"].astype(np.int64)
         self._M = None
+
+    @property
+    def zeroDofs(self):
+        """Sorted, unique global zero DoFs (int64)."""
+        if self._zeroDofs is None:
+            self._zeroDofs = _sorted_unique(self._zeroDofsRaw)
+        return self._zeroDofs
+
+    @zeroDofs.setter
+    def zeroDofs(self, z):
+        self._zeroDofsRaw = np.asarray(z, dtype=np.int64).ravel()
+        self._zeroDofs = None
+        self._mask = None
 
     def _set_control_net(self, P):
         """P: [ncp, nsd+1] host array (torch pinned or numpy), or a list of
@@ -970,7 +992,7 @@ class ExtractedSpline(object):
         """Device 0/1 mask over the IGA DoFs of all fields (field-major)."""
         if self._mask is None:
             if self.nFields == 1:
-                self._mask = self._patch.bc_mask(self.zeroDofs)
+                self._mask = self._patch.bc_mask(self._zeroDofsRaw)
             else:
                 from . import multifield as MF
                 import torch
