@@ -59,31 +59,38 @@ class DofList(list):
     that a 4e5-entry zero-DoF list does not have to be converted back element by element
     (30 ms per step at 256^3).  Any in-place edit other than ``+=`` drops the arrays."""
 
+    MAX_CHUNKS = 64          # many tiny pieces: converting the list itself is cheaper
+
     def __init__(self, items=(), chunks=None):
         list.__init__(self, items)
         self._chunks = chunks if chunks is not None else ([] if len(self) == 0 else None)
+        self._n = sum(c.size for c in self._chunks) if self._chunks is not None else 0
 
     @staticmethod
     def from_array(a):
         a = np.ascontiguousarray(a, dtype=np.int64).ravel()
         return DofList(a.tolist(), [a])
 
+    def _valid(self):
+        return self._chunks is not None and self._n == len(self)
+
     def asarray(self):
         """int64 array of the entries (duplicates and order kept)."""
-        ch = self._chunks
-        if ch and sum(c.size for c in ch) == len(self):
+        if self._valid() and self._chunks:
+            ch = self._chunks
             return ch[0] if len(ch) == 1 else np.concatenate(ch)
         return np.array(self, dtype=np.int64)
 
     def __iadd__(self, other):
-        n0 = len(self)
+        ok = self._valid() and len(self._chunks) < self.MAX_CHUNKS
         list.__iadd__(self, other)
-        if self._chunks is not None and sum(c.size for c in self._chunks) == n0:
-            if isinstance(other, DofList) and other._chunks is not None \
-                    and sum(c.size for c in other._chunks) == len(other):
-                self._chunks = self._chunks + other._chunks
+        if ok:
+            if isinstance(other, DofList) and other._valid():
+                new = other._chunks
             else:
-                self._chunks = self._chunks + [np.array(other, dtype=np.int64).ravel()]
+                new = [np.array(other, dtype=np.int64).ravel()]
+            self._chunks = self._chunks + new
+            self._n += sum(c.size for c in new)
         else:
             self._chunks = None
         return self
