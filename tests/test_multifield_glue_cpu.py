@@ -153,7 +153,9 @@ class FakePatch(object):
         return FakeWinMatrix(self.window("A" if kind == "fe" else "C"),
                              torch.from_numpy(np.ascontiguousarray(K).ravel()))
 
-    def assemble_vector(self, terms, funcs, kind="fe", out=None):
+    def assemble_vector(self, terms, funcs, kind="fe", out=None, cache=None):
+        if cache is not None:
+            cache["calls"] = cache.get("calls", 0) + 1
         b = torch.from_numpy(self._integrator(kind, funcs).vector(terms))
         if out is None:
             return b
@@ -176,6 +178,11 @@ class FakePatch(object):
         m = torch.zeros(self.n_iga, dtype=torch.uint8)
         m[torch.from_numpy(np.asarray(zeroDofs, dtype=np.int64))] = 1
         return m
+
+    def apply_bcs_matrix(self, Cm, mask, diag=1.0):
+        self.lib.tg_win_zero_rows_cols(Cm.window, Cm.vals.data_ptr(), mask.data_ptr(),
+                                       mask.data_ptr(), float(diag), 0, None)
+        return Cm
 
     def apply_bcs_vector(self, b, mask):
         self.lib.tg_zero_entries(b.data_ptr(), mask.data_ptr(), b.numel(), None)
@@ -367,3 +374,49 @@ def test_fe_to_iga_round_trip(cpu_backend):
     ls = spl.FEtoIGA(g).get_local()
     ref = np.linalg.lstsq(Ms.toarray(), fe, rcond=None)[0]
     assert np.abs(ls - ref).max() < 1e-9
+
+
+def test_matrix_free_operator_equals_the_assembled_matrix(cpu_backend):
+    """mode="matfree" (tigar_b200/matfree.py): the operator action assembled as a linear
+    form equals C x, BCs in operator form equal zeroRowsColumns, and the CG solve through
+    the API reproduces the oracle's LU solution."""
+    from tigar_b200 import api as A
+    from tigar_b200 import ufl_lite as U
+    from tigar_b200.matfree import FormOperator
+    spl, prob, n = build("fused", cpu_backend)
+    spl.nFields = 1
+    spl.V = A.FunctionSpace(spl, 1)
+    spl.zeroDofs = spl.zeroDofs[spl.zeroDofs < n]
+    u, v = A.TrialFunction(spl.V), A.TestFunction(spl.V)
+    x = spl.spatialCoordinates()
+    a = U.inner(spl.grad(u), spl.grad(v)) * spl.dx + 0.3 * u * v * spl.dx
+    L = U.inner(U.sin(2.0 * x[0]) + x[1], v) * spl.dx
+    C = spl.assembleMatrix(a, diag=2.5)                   # fused: the matrix itself
+    C0 = spl.assembleMatrix(a, applyBCs=False)
+    b = spl.assembleVector(L)
+    spl.mode = "matfree"
+    op = spl.assembleMatrix(a, diag=2.5)
+    assert isinstance(op, FormOperator) and op.shape == (n, n)
+    rng = np.random.RandomState(4)
+    xv = torch.from_numpy(rng.rand(n))
+    y = op.matvec(xv)
+    assert np.abs(y.numpy() - C.dense() @ xv.numpy()).max() < 1e-12 * np.abs(C.dense()).max()
+    op0 = spl.assembleMatrix(a, applyBCs=False)
+    y0 = op0.matvec(xv)
+    assert np.abs(y0.numpy() - C0.dense() @ xv.numpy()).max() < 1e-12 * np.abs(C0.dense()).max()
+    # Jacobi diagonal from the (transiently) assembled matrix
+    assert np.allclose(op0.jacobi_dinv().numpy(), 1.0 / np.diag(C0.dense()), rtol=1e-13)
+    # solve through the API
+    ks = A.KrylovSolver("cg", "jacobi")
+    ks.parameters["relative_tolerance"] = 1e-13
+    spl.setSolverOptions(linearSolver=ks)
+    uh = A.Function(spl.V)
+    Uv = spl.solveLinearVariationalProblem(a == L, uh).get_local()
+    Cd = C.dense().copy()
+    z = spl.zeroDofs
+    Cd[z, z] = 1.0                                         # default diag of the driver
+    ref = np.linalg.solve(Cd, b.get_local())
+    assert np.linalg.norm(Uv - ref) < 1e-10 * np.linalg.norm(ref)
+    assert not Uv[z].any()
+    # the Gauss-point program is compiled once per operator, not once per iteration
+    assert spl.lastSolve["iterations"] > 5

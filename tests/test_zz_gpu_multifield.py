@@ -171,3 +171,51 @@ def test_fe_to_iga_round_trip_on_the_device():
     w = Function(spline.V)
     w.set_iga(dev.from_np(Uv))
     assert np.abs(spline.FEtoIGA(w).get_local() - Uv).max() < 1e-9
+
+
+@pytest.mark.skipif(os.environ.get("TIGAR_B200_UNVERIFIED") != "1",
+                    reason="never run on a device yet -- opt in with TIGAR_B200_UNVERIFIED=1")
+@pytest.mark.parametrize("deg,nels", [([3, 3, 3], [5, 4, 9]), ([2, 2], [9, 8])])
+def test_matrix_free_mode_on_the_device(deg, nels):
+    """mode="matfree" (tigar_b200/matfree.py, SURVEY 7.2 hard part 1): operator action =
+    assembled matrix times vector, slab-wise Jacobi diagonal = diagonal of the matrix,
+    solve = oracle LU solution (1e-10)."""
+    import torch
+    from tIGAr import TrialFunction, TestFunction, Function, KrylovSolver, inner, sin
+    from tigar_b200 import dev
+    from gpu_util import make_pair
+    kv = [OB.uniform_knots(p, 0.0, 1.0, n) for p, n in zip(deg, nels)]
+    gen, fused, pr = make_pair(deg, kv, mode="fused")
+    gen2, mf, _ = make_pair(deg, kv, mode="matfree")
+
+    def forms(spline):
+        u, v = TrialFunction(spline.V), TestFunction(spline.V)
+        x = spline.spatialCoordinates()
+        f = 1.0
+        for d in range(len(x)):
+            f = f * sin(math.pi * x[d])
+        return (inner(spline.grad(u), spline.grad(v)) * spline.dx,
+                inner(f * (len(x) * math.pi ** 2), v) * spline.dx)
+    a, L = forms(fused)
+    C = fused.assembleMatrix(a, diag=2.5)
+    a2, L2 = forms(mf)
+    op = mf.assembleMatrix(a2, diag=2.5)
+    n = fused._patch.n_iga
+    xv = dev.from_np(np.random.RandomState(0).rand(n))
+    y = dev.to_np(op.matvec(xv))
+    yref = dev.to_np(C.matvec(xv))
+    assert rel(y, yref) < 1e-12
+    C0 = fused.assembleMatrix(a, applyBCs=False).to_scipy()
+    op0 = mf.assembleMatrix(a2, applyBCs=False)
+    d1 = dev.to_np(op0.jacobi_dinv(1))
+    assert rel(d1, 1.0 / C0.diagonal()) < 1e-13
+    op0._dinv = None
+    d2 = dev.to_np(op0.jacobi_dinv(2))
+    assert rel(d2, d1) < 1e-13
+    ks = KrylovSolver("cg", "jacobi")
+    ks.parameters["relative_tolerance"] = 1e-13
+    mf.setSolverOptions(linearSolver=ks)
+    uh = Function(mf.V)
+    U = mf.solveLinearVariationalProblem(a2 == L2, uh)
+    Uo = pr.run(lambda X: len(deg) * math.pi ** 2 * np.prod(np.sin(math.pi * X[..., :len(deg)]), axis=-1))
+    assert rel(U.get_local(), Uo) < 1e-10

@@ -724,8 +724,10 @@ class ExtractedSpline(object):
                 raise NotImplementedError("multi-GPU runs use the element-fused path")
             mode = "fused"
         self.mode = mode or os.environ.get("TIGAR_B200_MODE") or self._auto_mode()
-        if self.mode not in ("csr", "fused"):
-            raise ValueError("mode must be 'csr' or 'fused'")
+        if self.mode not in ("csr", "fused", "matfree"):
+            raise ValueError("mode must be 'csr', 'fused' or 'matfree'")
+        if self.mode == "matfree" and (self._patch.part is not None or self.nFields != 1):
+            raise NotImplementedError("matrix-free mode: one field, one GPU")
         self.genericSetup()
 
     # -- construction ------------------------------------------------------
@@ -830,7 +832,12 @@ class ExtractedSpline(object):
         need = 8 * (p.window("A").nnz + p.window("M").nnz + p.window("P").nnz
                     + p.window("C").nnz) + 8 * (2 * p.n_fe)
         free, _ = torch.cuda.mem_get_info()
-        return "csr" if need < 0.5 * free else "fused"
+        if need < 0.5 * free:
+            return "csr"
+        # the element-fused path still stores C; beyond that only the operator action fits
+        if self.nFields == 1 and p.part is None and 8 * p.window("C").nnz > 0.9 * free:
+            return "matfree"
+        return "fused"
 
     def M_matrix(self):
         if self._M is None:
@@ -1056,6 +1063,13 @@ class ExtractedSpline(object):
         return MTAM
 
     def assembleMatrix(self, form, applyBCs=True, diag=1):
+        if self.mode == "matfree":
+            from .matfree import FormOperator
+            sc = form.scalar()
+            if sc.arity() != 2:
+                raise ValueError("assembleMatrix needs a bilinear form")
+            return FormOperator(self, {(k[0], k[1]): v for k, v in self._weighted(sc).items()},
+                                applyBCs, diag)
         if self.mode == "csr":
             return self.extractMatrix(self._assemble_kind(form, "fe"), applyBCs, diag)
         MTAM = self._assemble_kind(form, "iga")
@@ -1069,7 +1083,7 @@ class ExtractedSpline(object):
         """common.py:1223-1234.  Matrix and vector share one Gauss-point pass."""
         kind = "fe" if self.mode == "csr" else "iga"
         ms, vs = lhsForm.scalar(), rhsForm.scalar()
-        if (self.nFields > 1 or ms.arity() != 2 or vs.arity() != 1
+        if (self.nFields > 1 or self.mode == "matfree" or ms.arity() != 2 or vs.arity() != 1
                 or any(k[0] is None for k in vs.terms)):
             return (self.assembleMatrix(lhsForm, applyBCs),
                     self.assembleVector(rhsForm, applyBCs))
@@ -1090,6 +1104,13 @@ class ExtractedSpline(object):
         rtol = prm.get("relative_tolerance", self.cgRelativeTolerance)
         atol = prm.get("absolute_tolerance", 0.0)
         maxit = prm.get("maximum_iterations", 200000)
+        from .matfree import FormOperator
+        if isinstance(MTAM, FormOperator):
+            from .matfree import solve_matfree_cg
+            x, its, rel = solve_matfree_cg(MTAM, MTb.t, rtol, atol, maxit)
+            self.lastSolve = dict(iterations=its, relative_residual=rel)
+            u.set_iga(x)
+            return DeviceVector(x)
         if self.nFields > 1:
             from . import multifield as MF
             x, its, rel = MF.solve_block_cg(MTAM, MTb.t, rtol, atol, maxit)

@@ -638,14 +638,20 @@ class TensorPatch(object):
                                               dev.stream()))
         return A, b
 
-    def assemble_vector(self, terms, funcs, kind="fe", out=None):
-        """terms: {alphaTest: Node}."""
+    def assemble_vector(self, terms, funcs, kind="fe", out=None, cache=None):
+        """terms: {alphaTest: Node}.  ``cache``: a dict that keeps the compiled
+        Gauss-point program between calls with the SAME terms and the same function
+        tensors (the matrix-free operator calls this once per CG iteration)."""
         alS = sorted(set(pad3(k) for k in terms))
         nS = len(alS)
-        outputs = [S.ZERO] * nS
-        for a, node in terms.items():
-            outputs[alS.index(pad3(a))] = node
-        P = self._qp_setup(outputs, funcs)
+        P = cache.get("P") if cache is not None else None
+        if P is None:
+            outputs = [S.ZERO] * nS
+            for a, node in terms.items():
+                outputs[alS.index(pad3(a))] = node
+            P = self._qp_setup(outputs, funcs)
+            if cache is not None:
+                cache["P"] = P
         nder = max(P["nder"], max(max(a) for a in alS))
         B = self.basis(kind, nder)
         if self.part is not None:

@@ -1,0 +1,157 @@
+"""
+Matrix-free IGA operator (SURVEY 7.2 hard part 1): ``C = M^T A_FE M`` of a 3-D cubic
+patch needs 4 kB per DoF (557 GB at 512^3), so beyond ~300^3 cells on one GPU the system
+matrix cannot exist.  The action of the operator, however, is a linear form,
+
+    (C x)_i = a(x_h, N_i) ,   x_h = sum_j x_j N_j ,
+
+i.e. exactly what ``assembleVector`` computes for a residual that contains a Function
+(the Newton path, common.py:1304-1348): one Gauss-point pass that interpolates the jets
+of ``x_h`` and evaluates the flux coefficients, followed by the sum-factorised vector
+assembly.  ``FormOperator`` therefore needs NO new kernel: it turns the bilinear form's
+terms ``c * D^a v * D^b u`` into the linear-form terms ``(c * D^b x_h) * D^a v`` once,
+keeps the compiled program, and runs the two verified kernels per application.  It is
+~18x slower per CG iteration than the windowed SpMV where the matrix fits (measured
+shares at 256^3: Gauss-point pass 0.10 s + vector assembly 0.08 s against 10 ms), and the
+only option where it does not.
+
+Homogeneous BCs (common.py:1199-1200, 1154-1158) are applied in operator form,
+``P C P + diag (I - P)`` with ``P`` the projector that zeroes the constrained DoFs; inside
+CG every vector has zeros there (b is masked), so the application reduces to
+``y = C p; y[zeroDofs] = 0``.  The Jacobi diagonal is taken from the assembled matrix one
+row slab at a time (the slab partition of multigpu.py, run sequentially on this GPU), so
+that only ``1/nparts`` of the matrix exists at any moment.
+"""
+import math
+
+from . import symbolic as S
+from .multifield import BlockOps
+
+
+class FormOperator(object):
+    """``assembleMatrix(form)`` in matrix-free mode: applies M^T A M without forming it."""
+
+    def __init__(self, spline, mterms, applyBCs=True, diag=1.0):
+        from . import dev
+        from .api import Function
+        self.spline = spline
+        self.patch = spline._patch
+        self.n = self.patch.n_iga
+        self.mterms = dict(mterms)             # {(alphaTest, alphaTrial): node}, weighted
+        self.applyBCs = applyBCs
+        self.diag = float(diag)
+        self.xvec = dev.zeros(self.n)          # the operand lives here (aliased by CG's p)
+        self.x = Function(spline.V)
+        self.x.set_iga(self.xvec)
+        vt = {}
+        for (aT, aU), node in self.mterms.items():
+            k = tuple(aT[:3])
+            term = S.mul(node, S.jet(self.x.fid, 0, tuple(aU[:3])))
+            vt[k] = S.add(vt[k], term) if k in vt else term
+        self.vterms = vt
+        self._cache = {}
+        self._funcs = spline._funcs("iga")
+        self._dinv = None
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    def apply(self, y):
+        """y = C * self.xvec (no BCs)."""
+        y.zero_()
+        self.patch.assemble_vector(self.vterms, self._funcs, "iga", out=y, cache=self._cache)
+        return y
+
+    def matvec(self, x, y=None):
+        """y = (P C P + diag (I - P)) x for an arbitrary x (copies x into the operand)."""
+        from . import dev
+        from ._lib import lib, check
+        y = dev.empty(self.n) if y is None else y
+        self.xvec.copy_(x)
+        mask = self.spline._bc_mask() if self.applyBCs else None
+        if mask is not None:
+            check(lib.tg_zero_entries(dev.ptr(self.xvec), dev.ptr(mask), self.n, dev.stream()))
+        self.apply(y)
+        if mask is not None:
+            check(lib.tg_zero_entries(dev.ptr(y), dev.ptr(mask), self.n, dev.stream()))
+            # + diag (I - P) x = diag * (x - P x)
+            check(lib.tg_axpy(dev.ptr(y), self.diag, dev.ptr(x), self.n, dev.stream()))
+            check(lib.tg_axpy(dev.ptr(y), -self.diag, dev.ptr(self.xvec), self.n, dev.stream()))
+        return y
+
+    # -- Jacobi diagonal -----------------------------------------------------------
+    def slab_count(self, budget_bytes=24 << 30):
+        nnz = self.patch.window("C").nnz
+        return max(1, int(math.ceil(8.0 * nnz / budget_bytes)))
+
+    def jacobi_dinv(self, nparts=None):
+        """1 / diag(C), from the matrix assembled one row slab at a time."""
+        if self._dinv is not None:
+            return self._dinv
+        from . import dev
+        from ._lib import lib, check
+        from .engine import TensorPatch
+        p = self.patch
+        nparts = self.slab_count() if nparts is None else int(nparts)
+        if nparts > 1:                       # slabs at least p + 1 cell layers thick
+            nparts = max(1, min(nparts, p.nel[-1] // (p.degrees[-1] + 1)))
+        dinv = dev.empty(self.n)
+        if nparts == 1:
+            Cm = p.assemble_matrix(self.mterms, self._funcs, "iga")
+            check(lib.tg_win_diag_inv(Cm.window.ref(), dev.ptr(Cm.vals), 0, dev.ptr(dinv),
+                                      dev.stream()))
+            del Cm
+        else:
+            for r in range(nparts):
+                sub = TensorPatch(p.degrees, None, quadDeg=p.quadDeg, eps=p.eps,
+                                  splines=p.splines, part=(r, nparts))
+                Cm = sub.assemble_matrix(self.mterms, self._funcs, "iga")
+                pp = sub.pp
+                check(lib.tg_win_diag_inv(Cm.window.ref(), dev.ptr(Cm.vals),
+                                          pp["k0"] - pp["c0"],
+                                          dev.ptr(dinv) + 8 * sub.plane * pp["k0"], dev.stream()))
+                dev.sync()
+                del Cm, sub
+        # constrained rows: their dinv is never used (r and p are zero there inside CG)
+        self._dinv = dinv
+        return dinv
+
+
+class MatFreeOps(BlockOps):
+    """``ops`` of multigpu.dist_cg for a FormOperator (one GPU)."""
+
+    def __init__(self, op, jacobi=True):
+        from . import dev
+        from ._lib import lib, check
+        self.dev, self.lib, self.check = dev, lib, check
+        self.op = op
+        self.n = op.n
+        self.jacobi = jacobi
+
+    def begin(self, b):
+        dev, lib = self.dev, self.lib
+        n = self.n
+        self.b = b
+        self.x = dev.zeros(n)
+        self.r = dev.empty(n)
+        self.q = dev.zeros(n)
+        self.p = self.op.xvec                  # the operator reads its operand from p
+        self.p.zero_()
+        self.scratch = dev.empty(lib.tg_cg_scratch_len())
+        self.s = dev.zeros(8)
+        self.flip = 0
+        self.dinv = self.op.jacobi_dinv() if self.jacobi else dev.zeros(n) + 1.0
+        self.mask = self.op.spline._bc_mask() if self.op.applyBCs else None
+
+    def matvec(self, x, y):
+        assert x is self.p
+        self.op.apply(y)
+        if self.mask is not None:
+            self.check(self.lib.tg_zero_entries(self.dev.ptr(y), self.dev.ptr(self.mask), self.n,
+                                                self.dev.stream()))
+
+
+def solve_matfree_cg(op, b, rtol=1e-12, atol=0.0, maxit=100000, check_every=5, jacobi=True):
+    from .multigpu import dist_cg
+    return dist_cg(MatFreeOps(op, jacobi), b, rtol, atol, maxit, check_every)
