@@ -287,7 +287,7 @@ def run_ours(args):
     lib.tg_prof_get(C.byref(spmv_ms), C.byref(spmv_n))
     lib.tg_prof_enable(0)
     clocks = sampler.stop()
-    W = MTAM.window
+    W = getattr(MTAM, "window", None)          # None: matrix-free operator (--mode matfree)
     stage_ms = {"extract": 0.0, "assemble_ptap_bcs": 0.0, "solve": 0.0}
     for ev in stages:
         stage_ms["extract"] += ev[0].elapsed_time(ev[1])
@@ -317,7 +317,7 @@ def run_ours(args):
            "d2h_bytes_per_step": int(n_dofs * 8)}
 
     peak, which = measured_peaks()
-    bytes_per_launch = spmv_bytes(W)
+    bytes_per_launch = spmv_bytes(W) if W is not None else 0
     avg_ms = spmv_ms.value / max(spmv_n.value, 1)
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     kname = {0: "k_win_spmv<true>", 1: "k_win_spmv_tma<true>", 2: "k_sell_spmv<7,true>", 3: "k_win_spmv_pf<true>"}[
@@ -346,8 +346,10 @@ def run_ours(args):
                    "degree": P, "cells": nel ** 3, "iga_dofs": n_dofs, "path": mode,
                    "quad_degree": 2 * P, "cg_rtol": CG_RTOL, "cg_iterations": iters,
                    "preconditioner": "jacobi",
-                   "l2": "inputs larger than L2 (matrix %.1f GB streamed every CG iteration)"
-                         % (8e-9 * W.nnz)},
+                   "l2": ("inputs larger than L2 (matrix %.1f GB streamed every CG iteration)"
+                          % (8e-9 * W.nnz)) if W is not None else
+                         "inputs larger than L2 (matrix-free: control net, operand and "
+                         "coefficient chunks streamed every CG iteration)"},
         "stage_ms": stage_ms, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline}
 
@@ -422,7 +424,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nel", type=int, default=256)
-    ap.add_argument("--mode", default="fused", choices=["fused", "csr"])
+    ap.add_argument("--mode", default="fused", choices=["fused", "csr", "matfree"])
     ap.add_argument("--cpu-nel", type=int, default=20)
     ap.add_argument("--ref-nel", type=int, default=16)
     ap.add_argument("--ref-procs", type=int, default=0, help="CPU arm: concurrent copies (0 = all cores)")
