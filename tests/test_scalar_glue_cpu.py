@@ -1,0 +1,201 @@
+"""CPU run of the SCALAR hot path's Python (the code bench.py and smoke() drive:
+EqualOrderSpline -> ExtractedSpline(...) -> assembleLinearSystem -> solveLinearSystem,
+error functionals, project, Newton, writeExtraction / ExtractedSpline(dirname)) with
+``engine.TensorPatch`` replaced by the host stand-in of test_multifield_glue_cpu.py and the
+C-ABI calls by numpy twins.  Guards the API layer against regressions between GPU runs; the
+kernels themselves are covered by the ``-m gpu`` tests.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bsplines as OB
+from oracle import pipeline as OP
+from test_multifield_glue_cpu import FakePatch, FakeWinMatrix, cpu_backend  # noqa: F401
+
+
+class ScalarFakePatch(FakePatch):
+    """+ the scalar-path entry points of engine.TensorPatch."""
+
+    def __init__(self, degrees, kvecs, quadDeg=None, eps=None, splines=None, part=None, lib=None):
+        deg = [s.p for s in splines]
+        ts = OB.TensorSpline(deg, [np.asarray(s.knots, dtype=float) for s in splines])
+        self.quadDeg = 2 * max(deg) if quadDeg is None else quadDeg
+        FakePatch.__init__(self, ts, None, self.quadDeg // 2 + 1, lib)
+        self.degrees, self.splines, self.eps = deg, splines, eps
+        self.nel = [s.nel for s in ts.splines]
+        self.order = 4
+
+    def _integrator(self, kind, funcs):
+        from test_multifield_cpu import HostIntegrator
+        from oracle import assembly as OA
+        if kind not in self._H:
+            H = HostIntegrator(self.ts, None, self.nq, {}, order=self.order)
+            if kind == "fe":
+                pf = self.ts.getDegree()
+                H.tabs = [OA.tab_fe(s, pf, self.nq, self.order) for s in self.ts.splines]
+                ncell = int(np.prod([tb.T.shape[0] for tb in H.tabs]))
+                H.blk = OA.CellBlock(H.tabs, np.arange(ncell), self.order)
+                H.n = self.n_fe
+            self._H[kind] = H
+        H = self._H[kind]
+        H.funcs = {fid: funcs[fid].numpy() for fid in list(funcs.keys())}
+        return H
+
+    def assemble_system(self, mterms, vterms, funcs, kind="fe"):
+        return (self.assemble_matrix(mterms, funcs, kind),
+                self.assemble_vector(vterms, funcs, kind))
+
+    def assemble_scalar(self, node, funcs, kind="fe"):
+        return float(self._integrator(kind, funcs)._eval([node])[0].sum())
+
+    def fe_node_coords(self):
+        from oracle import extraction as OX
+        return OX.fe_node_coords(self.ts)
+
+    @property
+    def nfe(self):
+        from oracle import extraction as OX
+        return OX.n_fe_nodes(self.ts)
+
+
+@pytest.fixture
+def scalar_backend(cpu_backend, monkeypatch):  # noqa: F811
+    from tigar_b200 import api as A
+    monkeypatch.setattr(A, "TensorPatch",
+                        lambda *a, **k: ScalarFakePatch(*a, lib=cpu_backend, **k))
+    return cpu_backend
+
+
+def make(deg, nels, mode, nLayers=1, lo=0.0, hi=1.0):
+    from tIGAr import EqualOrderSpline, ExtractedSpline
+    from tIGAr.BSplines import ExplicitBSplineControlMesh, uniformKnots
+    kv = [uniformKnots(p, lo, hi, n) for p, n in zip(deg, nels)]
+    gen = EqualOrderSpline(1, ExplicitBSplineControlMesh(deg, kv))
+    sp = gen.getScalarSpline(0)
+    for d in range(len(deg)):
+        for side in (0, 1):
+            gen.addZeroDofs(0, sp.getSideDofs(d, side, nLayers))
+    spline = ExtractedSpline(gen, 2 * max(deg), mode=mode)
+    return gen, spline, kv
+
+
+@pytest.mark.parametrize("mode", ["fused", "csr", "matfree"])
+def test_poisson_through_the_real_constructor_path(scalar_backend, mode):
+    """The flow of demos/poisson/poisson.py (and of bench.one_step / smoke())."""
+    from tIGAr import (TrialFunction, TestFunction, Function, KrylovSolver, inner, sin, pi,
+                       assemble)
+    deg, nels = [2, 2], [6, 5]
+    gen, spline, kv = make(deg, nels, mode)
+    assert spline.mode == mode and list(spline.zeroDofs) == sorted(set(gen.zeroDofs))
+    pr = OP.Problem(deg, [np.asarray(k) for k in kv])
+    Uo = pr.run(lambda X: 2 * math.pi ** 2 * np.prod(np.sin(math.pi * X[..., :2]), axis=-1))
+    u, v = TrialFunction(spline.V), TestFunction(spline.V)
+    x = spline.spatialCoordinates()
+    soln = sin(pi * x[0]) * sin(pi * x[1])
+    f = -spline.div(spline.grad(soln))
+    ks = KrylovSolver("cg", "jacobi")
+    ks.parameters["relative_tolerance"] = 1e-13
+    spline.setSolverOptions(linearSolver=ks)
+    uh = Function(spline.V)
+    U = spline.solveLinearVariationalProblem(
+        inner(spline.grad(u), spline.grad(v)) * spline.dx == inner(f, v) * spline.dx, uh)
+    assert np.linalg.norm(U.get_local() - Uo) < 1e-10 * np.linalg.norm(Uo)
+    err = math.sqrt(assemble(((uh - soln) ** 2) * spline.dx))
+    assert abs(err - pr.error(Uo, "l2", lambda X: np.prod(np.sin(math.pi * X[..., :2]), axis=-1))) < 1e-9
+    if mode != "matfree":
+        MTAM, MTb = spline.assembleLinearSystem(
+            inner(spline.grad(u), spline.grad(v)) * spline.dx, inner(f, v) * spline.dx)
+        assert abs(MTAM.to_scipy() - pr.C).max() < 1e-12 * abs(pr.C).max()
+        assert np.abs(MTb.get_local() - pr.b).max() < 1e-12 * np.abs(pr.b).max()
+
+
+def test_biharmonic_residual_form_and_two_bc_layers(scalar_backend):
+    """demos/biharmonic/biharmonic.py: residual split with lhs/rhs, laplacians through
+    div(grad()), two layers of zero DoFs."""
+    from tIGAr import TrialFunction, TestFunction, Function, KrylovSolver, inner, cos, pi
+    deg, nels = [3, 3], [5, 5]
+    gen, spline, kv = make(deg, nels, "fused", nLayers=2, lo=-1.0, hi=1.0)
+    u, v = TrialFunction(spline.V), TestFunction(spline.V)
+    x = spline.spatialCoordinates()
+    soln = (cos(pi * x[0]) + 1.0) * (cos(pi * x[1]) + 1.0)
+
+    def lap(w):
+        return spline.div(spline.grad(w))
+    f = lap(lap(soln))
+    res = inner(lap(u), lap(v)) * spline.dx - inner(f, v) * spline.dx
+    ks = KrylovSolver("cg", "jacobi")
+    ks.parameters["relative_tolerance"] = 1e-13
+    spline.setSolverOptions(linearSolver=ks)
+    uh = Function(spline.V)
+    U = spline.solveLinearVariationalProblem(res, uh).get_local()
+    pr = OP.Problem(deg, [np.asarray(k) for k in kv], form="biharmonic", nLayers=2)
+
+    def f_np(X):
+        cx, cy = np.cos(math.pi * X[..., 0]), np.cos(math.pi * X[..., 1])
+        return math.pi ** 4 * (cx * (cy + 1) + 2 * cx * cy + (cx + 1) * cy)
+    Uo = pr.run(f_np)
+    assert np.linalg.norm(U - Uo) < 1e-8 * np.linalg.norm(Uo)
+
+
+def test_newton_projection_and_extraction_round_trip(scalar_backend, tmp_path):
+    from tIGAr import (TrialFunction, TestFunction, Function, KrylovSolver, ExtractedSpline,
+                       inner, derivative, sin, pi)
+    deg, nels = [2, 2], [5, 4]
+    gen, spline, kv = make(deg, nels, "fused")
+    ks = KrylovSolver("cg", "jacobi")
+    ks.parameters["relative_tolerance"] = 1e-13
+    spline.setSolverOptions(maxIters=8, relativeTolerance=1e-10, linearSolver=ks)
+    v = TestFunction(spline.V)
+    x = spline.spatialCoordinates()
+    uh = Function(spline.V)
+    # nonlinear reaction-diffusion residual, Newton with the Gateaux tangent
+    res = (inner(spline.grad(uh), spline.grad(v)) + (uh + uh ** 3) * v
+           - 10.0 * sin(pi * x[0]) * sin(pi * x[1]) * v) * spline.dx
+    spline.solveNonlinearVariationalProblem(res, derivative(res, uh), uh)
+    R = spline.assembleVector(res).get_local()
+    assert np.abs(R).max() < 1e-8
+    # L2 projection (common.py:1392-1433) reproduces a function of the spline space
+    g = spline.project(x[0] * x[1] + 0.5, rationalize=False)
+    w = Function(spline.V)
+    w.set_iga(g.iga.clone())
+    from tIGAr import assemble
+    assert assemble(((w - (x[0] * x[1] + 0.5)) ** 2) * spline.dx) < 1e-20
+    # on-disk round trip
+    d = str(tmp_path / "extraction")
+    gen.writeExtraction(d)
+    sp2 = ExtractedSpline(d, 4, mode="fused")
+    assert list(sp2.zeroDofs) == list(spline.zeroDofs) and sp2.nsd == spline.nsd
+    u2, v2 = TrialFunction(sp2.V), TestFunction(sp2.V)
+    A1 = sp2.assembleMatrix(inner(sp2.grad(u2), sp2.grad(v2)) * sp2.dx)
+    u, vv = TrialFunction(spline.V), TestFunction(spline.V)
+    A0 = spline.assembleMatrix(inner(spline.grad(u), spline.grad(vv)) * spline.dx)
+    assert abs(A1.to_scipy() - A0.to_scipy()).max() < 1e-13
+
+
+def test_bench_one_step_runs_on_the_emulated_backend(scalar_backend, monkeypatch):
+    """bench.one_step (the timed body of bench.py) end to end on the host stand-ins, with
+    resident control-net columns and with the host control net; result against the
+    oracle."""
+    import bench as B
+
+    class _Event(object):
+        def __init__(self, enable_timing=True):
+            pass
+
+        def record(self):
+            pass
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    nel = 3
+    kv, cm, pinned = B.build_inputs(nel)
+    cols = [pinned[:, i].contiguous() for i in range(4)]
+    pr = OP.Problem([3] * 3, [OB.uniform_knots(3, 0.0, 1.0, nel)] * 3)
+    Uo = pr.run(lambda X: 3 * math.pi ** 2 * np.prod(np.sin(math.pi * X), axis=-1))
+    for net, to_host in ((cols, False), (pinned, True)):
+        n, its, ev, res, MTAM = B.one_step(kv, cm, net, "fused", 1e-12, to_host)
+        Uv = res if to_host else res.numpy()
+        assert n == len(Uo) == (nel + 3) ** 3 and its > 0 and len(ev) == 5
+        assert np.linalg.norm(Uv - Uo) < 1e-9 * np.linalg.norm(Uo)
+        assert B.spmv_bytes.__name__ == "spmv_bytes" and hasattr(MTAM, "window")
