@@ -148,7 +148,9 @@ class FakePatch(object):
         n = {"A": self.n_fe, "C": self.n_iga}[name]
         return FakeWindow(n, n)
 
-    def assemble_matrix(self, terms, funcs, kind="fe", out=None):
+    def assemble_matrix(self, terms, funcs, kind="fe", out=None, cache=None):
+        if cache is not None:
+            cache["calls"] = cache.get("calls", 0) + 1
         K = self._integrator(kind, funcs).matrix(terms).toarray()
         return FakeWinMatrix(self.window("A" if kind == "fe" else "C"),
                              torch.from_numpy(np.ascontiguousarray(K).ravel()))
@@ -267,11 +269,13 @@ def test_multifield_linear_solve_through_the_api(cpu_backend, mode):
     assert np.linalg.norm(U2.get_local() - Uo) < 1e-10 * np.linalg.norm(Uo)
 
 
-def test_multifield_newton_converges_in_one_step_on_the_linear_problem(cpu_backend):
+def test_multifield_newton_converges_in_one_step_on_the_linear_problem(cpu_backend, monkeypatch):
     """solveNonlinearVariationalProblem (common.py:1304-1348) with J = derivative(R, u)
-    on a multi-field residual: one Newton step solves the linear problem."""
+    on a multi-field residual: one Newton step solves the linear problem.  Run with the
+    opt-in program cache: every block's cache entry is hit once per Newton iteration."""
     from tigar_b200 import api as A
     from tigar_b200 import ufl_lite as U
+    monkeypatch.setenv("TIGAR_B200_PROG_CACHE", "1")
     spl, prob, n = build("fused", cpu_backend)
     Uo = prob.solve(body_force)
     v = A.TestFunction(spl.V)
@@ -284,6 +288,8 @@ def test_multifield_newton_converges_in_one_step_on_the_linear_problem(cpu_backe
     spl.setSolverOptions(maxIters=4, relativeTolerance=1e-9, linearSolver=ks)
     spl.solveNonlinearVariationalProblem(R, J, uh)
     assert np.linalg.norm(uh.iga.numpy() - Uo) < 1e-9 * np.linalg.norm(Uo)
+    calls = sorted((k[0][0], c["calls"]) for k, c in spl._prog_cache.items())
+    assert len(calls) == 6 and all(c == 2 for _, c in calls), calls   # 4 blocks + 2 vectors, 2 its
 
 
 def test_missing_diagonal_block_is_created_for_the_bc_diagonal(cpu_backend):

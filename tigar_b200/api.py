@@ -961,15 +961,32 @@ class ExtractedSpline(object):
         if ar == 2:
             blocks = {}
             for fg, bt in sorted(MF.split_matrix_terms(terms, nf).items()):
-                blocks[fg] = p.assemble_matrix(bt, funcs, kind)
+                blocks[fg] = p.assemble_matrix(bt, funcs, kind,
+                                               cache=self._program_cache(("m", kind, fg), bt))
             W = p.window("A" if kind == "fe" else "C")
             return MF.BlockMatrix(nf, blocks, W.nrows)
         parts = MF.split_vector_terms(terms, nf)
         n = p.n_fe if kind == "fe" else p.n_iga
         out = dev.zeros(nf * n)
         for f, vt in sorted(parts.items()):
-            p.assemble_vector(vt, funcs, kind, out=out[f * n:(f + 1) * n])
+            p.assemble_vector(vt, funcs, kind, out=out[f * n:(f + 1) * n],
+                              cache=self._program_cache(("v", kind, f), vt))
         return out
+
+    def _program_cache(self, tag, terms):
+        """Per-block cache of compiled Gauss-point programs for Newton / time loops that
+        assemble the SAME forms again and again (engine._setup_cached; symbolic compilation
+        of a shell tangent block costs ~0.2 s of Python per call).  Keyed by the identity
+        of the (hash-consed, immutable) coefficient nodes and the current values of the
+        mutable Parameters, which are baked into a program when it is compiled.
+        Opt-in (``TIGAR_B200_PROG_CACHE=1``) until it has run on a device."""
+        if os.environ.get("TIGAR_B200_PROG_CACHE") != "1":
+            return None
+        if getattr(self, "_prog_cache", None) is None:
+            self._prog_cache = {}
+        key = (tag, tuple(sorted((k, n.uid) for k, n in terms.items())),
+               tuple(sorted(S.PARAMS.items())))
+        return self._prog_cache.setdefault(key, {})
 
     def _assemble_kind(self, form, kind):
         sc = form.scalar()

@@ -510,6 +510,22 @@ class TensorPatch(object):
                  outregs=i32arr(prog.outregs), nout=len(prog.outregs), nder=nder)
         return P
 
+    def _setup_cached(self, cache, outputs, funcs):
+        """``_qp_setup`` with an optional per-caller cache (a dict): the compiled program,
+        its device copy and its JIT kernels are kept, the coefficient-function pointers are
+        re-bound on every call (Functions may have been given new tensors).  ``outputs`` is
+        a callable that builds the output nodes (only evaluated on a miss)."""
+        if cache is None:
+            return self._qp_setup(outputs(), funcs)
+        P = cache.get("P")
+        if P is None:
+            P = self._qp_setup(outputs(), funcs)
+            cache["P"] = P
+        else:
+            P["keep"] = [funcs[f] for f in P["fids"]]
+            P["coefs"] = vparr([dev.ptr(t) for t in P["keep"]])
+        return P
+
     def _qp_eval(self, B, P, cell0, ncells, out):
         from . import jit
         if jit.enabled() and len(P["fids"]) <= jit.MAXFUN:
@@ -541,10 +557,11 @@ class TensorPatch(object):
         a, b = pad3(k[0]), pad3(k[1])
         return (a[2], b[2], a[1], b[1], a[0], b[0])
 
-    def assemble_matrix(self, terms, funcs, kind="fe", out=None):
+    def assemble_matrix(self, terms, funcs, kind="fe", out=None, cache=None):
         """terms: {(alphaTest, alphaTrial): Node} (coefficient already includes
         J and the quadrature weight).  kind 'fe' -> A_FE on the Lagrange
-        basis; kind 'iga' -> sum_e M_e^T K_e M_e on the spline basis."""
+        basis; kind 'iga' -> sum_e M_e^T K_e M_e on the spline basis.
+        ``cache``: see ``_setup_cached`` (same terms on every call)."""
         alS = sorted(set(pad3(k[0]) for k in terms))
         alT = sorted(set(pad3(k[1]) for k in terms))
         nS, nT = len(alS), len(alT)
@@ -556,7 +573,7 @@ class TensorPatch(object):
         if lib.tg_assemble_sf_supported(B.ref()):
             # sum-factorised kernel: one coefficient slot per non-zero term
             keys = sorted(terms, key=self._sf_key)
-            P = self._qp_setup([terms[k] for k in keys], funcs)
+            P = self._setup_cached(cache, lambda: [terms[k] for k in keys], funcs)
             tl = []
             for i, k in enumerate(keys):
                 tl += [i] + list(pad3(k[0])) + list(pad3(k[1]))
@@ -574,8 +591,8 @@ class TensorPatch(object):
         grid = [[S.ZERO] * nT for _ in range(nS)]
         for (a, b), node in terms.items():
             grid[alS.index(pad3(a))][alT.index(pad3(b))] = node
-        outputs = [grid[s][t] for s in range(nS) for t in range(nT)]
-        P = self._qp_setup(outputs, funcs)
+        P = self._setup_cached(cache, lambda: [grid[s][t] for s in range(nS) for t in range(nT)],
+                               funcs)
         aS = i32arr([x for a in alS for x in a])
         aT = i32arr([x for a in alT for x in a])
         per_cell = nS * nT * B.nqp * 8
@@ -644,14 +661,12 @@ class TensorPatch(object):
         tensors (the matrix-free operator calls this once per CG iteration)."""
         alS = sorted(set(pad3(k) for k in terms))
         nS = len(alS)
-        P = cache.get("P") if cache is not None else None
-        if P is None:
-            outputs = [S.ZERO] * nS
+        def outputs():
+            out_nodes = [S.ZERO] * nS
             for a, node in terms.items():
-                outputs[alS.index(pad3(a))] = node
-            P = self._qp_setup(outputs, funcs)
-            if cache is not None:
-                cache["P"] = P
+                out_nodes[alS.index(pad3(a))] = node
+            return out_nodes
+        P = self._setup_cached(cache, outputs, funcs)
         nder = max(P["nder"], max(max(a) for a in alS))
         B = self.basis(kind, nder)
         if self.part is not None:
