@@ -224,3 +224,26 @@ def test_reference_demos_run_unmodified_on_the_api_layer(demo, rate, tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     rates = [float(x) for x in re.findall(r"\(rate = ([0-9][0-9.eE+-]*)\)", out.stdout)]
     assert len(rates) == 2 and all(abs(r - rate) < 0.15 for r in rates), out.stdout[-1000:]
+
+
+@pytest.mark.parametrize("script,args,pattern,check", [
+    ("poisson_explicit.py", ["2", "4", "3"], r"rate ([0-9.]+)\)", lambda r: abs(r[-1] - 3.0) < 0.2),
+    ("biharmonic.py", ["3", "4", "2"], r"rate ([0-9.]+)\)", lambda r: abs(r[-1] - 2.0) < 0.5),
+    ("poisson_annulus.py", ["2", "4", "2"], r"rate ([0-9.]+)\)", lambda r: r[-1] > 2.5),
+    ("elasticity.py", ["2", "4", "3"], r"rate ([0-9.]+)\)", lambda r: abs(r[-1] - 3.0) < 0.2),
+    ("scordelis_lo.py", ["6", "0.001"], r"Relative norm: ([0-9.eE+-]+)", lambda r: r[-1] < 1e-6),
+])
+def test_examples_run_on_the_api_layer(script, args, pattern, check, tmp_path):
+    """examples/*.py through tests/run_emulated.py at tiny sizes: the scripts stay in step
+    with the API (their device runs are recorded in profiles/r1_examples.log)."""
+    import os
+    import re
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    ex = os.path.join(os.path.dirname(here), "examples", script)
+    out = subprocess.run([sys.executable, os.path.join(here, "run_emulated.py"), ex] + args,
+                         cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    vals = [float(x) for x in re.findall(pattern, out.stdout)]
+    assert vals and check(vals), out.stdout[-1500:]
