@@ -322,6 +322,8 @@ def run_ours(args):
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     kname = {0: "k_win_spmv<true>", 1: "k_win_spmv_tma<true>", 2: "k_sell_spmv<7,true>", 3: "k_win_spmv_pf<true>"}[
         int(lib.tg_last_spmv_kind())]
+    if W is None:
+        kname = "none timed (matrix-free: tigar_qp + k_assemble_vector per CG iteration)"
     roofline = {"bound": "hbm", "kernel": kname + " (CG matvec + p.Ap partials)",
                 "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None,
