@@ -211,3 +211,38 @@ def test_shell_tangent_block_kernel_compiles_for_sm100a(roof):
     jets = [(fids.index(f), c, al) for (f, c, al) in prog.jets]
     src, nth = jit.generate(prog, 2, [4, 4, 1], [4, 4, 1], 3, jets, len(fids))
     assert nth == 32 and jit.check_source(src) > 1000
+
+
+def test_generated_cuda_of_a_shell_tangent_block_runs_correctly_on_host_threads(roof):
+    """The CUDA source the form compiler generates for one tangent block of the shell
+    (jit.generate: sum-factorised second-derivative jets of 7 functions through shared
+    memory, ~4 300-operation straight-line program, 36 outputs per Gauss point) is compiled
+    UNCHANGED for the host (tests/cuda_emu.py: CUDA threads -> std::threads, __syncthreads
+    -> std::barrier) and must reproduce the host interpreter's coefficients at every Gauss
+    point of every cell."""
+    import cuda_emu
+    from tigar_b200 import symbolic as S
+    from tigar_b200 import jit
+    from oracle import assembly as OA
+    bt = roof.jterms[(0, 2)]
+    alS = sorted(set(k[0] for k in bt))
+    alT = sorted(set(k[1] for k in bt))
+    grid = [[S.ZERO] * len(alT) for _ in alS]
+    for (a, b), node in bt.items():
+        grid[alS.index(a)][alT.index(b)] = node
+    outputs = [grid[s][t] for s in range(len(alS)) for t in range(len(alT))]
+    prog = S.compile_program(outputs, 2)
+    fids = sorted(set(j[0] for j in prog.jets))
+    jets = [(fids.index(f), c, al) for (f, c, al) in prog.jets]
+    nd = 3                                                     # derivative orders 0..2
+    src, nth = jit.generate(prog, 2, [4, 4, 1], [4, 4, 1], nd, jets, len(fids))
+    rng = np.random.RandomState(11)
+    Uv = 1e-2 * rng.rand(3 * roof.n)
+    roof.set_state(Uv)
+    tabs = [OA.tab_iga(s, 4, nd - 1) for s in roof.ts.splines]
+    ncell = int(np.prod([tb.T.shape[0] for tb in tabs]))
+    got = cuda_emu.run_qp_kernel(src, nth, tabs, [roof.H.funcs[f] for f in fids],
+                                 len(outputs), ncell)
+    ref = np.stack(roof.H._eval(outputs), axis=1)              # [cell, output, qp]
+    scale = np.abs(ref).max()
+    assert scale > 0 and np.abs(got - ref).max() < 1e-11 * scale
