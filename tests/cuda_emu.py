@@ -38,7 +38,7 @@ extern "C" void emu_run(const QpArgs* A, int nblocks, int nth) {
     emu_bar = &bar;
     std::vector<std::thread> th;
     for (int t = 0; t < nth; t++)
-      th.emplace_back([=]() { threadIdx.x = t; blockIdx.x = b; tigar_qp(*A);
+      th.emplace_back([=]() { threadIdx.x = t; blockIdx.x = b; KERNEL(*A);
                               });
     for (auto& x : th) x.join();
   }
@@ -46,9 +46,9 @@ extern "C" void emu_run(const QpArgs* A, int nblocks, int nth) {
 """
 
 
-def build(src):
+def build(src, kernel="tigar_qp"):
     """Compile generated CUDA source for the host; returns the loaded library."""
-    code = PRELUDE + src + RUNNER
+    code = PRELUDE + src + RUNNER.replace("KERNEL", kernel)
     key = hashlib.sha1(code.encode()).hexdigest()[:16]
     d = os.path.join(tempfile.gettempdir(), "tigar_cuda_emu")
     os.makedirs(d, exist_ok=True)
@@ -94,3 +94,42 @@ def run_qp_kernel(src, nth, tabs, coefs, nout, ncells, cell0=0):
     lib.emu_run.argtypes = [C.POINTER(QpArgs), C.c_int, C.c_int]
     lib.emu_run(C.byref(A), int(ncells), int(nth))
     return out
+
+
+def run_op_kernel(src, nth, tabs, coefs, y, stride):
+    """Fused operator kernel (jit.generate(..., op=...), ``tigar_op``): one launch per colour
+    of the cell lattice (``stride`` cells apart per direction), accumulating into ``y``."""
+    import itertools
+    from tigar_b200.jit import OpArgs
+    lib = build(src, "tigar_op")
+    dim = len(tabs)
+    keep = []
+
+    def ptr(a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data
+    A = OpArgs()
+    for d in range(3):
+        if d < dim:
+            tb = tabs[d]
+            A.tab[d], A.idx[d] = ptr(tb.T, np.float64), ptr(tb.idx, np.int32)
+            A.wq[d], A.xq[d] = ptr(tb.w, np.float64), ptr(tb.x, np.float64)
+            A.n[d], A.nel[d] = int(tb.n), int(tb.T.shape[0])
+        else:
+            A.n[d], A.nel[d] = 1, 1
+    for i, c in enumerate(coefs):
+        A.coef[i] = ptr(c, np.float64)
+    assert y.dtype == np.float64 and y.flags.c_contiguous
+    A.y = y.ctypes.data
+    lib.emu_run.argtypes = [C.POINTER(OpArgs), C.c_int, C.c_int]
+    nel = [int(A.nel[d]) for d in range(3)]
+    st = list(stride) + [1] * (3 - len(stride))
+    launches = 0
+    for o in itertools.product(*[range(min(st[d], nel[d])) for d in range(3)]):
+        cn = [(nel[d] - o[d] + st[d] - 1) // st[d] for d in range(3)]
+        for d in range(3):
+            A.co[d], A.cs[d], A.cn[d] = o[d], st[d], cn[d]
+        lib.emu_run(C.byref(A), int(np.prod(cn)), int(nth))
+        launches += 1
+    return launches

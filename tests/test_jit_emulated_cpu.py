@@ -63,3 +63,48 @@ def test_generated_poisson_system_kernel_equals_interpreter(deg, nel):
     for s in range(len(outputs)):
         sc = np.abs(ref[:, s]).max()
         assert np.abs(got[:, s] - ref[:, s]).max() <= 1e-12 * max(sc, 1e-300), s
+
+
+@pytest.mark.parametrize("deg,nel", [([3, 3, 3], [5, 2, 3]), ([2, 2, 2], [3, 3, 2]), ([3, 3], [5, 6])])
+def test_fused_operator_kernel_applies_the_matrix(deg, nel):
+    """jit.generate(..., op=...): the one-kernel matrix-free operator (Gauss-point program +
+    test-function contraction + coloured scatter) on host threads equals C x with C
+    integrated on the host from the same bilinear terms."""
+    from tigar_b200 import api as A
+    from tigar_b200 import ufl_lite as U
+    dim = len(deg)
+    kv = [OB.uniform_knots(p, 0.0, 1.0, n) for p, n in zip(deg, nel)]
+    ts = OB.TensorSpline(deg, kv)
+    P = curved_net(ts, dim)
+    spl = symbolic_spline(dim, dim, 1, ts.ncp)
+    u, v = A.TrialFunction(spl.V), A.TestFunction(spl.V)
+    a = (U.inner(spl.grad(u), spl.grad(v)) + 0.7 * u * v) * spl.dx
+    mt = spl._weighted(a.scalar())
+    xf = A.Function(spl.V)
+    vt = {}
+    for (aT, aU), node in mt.items():
+        term = S.mul(node, S.jet(xf.fid, 0, tuple(aU)))
+        vt[aT] = S.add(vt[aT], term) if aT in vt else term
+    keys = sorted(vt)
+    outputs = [vt[k] for k in keys]
+    prog = S.compile_program(outputs, dim)
+    fids = sorted(set(j[0] for j in prog.jets))
+    jets = [(fids.index(fid), c, al) for (fid, c, al) in prog.jets]
+    nder = max(max(max(al) for (_, _, al) in prog.jets), max(max(k) for k in keys))
+    nq = max(deg) + 1
+    nloc = [p + 1 for p in deg] + [1] * (3 - dim)
+    nqs = [nq] * dim + [1] * (3 - dim)
+    src, nth = jit.generate(prog, dim, nloc, nqs, nder + 1, jets, len(fids), op=keys)
+    assert jit.check_source(src) > 1000                      # NVRTC, sm_100a
+    rng = np.random.RandomState(8)
+    xv = rng.rand(ts.ncp)
+    funcs = {fn.fid: P[:, i].copy() for i, fn in enumerate(spl.cpFuncs)}
+    funcs[xf.fid] = xv
+    H = HostIntegrator(ts, P, nq, funcs, order=nder)
+    Cx = H.matrix({(k[0], k[1]): n for k, n in mt.items()}) @ xv
+    tabs = [OA.tab_iga(s, nq, nder) for s in ts.splines]
+    y = np.zeros(ts.ncp)
+    launches = cuda_emu.run_op_kernel(src, nth, tabs, [funcs[f] for f in fids], y,
+                                      [p + 1 for p in deg])
+    assert launches == int(np.prod([min(p + 1, n) for p, n in zip(deg, nel)]))
+    assert np.abs(y - Cx).max() < 1e-12 * np.abs(Cx).max()

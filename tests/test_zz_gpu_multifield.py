@@ -205,6 +205,13 @@ def test_matrix_free_mode_on_the_device(deg, nels):
     y = dev.to_np(op.matvec(xv))
     yref = dev.to_np(C.matvec(xv))
     assert rel(y, yref) < 1e-12
+    # the one-kernel variant (jit.generate(..., op=...)), same operator
+    os.environ["TIGAR_B200_MF_FUSED"] = "1"
+    try:
+        yf = dev.to_np(op.matvec(xv))
+    finally:
+        del os.environ["TIGAR_B200_MF_FUSED"]
+    assert rel(yf, yref) < 1e-12
     C0 = fused.assembleMatrix(a, applyBCs=False).to_scipy()
     op0 = mf.assembleMatrix(a2, applyBCs=False)
     d1 = dev.to_np(op0.jacobi_dinv(1))

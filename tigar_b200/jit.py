@@ -35,6 +35,23 @@ class QpArgs(C.Structure):
                 ("cell0", c_i64), ("out", c_vp)]
 
 
+class OpArgs(C.Structure):
+    """QpArgs + the colour lattice of the launch and the output vector (fused
+    matrix-free operator kernel, ``generate(..., op=...)``)."""
+    _fields_ = [("tab", c_vp * 3), ("idx", c_vp * 3), ("wq", c_vp * 3), ("xq", c_vp * 3),
+                ("coef", c_vp * MAXFUN), ("n", c_i32 * 3), ("nel", c_i32 * 3),
+                ("cell0", c_i64), ("out", c_vp), ("co", c_i32 * 3), ("cs", c_i32 * 3),
+                ("cn", c_i32 * 3), ("y", c_vp)]
+
+
+_PRELUDE_OP = r"""
+struct QpArgs {
+  const double* tab[3]; const int* idx[3]; const double* wq[3]; const double* xq[3];
+  const double* coef[%(MAXFUN)d]; int n[3]; int nel[3]; long long cell0; double* out;
+  int co[3]; int cs[3]; int cn[3]; double* y;
+};
+"""
+
 _PRELUDE = r"""
 struct QpArgs {
   const double* tab[3]; const int* idx[3]; const double* wq[3]; const double* xq[3];
@@ -43,30 +60,47 @@ struct QpArgs {
 """
 
 
-def generate(prog, dim, nloc, nq, nd, jets, nfun):
+def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None):
     """CUDA source of the kernel for ``prog``.  jets: list of (fpos, comp, al3)
-    in register order; nloc/nq: per-direction sizes (padded to 3 with 1)."""
+    in register order; nloc/nq: per-direction sizes (padded to 3 with 1).
+
+    ``op``: list of test multi-indices, one per program output.  The kernel (``tigar_op``)
+    then does not store the outputs but contracts output ``s`` with ``D^op[s]`` of the
+    test basis (sum-factorised through shared memory, as k_assemble_vector does) and adds
+    the element vector into ``A.y``: the action of a bilinear form on a Function in ONE
+    kernel, with no coefficient buffer (matrix-free operator, tigar_b200/matfree.py).
+    Cells of a launch form the lattice ``co + cs * i`` (colouring: cs = nloc keeps the
+    scatter exclusive)."""
     n0, n1, n2 = nloc
     q0, q1, q2 = nq
     nen, nqp = n0 * n1 * n2, q0 * q1 * q2
     nth = ((nqp + 31) // 32) * 32
     L = []
     w = L.append
-    w(_PRELUDE % dict(MAXFUN=MAXFUN))
+    w((_PRELUDE if op is None else _PRELUDE_OP) % dict(MAXFUN=MAXFUN))
     w("#define N0 %d\n#define N1 %d\n#define N2 %d\n#define Q0 %d\n#define Q1 %d\n#define Q2 %d"
       % (n0, n1, n2, q0, q1, q2))
     w("#define ND %d\n#define NEN %d\n#define NQP %d\n#define NTH %d\n#define DIM %d"
       % (nd, nen, nqp, nth, dim))
-    w('extern "C" __global__ void __launch_bounds__(NTH) tigar_qp(const QpArgs A) {')
+    w('extern "C" __global__ void __launch_bounds__(NTH) %s(const QpArgs A) {'
+      % ("tigar_qp" if op is None else "tigar_op"))
     w("  __shared__ double tb0[Q0*N0*ND], tb1[Q1*N1*ND], tb2[Q2*N2*ND];")
     w("  __shared__ double cf[NEN], s1[Q0*N1*N2], s2[Q0*Q1*N2];")
     w("  const int tid = threadIdx.x;")
     w("  const long long cl = blockIdx.x;")
-    w("  long long c = A.cell0 + cl;")
-    w("  int e0 = (int)(c % A.nel[0]), e1 = 0, e2 = 0;")
-    if dim > 1:
-        w("  { long long r = c / A.nel[0]; e1 = (int)(r % A.nel[1]); " +
-          ("e2 = (int)(r / A.nel[1]);" if dim > 2 else "") + " }")
+    if op is None:
+        w("  long long c = A.cell0 + cl;")
+        w("  int e0 = (int)(c % A.nel[0]), e1 = 0, e2 = 0;")
+        if dim > 1:
+            w("  { long long r = c / A.nel[0]; e1 = (int)(r % A.nel[1]); " +
+              ("e2 = (int)(r / A.nel[1]);" if dim > 2 else "") + " }")
+    else:
+        w("  __shared__ double cq[NQP], u1[N0*Q1*Q2], u2[N0*N1*Q2], accs[NEN];")
+        w("  int e0 = A.co[0] + A.cs[0] * (int)(cl % A.cn[0]), e1 = 0, e2 = 0;")
+        if dim > 1:
+            w("  { long long r = cl / A.cn[0]; e1 = A.co[1] + A.cs[1] * (int)(r % A.cn[1]); " +
+              ("e2 = A.co[2] + A.cs[2] * (int)(r / A.cn[1]);" if dim > 2 else "") + " }")
+        w("  for (int a = tid; a < NEN; a += NTH) accs[a] = 0.0;")
     w("  for (int i = tid; i < Q0*N0*ND; i += NTH) tb0[i] = A.tab[0][(long long)e0*Q0*N0*ND + i];")
     if dim > 1:
         w("  for (int i = tid; i < Q1*N1*ND; i += NTH) tb1[i] = A.tab[1][(long long)e1*Q1*N1*ND + i];")
@@ -115,7 +149,13 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun):
                         w("  if (active) { double acc = 0.0;")
                         w("    #pragma unroll\n    for (int l = 0; l < N2; l++) acc += s2[(l*Q1 + qb)*Q0 + qa] * tb2[(qc*N2 + l)*ND + %d];" % al[2])
                         w("    j%d = acc; }" % k)
-    w("  if (!active) return;")
+    if op is None:
+        w("  if (!active) return;")
+    else:
+        if len(op) != len(prog.outregs):
+            raise ValueError("one test multi-index per program output")
+        w("  double %s;" % ", ".join("ov%d = 0.0" % i for i in range(len(op))))
+        w("  if (active) {")
     # fixed registers
     names = {}
     for d in range(dim):
@@ -133,8 +173,8 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun):
     # straight-line program in SSA form (registers are re-used by the allocator,
     # so every definition gets a fresh C variable)
     ver = 0
-    for (op, dst, a, b) in prog.prog:
-        nm = _NAMES[op]
+    for (opc, dst, a, b) in prog.prog:
+        nm = _NAMES[opc]
         var = "t%d" % ver
         ver += 1
         if nm == "const":
@@ -147,9 +187,46 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun):
             expr = _BIN[nm] % (names[a], names[b])
         w("  const double %s = %s;" % (var, expr))
         names[dst] = var
-    w("  double* o = A.out + cl * (long long)%d * NQP + tid;" % len(prog.outregs))
+    if op is None:
+        w("  double* o = A.out + cl * (long long)%d * NQP + tid;" % len(prog.outregs))
+        for s, r in enumerate(prog.outregs):
+            w("  o[%d * NQP] = %s;" % (s, names[r]))
+        w("}")
+        return "\n".join(L), nth
     for s, r in enumerate(prog.outregs):
-        w("  o[%d * NQP] = %s;" % (s, names[r]))
+        w("  ov%d = %s;" % (s, names[r]))
+    w("  }")
+    # test-function contraction, one output slot at a time (u1, u2 as in k_assemble_vector)
+    for s, al in enumerate(op):
+        al = tuple(al) + (0,) * (3 - len(al))
+        w("  __syncthreads();")
+        w("  if (active) cq[tid] = ov%d;" % s)
+        w("  __syncthreads();")
+        w("  for (int o = tid; o < N0*Q1*Q2; o += NTH) {")
+        w("    int a0 = o %% N0, r = o / N0; double acc = 0.0;".replace("%%", "%"))
+        w("    #pragma unroll\n    for (int q = 0; q < Q0; q++) acc += tb0[(q*N0 + a0)*ND + %d] * cq[r*Q0 + q];" % al[0])
+        w("    u1[o] = acc;\n  }")
+        w("  __syncthreads();")
+        w("  for (int o = tid; o < N0*N1*Q2; o += NTH) {")
+        w("    int a0 = o %% N0, t = o / N0, a1 = t %% N1, q2 = t / N1; double acc = 0.0;"
+          .replace("%%", "%"))
+        w("    #pragma unroll\n    for (int q = 0; q < Q1; q++) acc += tb1[(q*N1 + a1)*ND + %d] * u1[(q2*Q1 + q)*N0 + a0];" % al[1])
+        w("    u2[o] = acc;\n  }")
+        w("  __syncthreads();")
+        w("  for (int a = tid; a < NEN; a += NTH) {")
+        w("    int a01 = a %% (N0*N1), a2 = a / (N0*N1); double acc = 0.0;".replace("%%", "%"))
+        w("    #pragma unroll\n    for (int q = 0; q < Q2; q++) acc += tb2[(q*N2 + a2)*ND + %d] * u2[q*N0*N1 + a01];" % al[2])
+        w("    accs[a] += acc;\n  }")
+    w("  __syncthreads();")
+    w("  for (int a = tid; a < NEN; a += NTH) {")
+    w("    int l0 = a %% N0, t = a / N0, l1 = t %% N1, l2 = t / N1;".replace("%%", "%"))
+    w("    long long g = A.idx[0][e0*N0 + l0];")
+    if dim > 1:
+        w("    g += (long long)A.n[0] * A.idx[1][e1*N1 + l1];")
+    if dim > 2:
+        w("    g += (long long)A.n[0] * A.n[1] * A.idx[2][e2*N2 + l2];")
+    w("    A.y[g] += accs[a];")
+    w("  }")
     w("}")
     return "\n".join(L), nth
 
@@ -192,3 +269,41 @@ def launch(kernel, B, coef_ptrs, cell0, ncells, out):
     a.cell0 = cell0
     a.out = dev.ptr(out)
     check(lib.tg_jit_launch(h, ncells, nth, 0, C.byref(a), C.sizeof(a), dev.stream()))
+
+
+# ---- fused matrix-free operator kernel (generate(..., op=...)) -------------------------------
+def get_op_kernel(prog, dim, nloc, nq, nd, jets, nfun, op):
+    src, nth = generate(prog, dim, nloc, nq, nd, jets, nfun, op=op)
+    key = hashlib.sha1(src.encode()).hexdigest()
+    k = _cache.get(key)
+    if k is None:
+        h = C.c_void_p()
+        check(lib.tg_jit_compile(src.encode(), b"tigar_op", C.byref(h)))
+        k = (h, nth)
+        _cache[key] = k
+    return k
+
+
+def launch_op(kernel, B, coef_ptrs, y, stride):
+    """One launch per colour of the cell lattice (cells ``stride`` apart per direction never
+    share a basis function when stride = nloc), accumulating into ``y``."""
+    import itertools
+    h, nth = kernel
+    a = OpArgs()
+    b = B.c
+    for d in range(3):
+        a.tab[d], a.idx[d], a.wq[d], a.xq[d] = b.tab[d], b.idx[d], b.wq[d], b.xq[d]
+        a.n[d], a.nel[d] = b.n[d], b.nel[d]
+    for i, p in enumerate(coef_ptrs):
+        a.coef[i] = p
+    a.y = dev.ptr(y)
+    dim = int(b.dim)
+    nel = [int(b.nel[d]) if d < dim else 1 for d in range(3)]
+    st = [int(stride[d]) if d < dim else 1 for d in range(3)]
+    for o in itertools.product(*[range(min(st[d], nel[d])) for d in range(3)]):
+        grid = 1
+        for d in range(3):
+            a.co[d], a.cs[d] = o[d], st[d]
+            a.cn[d] = (nel[d] - o[d] + st[d] - 1) // st[d]
+            grid *= int(a.cn[d])
+        check(lib.tg_jit_launch(h, grid, nth, 0, C.byref(a), C.sizeof(a), dev.stream()))

@@ -23,6 +23,7 @@ row slab at a time (the slab partition of multigpu.py, run sequentially on this 
 that only ``1/nparts`` of the matrix exists at any moment.
 """
 import math
+import os
 
 from . import symbolic as S
 from .multifield import BlockOps
@@ -60,7 +61,35 @@ class FormOperator(object):
     def apply(self, y):
         """y = C * self.xvec (no BCs)."""
         y.zero_()
+        if os.environ.get("TIGAR_B200_MF_FUSED") == "1":
+            return self._apply_fused(y)
         self.patch.assemble_vector(self.vterms, self._funcs, "iga", out=y, cache=self._cache)
+        return y
+
+    def _apply_fused(self, y):
+        """One generated kernel per colour instead of Gauss-point pass + vector assembly:
+        the flux coefficients never leave the SM (jit.generate(..., op=...); numerics
+        checked on host threads in tests/test_jit_emulated_cpu.py).  Opt-in
+        (``TIGAR_B200_MF_FUSED=1``) until it has run on a device."""
+        from . import dev, jit
+        K = self._cache.get("fused")
+        if K is None:
+            p = self.patch
+            keys = sorted(self.vterms)
+            prog = S.compile_program([self.vterms[k] for k in keys], p.dim)
+            fids = sorted(set(j[0] for j in prog.jets))
+            if len(fids) > jit.MAXFUN:
+                raise ValueError("too many coefficient functions for the generated kernel")
+            jets = [(fids.index(f), c, tuple(al) + (0,) * (3 - len(al))) for (f, c, al) in prog.jets]
+            nder = max([max(al) for (_, _, al) in prog.jets] + [max(k) for k in keys])
+            B = p.basis("iga", nder)
+            nloc = list(B.nloc) + [1] * (3 - p.dim)
+            nq = [int(B.c.nq[d]) for d in range(3)]
+            kern = jit.get_op_kernel(prog, p.dim, nloc, nq, B.nder + 1, jets, len(fids), keys)
+            K = dict(kern=kern, B=B, fids=fids, stride=list(B.nloc))
+            self._cache["fused"] = K
+        ptrs = [dev.ptr(self._funcs[f]) for f in K["fids"]]
+        jit.launch_op(K["kern"], K["B"], ptrs, y, K["stride"])
         return y
 
     def matvec(self, x, y=None):
