@@ -108,3 +108,37 @@ def test_fused_operator_kernel_applies_the_matrix(deg, nel):
                                       [p + 1 for p in deg])
     assert launches == int(np.prod([min(p + 1, n) for p, n in zip(deg, nel)]))
     assert np.abs(y - Cx).max() < 1e-12 * np.abs(Cx).max()
+
+
+@pytest.mark.parametrize("deg,nel", [([3, 3, 3], [4, 2, 3]), ([2, 2], [4, 5])])
+def test_generated_diagonal_kernel_gives_the_matrix_diagonal(deg, nel):
+    """jit.generate(..., op=pairs, diag=True): the Jacobi diagonal of the matrix-free
+    operator straight from the bilinear terms, on host threads, against the diagonal of the
+    host-integrated matrix."""
+    from tigar_b200 import api as A
+    from tigar_b200 import ufl_lite as U
+    dim = len(deg)
+    kv = [OB.uniform_knots(p, 0.0, 1.0, n) for p, n in zip(deg, nel)]
+    ts = OB.TensorSpline(deg, kv)
+    P = curved_net(ts, dim)
+    spl = symbolic_spline(dim, dim, 1, ts.ncp)
+    u, v = A.TrialFunction(spl.V), A.TestFunction(spl.V)
+    a = (U.inner(spl.grad(u), spl.grad(v)) + 0.7 * u * v) * spl.dx
+    mt = spl._weighted(a.scalar())
+    keys = sorted(mt)
+    prog = S.compile_program([mt[k] for k in keys], dim)
+    fids = sorted(set(j[0] for j in prog.jets))
+    jets = [(fids.index(fid), c, al) for (fid, c, al) in prog.jets]
+    nder = max(max(max(al) for (_, _, al) in prog.jets), max(max(k[0] + k[1]) for k in keys))
+    nq = max(deg) + 1
+    nloc = [p + 1 for p in deg] + [1] * (3 - dim)
+    src, nth = jit.generate(prog, dim, nloc, [nq] * dim + [1] * (3 - dim), nder + 1, jets,
+                            len(fids), op=keys, diag=True)
+    assert jit.check_source(src) > 1000
+    funcs = {fn.fid: P[:, i].copy() for i, fn in enumerate(spl.cpFuncs)}
+    H = HostIntegrator(ts, P, nq, funcs, order=nder)
+    ref = H.matrix({(k[0], k[1]): n for k, n in mt.items()}).diagonal()
+    tabs = [OA.tab_iga(s, nq, nder) for s in ts.splines]
+    y = np.zeros(ts.ncp)
+    cuda_emu.run_op_kernel(src, nth, tabs, [funcs[f] for f in fids], y, [p + 1 for p in deg])
+    assert np.abs(y - ref).max() < 1e-12 * np.abs(ref).max()

@@ -60,7 +60,7 @@ struct QpArgs {
 """
 
 
-def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None):
+def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False):
     """CUDA source of the kernel for ``prog``.  jets: list of (fpos, comp, al3)
     in register order; nloc/nq: per-direction sizes (padded to 3 with 1).
 
@@ -70,7 +70,12 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None):
     the element vector into ``A.y``: the action of a bilinear form on a Function in ONE
     kernel, with no coefficient buffer (matrix-free operator, tigar_b200/matfree.py).
     Cells of a launch form the lattice ``co + cs * i`` (colouring: cs = nloc keeps the
-    scatter exclusive)."""
+    scatter exclusive).
+
+    ``diag=True`` (with ``op`` = list of (test, trial) multi-index pairs, one per output):
+    the kernel adds the DIAGONAL of the element matrices instead,
+    ``y[g(a)] += sum_s sum_q out_s(q) D^test_s N_a(q) D^trial_s N_a(q)`` -- the Jacobi
+    preconditioner of the matrix-free operator without ever assembling a matrix."""
     n0, n1, n2 = nloc
     q0, q1, q2 = nq
     nen, nqp = n0 * n1 * n2, q0 * q1 * q2
@@ -196,8 +201,29 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None):
     for s, r in enumerate(prog.outregs):
         w("  ov%d = %s;" % (s, names[r]))
     w("  }")
+    if diag:
+        for s, (aS, aT) in enumerate(op):
+            aS = tuple(aS) + (0,) * (3 - len(aS))
+            aT = tuple(aT) + (0,) * (3 - len(aT))
+            w("  __syncthreads();")
+            w("  if (active) cq[tid] = ov%d;" % s)
+            w("  __syncthreads();")
+            w("  for (int a = tid; a < NEN; a += NTH) {")
+            w("    int l0 = a %% N0, t = a / N0, l1 = t %% N1, l2 = t / N1; double acc = 0.0;"
+              .replace("%%", "%"))
+            w("    for (int q2 = 0; q2 < Q2; q2++) {")
+            w("      const double w2 = tb2[(q2*N2 + l2)*ND + %d] * tb2[(q2*N2 + l2)*ND + %d];"
+              % (aS[2], aT[2]))
+            w("      for (int q1 = 0; q1 < Q1; q1++) {")
+            w("        const double w1 = w2 * tb1[(q1*N1 + l1)*ND + %d] * tb1[(q1*N1 + l1)*ND + %d];"
+              % (aS[1], aT[1]))
+            w("        #pragma unroll\n        for (int q0 = 0; q0 < Q0; q0++)")
+            w("          acc += w1 * tb0[(q0*N0 + l0)*ND + %d] * tb0[(q0*N0 + l0)*ND + %d] * cq[(q2*Q1 + q1)*Q0 + q0];"
+              % (aS[0], aT[0]))
+            w("      }\n    }")
+            w("    accs[a] += acc;\n  }")
     # test-function contraction, one output slot at a time (u1, u2 as in k_assemble_vector)
-    for s, al in enumerate(op):
+    for s, al in enumerate([] if diag else op):
         al = tuple(al) + (0,) * (3 - len(al))
         w("  __syncthreads();")
         w("  if (active) cq[tid] = ov%d;" % s)
@@ -272,8 +298,8 @@ def launch(kernel, B, coef_ptrs, cell0, ncells, out):
 
 
 # ---- fused matrix-free operator kernel (generate(..., op=...)) -------------------------------
-def get_op_kernel(prog, dim, nloc, nq, nd, jets, nfun, op):
-    src, nth = generate(prog, dim, nloc, nq, nd, jets, nfun, op=op)
+def get_op_kernel(prog, dim, nloc, nq, nd, jets, nfun, op, diag=False):
+    src, nth = generate(prog, dim, nloc, nq, nd, jets, nfun, op=op, diag=diag)
     key = hashlib.sha1(src.encode()).hexdigest()
     k = _cache.get(key)
     if k is None:
