@@ -219,6 +219,13 @@ def test_matrix_free_mode_on_the_device(deg, nels):
     op0._dinv = None
     d2 = dev.to_np(op0.jacobi_dinv(2))
     assert rel(d2, d1) < 1e-13
+    op0._dinv = None
+    os.environ["TIGAR_B200_MF_FUSED"] = "1"
+    try:
+        d3 = dev.to_np(op0.jacobi_dinv())                 # generated diagonal kernel
+    finally:
+        del os.environ["TIGAR_B200_MF_FUSED"]
+    assert rel(d3, d1) < 1e-12
     ks = KrylovSolver("cg", "jacobi")
     ks.parameters["relative_tolerance"] = 1e-13
     mf.setSolverOptions(linearSolver=ks)

@@ -122,6 +122,9 @@ class FormOperator(object):
         from ._lib import lib, check
         from .engine import TensorPatch
         p = self.patch
+        if os.environ.get("TIGAR_B200_MF_FUSED") == "1" and nparts is None:
+            self._dinv = self._dinv_generated()
+            return self._dinv
         nparts = self.slab_count() if nparts is None else int(nparts)
         if nparts > 1:                       # slabs at least p + 1 cell layers thick
             nparts = max(1, min(nparts, p.nel[-1] // (p.degrees[-1] + 1)))
@@ -145,6 +148,29 @@ class FormOperator(object):
         # constrained rows: their dinv is never used (r and p are zero there inside CG)
         self._dinv = dinv
         return dinv
+
+
+    def _dinv_generated(self):
+        """1 / diag(C) from a generated kernel that sums the diagonal of the element matrices
+        (jit.generate(..., diag=True)): no matrix, not even slab-wise.  Same opt-in as
+        ``_apply_fused``; numerics checked on host threads (tests/test_jit_emulated_cpu.py)."""
+        from . import dev, jit
+        p = self.patch
+        keys = sorted(self.mterms)
+        prog = S.compile_program([self.mterms[k] for k in keys], p.dim)
+        fids = sorted(set(j[0] for j in prog.jets))
+        jets = [(fids.index(f), c, tuple(al) + (0,) * (3 - len(al))) for (f, c, al) in prog.jets]
+        nder = max([max(al) for (_, _, al) in prog.jets]
+                   + [max(tuple(k[0]) + tuple(k[1])) for k in keys])
+        B = p.basis("iga", nder)
+        nloc = list(B.nloc) + [1] * (3 - p.dim)
+        nq = [int(B.c.nq[d]) for d in range(3)]
+        pairs = [(tuple(k[0][:3]), tuple(k[1][:3])) for k in keys]
+        kern = jit.get_op_kernel(prog, p.dim, nloc, nq, B.nder + 1, jets, len(fids), pairs,
+                                 diag=True)
+        d = dev.zeros(self.n)
+        jit.launch_op(kern, B, [dev.ptr(self._funcs[f]) for f in fids], d, list(B.nloc))
+        return d.reciprocal_()                 # one-time element-wise reciprocal
 
 
 class MatFreeOps(BlockOps):
