@@ -247,3 +247,68 @@ def test_examples_run_on_the_api_layer(script, args, pattern, check, tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     vals = [float(x) for x in re.findall(pattern, out.stdout)]
     assert vals and check(vals), out.stdout[-1500:]
+
+
+class _EmuBasis(object):
+    """What matfree._apply_fused / _dinv_generated read from engine.Basis."""
+
+    def __init__(self, patch, nder):
+        from oracle import assembly as OA
+
+        class _C(object):
+            pass
+        self.nder = nder
+        self.nloc = [s.p + 1 for s in patch.ts.splines]
+        self.c = _C()
+        self.c.nq = [patch.nq] * patch.dim + [1] * (3 - patch.dim)
+        self.tabs = [OA.tab_iga(s, patch.nq, nder) for s in patch.ts.splines]
+
+
+def test_matfree_generated_kernels_through_the_operator_glue(scalar_backend, monkeypatch):
+    """TIGAR_B200_MF_FUSED=1: FormOperator drives the generated operator / diagonal kernels
+    (program, jets, derivative order, test multi-indices, function pointers, colour stride).
+    The kernels run on host threads (tests/cuda_emu.py) in place of the NVRTC module."""
+    import ctypes
+    import cuda_emu
+    from tigar_b200 import jit
+    from tIGAr import TrialFunction, TestFunction, Function, KrylovSolver, inner, sin
+    monkeypatch.setenv("TIGAR_B200_MF_FUSED", "1")
+    monkeypatch.setattr(ScalarFakePatch, "basis", lambda self, kind, nder: _EmuBasis(self, nder),
+                        raising=False)
+    monkeypatch.setattr(jit, "get_op_kernel",
+                        lambda prog, dim, nloc, nq, nd, jets, nfun, op, diag=False:
+                        jit.generate(prog, dim, nloc, nq, nd, jets, nfun, op=op, diag=diag))
+
+    def launch_op(kernel, B, ptrs, y, stride):
+        src, nth = kernel
+        n = y.numel()
+        coefs = [np.ctypeslib.as_array((ctypes.c_double * n).from_address(int(p))) for p in ptrs]
+        cuda_emu.run_op_kernel(src, nth, B.tabs, coefs, y.numpy(), stride)
+    monkeypatch.setattr(jit, "launch_op", launch_op)
+
+    deg, nels = [2, 2], [5, 4]
+    gen, spline, kv = make(deg, nels, "matfree")
+    gen2, fused, _ = make(deg, nels, "fused")
+
+    def forms(sp):
+        u, v = TrialFunction(sp.V), TestFunction(sp.V)
+        x = sp.spatialCoordinates()
+        return ((inner(sp.grad(u), sp.grad(v)) + 0.5 * u * v) * sp.dx,
+                inner(sin(3.0 * x[0]) + x[1], v) * sp.dx)
+    a, L = forms(spline)
+    af, Lf = forms(fused)
+    C = fused.assembleMatrix(af, diag=1.0)
+    op = spline.assembleMatrix(a, diag=1.0)
+    xv = torch.from_numpy(np.random.RandomState(1).rand(C.window.nrows))
+    assert np.abs(op.matvec(xv).numpy() - C.dense() @ xv.numpy()).max() < 1e-12 * np.abs(C.dense()).max()
+    C0 = fused.assembleMatrix(af, applyBCs=False)
+    op0 = spline.assembleMatrix(a, applyBCs=False)
+    assert np.allclose(op0.jacobi_dinv().numpy(), 1.0 / np.diag(C0.dense()), rtol=1e-12)
+    ks = KrylovSolver("cg", "jacobi")
+    ks.parameters["relative_tolerance"] = 1e-13
+    spline.setSolverOptions(linearSolver=ks)
+    fused.setSolverOptions(linearSolver=ks)
+    uh, uf = Function(spline.V), Function(fused.V)
+    U1 = spline.solveLinearVariationalProblem(a == L, uh).get_local()
+    U2 = fused.solveLinearVariationalProblem(af == Lf, uf).get_local()
+    assert np.linalg.norm(U1 - U2) < 1e-10 * np.linalg.norm(U2)
