@@ -382,13 +382,14 @@ def test_fe_to_iga_round_trip(cpu_backend):
     assert np.abs(ls - ref).max() < 1e-9
 
 
-def test_matrix_free_operator_equals_the_assembled_matrix(cpu_backend):
+def test_matrix_free_operator_equals_the_assembled_matrix(cpu_backend, monkeypatch):
     """mode="matfree" (tigar_b200/matfree.py): the operator action assembled as a linear
     form equals C x, BCs in operator form equal zeroRowsColumns, and the CG solve through
     the API reproduces the oracle's LU solution."""
     from tigar_b200 import api as A
     from tigar_b200 import ufl_lite as U
     from tigar_b200.matfree import FormOperator
+    monkeypatch.setenv("TIGAR_B200_MF_FUSED", "0")          # the two-kernel path
     spl, prob, n = build("fused", cpu_backend)
     spl.nFields = 1
     spl.V = A.FunctionSpace(spl, 1)

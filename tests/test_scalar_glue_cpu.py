@@ -83,8 +83,9 @@ def make(deg, nels, mode, nLayers=1, lo=0.0, hi=1.0):
 
 
 @pytest.mark.parametrize("mode", ["fused", "csr", "matfree"])
-def test_poisson_through_the_real_constructor_path(scalar_backend, mode):
+def test_poisson_through_the_real_constructor_path(scalar_backend, mode, monkeypatch):
     """The flow of demos/poisson/poisson.py (and of bench.one_step / smoke())."""
+    monkeypatch.setenv("TIGAR_B200_MF_FUSED", "0")          # matfree: the two-kernel path
     from tIGAr import (TrialFunction, TestFunction, Function, KrylovSolver, inner, sin, pi,
                        assemble)
     deg, nels = [2, 2], [6, 5]
@@ -250,7 +251,8 @@ def test_examples_run_on_the_api_layer(script, args, pattern, check, tmp_path):
 
 
 class _EmuBasis(object):
-    """What matfree._apply_fused / _dinv_generated read from engine.Basis."""
+    """What matfree / jit.launch_op read from engine.Basis: ``c`` mirrors the tg_basis
+    struct with HOST addresses of the oracle's tables."""
 
     def __init__(self, patch, nder):
         from oracle import assembly as OA
@@ -259,9 +261,46 @@ class _EmuBasis(object):
             pass
         self.nder = nder
         self.nloc = [s.p + 1 for s in patch.ts.splines]
-        self.c = _C()
-        self.c.nq = [patch.nq] * patch.dim + [1] * (3 - patch.dim)
-        self.tabs = [OA.tab_iga(s, patch.nq, nder) for s in patch.ts.splines]
+        tabs = [OA.tab_iga(s, patch.nq, nder) for s in patch.ts.splines]
+        self.keep = []
+        c = self.c = _C()
+        c.dim = patch.dim
+        c.nq = [patch.nq] * patch.dim + [1] * (3 - patch.dim)
+        c.tab, c.idx, c.wq, c.xq = [0] * 3, [0] * 3, [0] * 3, [0] * 3
+        c.n, c.nel = [1] * 3, [1] * 3
+        for d, tb in enumerate(tabs):
+            arrs = [np.ascontiguousarray(tb.T, dtype=np.float64),
+                    np.ascontiguousarray(tb.idx, dtype=np.int32),
+                    np.ascontiguousarray(tb.w, dtype=np.float64),
+                    np.ascontiguousarray(tb.x, dtype=np.float64)]
+            self.keep += arrs
+            c.tab[d], c.idx[d], c.wq[d], c.xq[d] = [a.ctypes.data for a in arrs]
+            c.n[d], c.nel[d] = int(tb.n), int(tb.T.shape[0])
+
+
+class _EmuJitLib(object):
+    """tg_jit_compile / tg_jit_launch on host threads: the kernel handle is the host build
+    of the generated source, the launch receives the very OpArgs block jit.launch_op
+    filled."""
+
+    def __init__(self):
+        self.libs = []
+        self.launches = 0
+
+    def tg_jit_compile(self, src, name, handle_ref):
+        import ctypes
+        import cuda_emu
+        from tigar_b200.jit import OpArgs
+        lib = cuda_emu.build(src.decode(), name.decode())
+        lib.emu_run.argtypes = [ctypes.POINTER(OpArgs), ctypes.c_int, ctypes.c_int]
+        self.libs.append(lib)
+        handle_ref._obj.value = len(self.libs)            # 1-based handle
+        return 0
+
+    def tg_jit_launch(self, h, grid, nth, smem, args_ref, nbytes, stream):
+        self.launches += 1
+        self.libs[h.value - 1].emu_run(args_ref, int(grid), int(nth))
+        return 0
 
 
 def test_matfree_generated_kernels_through_the_operator_glue(scalar_backend, monkeypatch):
@@ -275,16 +314,10 @@ def test_matfree_generated_kernels_through_the_operator_glue(scalar_backend, mon
     monkeypatch.setenv("TIGAR_B200_MF_FUSED", "1")
     monkeypatch.setattr(ScalarFakePatch, "basis", lambda self, kind, nder: _EmuBasis(self, nder),
                         raising=False)
-    monkeypatch.setattr(jit, "get_op_kernel",
-                        lambda prog, dim, nloc, nq, nd, jets, nfun, op, diag=False:
-                        jit.generate(prog, dim, nloc, nq, nd, jets, nfun, op=op, diag=diag))
-
-    def launch_op(kernel, B, ptrs, y, stride):
-        src, nth = kernel
-        n = y.numel()
-        coefs = [np.ctypeslib.as_array((ctypes.c_double * n).from_address(int(p))) for p in ptrs]
-        cuda_emu.run_op_kernel(src, nth, B.tabs, coefs, y.numpy(), stride)
-    monkeypatch.setattr(jit, "launch_op", launch_op)
+    emu = _EmuJitLib()
+    monkeypatch.setattr(jit, "lib", emu)
+    monkeypatch.setattr(jit, "check", lambda rc: None)
+    monkeypatch.setattr(jit, "_cache", {})
 
     deg, nels = [2, 2], [5, 4]
     gen, spline, kv = make(deg, nels, "matfree")
@@ -312,3 +345,5 @@ def test_matfree_generated_kernels_through_the_operator_glue(scalar_backend, mon
     U1 = spline.solveLinearVariationalProblem(a == L, uh).get_local()
     U2 = fused.solveLinearVariationalProblem(af == Lf, uf).get_local()
     assert np.linalg.norm(U1 - U2) < 1e-10 * np.linalg.norm(U2)
+    # 9 colours per application (stride p + 1 = 3 in two directions), every one launched
+    assert emu.launches % 9 == 0 and emu.launches >= 9 * (spline.lastSolve["iterations"] + 2)

@@ -61,7 +61,7 @@ class FormOperator(object):
     def apply(self, y):
         """y = C * self.xvec (no BCs)."""
         y.zero_()
-        if os.environ.get("TIGAR_B200_MF_FUSED") == "1":
+        if os.environ.get("TIGAR_B200_MF_FUSED", "1") == "1":
             return self._apply_fused(y)
         self.patch.assemble_vector(self.vterms, self._funcs, "iga", out=y, cache=self._cache)
         return y
@@ -69,8 +69,9 @@ class FormOperator(object):
     def _apply_fused(self, y):
         """One generated kernel per colour instead of Gauss-point pass + vector assembly:
         the flux coefficients never leave the SM (jit.generate(..., op=...); numerics
-        checked on host threads in tests/test_jit_emulated_cpu.py).  Opt-in
-        (``TIGAR_B200_MF_FUSED=1``) until it has run on a device."""
+        checked on host threads in tests/test_jit_emulated_cpu.py and, through this very
+        glue, in tests/test_scalar_glue_cpu.py).  Default of the matrix-free mode;
+        ``TIGAR_B200_MF_FUSED=0`` selects the two-kernel path above."""
         from . import dev, jit
         K = self._cache.get("fused")
         if K is None:
@@ -122,7 +123,7 @@ class FormOperator(object):
         from ._lib import lib, check
         from .engine import TensorPatch
         p = self.patch
-        if os.environ.get("TIGAR_B200_MF_FUSED") == "1" and nparts is None:
+        if os.environ.get("TIGAR_B200_MF_FUSED", "1") == "1" and nparts is None:
             self._dinv = self._dinv_generated()
             return self._dinv
         nparts = self.slab_count() if nparts is None else int(nparts)
@@ -152,7 +153,7 @@ class FormOperator(object):
 
     def _dinv_generated(self):
         """1 / diag(C) from a generated kernel that sums the diagonal of the element matrices
-        (jit.generate(..., diag=True)): no matrix, not even slab-wise.  Same opt-in as
+        (jit.generate(..., diag=True)): no matrix, not even slab-wise.  Same switch as
         ``_apply_fused``; numerics checked on host threads (tests/test_jit_emulated_cpu.py)."""
         from . import dev, jit
         p = self.patch

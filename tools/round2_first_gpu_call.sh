@@ -20,8 +20,8 @@ timeout 300 python bench.py --mode matfree --nel 128 --steps 1 --warmup 1 --no-p
                                                                         > gpurun_out/r2_bench_matfree_128.json 2> gpurun_out/r2_bench_matfree_128.err
 timeout 300 python bench.py --mode fused   --nel 128 --steps 1 --warmup 1 --no-ptap --no-cpu \
                                                                         > gpurun_out/r2_bench_fused_128.json 2> gpurun_out/r2_bench_fused_128.err
-TIGAR_B200_MF_FUSED=1 timeout 300 python bench.py --mode matfree --nel 128 --steps 1 --warmup 1 --no-ptap --no-cpu \
-                                                                        > gpurun_out/r2_bench_matfree_fusedkernel_128.json 2> gpurun_out/r2_bench_matfree_fusedkernel_128.err
+TIGAR_B200_MF_FUSED=0 timeout 300 python bench.py --mode matfree --nel 128 --steps 1 --warmup 1 --no-ptap --no-cpu \
+                                                                        > gpurun_out/r2_bench_matfree_twokernel_128.json 2> gpurun_out/r2_bench_matfree_twokernel_128.err
 # ... and the north_star's 512^3 patch on ONE GPU (no matrix; expect minutes)
 timeout 1200 python bench.py --mode matfree --nel 512 --steps 1 --warmup 0 --no-ptap --no-cpu \
                                                                         > gpurun_out/r2_bench_matfree_512.json 2> gpurun_out/r2_bench_matfree_512.err
