@@ -98,6 +98,13 @@ int tg_bspline_eval_batch(const double* knots, int32_t nk,
                           int32_t* span, int32_t* nodes, double* vals,
                           void* stream);
 
+/* One column of the homogeneous control net of a tensor-product control mesh on the device:
+ * out[i] = g[i_d] (g = per-direction values, e.g. Greville abscissae; NULL: out[i] = cval).
+ * ExplicitBSplineControlMesh.getHomogeneousCoordinate (BSplines.py:935-960) for all control
+ * points at once (the per-point Python loop of common.py:373-375).                          */
+int tg_tensor_column(double* out, const double* g, int32_t n0, int32_t n1, int32_t n2,
+                     int32_t d, double cval, void* stream);
+
 /* FE node coordinates of the CG Q_pf mesh in one direction
  * (DOLFIN tabulate_dof_coordinates, common.py:1471-1472): node e*pf+a.     */
 int tg_fe_nodes_1d(const double* uniqueKnots, int32_t nel, int32_t pf,
@@ -404,6 +411,89 @@ int tg_cg_xpby(double* p, const double* r, const double* dinv, int64_t n,
                const double* num, const double* den, void* stream);
 int tg_dot(const double* a, const double* b, int64_t n, double* scratch,
            double* out1, void* stream);
+
+/* ---- dense FP64 building blocks of the solve stage (tg_dense.cu) -------------------------- */
+/* C = alpha op(A) op(B) + beta C, column-major, strided batch (blockIdx.z); op = transpose when
+ * the flag is non-zero.  Hand-written DFMA kernel (64x64x16 tiles, 4x4 per thread).          */
+int tg_dgemm_batched(int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K,
+                     double alpha, const double* A, int32_t lda, int64_t strideA,
+                     const double* B, int32_t ldb, int64_t strideB, double beta,
+                     double* C, int32_t ldc, int64_t strideC, int32_t batch, void* stream);
+/* measured DFMA peak of the current device in TFLOP/s (best of 5 after warm-up; synchronises):
+ * the roofline denominator of the FP64-bound kernels.  scratch1: one device double.          */
+int tg_fp64_peak(double* scratch1, double* h_tflops, void* stream);
+
+/* Fast-diagonalisation preconditioner for the KSP solve (solve(), common.py:1255-1258): the
+ * tensor-product operator  sigma M(x)M(x)M + sum_d c_d K_d (x) M (x) M  is inverted exactly in the
+ * generalised eigenbasis K_d U_d = M_d U_d Lambda_d (1-D, host setup): three mode products with
+ * U_d^T (tg_dgemm_batched), this scaling, three mode products with U_d.
+ *   t[i0,i1,i2] /= (sigma + l0[i0] + l1[i1] + l2[i2])^pw   (0 where the sum is not finite and
+ *   positive: constrained hyperplanes carry +inf).  l1 / l2 may be NULL (1-D / 2-D).          */
+int tg_fd_scale(double* t, const double* l0, const double* l1, const double* l2,
+                int32_t n0, int32_t n1, int32_t n2, double sigma, int32_t pw, void* stream);
+/* dst = mask ? 0 : src ;  z = mask ? r*cinv : z  (constrained rows are diag*identity,
+ * zeroRowsColumns(zeroDofs, diag), common.py:1199-1200)                                       */
+int tg_masked_copy(double* dst, const double* src, const uint8_t* mask, int64_t n, void* stream);
+int tg_masked_fix(double* z, const double* r, const uint8_t* mask, double cinv, int64_t n,
+                  void* stream);
+/* out4[a] = sum over unconstrained DoFs of diagC[i] * b_a[i], b_a the Kronecker products of the
+ * 1-D diagonals (a < 3: k_a (x) m (x) m ; a = 3: m (x) m (x) m): right-hand side of the
+ * least-squares fit of c_d and sigma to diag(C).  scratch: 256 doubles.                       */
+int tg_fd_fit(const double* diagC, const uint8_t* mask, const double* kd0, const double* kd1,
+              const double* kd2, const double* md0, const double* md1, const double* md2,
+              int32_t n0, int32_t n1, int32_t n2, double* scratch, double* out4, void* stream);
+/* preconditioned CG, vector kernels (driver: tigar_b200/solvers.py):
+ *   xpby       : p = z + beta p
+ *   pcg_update : x += a p ; r -= a q ; out1[0] = r.r   (scratch: tg_cg_scratch_len())         */
+int tg_xpby(double* p, double beta, const double* z, int64_t n, void* stream);
+int tg_pcg_update(double* x, double* r, const double* p, const double* q, double a, int64_t n,
+                  double* scratch, double* out1, void* stream);
+
+/* ---- direct solve: band Cholesky on the device (tg_band.cu) -------------------------------- */
+/* The reference's default solve() is a sparse direct LU (common.py:1255-1256).  In the
+ * reference's own DoF numbering the IGA matrix of a 2-D (or small 3-D) patch is banded;
+ * LAPACK lower band storage AB[(i-j) + j*ldab], ldab >= bw + 32, zero-initialised.
+ * info: device int32, zero-initialised; from_win sets -1 if a non-zero lies outside the band,
+ * cholesky sets k+1 if the pivot block at column k is not positive definite.                  */
+int tg_band_from_win(const tg_win* h_w, const double* vals, int32_t bw, int32_t ldab,
+                     double* AB, int32_t* info, void* stream);
+int tg_band_cholesky(int64_t n, int32_t bw, int32_t ldab, double* AB, int32_t* info,
+                     void* stream);
+/* L L^T x = b ; b is overwritten (work), work: n doubles, x must not alias b.                 */
+int tg_band_solve(int64_t n, int32_t bw, int32_t ldab, const double* AB, double* b,
+                  double* work, double* x, void* stream);
+/* out2 = {max |a_ij - a_ji|, max |a_ij|} over a whole square windowed matrix (zero-initialise
+ * out2): symmetry test in front of Cholesky / CG.                                             */
+int tg_win_asym(const tg_win* h_w, const double* vals, double* out2, void* stream);
+
+/* ---- global sum-factorised assembly of the extracted system (tg_gsf.cu) --------------------- */
+/* dolfin.assemble + MatPtAP (common.py:1215-1216, 1194-1195) for a tensor-product spline, A_FE
+ * and M never formed: the quadrature sum is contracted one direction at a time over the whole
+ * patch; every stage is one "march" launch per output kind.  Arrays are blocked as
+ * [kind][cell of the marched direction][inner][nq]; see the header of tg_gsf.cu.
+ *   X, skin, scell, cbase  input, X[k*skin + (e - cbase)*scell + inner*nq + q]
+ *   c0, c1, nel            cells marched [c0, c1) of nel (chunks of the last direction)
+ *   nloc, nq, nd, tab, idx 1-D tables of the direction ([nel][nq][nloc][nd], [nel][nloc])
+ *   rowbase[n_d]           S_d[i] - lo_d[i] of the system window: f(i,j) = rowbase[i] + j
+ *   plan (device int32)    [nout][1 + 3*maxin]: nin, then (input kind, test order, trial order)
+ *   pair                   1: matrix (pairs of functions), 0: load vector (f = i)
+ *   ninner, nv, nw         inner = (u*nv + v)*nw + w
+ *   Y, skout, so_*         output of a non-last stage, Y[k*skout + f*so_f + u*so_u + v*so_v + w]
+ *   last                   1: writes `out` = values of the windowed matrix h_W (local rows; rows
+ *                          outside [row0, row0+nr) of the last direction are skipped) or, for
+ *                          pair = 0, the vector slab [vec_row0, vec_row0+vec_nr) of the last
+ *                          direction; ninner = F0*F1 (pair) or the plane size; h_F0 = total 1-D
+ *                          window length of the first direction.
+ * tg_gsf_supported(nloc, nq): instantiated for 2 <= nloc <= 5, nq in {nloc, nloc+1}.           */
+int tg_gsf_supported(int32_t nloc, int32_t nq);
+int tg_gsf_stage(const double* X, int64_t skin, int64_t scell, int32_t cbase,
+                 int32_t c0, int32_t c1, int32_t nel, int32_t nloc, int32_t nq,
+                 int32_t nd, const double* tab, const int32_t* idx,
+                 const int64_t* rowbase, const int32_t* plan, int32_t nout,
+                 int32_t maxin, int32_t pair, int64_t ninner, int32_t nv, int32_t nw,
+                 double* Y, int64_t skout, int64_t so_f, int64_t so_u, int64_t so_v,
+                 int32_t last, const tg_win* h_W, int64_t h_F0, int32_t vec_row0,
+                 int32_t vec_nr, double* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -193,6 +193,10 @@ class FakePatch(object):
     def solve_cg(self, Cm, b, x=None, rtol=1e-12, atol=0.0, maxit=100000, check_every=5):
         return torch.from_numpy(np.linalg.solve(Cm.dense(), b.numpy())), 1, 0.0
 
+    def solve(self, Cm, b, x=None, rtol=1e-12, atol=0.0, maxit=100000, method="auto", mask=None,
+              diag=1.0):
+        return self.solve_cg(Cm, b, x, rtol, atol, maxit) + (method,)
+
 
 @pytest.fixture
 def cpu_backend(monkeypatch):

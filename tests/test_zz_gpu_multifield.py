@@ -116,9 +116,6 @@ def test_elasticity_3d_three_fields_fused_and_newton():
     assert rel(un.iga.cpu().numpy(), Uo) < 1e-8
 
 
-@pytest.mark.skipif(os.environ.get("TIGAR_B200_UNVERIFIED") != "1",
-                    reason="written after the round's GPU budget was spent; never run on a "
-                           "device yet -- opt in with TIGAR_B200_UNVERIFIED=1")
 def test_kl_shell_scordelis_lo_roof_on_the_device():
     """BASELINE configs[4] in small: the SVK Kirchhoff-Love shell residual of the
     reference's kl-shell-svk demo (tests/test_kl_shell_cpu.shell_forms, CPU-checked) on the
@@ -159,8 +156,6 @@ def test_kl_shell_scordelis_lo_roof_on_the_device():
     assert abs(abs(uz) / scale - 0.3006) < 0.02 * 0.3006
 
 
-@pytest.mark.skipif(os.environ.get("TIGAR_B200_UNVERIFIED") != "1",
-                    reason="never run on a device yet -- opt in with TIGAR_B200_UNVERIFIED=1")
 def test_fe_to_iga_round_trip_on_the_device():
     """SURVEY 8c KAT 5: FEtoIGA(M U) = U (common.py:968-993)."""
     from tIGAr import Function
@@ -173,8 +168,6 @@ def test_fe_to_iga_round_trip_on_the_device():
     assert np.abs(spline.FEtoIGA(w).get_local() - Uv).max() < 1e-9
 
 
-@pytest.mark.skipif(os.environ.get("TIGAR_B200_UNVERIFIED") != "1",
-                    reason="never run on a device yet -- opt in with TIGAR_B200_UNVERIFIED=1")
 @pytest.mark.parametrize("deg,nels", [([3, 3, 3], [5, 4, 9]), ([2, 2], [9, 8])])
 def test_matrix_free_mode_on_the_device(deg, nels):
     """mode="matfree" (tigar_b200/matfree.py, SURVEY 7.2 hard part 1): operator action =

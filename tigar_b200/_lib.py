@@ -109,6 +109,25 @@ SIGNATURES = {
     "tg_cg_xpby": [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
     "tg_dot": [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
     "tg_axpy": [c_vp, c_dbl, c_vp, c_i64, c_vp],
+    "tg_dgemm_batched": [c_i32, c_i32, c_i32, c_i32, c_i32, c_dbl, c_vp, c_i32, c_i64,
+                         c_vp, c_i32, c_i64, c_dbl, c_vp, c_i32, c_i64, c_i32, c_vp],
+    "tg_fp64_peak": [c_vp, C.POINTER(c_dbl), c_vp],
+    "tg_fd_scale": [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_dbl, c_i32, c_vp],
+    "tg_masked_copy": [c_vp, c_vp, c_vp, c_i64, c_vp],
+    "tg_masked_fix": [c_vp, c_vp, c_vp, c_dbl, c_i64, c_vp],
+    "tg_fd_fit": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32,
+                  c_vp, c_vp, c_vp],
+    "tg_xpby": [c_vp, c_dbl, c_vp, c_i64, c_vp],
+    "tg_pcg_update": [c_vp, c_vp, c_vp, c_vp, c_dbl, c_i64, c_vp, c_vp, c_vp],
+    "tg_band_from_win": [PW, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp],
+    "tg_band_cholesky": [c_i64, c_i32, c_i32, c_vp, c_vp, c_vp],
+    "tg_band_solve": [c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "tg_win_asym": [PW, c_vp, c_vp, c_vp],
+    "tg_tensor_column": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_dbl, c_vp],
+    "tg_gsf_supported": [c_i32, c_i32],
+    "tg_gsf_stage": [c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp,
+                     c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_vp, c_i64,
+                     c_i64, c_i64, c_i64, c_i32, PW, c_i64, c_i32, c_i32, c_vp, c_vp],
 }
 _RESTYPES = {"tg_last_error": C.c_char_p, "tg_prof_enable": None, "tg_prof_get": None, "tg_launch_count": c_i64, "tg_win_storage": c_i64}
 

@@ -753,7 +753,14 @@ class ExtractedSpline(object):
         self.V = FunctionSpace(self, self.nFields)
         self.V_control = FunctionSpace(self, 1, control=True)
         self.VE, self.VE_control = generator.VE, generator.VE_control
-        P = self._controlNetArg if self._controlNetArg is not None else generator.controlNet()
+        if self._controlNetArg is not None:
+            P = self._controlNetArg
+        else:
+            cm = generator.getControlMesh() if hasattr(generator, "getControlMesh") else None
+            if hasattr(cm, "controlNetDevice") and dev.device().type == "cuda":
+                P = cm.controlNetDevice()          # generated on the device (no host loop)
+            else:
+                P = generator.controlNet()
         self._set_control_net(P)
         z = generator.zeroDofs
         # raw list (duplicates allowed, e.g. patch corners): the device mask does not need
@@ -1135,13 +1142,49 @@ class ExtractedSpline(object):
             u.set_iga(x)
             return DeviceVector(x)
         x0 = None if u.iga is None else u.iga.clone()
-        x, its, rel = self._patch.solve_cg(MTAM, MTb.t, x0, rtol, atol, maxit)
-        self.lastSolve = dict(iterations=its, relative_residual=rel)
+        method = self._solver_method(ls)
+        mask = getattr(MTAM, "bc_mask", None)
+        x, its, rel, used = self._patch.solve(MTAM, MTb.t, x0, rtol, atol, maxit, method, mask,
+                                              getattr(MTAM, "bc_diag", 1.0))
+        self.lastSolve = dict(iterations=its, relative_residual=rel, method=used)
+        self._check_converged(ls, its, rel, maxit, rtol, atol)
         if self._patch.part is not None:       # replicate the IGA DoF vector on every rank
             from .multigpu import gather_planes
             x = gather_planes(x, self._patch)
         u.set_iga(x)
         return DeviceVector(x)
+
+    @staticmethod
+    def _solver_method(ls):
+        """Which device solver stands in for ``dolfin.solve``: no ``linearSolver`` means the
+        reference's default direct LU (common.py:1255-1256) -> "auto" (band Cholesky while it
+        fits, FD-preconditioned CG beyond); a user Krylov solver with a Jacobi / no
+        preconditioner gets Jacobi-CG; any stronger PETSc preconditioner name maps to FD-CG."""
+        if ls is None:
+            return "auto"
+        m = getattr(ls, "solver_method", None)
+        if m:
+            return m
+        pc = str(getattr(ls, "preconditioner", "jacobi")).lower()
+        if pc in ("jacobi", "none", "default", "bjacobi"):
+            return "jacobi"
+        if pc in ("lu", "cholesky", "direct"):
+            return "direct"
+        return "fd"
+
+    def _check_converged(self, ls, its, rel, maxit, rtol, atol):
+        """The reference's LU cannot 'not converge'; an iterative stand-in can.  Raise (or
+        warn, when the user's solver says error_on_nonconvergence=False) instead of returning
+        an unconverged vector silently."""
+        if its < maxit or rel <= max(rtol, 1e-300):
+            return
+        msg = ("linear solver stopped at the iteration limit (%d) with relative residual %.3e "
+               "> %.3e" % (its, rel, rtol))
+        prm = ls.parameters if ls is not None else {}
+        if prm.get("error_on_nonconvergence", True):
+            raise RuntimeError(msg)
+        import warnings
+        warnings.warn(msg)
 
     def solveLinearVariationalProblem(self, residualForm, u, applyBCs=True):
         if isinstance(residualForm, U.Equation):

@@ -129,6 +129,12 @@ static int tg_dgemm_launch(int ta, int tb, int M, int N, int K, double alpha, co
   return 0;
 }
 
+// trailing update of the band factorisation: C (M x M, lower) = alpha * A A^T + beta * C
+int tg_dgemm_lower_nt(int M, int K, double alpha, const double* A, int lda, double beta,
+                      double* C, int ldc, cudaStream_t st) {
+  return tg_dgemm_launch(0, 1, M, M, K, alpha, A, lda, 0, A, lda, 0, beta, C, ldc, 0, 1, 1, st);
+}
+
 extern "C" int tg_dgemm_batched(int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K,
                                 double alpha, const double* A, int32_t lda, int64_t strideA,
                                 const double* B, int32_t ldb, int64_t strideB, double beta,

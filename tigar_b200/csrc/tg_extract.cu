@@ -203,3 +203,30 @@ extern "C" int tg_mt_vec(const tg_win* h_wM, const tg_win* h_wT, const double* M
   TG_LAUNCH_CHECK();
   return 0;
 }
+
+// out[i] = g[i_d] (g == NULL: out[i] = cval): one column of the homogeneous control net of an
+// ExplicitBSplineControlMesh on the device -- control point = Greville abscissa of direction d,
+// weight 1 (getHomogeneousCoordinate, BSplines.py:935-960, looped per control point by
+// common.py:373-375; here one coalesced pass per column).
+__global__ void k_tensor_column(double* __restrict__ out, const double* __restrict__ g, int n0,
+                                int n1, int n2, int d, double cval) {
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (!g) { out[i] = cval; continue; }
+    const int64_t r = i / n0;
+    const int id = (d == 0) ? (int)(i - r * n0) : (d == 1) ? (int)(r % n1) : (int)(r / n1);
+    out[i] = g[id];
+  }
+}
+
+extern "C" int tg_tensor_column(double* out, const double* g, int32_t n0, int32_t n1, int32_t n2,
+                                int32_t d, double cval, void* stream) {
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  if (n == 0) return 0;
+  int64_t grid = tg_cdiv(n, 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  k_tensor_column<<<(unsigned)grid, 256, 0, tg_stream(stream)>>>(out, g, n0, n1, n2, d, cval);
+  TG_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,319 @@
+// Global sum-factorised assembly of the extracted system (element-fused path):
+//   C[(i0,i1,i2),(j0,j1,j2)] = sum_terms sum_q  c_t(q) * prod_d D^{a_d}N_{i_d}(q_d) D^{b_d}N_{j_d}(q_d)
+// (dolfin.assemble + MatPtAP of common.py:1215-1216, 1194-1195 for a tensor-product spline, with
+// A_FE and M never formed).  Instead of building 64x64 element matrices and scattering them
+// (coloured read-modify-write: 23x the compulsory traffic), the quadrature
+// sum is contracted ONE DIRECTION AT A TIME over the whole patch:
+//
+//   X0[slot][q0,q1,q2]  --d=0-->  Y1[k1][(i0,j0)][q1,q2]  --d=1-->  Y2[k2][(i0,j0)][(i1,j1)][q2]
+//                       --d=2-->  C
+//
+// Each stage is the same "march": a thread owns one inner index (everything except the marched
+// direction), walks the cells of the direction in order, keeps the (p+1)^2 partial sums of the
+// basis-function PAIRS of the current cell in registers, and when the march leaves the support
+// of a pair writes the finished sum -- every output is written exactly once, in a fixed order,
+// without atomics or colours.  6x fewer flops than element-wise sum factorisation (1.3 vs 7.7
+// TFLOP at 256^3 cubic) and streaming, fully coalesced traffic:
+//   every array is blocked as [kind][cell of the marched direction][inner][NQ], the NQ Gauss
+//   points of a cell contiguous (one 32-byte vector load per thread and cell), consecutive
+//   threads consecutive inner indices; the writer of a stage lays its output out for the next.
+// Terms that agree in the derivative orders of the remaining directions are summed as soon as
+// they meet ("kinds": 9 -> 9 -> 4 -> 1 for the Laplacian).  The last direction is processed in
+// chunks of cell layers (bounded intermediates); partial sums that cross a chunk boundary are
+// added to C by the next chunk (flag per pair, uniform over the CTA).
+// The load vector takes the same route with (p+1) sums per thread.
+#include "tg_common.cuh"
+#include <string.h>
+
+#define GSF_CB 8
+#define GSF_THREADS 256
+
+struct GsfArgs {
+  const double* X;
+  long long skin, scell;   // X[k*skin + (e - cbase)*scell + inner*NQ + q]
+  int cbase;               // global cell index of X's first cell
+  int c0, c1;              // cells marched: [c0, c1)
+  int nel;                 // cells of this direction
+  long long ninner;
+  int nv, nw;              // inner = (u*nv + v)*nw + w
+  double* Y;
+  long long skout, so_f, so_u, so_v;   // Y[k*skout + f*so_f + u*so_u + v*so_v + w]
+  const double* tab;       // [nel][NQ][NL][nd]
+  int nd;
+  const int* idx;          // [nel][NL] ; first[e] = idx[e*NL]
+  const int64_t* rowbase;  // pairs: f(i,j) = rowbase[i] + j
+  const int* plan;         // [nout][1 + 3*maxin] : nin, (kin, al, be)*
+  int maxin;
+  // last stage only -------------------------------------------------------
+  int dim;                 // 2 or 3
+  int n0, n1;              // rows of the plane directions (n1 = 1 in 2-D)
+  const int64_t* S0;     // [n0+1] prefix sums of the first-direction window lengths
+  const int64_t* S1;     // [n1+1] (3-D)
+  long long F0;
+  const int64_t* rowptr; // local rows of C
+  const int* loL;          // [nrL] window start of the last direction (local columns)
+  int row0L, nrL, col0L;   // owned rows of the last direction / column shift
+  double* out;             // C values or the load vector
+};
+
+template <int NL, bool PAIR>
+struct GsfAcc {
+  double v[PAIR ? NL * NL : NL];
+};
+
+template <int NL, int NQ, bool PAIR, bool LAST>
+__global__ void __launch_bounds__(GSF_THREADS)
+k_gsf(const __grid_constant__ GsfArgs A) {
+  constexpr int NLP = (NL + 1) & ~1;
+  __shared__ __align__(16) double stab[GSF_CB * NQ * 3 * NLP];   // [c][q][k][a]
+  __shared__ int sfirst[GSF_CB + 1];
+  const int tid = threadIdx.x;
+  const int ko = blockIdx.y;
+  const int* plan = A.plan + (long long)ko * (1 + 3 * A.maxin);
+  const int nin = plan[0];
+  const long long t = blockIdx.x * (long long)GSF_THREADS + tid;
+
+  // ---- what this thread owns -------------------------------------------------------
+  bool active;
+  long long inner = 0, uoff = 0;
+  long long rowoff = 0, inrow = 0, len01 = 1;        // LAST && PAIR
+  if (!LAST) {
+    active = t < A.ninner;
+    if (active) {
+      inner = t;
+      const long long w = t % A.nw, r = t / A.nw;
+      const long long v = r % A.nv, u = r / A.nv;
+      uoff = u * A.so_u + v * A.so_v + w;
+    }
+  } else if (!PAIR) {
+    active = t < A.ninner;
+    inner = t;
+  } else {
+    const long long F1 = (A.dim == 3) ? A.S1[A.n1] : 1;
+    active = t < A.F0 * F1;
+    if (active) {
+      long long rem = t;
+      int i1 = 0;
+      long long l1 = 1, f1 = 0;
+      if (A.dim == 3) {
+        int lo = 0, hi = A.n1;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (A.S1[mid] * A.F0 <= t) lo = mid; else hi = mid;
+        }
+        i1 = lo;
+        rem = t - A.S1[i1] * A.F0;
+        l1 = A.S1[i1 + 1] - A.S1[i1];
+      }
+      int lo = 0, hi = A.n0;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (A.S0[mid] * l1 <= rem) lo = mid; else hi = mid;
+      }
+      const int i0 = lo;
+      const long long rem2 = rem - A.S0[i0] * l1;
+      const long long l0 = A.S0[i0 + 1] - A.S0[i0];
+      const long long dj1 = rem2 / l0, dj0 = rem2 - dj1 * l0;
+      f1 = (A.dim == 3) ? A.S1[i1] + dj1 : 0;
+      inner = f1 * A.F0 + A.S0[i0] + dj0;
+      rowoff = (long long)i1 * A.n0 + i0;
+      inrow = rem2;
+      len01 = l0 * l1;
+    }
+  }
+  const long long nplane = (long long)A.n0 * A.n1;
+
+  GsfAcc<NL, PAIR> acc;
+#pragma unroll
+  for (int i = 0; i < (PAIR ? NL * NL : NL); i++) acc.v[i] = 0.0;
+
+  // pairs that were already in flight before c0 (chunked last direction): their sums are ADDED
+  unsigned carried = 0;
+  if (LAST && A.c0 > 0) {
+    const int s = A.idx[(long long)A.c0 * NL] - A.idx[(long long)(A.c0 - 1) * NL];
+#pragma unroll
+    for (int a = 0; a < NL; a++)
+#pragma unroll
+      for (int b = 0; b < (PAIR ? NL : 1); b++)
+        if (a + s < NL && (!PAIR || b + s < NL)) carried |= 1u << (a * NL + b);
+  }
+
+  auto store = [&](double val, int i, int j, bool add) {
+    if (!LAST) {
+      const long long f = PAIR ? A.rowbase[i] + j : i;
+      A.Y[ko * A.skout + f * A.so_f + uoff] = val;
+    } else {
+      const int r = i - A.row0L;
+      if (r < 0 || r >= A.nrL) return;
+      double* p;
+      if (PAIR)
+        p = A.out + A.rowptr[r * nplane + rowoff] + (long long)(j - A.col0L - A.loL[r]) * len01 + inrow;
+      else
+        p = A.out + r * nplane + inner;
+      *p = add ? *p + val : val;
+    }
+  };
+
+  for (int cb = A.c0; cb < A.c1; cb += GSF_CB) {
+    const int ncb = min(GSF_CB, A.c1 - cb);
+    __syncthreads();
+    for (int e = tid; e < ncb * NQ * A.nd * NL; e += GSF_THREADS) {
+      // global [c][q][a][k] -> shared [c][q][k][a]
+      const int k = e % A.nd;
+      int r = e / A.nd;
+      const int a = r % NL;
+      r /= NL;                                  // r = c*NQ + q
+      stab[(r * 3 + k) * NLP + a] = A.tab[(long long)cb * NQ * NL * A.nd + e];
+    }
+    if (tid <= ncb) {
+      const int e = cb + tid;
+      sfirst[tid] = (e < A.nel) ? A.idx[(long long)e * NL] : (A.idx[(long long)(A.nel - 1) * NL] + NL);
+    }
+    __syncthreads();
+    for (int c = 0; c < ncb; c++) {
+      const int e = cb + c;
+      if (active) {
+        for (int in = 0; in < nin; in++) {
+          const int kin = plan[1 + 3 * in], al = plan[2 + 3 * in], be = plan[3 + 3 * in];
+          const double* xp = A.X + kin * A.skin + (long long)(e - A.cbase) * A.scell + inner * NQ;
+          double x[NQ];
+          if constexpr (NQ % 2 == 0) {
+#pragma unroll
+            for (int q = 0; q < NQ; q += 2) {
+              const double2 v = __ldcs(reinterpret_cast<const double2*>(xp + q));
+              x[q] = v.x;
+              x[q + 1] = v.y;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < NQ; q++) x[q] = __ldcs(xp + q);
+          }
+#pragma unroll
+          for (int q = 0; q < NQ; q++) {
+            const double* ta = &stab[((c * NQ + q) * 3 + al) * NLP];
+            if (PAIR) {
+              const double* tb = &stab[((c * NQ + q) * 3 + be) * NLP];
+              double y[NL];
+#pragma unroll
+              for (int b = 0; b < NL; b++) y[b] = tb[b] * x[q];
+#pragma unroll
+              for (int a = 0; a < NL; a++) {
+                const double ta_a = ta[a];
+#pragma unroll
+                for (int b = 0; b < NL; b++) acc.v[a * NL + b] = fma(ta_a, y[b], acc.v[a * NL + b]);
+              }
+            } else {
+#pragma unroll
+              for (int a = 0; a < NL; a++) acc.v[a] = fma(ta[a], x[q], acc.v[a]);
+            }
+          }
+        }
+      }
+      // pairs / functions whose support ends with this cell are complete
+      const int first = sfirst[c];
+      int s = sfirst[c + 1] - first;
+      if (s > NL || e + 1 == A.c1) s = NL;      // end of the direction or of the chunk: flush all
+      if (active) {
+#pragma unroll
+        for (int a = 0; a < NL; a++)
+#pragma unroll
+          for (int b = 0; b < (PAIR ? NL : 1); b++)
+            if (a < s || (PAIR && b < s))
+              store(acc.v[PAIR ? a * NL + b : a], first + a, first + b,
+                    (carried >> (a * NL + b)) & 1u);
+      }
+      // shift the window of partial sums by s functions (s is uniform over the CTA)
+      unsigned nc = 0;
+#pragma unroll
+      for (int ss = 1; ss <= NL; ss++) {
+        if (s != ss) continue;
+#pragma unroll
+        for (int a = 0; a < NL; a++)
+#pragma unroll
+          for (int b = 0; b < (PAIR ? NL : 1); b++) {
+            const bool keep = (a + ss < NL) && (!PAIR || b + ss < NL);
+            const int src = PAIR ? (a + ss) * NL + (b + ss) : a + ss;
+            acc.v[PAIR ? a * NL + b : a] = keep ? acc.v[keep ? src : 0] : 0.0;
+            if (keep && ((carried >> (keep ? (a + ss) * NL + (PAIR ? b + ss : 0) : 0)) & 1u))
+              nc |= 1u << (a * NL + b);
+          }
+      }
+      carried = nc;
+    }
+  }
+}
+
+template <int NL, int NQ>
+static int gsf_launch2(const GsfArgs& A, int pair, int last, long long nthreads, int nout,
+                       cudaStream_t st) {
+  dim3 grid((unsigned)tg_cdiv(nthreads, GSF_THREADS), (unsigned)nout);
+  if (pair && last) k_gsf<NL, NQ, true, true><<<grid, GSF_THREADS, 0, st>>>(A);
+  else if (pair) k_gsf<NL, NQ, true, false><<<grid, GSF_THREADS, 0, st>>>(A);
+  else if (last) k_gsf<NL, NQ, false, true><<<grid, GSF_THREADS, 0, st>>>(A);
+  else k_gsf<NL, NQ, false, false><<<grid, GSF_THREADS, 0, st>>>(A);
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tg_gsf_supported(int32_t nloc, int32_t nq) {
+  return (nloc >= 2 && nloc <= 5 && (nq == nloc || nq == nloc + 1)) ? 1 : 0;
+}
+
+// One march stage.  See the file header for the layouts; h_* are host scalars.
+//   X            input  [nin_kinds][cells c >= cbase][ninner][nq]  (kind stride skin, cell stride
+//                scell = ninner*nq unless the caller says otherwise)
+//   pair != 0    matrix (pairs of functions), else load vector
+//   last != 0    writes C (windowed CSR h_W, local rows) / the vector, else Y with
+//                Y[k*skout + f*so_f + u*so_u + v*so_v + w], inner = (u*nv + v)*nw + w
+//   tab/idx      1-D tables of the direction ([nel][nq][nloc][nd], [nel][nloc]); rowbase[n_d]
+//                = S_d[i] - lo_d[i] of the (global) C window: f(i,j) = rowbase[i] + j
+//   plan         device int32 [nout][1 + 3*maxin]
+extern "C" int tg_gsf_stage(const double* X, int64_t skin, int64_t scell, int32_t cbase,
+                            int32_t c0, int32_t c1, int32_t nel, int32_t nloc, int32_t nq,
+                            int32_t nd, const double* tab, const int32_t* idx,
+                            const int64_t* rowbase, const int32_t* plan, int32_t nout,
+                            int32_t maxin, int32_t pair, int64_t ninner, int32_t nv, int32_t nw,
+                            double* Y, int64_t skout, int64_t so_f, int64_t so_u, int64_t so_v,
+                            int32_t last, const tg_win* h_W, int64_t h_F0, int32_t vec_row0,
+                            int32_t vec_nr, double* out, void* stream) {
+  TG_REQUIRE(tg_gsf_supported(nloc, nq), "gsf: unsupported (nloc, nq)");
+  TG_REQUIRE(nd >= 1 && nd <= 3, "gsf: tables hold derivative orders 0..2");
+  GsfArgs A;
+  memset(&A, 0, sizeof(A));
+  A.X = X; A.skin = skin; A.scell = scell; A.cbase = cbase; A.c0 = c0; A.c1 = c1; A.nel = nel;
+  A.ninner = ninner; A.nv = nv > 0 ? nv : 1; A.nw = nw > 0 ? nw : 1;
+  A.Y = Y; A.skout = skout; A.so_f = so_f; A.so_u = so_u; A.so_v = so_v;
+  A.tab = tab; A.nd = nd; A.idx = idx; A.rowbase = rowbase; A.plan = plan; A.maxin = maxin;
+  long long nthreads = ninner;
+  A.n0 = 1; A.n1 = 1; A.dim = 2;
+  if (last) {
+    A.out = out;
+    if (pair) {
+      TG_REQUIRE(h_W && h_W->layout == 0 && (h_W->dim == 2 || h_W->dim == 3),
+                 "gsf: last stage needs a 2-D/3-D row-major window");
+      const int L = h_W->dim - 1;
+      A.dim = h_W->dim;
+      A.n0 = h_W->nr[0];
+      A.n1 = (h_W->dim == 3) ? h_W->nr[1] : 1;
+      A.S0 = h_W->S[0];
+      A.S1 = (h_W->dim == 3) ? h_W->S[1] : nullptr;
+      A.rowptr = h_W->rowptr;
+      A.loL = h_W->lo[L];
+      A.row0L = h_W->row0[L]; A.nrL = h_W->nr[L]; A.col0L = h_W->col0[L];
+      A.F0 = h_F0;             // = S0[n0] (the prefix sums live on the device)
+      nthreads = ninner;       // = F0 * F1, computed by the caller
+    } else {
+      A.row0L = vec_row0; A.nrL = vec_nr;
+      A.n0 = (int)ninner;      // plane size as n0*n1 with n1 = 1
+    }
+  }
+  if (nthreads <= 0 || c1 <= c0) return 0;
+  cudaStream_t st = tg_stream(stream);
+#define GSF_CASE(NL_, NQ_) \
+  if (nloc == NL_ && nq == NQ_) return gsf_launch2<NL_, NQ_>(A, pair, last, nthreads, nout, st);
+  GSF_CASE(2, 2) GSF_CASE(2, 3) GSF_CASE(3, 3) GSF_CASE(3, 4) GSF_CASE(4, 4) GSF_CASE(4, 5)
+  GSF_CASE(5, 5) GSF_CASE(5, 6)
+#undef GSF_CASE
+  tg_set_error("gsf: no instantiation for nloc=%d nq=%d", nloc, nq);
+  return 2;
+}

@@ -526,8 +526,23 @@ class TensorPatch(object):
             P["coefs"] = vparr([dev.ptr(t) for t in P["keep"]])
         return P
 
-    def _qp_eval(self, B, P, cell0, ncells, out):
+    def _qp_eval(self, B, P, cell0, ncells, out, gsf=None):
+        """``gsf=(sstride, lc, elast0)``: store the outputs in the layout of the global
+        sum-factorised assembly (generated kernels only)."""
         from . import jit
+        if gsf is not None:
+            key = ("gsf", B.nder)
+            k = P.setdefault("jit", {}).get(key)
+            if k is None:
+                fpos = {f: i for i, f in enumerate(P["fids"])}
+                jets = [(fpos[f], comp, pad3(al)) for (f, comp, al) in P["prog"].jets]
+                nloc = B.nloc + [1] * (3 - self.dim)
+                nq = [B.c.nq[d] for d in range(3)]
+                k = jit.get_kernel(P["prog"], self.dim, nloc, nq, B.nder + 1, jets,
+                                   len(P["fids"]), layout="gsf")
+                P["jit"][key] = k
+            jit.launch(k, B, [dev.ptr(t) for t in P["keep"]], cell0, ncells, out, gsf=gsf)
+            return
         if jit.enabled() and len(P["fids"]) <= jit.MAXFUN:
             k = P.setdefault("jit", {}).get(B.nder)
             if k is None:
@@ -557,6 +572,152 @@ class TensorPatch(object):
         a, b = pad3(k[0]), pad3(k[1])
         return (a[2], b[2], a[1], b[1], a[0], b[0])
 
+    # ---- global sum-factorised assembly (csrc/tg_gsf.cu) ---------------------------------
+    def _gsf_ok(self, B, W, P):
+        """The march kernels cover 2-D / 3-D patches, row-major windows, generated
+        Gauss-point kernels and tables up to second derivatives."""
+        from . import jit
+        if os.environ.get("TIGAR_B200_GSF", "1") != "1" or self.dim not in (2, 3):
+            return False
+        if W is not None and W.layout != 0:
+            return False
+        if not jit.enabled() or len(P["fids"]) > jit.MAXFUN or B.nder > 2:
+            return False
+        return all(lib.tg_gsf_supported(B.nloc[d], int(B.c.nq[d])) for d in range(self.dim))
+
+    @staticmethod
+    def _gsf_plan(entries, dim, pair):
+        """entries: [(input kind, ((al, be),)*dim)] -> per stage (nout, maxin, host plan).
+        Terms whose derivative orders agree in all REMAINING directions share an output kind."""
+        stages, cur = [], list(entries)
+        for d in range(dim):
+            outs, plan = {}, {}
+            for kin, sig in cur:
+                ko = outs.setdefault(sig[1:], len(outs))
+                plan.setdefault(ko, []).append((kin, sig[0][0], sig[0][1] if pair else 0))
+            maxin = max(len(v) for v in plan.values())
+            tab = np.zeros((len(outs), 1 + 3 * maxin), dtype=np.int32)
+            for ko, lst in plan.items():
+                tab[ko, 0] = len(lst)
+                tab[ko, 1:1 + 3 * len(lst)] = np.array(lst, dtype=np.int32).ravel()
+            stages.append((len(outs), maxin, tab))
+            cur = [(ko, rest) for rest, ko in outs.items()]
+        assert stages[-1][0] == 1
+        return stages
+
+    def _gsf_dir(self, B, Wg, d, pair):
+        """Per-direction device constants of the march: rowbase, F_d (pairs) or n_d."""
+        key = ("gsf", B.kind, d, pair, id(Wg))
+        hit = self._bases.get(key)
+        if hit is None:
+            if pair:
+                S = np.concatenate([[0], np.cumsum(Wg.len[d])]).astype(np.int64)
+                rb = dev.from_np((S[:-1] - Wg.lo[d].astype(np.int64)).astype(np.int64))
+                hit = (rb, int(S[-1]))
+            else:
+                hit = (dev.zeros(1, dev.I64), int(B.c.n[d]))
+            self._bases[key] = hit
+        return hit
+
+    def _gsf_run(self, B, kind, P, nslots, mentries, ventries, A, b, vrow0, vnr):
+        """One pass over the cell layers of this patch (or slab): Gauss-point kernel into the
+        blocked coefficient layout, then the march stages of the matrix (``mentries``) and of
+        the load vector (``ventries``).  A / b may be None."""
+        dim, L = self.dim, self.dim - 1
+        nel = [int(B.c.nel[d]) for d in range(dim)]
+        nq = [int(B.c.nq[d]) for d in range(dim)]
+        nl = list(B.nloc)
+        nqp = B.nqp
+        nd = B.nder + 1
+        Wg = self._global_window("A" if kind == "fe" else "C")
+        mst = self._gsf_plan(mentries, dim, True) if A is not None else None
+        vst = self._gsf_plan(ventries, dim, False) if b is not None else None
+        F = [self._gsf_dir(B, Wg, d, True)[1] for d in range(dim)]
+        n = [int(B.c.n[d]) for d in range(dim)]
+        plane_cells = int(np.prod(nel[:L]))
+        # bytes per layer of the last direction: coefficients + intermediates
+        per = nslots * plane_cells * nqp
+        for st, G in ((mst, F), (vst, n)):
+            if st is None:
+                continue
+            if dim == 3:
+                per += st[0][0] * nel[1] * G[0] * nq[2] * nq[1] + st[1][0] * G[1] * G[0] * nq[2]
+            else:
+                per += st[0][0] * G[0] * nq[1]
+        budget = float(os.environ.get("TIGAR_B200_GSF_GB", "20")) * 2 ** 30
+        lc_max = max(1, min(self.slab_hi - self.slab_lo, int(budget // (8 * per))))
+        W = A.window if A is not None else None
+        bufs = {}
+
+        def buf(name, nelem):
+            t = bufs.get(name)
+            if t is None or t.numel() < nelem:
+                t = dev.empty(nelem)
+                bufs[name] = t
+            return t
+        plans = {}
+
+        def dplan(tag, tab):
+            if tag not in plans:
+                plans[tag] = dev.from_np(tab.ravel())
+            return plans[tag]
+        tabs = [(B.c.tab[d], B.c.idx[d]) for d in range(dim)]
+        k = self.slab_lo
+        while k < self.slab_hi:
+            lc = min(lc_max, self.slab_hi - k)
+            ncells = lc * plane_cells
+            X0 = buf("X0", nslots * ncells * nqp)
+            self._qp_eval(B, P, k * plane_cells, ncells, X0, gsf=(ncells * nqp, lc, k))
+            for pair, st, G, out in ((1, mst, F, A), (0, vst, n, b)):
+                if st is None:
+                    continue
+                tag = "m" if pair else "v"
+                rbs = [self._gsf_dir(B, Wg, d, bool(pair))[0] for d in range(dim)]
+                outp = dev.ptr(out.vals) if pair else dev.ptr(out)
+                if dim == 3:
+                    nq2c = lc * nq[2]
+                    # stage 1: march e0; inner = (e1, q2c, q1l)
+                    n1o, mi1, t1 = st[0]
+                    Y1 = buf(tag + "Y1", n1o * nel[1] * G[0] * nq2c * nq[1])
+                    ninner = nel[1] * nq2c * nq[1]
+                    check(lib.tg_gsf_stage(
+                        dev.ptr(X0), ncells * nqp, ninner * nq[0], 0, 0, nel[0], nel[0], nl[0],
+                        nq[0], nd, tabs[0][0], tabs[0][1], dev.ptr(rbs[0]),
+                        dev.ptr(dplan((tag, 0), t1)), n1o, mi1, pair, ninner, nq2c, nq[1],
+                        dev.ptr(Y1), nel[1] * G[0] * nq2c * nq[1], nq2c * nq[1],
+                        G[0] * nq2c * nq[1], nq[1], 0, None, 0, 0, 0, None, dev.stream()))
+                    # stage 2: march e1; inner = (f0, e2l, q2l)
+                    n2o, mi2, t2 = st[1]
+                    Y2 = buf(tag + "Y2", n2o * lc * G[1] * G[0] * nq[2])
+                    ninner = G[0] * nq2c
+                    check(lib.tg_gsf_stage(
+                        dev.ptr(Y1), nel[1] * G[0] * nq2c * nq[1], ninner * nq[1], 0, 0, nel[1],
+                        nel[1], nl[1], nq[1], nd, tabs[1][0], tabs[1][1], dev.ptr(rbs[1]),
+                        dev.ptr(dplan((tag, 1), t2)), n2o, mi2, pair, ninner, lc, nq[2],
+                        dev.ptr(Y2), lc * G[1] * G[0] * nq[2], G[0] * nq[2], nq[2],
+                        G[1] * G[0] * nq[2], 0, None, 0, 0, 0, None, dev.stream()))
+                    Xl, skl, scl, ninl = Y2, lc * G[1] * G[0] * nq[2], G[1] * G[0] * nq[2], G[1] * G[0]
+                else:
+                    # stage 1: march e0; inner = (e1c, q1l)
+                    n1o, mi1, t1 = st[0]
+                    Y1 = buf(tag + "Y1", n1o * lc * G[0] * nq[1])
+                    ninner = lc * nq[1]
+                    check(lib.tg_gsf_stage(
+                        dev.ptr(X0), ncells * nqp, ninner * nq[0], 0, 0, nel[0], nel[0], nl[0],
+                        nq[0], nd, tabs[0][0], tabs[0][1], dev.ptr(rbs[0]),
+                        dev.ptr(dplan((tag, 0), t1)), n1o, mi1, pair, ninner, 1, nq[1],
+                        dev.ptr(Y1), lc * G[0] * nq[1], nq[1], G[0] * nq[1], 0, 0, None, 0, 0, 0,
+                        None, dev.stream()))
+                    Xl, skl, scl, ninl = Y1, lc * G[0] * nq[1], G[0] * nq[1], G[0]
+                nlo, mil, tl = st[L]
+                check(lib.tg_gsf_stage(
+                    dev.ptr(Xl), skl, scl, k, k, k + lc, nel[L], nl[L], nq[L], nd, tabs[L][0],
+                    tabs[L][1], dev.ptr(rbs[L]), dev.ptr(dplan((tag, L), tl)), nlo, mil, pair,
+                    ninl, 1, 1, None, 0, 0, 0, 0, 1, W.ref() if pair else None, G[0],
+                    vrow0, vnr, outp, dev.stream()))
+            k += lc
+        self.launches += 1
+
     def assemble_matrix(self, terms, funcs, kind="fe", out=None, cache=None):
         """terms: {(alphaTest, alphaTrial): Node} (coefficient already includes
         J and the quadrature weight).  kind 'fe' -> A_FE on the Lagrange
@@ -570,6 +731,15 @@ class TensorPatch(object):
         order = max(max(max(a) for a in alS + alT), self.jet_order(list(terms.values())))
         B = self.basis(kind, order)
         stride = i32arr([2] * self.dim if kind == "fe" else B.nloc)
+        if out is None and self.dim in (2, 3):
+            keys = sorted(terms, key=self._sf_key)
+            P = self._setup_cached(cache, lambda: [terms[k] for k in keys], funcs)
+            if self._gsf_ok(B, W, P):
+                ent = [(i, tuple((pad3(k[0])[d], pad3(k[1])[d]) for d in range(self.dim)))
+                       for i, k in enumerate(keys)]
+                A = WinMatrix(W, dev.empty(W.storage()))
+                self._gsf_run(B, kind, P, len(keys), ent, None, A, None, 0, 0)
+                return A
         if lib.tg_assemble_sf_supported(B.ref()):
             # sum-factorised kernel: one coefficient slot per non-zero term
             keys = sorted(terms, key=self._sf_key)
@@ -617,10 +787,28 @@ class TensorPatch(object):
         order = max([max(pad3(k[0]) + pad3(k[1])) for k in mk] + [max(a) for a in alS]
                     + [self.jet_order(nodes)])
         B = self.basis(kind, order)
+        W = self.window("A" if kind == "fe" else "C")
+        P = None
+        if self.dim in (2, 3) and (self.part is None or kind == "iga"):
+            P = self._qp_setup(nodes, funcs)
+            if self._gsf_ok(B, W, P):
+                dim = self.dim
+                nm = len(mk)
+                ment = [(i, tuple((pad3(k[0])[d], pad3(k[1])[d]) for d in range(dim)))
+                        for i, k in enumerate(mk)]
+                vent = [(nm + i, tuple((a[d], 0) for d in range(dim))) for i, a in enumerate(alS)]
+                A = WinMatrix(W, dev.empty(W.storage()))
+                if self.part is not None:
+                    b = dev.empty(self.n_loc)
+                    r0, nr = self.pp["k0"], self.pp["k1"] - self.pp["k0"]
+                else:
+                    b = dev.empty(B.ntot)
+                    r0, nr = 0, int(B.c.n[dim - 1])
+                self._gsf_run(B, kind, P, nm + len(alS), ment, vent, A, b, r0, nr)
+                return A, b
         if not lib.tg_assemble_sf_supported(B.ref()):
             return (self.assemble_matrix(mterms, funcs, kind),
                     self.assemble_vector(vterms, funcs, kind))
-        W = self.window("A" if kind == "fe" else "C")
         A = WinMatrix(W)
         if self.part is not None:
             if kind != "iga":
@@ -632,7 +820,8 @@ class TensorPatch(object):
             b = dev.zeros(B.ntot)
             vrow0 = i32arr([0] * self.dim)
             vnr = i32arr([B.c.n[d] for d in range(self.dim)])
-        P = self._qp_setup(nodes, funcs)
+        if P is None:
+            P = self._qp_setup(nodes, funcs)
         nm, nv = len(mk), len(alS)
         nslots = nm + nv
         tl = []
@@ -669,6 +858,18 @@ class TensorPatch(object):
         P = self._setup_cached(cache, outputs, funcs)
         nder = max(P["nder"], max(max(a) for a in alS))
         B = self.basis(kind, nder)
+        if self.dim in (2, 3) and (self.part is None or kind == "iga") and \
+                self._gsf_ok(B, None, P):
+            dim = self.dim
+            vent = [(i, tuple((a[d], 0) for d in range(dim))) for i, a in enumerate(alS)]
+            if self.part is not None:
+                b = dev.empty(self.n_loc) if out is None else out
+                r0, nr = self.pp["k0"], self.pp["k1"] - self.pp["k0"]
+            else:
+                b = dev.empty(B.ntot) if out is None else out
+                r0, nr = 0, int(B.c.n[dim - 1])
+            self._gsf_run(B, kind, P, nS, None, vent, None, b, r0, nr)
+            return b
         if self.part is not None:
             if kind != "iga":
                 raise NotImplementedError("slab partition exists for the fused path only")
@@ -1022,6 +1223,7 @@ class TensorPatch(object):
         return m
 
     def apply_bcs_matrix(self, Cm, mask, diag=1.0):
+        Cm.bc_mask, Cm.bc_diag = mask, float(diag)      # read by the preconditioned solvers
         if self.part is not None:
             pp, pl = self.pp, self.plane
             rowmask = mask[pp["k0"] * pl:pp["k1"] * pl]
@@ -1039,6 +1241,42 @@ class TensorPatch(object):
             mask = mask[self.pp["k0"] * self.plane:self.pp["k1"] * self.plane]
         check(lib.tg_zero_entries(dev.ptr(b), dev.ptr(mask), b.numel(), dev.stream()))
         return b
+
+    def solve(self, Cm, b, x=None, rtol=1e-12, atol=0.0, maxit=100000, method="auto",
+              mask=None, diag=1.0):
+        """solve() of common.py:1255-1258 on one windowed system.  ``method``:
+        "direct" (band Cholesky), "fd" (CG preconditioned by fast diagonalisation),
+        "jacobi" (Jacobi-CG), or "auto": the reference's default is a direct LU, so the band
+        solver is used while it is affordable (2-D patches, small 3-D ones), FD-CG beyond.
+        Returns (x, iterations, relative residual, method used)."""
+        from . import solvers
+        method = os.environ.get("TIGAR_B200_SOLVER", method)
+        if self.part is not None:
+            method = "jacobi" if method in ("auto", "direct") else method
+        if method == "auto":
+            import torch
+            free, _ = torch.cuda.mem_get_info()
+            method = "direct" if solvers.direct_affordable(Cm.window, free) else "fd"
+        if method == "direct":
+            bc = solvers.BandCholesky(Cm).factor()
+            xs = bc.solve(b)
+            # true relative residual of the direct solution (one SpMV)
+            r = Cm.matvec(xs)
+            r.sub_(b)
+            bb = float(b.norm())
+            rel = float(r.norm()) / bb if bb > 0 else 0.0
+            return xs, 1, rel, "direct"
+        if method == "fd":
+            if self.part is not None:
+                from .multigpu import solve_fd_pcg_dist
+                xs, its, rel = solve_fd_pcg_dist(self, Cm, b, mask, diag, rtol, atol, maxit)
+                return xs, its, rel, "fd"
+            xs, its, rel, _ = solvers.solve_fd_pcg(self, Cm, b, mask, diag, x, rtol, atol, maxit)
+            return xs, its, rel, "fd"
+        if method != "jacobi":
+            raise ValueError("unknown solver method %r" % (method,))
+        xs, its, rel = self.solve_cg(Cm, b, x, rtol, atol, maxit)
+        return xs, its, rel, "jacobi"
 
     def solve_cg(self, Cm, b, x=None, rtol=1e-12, atol=0.0, maxit=100000, check_every=5):
         if self.part is not None:

@@ -32,7 +32,8 @@ MAXFUN = 16
 class QpArgs(C.Structure):
     _fields_ = [("tab", c_vp * 3), ("idx", c_vp * 3), ("wq", c_vp * 3), ("xq", c_vp * 3),
                 ("coef", c_vp * MAXFUN), ("n", c_i32 * 3), ("nel", c_i32 * 3),
-                ("cell0", c_i64), ("out", c_vp)]
+                ("cell0", c_i64), ("out", c_vp), ("sstride", c_i64), ("lc", c_i32),
+                ("elast0", c_i32)]
 
 
 class OpArgs(C.Structure):
@@ -40,7 +41,8 @@ class OpArgs(C.Structure):
     matrix-free operator kernel, ``generate(..., op=...)``)."""
     _fields_ = [("tab", c_vp * 3), ("idx", c_vp * 3), ("wq", c_vp * 3), ("xq", c_vp * 3),
                 ("coef", c_vp * MAXFUN), ("n", c_i32 * 3), ("nel", c_i32 * 3),
-                ("cell0", c_i64), ("out", c_vp), ("co", c_i32 * 3), ("cs", c_i32 * 3),
+                ("cell0", c_i64), ("out", c_vp), ("sstride", c_i64), ("lc", c_i32),
+                ("elast0", c_i32), ("co", c_i32 * 3), ("cs", c_i32 * 3),
                 ("cn", c_i32 * 3), ("y", c_vp)]
 
 
@@ -48,6 +50,7 @@ _PRELUDE_OP = r"""
 struct QpArgs {
   const double* tab[3]; const int* idx[3]; const double* wq[3]; const double* xq[3];
   const double* coef[%(MAXFUN)d]; int n[3]; int nel[3]; long long cell0; double* out;
+  long long sstride; int lc; int elast0;
   int co[3]; int cs[3]; int cn[3]; double* y;
 };
 """
@@ -56,11 +59,12 @@ _PRELUDE = r"""
 struct QpArgs {
   const double* tab[3]; const int* idx[3]; const double* wq[3]; const double* xq[3];
   const double* coef[%(MAXFUN)d]; int n[3]; int nel[3]; long long cell0; double* out;
+  long long sstride; int lc; int elast0;
 };
 """
 
 
-def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False):
+def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="cell"):
     """CUDA source of the kernel for ``prog``.  jets: list of (fpos, comp, al3)
     in register order; nloc/nq: per-direction sizes (padded to 3 with 1).
 
@@ -75,7 +79,12 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False):
     ``diag=True`` (with ``op`` = list of (test, trial) multi-index pairs, one per output):
     the kernel adds the DIAGONAL of the element matrices instead,
     ``y[g(a)] += sum_s sum_q out_s(q) D^test_s N_a(q) D^trial_s N_a(q)`` -- the Jacobi
-    preconditioner of the matrix-free operator without ever assembling a matrix."""
+    preconditioner of the matrix-free operator without ever assembling a matrix.
+
+    ``layout="gsf"``: the outputs are stored for the global sum-factorised assembly
+    (csrc/tg_gsf.cu), ``out[s*sstride + cellperm*NQP + qp]`` with the cells of the launch (whole
+    layers ``elast0 .. elast0+lc`` of the last direction) permuted so that the FIRST direction is
+    slowest: cellperm = (e0*nel1 + e1)*lc + (e2 - elast0)  [2-D: e0*lc + (e1 - elast0)]."""
     n0, n1, n2 = nloc
     q0, q1, q2 = nq
     nen, nqp = n0 * n1 * n2, q0 * q1 * q2
@@ -193,9 +202,19 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False):
         w("  const double %s = %s;" % (var, expr))
         names[dst] = var
     if op is None:
-        w("  double* o = A.out + cl * (long long)%d * NQP + tid;" % len(prog.outregs))
-        for s, r in enumerate(prog.outregs):
-            w("  o[%d * NQP] = %s;" % (s, names[r]))
+        if layout == "gsf":
+            if dim == 3:
+                w("  double* o = A.out + (((long long)e0 * A.nel[1] + e1) * A.lc + (e2 - A.elast0)) * NQP + tid;")
+            elif dim == 2:
+                w("  double* o = A.out + ((long long)e0 * A.lc + (e1 - A.elast0)) * NQP + tid;")
+            else:
+                raise ValueError("gsf layout needs a 2-D or 3-D patch")
+            for s, r in enumerate(prog.outregs):
+                w("  o[%d * A.sstride] = %s;" % (s, names[r]))
+        else:
+            w("  double* o = A.out + cl * (long long)%d * NQP + tid;" % len(prog.outregs))
+            for s, r in enumerate(prog.outregs):
+                w("  o[%d * NQP] = %s;" % (s, names[r]))
         w("}")
         return "\n".join(L), nth
     for s, r in enumerate(prog.outregs):
@@ -264,8 +283,8 @@ def enabled():
     return not os.environ.get("TIGAR_B200_NO_JIT")
 
 
-def get_kernel(prog, dim, nloc, nq, nd, jets, nfun):
-    src, nth = generate(prog, dim, nloc, nq, nd, jets, nfun)
+def get_kernel(prog, dim, nloc, nq, nd, jets, nfun, layout="cell"):
+    src, nth = generate(prog, dim, nloc, nq, nd, jets, nfun, layout=layout)
     key = hashlib.sha1(src.encode()).hexdigest()
     k = _cache.get(key)
     if k is None:
@@ -283,7 +302,8 @@ def check_source(src):
     return n.value
 
 
-def launch(kernel, B, coef_ptrs, cell0, ncells, out):
+def launch(kernel, B, coef_ptrs, cell0, ncells, out, gsf=None):
+    """``gsf=(sstride, lc, elast0)`` for kernels generated with layout="gsf"."""
     h, nth = kernel
     a = QpArgs()
     b = B.c
@@ -294,6 +314,8 @@ def launch(kernel, B, coef_ptrs, cell0, ncells, out):
         a.coef[i] = p
     a.cell0 = cell0
     a.out = dev.ptr(out)
+    if gsf is not None:
+        a.sstride, a.lc, a.elast0 = int(gsf[0]), int(gsf[1]), int(gsf[2])
     check(lib.tg_jit_launch(h, ncells, nth, 0, C.byref(a), C.sizeof(a), dev.stream()))
 
 

@@ -1,0 +1,369 @@
+"""
+Linear solvers behind ``ExtractedSpline.solveLinearSystem`` (common.py:1236-1263).
+
+The reference hands the extracted system to ``dolfin.solve`` -- a sparse direct LU through
+PETSc by default (common.py:1255-1256) -- or to a user ``linearSolver`` (PETSc KSP + PC).
+Here the same role is played by three device solvers, all FP64, all on the C-ABI kernels:
+
+* ``BandCholesky``  -- direct: blocked band Cholesky (tg_band.cu).  In the reference's DoF
+  numbering the IGA matrix of a 2-D patch (or a small 3-D one) is banded with half-bandwidth
+  ``sum_d p_d * stride_d``; used whenever the band fits (every 2-D BASELINE config: the
+  biharmonic system has cond ~ h^-4 and defeats point-Jacobi CG).
+* ``FastDiag`` + ``pcg`` -- CG preconditioned by fast diagonalisation of the tensor-product
+  operator ``sigma M(x)M(x)M + sum_d c_d K_d (x) M (x) M`` on the parametric domain (exact inverse
+  for an affine geometry, h- and p-robust otherwise): three dense mode products with the 1-D
+  generalised eigenvectors, a scaling, three mode products back (tg_dgemm_batched,
+  tg_fd_scale).  ``c_d`` and ``sigma`` are a least-squares fit to diag(C), so anisotropic /
+  curved geometries are followed without looking at the form.
+* Jacobi-CG (tg_win_solve_cg) -- what a user ``KrylovSolver("cg", "jacobi")`` asks for.
+
+Host side: only 1-D quantities (the n_d x n_d generalised eigenproblems, like the Gauss rules
+and knot tables elsewhere) and the CG scalars.
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+from . import dev
+from ._lib import lib, check
+
+
+class SolverBreakdown(RuntimeError):
+    """p.Ap <= 0 or a non-positive pivot: the matrix is not symmetric positive definite."""
+
+
+# ------------------------------------------------------------------------------------------
+def _dir_matrices(D):
+    """1-D mass and stiffness matrices of one parametric direction on the parametric domain,
+    from the device tables of the hot path (exact: nq = p+1 Gauss points per span)."""
+    t = D.table(1)
+    np1, nq, nel = D.p + 1, D.nq, D.nel
+    tab = dev.to_np(t["tabN"]).reshape(nel, nq, np1, 2)
+    idx = dev.to_np(t["idxN"]).reshape(nel, np1).astype(np.int64)
+    wq = dev.to_np(t["wq"]).reshape(nel, nq)
+    Me = np.einsum("eq,eqi,eqj->eij", wq, tab[..., 0], tab[..., 0])
+    Ke = np.einsum("eq,eqi,eqj->eij", wq, tab[..., 1], tab[..., 1])
+    n = D.ncp
+    M = np.zeros((n, n))
+    K = np.zeros((n, n))
+    I = np.repeat(idx[:, :, None], np1, axis=2)
+    J = np.repeat(idx[:, None, :], np1, axis=1)
+    np.add.at(M, (I, J), Me)
+    np.add.at(K, (I, J), Ke)
+    return M, K
+
+
+_eig_cache = {}
+
+
+def _gen_eig(D, free):
+    """(lam, U) of K u = lam M u restricted to the ``free`` indices, embedded in n x n:
+    constrained rows/columns of U are zero and carry lam = +inf."""
+    key = (D.p, D.nq, tuple(np.asarray(D.s.knots, dtype=np.float64).tolist()), free.tobytes())
+    hit = _eig_cache.get(key)
+    if hit is not None:
+        return hit
+    import scipy.linalg as sla
+    M, K = _dir_matrices(D)
+    n = D.ncp
+    f = np.flatnonzero(free)
+    lam = np.full(n, np.inf)
+    U = np.zeros((n, n))
+    if f.size:
+        w, V = sla.eigh(K[np.ix_(f, f)], M[np.ix_(f, f)])
+        lam[f] = np.maximum(w, 0.0)
+        U[np.ix_(f, f)] = V
+    out = (lam, U, np.diag(M).copy(), np.diag(K).copy())
+    if len(_eig_cache) > 16:
+        _eig_cache.clear()
+    _eig_cache[key] = out
+    return out
+
+
+class FastDiag(object):
+    """z = B^-1 r with B the tensor-product surrogate of the extracted operator."""
+
+    def __init__(self, patch, mask=None, diag=1.0, dinv=None, weights=None):
+        """mask: device 0/1 over the IGA DoFs (constrained = 1) or None; ``diag``: the value
+        zeroRowsColumns put on constrained rows; dinv: device 1/diag(C) (for the fit of the
+        direction weights) or None -> unit weights."""
+        self.patch = patch
+        self.dim = patch.dim
+        self.n = patch.n_iga
+        self.nd = list(patch.ncp) + [1] * (3 - patch.dim)
+        self.mask = mask
+        self.cinv = 1.0 / float(diag) if diag else 1.0
+        free = self._free_planes(mask)
+        self.free = free
+        eig = [_gen_eig(D, free[d]) for d, D in enumerate(patch.dirs)]
+        c, sigma = (weights if weights is not None else self._fit(eig, dinv))
+        self.weights, self.sigma = c, sigma
+        self.lam = [dev.from_np(c[d] * eig[d][0]) for d in range(self.dim)]
+        self.U = [dev.from_np(np.asfortranarray(eig[d][1]).T.copy()) for d in range(self.dim)]
+        # from_np stores C-order; U^T in C order == U in column-major order
+        self.t1 = dev.empty(self.n)
+        self.t2 = dev.empty(self.n)
+
+    def _free_planes(self, mask):
+        """free[d][i] = False iff the whole hyperplane i_d = i is constrained."""
+        out = []
+        if mask is None:
+            return [np.ones(n, dtype=bool) for n in self.patch.ncp]
+        shape = tuple(reversed(self.patch.ncp))           # first direction fastest
+        m = mask.view(shape) != 0
+        for d in range(self.dim):
+            ax = self.dim - 1 - d
+            other = tuple(a for a in range(self.dim) if a != ax)
+            full = m.all(dim=other) if other else m
+            out.append(~dev.to_np(full).astype(bool))
+        return out
+
+    def _fit(self, eig, dinv):
+        dim = self.dim
+        if dinv is None:
+            return [1.0] * dim, 0.0
+        md = [eig[d][2] for d in range(dim)]
+        kd = [eig[d][3] for d in range(dim)]
+        d_md = [dev.from_np(a) for a in md]
+        d_kd = [dev.from_np(a) for a in kd]
+        scratch = dev.empty(256)
+        out4 = dev.zeros(4)
+        P = lambda L, d: dev.ptr(L[d]) if d < dim else None
+        # diag(C) = 1/dinv
+        d = dinv.reciprocal()
+        check(lib.tg_fd_fit(dev.ptr(d), dev.ptr(self.mask) if self.mask is not None else None,
+                            P(d_kd, 0), P(d_kd, 1), P(d_kd, 2), P(d_md, 0), P(d_md, 1),
+                            P(d_md, 2), self.nd[0], self.nd[1], self.nd[2], dev.ptr(scratch),
+                            dev.ptr(out4), dev.stream()))
+        rhs = dev.to_np(out4)
+        # Gram matrix of the Kronecker diagonals (separable sums over the free index sets)
+        nb = dim + 1
+
+        def f(a, dd):
+            v = kd[dd] if a == dd else md[dd]
+            return np.where(self.free[dd], v, 0.0)
+        G = np.ones((nb, nb))
+        for a in range(nb):
+            for b in range(nb):
+                for dd in range(dim):
+                    G[a, b] *= float(np.dot(f(a, dd), f(b, dd)))
+        r = np.concatenate([rhs[:dim], rhs[3:4]])
+        try:
+            sol = np.linalg.solve(G, r)
+        except np.linalg.LinAlgError:
+            return [1.0] * dim, 0.0
+        c, sigma = list(sol[:dim]), float(sol[dim])
+        if not all(np.isfinite(sol)) or min(c) <= 0.0:
+            # not a second-order operator (mass matrix, ...): fit sigma alone or give up
+            if all(abs(x) < 1e-8 * abs(sigma) for x in c) and sigma > 0:
+                return [0.0] * dim, sigma
+            return [1.0] * dim, 0.0
+        cmax = max(c)
+        return [float(x) for x in c], max(sigma, 0.0) if sigma > -1e-10 * cmax else 0.0
+
+    def _gemm(self, ta, tb, M, N, K, A, lda, sA, B, ldb, sB, Cc, ldc, sC, batch):
+        check(lib.tg_dgemm_batched(ta, tb, M, N, K, 1.0, A, lda, sA, B, ldb, sB, 0.0, Cc, ldc, sC,
+                                   batch, dev.stream()))
+
+    def apply(self, r, z):
+        n0, n1, n2 = self.nd
+        dim = self.dim
+        st = dev.stream()
+        t1, t2 = dev.ptr(self.t1), dev.ptr(self.t2)
+        U = [dev.ptr(u) for u in self.U]
+        check(lib.tg_masked_copy(t1, dev.ptr(r), dev.ptr(self.mask) if self.mask is not None
+                                 else None, self.n, st))
+        a, b = t1, t2
+        # forward: U_d^T along every direction
+        self._gemm(1, 0, n0, n1 * n2, n0, U[0], n0, 0, a, n0, 0, b, n0, 0, 1)
+        a, b = b, a
+        if dim > 1:
+            self._gemm(0, 0, n0, n1, n1, a, n0, n0 * n1, U[1], n1, 0, b, n0, n0 * n1, n2)
+            a, b = b, a
+        if dim > 2:
+            self._gemm(0, 0, n0 * n1, n2, n2, a, n0 * n1, 0, U[2], n2, 0, b, n0 * n1, 0, 1)
+            a, b = b, a
+        L = [dev.ptr(l) for l in self.lam] + [None] * (3 - dim)
+        check(lib.tg_fd_scale(a, L[0], L[1], L[2], n0, n1, n2, self.sigma, 1, st))
+        # backward: U_d
+        if dim > 2:
+            self._gemm(0, 1, n0 * n1, n2, n2, a, n0 * n1, 0, U[2], n2, 0, b, n0 * n1, 0, 1)
+            a, b = b, a
+        if dim > 1:
+            self._gemm(0, 1, n0, n1, n1, a, n0, n0 * n1, U[1], n1, 0, b, n0, n0 * n1, n2)
+            a, b = b, a
+        self._gemm(0, 0, n0, n1 * n2, n0, U[0], n0, 0, a, n0, 0, dev.ptr(z), n0, 0, 1)
+        if self.mask is not None:
+            check(lib.tg_masked_fix(dev.ptr(z), dev.ptr(r), dev.ptr(self.mask), self.cinv,
+                                    self.n, st))
+        return z
+
+    @property
+    def flops_per_apply(self):
+        n0, n1, n2 = self.nd
+        tot = n0 * n1 * n2
+        return 4.0 * tot * sum(self.nd[:self.dim])
+
+
+# ------------------------------------------------------------------------------------------
+class _Vec(object):
+    """Scalar helpers of the CG driver on one GPU (host-read dot products)."""
+
+    def __init__(self, n):
+        self.n = n
+        self.scratch = dev.empty(lib.tg_cg_scratch_len())
+        self.s = dev.zeros(4)
+
+    def dot(self, a, b):
+        check(lib.tg_dot(dev.ptr(a), dev.ptr(b), self.n, dev.ptr(self.scratch), dev.ptr(self.s),
+                         dev.stream()))
+        return self.reduce(float(self.s[0].item()))
+
+    def reduce(self, v):
+        return v
+
+
+def pcg(spmv_dot, precond, b, x0=None, rtol=1e-12, atol=0.0, maxit=10000, reduce=None,
+        exchange=None):
+    """Preconditioned CG.  ``spmv_dot(p, q) -> p.q`` computes q = A p and returns the (global)
+    dot product; ``precond(r, z)`` writes z = B^-1 r; ``reduce`` sums a host scalar over ranks.
+    Returns (x, iterations, relative residual).  Raises SolverBreakdown when p.Ap <= 0."""
+    n = b.numel()
+    V = _Vec(n)
+    if reduce is not None:
+        V.reduce = reduce
+    st = dev.stream
+    x = dev.zeros(n) if x0 is None else x0
+    r = b.clone()
+    q = dev.empty(n)
+    z = dev.empty(n)
+    bb = V.dot(b, b)
+    if x0 is not None:
+        spmv_dot(x, q)
+        check(lib.tg_axpy(dev.ptr(r), -1.0, dev.ptr(q), n, st()))
+    rr = V.dot(r, r)
+    tol2 = max(rtol * rtol * bb, atol * atol)
+    it = 0
+    if rr <= tol2:
+        return x, 0, (math.sqrt(rr / bb) if bb > 0 else 0.0)
+    precond(r, z)
+    p = z.clone()
+    rz = V.dot(r, z)
+    out1 = V.s[1:2]
+    while rr > tol2 and it < maxit:
+        pAp = spmv_dot(p, q)
+        if not (pAp > 0.0):
+            if pAp == 0.0 and rz == 0.0:
+                break
+            raise SolverBreakdown("CG breakdown at iteration %d: p.Ap = %g (matrix not symmetric "
+                                  "positive definite)" % (it, pAp))
+        alpha = rz / pAp
+        check(lib.tg_pcg_update(dev.ptr(x), dev.ptr(r), dev.ptr(p), dev.ptr(q), alpha, n,
+                                dev.ptr(V.scratch), dev.ptr(out1), st()))
+        rr = V.reduce(float(out1[0].item()))
+        it += 1
+        if not (rr == rr):
+            raise FloatingPointError("CG produced NaN at iteration %d" % it)
+        if rr <= tol2:
+            break
+        precond(r, z)
+        rz_new = V.dot(r, z)
+        check(lib.tg_xpby(dev.ptr(p), rz_new / rz, dev.ptr(z), n, st()))
+        rz = rz_new
+    return x, it, (math.sqrt(rr / bb) if bb > 0 else 0.0)
+
+
+def solve_fd_pcg(patch, Cm, b, mask=None, diag=1.0, x0=None, rtol=1e-12, atol=0.0, maxit=10000):
+    """FD-preconditioned CG on a windowed system matrix (one GPU)."""
+    n = Cm.window.nrows
+    dinv = dev.empty(n)
+    check(lib.tg_win_diag_inv(Cm.window.ref(), dev.ptr(Cm.vals), 0, dev.ptr(dinv), dev.stream()))
+    fd = FastDiag(patch, mask, diag, dinv)
+    del dinv
+    scratch = dev.empty(lib.tg_cg_scratch_len())
+    s = dev.zeros(2)
+
+    def spmv_dot(p, q):
+        check(lib.tg_win_spmv_dot(Cm.window.ref(), dev.ptr(Cm.vals), dev.ptr(p), 0, dev.ptr(q),
+                                  dev.ptr(scratch), dev.ptr(s), dev.stream()))
+        return float(s[0].item())
+    x, its, rel = pcg(spmv_dot, fd.apply, b, x0, rtol, atol, maxit)
+    return x, its, rel, fd
+
+
+# ------------------------------------------------------------------------------------------
+class BandCholesky(object):
+    """Direct solve of a windowed SPD system: band conversion, factorisation, solves."""
+
+    NB = 32
+
+    def __init__(self, Cm):
+        w = Cm.window
+        if w.layout != 0:
+            raise ValueError("band solver needs the row-major window layout")
+        self.n = w.nrows
+        self.bw = self.bandwidth(w)
+        self.ldab = self.bw + self.NB + ((self.bw + self.NB) & 1)
+        self.Cm = Cm
+        self.AB = None
+
+    @staticmethod
+    def bandwidth(w):
+        stride, bw = 1, 0
+        for d in range(w.dim):
+            r = np.arange(w.nr[d], dtype=np.int64)
+            reach = int(max((r - w.lo[d].astype(np.int64)).max(),
+                            (w.hi[d].astype(np.int64) - r).max()))
+            bw += reach * stride
+            stride *= w.nc[d]
+        return bw
+
+    @classmethod
+    def cost(cls, w):
+        """(bytes of band storage, flops of the factorisation)."""
+        n, bw = w.nrows, cls.bandwidth(w)
+        return 8.0 * n * (bw + cls.NB + 1), float(n) * (bw + cls.NB) ** 2
+
+    def factor(self, sym_tol=1e-9):
+        Cm, w = self.Cm, self.Cm.window
+        o2 = dev.zeros(2)
+        check(lib.tg_win_asym(w.ref(), dev.ptr(Cm.vals), dev.ptr(o2), dev.stream()))
+        asym, amax = o2.tolist()
+        if asym > sym_tol * max(amax, 1e-300):
+            raise SolverBreakdown("matrix is not symmetric (max |A - A^T| = %.3e, max |A| = %.3e): "
+                                  "the Cholesky/CG solvers need a symmetric form" % (asym, amax))
+        self.AB = dev.zeros(self.ldab * self.n)
+        info = dev.zeros(1, dev.I32)
+        check(lib.tg_band_from_win(w.ref(), dev.ptr(Cm.vals), self.bw, self.ldab, dev.ptr(self.AB),
+                                   dev.ptr(info), dev.stream()))
+        check(lib.tg_band_cholesky(self.n, self.bw, self.ldab, dev.ptr(self.AB), dev.ptr(info),
+                                   dev.stream()))
+        code = int(info.item())
+        if code != 0:
+            self.AB = None
+            raise SolverBreakdown("band Cholesky: %s" % (
+                "non-zero outside the computed band" if code < 0 else
+                "pivot block at row %d is not positive definite" % (code - 1)))
+        return self
+
+    def solve(self, b):
+        if self.AB is None:
+            self.factor()
+        work = dev.empty(self.n)
+        rhs = b.clone()
+        x = dev.empty(self.n)
+        check(lib.tg_band_solve(self.n, self.bw, self.ldab, dev.ptr(self.AB), dev.ptr(rhs),
+                                dev.ptr(work), dev.ptr(x), dev.stream()))
+        return x
+
+
+def direct_affordable(w, free_bytes=None):
+    """Policy: use the band solver when its storage and work are small next to the device."""
+    lim_gb = float(os.environ.get("TIGAR_B200_DIRECT_GB", "12"))
+    lim_flops = float(os.environ.get("TIGAR_B200_DIRECT_FLOPS", "3e13"))
+    nbytes, flops = BandCholesky.cost(w)
+    if free_bytes is not None and nbytes > 0.5 * free_bytes:
+        return False
+    return nbytes <= lim_gb * 2 ** 30 and flops <= lim_flops
