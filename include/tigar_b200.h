@@ -340,6 +340,12 @@ int tg_win_spmv_dot(const tg_win* h_w, const double* vals, const double* x, int6
 int tg_win_zero_rows_cols(const tg_win* h_w, double* vals, const uint8_t* rowmask,
                           const uint8_t* colmask, double diag, int32_t col_shift,
                           void* stream);
+/* same, for a constrained set that is a union of whole hyperplanes (the side DoFs of
+ * getSideDofs, BSplines.py:599-649): hp_d[c] != 0 marks hyperplane c of direction d (global
+ * coordinates; h_w's row0/col0 place a slab-local block).  Rows whose window reaches no
+ * constrained hyperplane are skipped after a few byte loads.  Row-major layout only.        */
+int tg_win_zero_rows_cols_hp(const tg_win* h_w, double* vals, const uint8_t* hp0,
+                             const uint8_t* hp1, const uint8_t* hp2, double diag, void* stream);
 int tg_win_diag_inv(const tg_win* h_w, const double* vals, int32_t col_shift, double* dinv,
                     void* stream);
 /* Jacobi-CG on a windowed matrix; same contract as tg_solve_cg.             */
@@ -427,10 +433,13 @@ int tg_fp64_peak(double* scratch1, double* h_tflops, void* stream);
  * tensor-product operator  sigma M(x)M(x)M + sum_d c_d K_d (x) M (x) M  is inverted exactly in the
  * generalised eigenbasis K_d U_d = M_d U_d Lambda_d (1-D, host setup): three mode products with
  * U_d^T (tg_dgemm_batched), this scaling, three mode products with U_d.
- *   t[i0,i1,i2] /= (sigma + l0[i0] + l1[i1] + l2[i2])^pw   (0 where the sum is not finite and
- *   positive: constrained hyperplanes carry +inf).  l1 / l2 may be NULL (1-D / 2-D).          */
+ *   t[pl, i2] /= (sigma + l0[i0] + l1[i1] + l2[i2])^pw   (0 where the sum is not finite and
+ *   positive: constrained hyperplanes carry +inf) for the mq plane entries pl = q0 .. q0+mq-1
+ *   (i0 = pl % n0, i1 = pl / n0; whole tensor: q0 = 0, mq = n0*n1; a chunk of planes on each
+ *   rank of a row-distributed solve).  l1 / l2 may be NULL (1-D / 2-D).                       */
 int tg_fd_scale(double* t, const double* l0, const double* l1, const double* l2,
-                int32_t n0, int32_t n1, int32_t n2, double sigma, int32_t pw, void* stream);
+                int32_t n0, int32_t n1, int32_t n2, int64_t q0, int64_t mq, double sigma,
+                int32_t pw, void* stream);
 /* dst = mask ? 0 : src ;  z = mask ? r*cinv : z  (constrained rows are diag*identity,
  * zeroRowsColumns(zeroDofs, diag), common.py:1199-1200)                                       */
 int tg_masked_copy(double* dst, const double* src, const uint8_t* mask, int64_t n, void* stream);

@@ -383,7 +383,9 @@ def test_sell_and_row_major_layouts_agree(deg, nels):
         finally:
             os.environ.pop("TIGAR_B200_LAYOUT", None)
     s, r = res["1"], res["0"]
-    assert abs(s[0] - r[0]).max() == 0.0 and abs(s[1] - r[1]).max() == 0.0   # same entries
+    # same entries up to summation order (row-major: march kernels, SELL: element kernels)
+    scale = abs(r[0]).max()
+    assert abs(s[0] - r[0]).max() < 1e-13 * scale and abs(s[1] - r[1]).max() < 1e-13 * scale
     assert np.abs(s[2] - s[0] @ s[4]).max() < 1e-12 and np.abs(r[2] - r[0] @ r[4]).max() < 1e-12
     assert rel(s[3], r[3]) < 1e-10
     import scipy.sparse.linalg as spla

@@ -182,7 +182,9 @@ def test_config2_biharmonic_512_equals_oracle_lu_at_full_size():
         uh = Function(spline.V)
         U = spline.solveLinearSystem(C, b, uh)
         assert spline.lastSolve["method"] == "direct"
-        assert spline.lastSolve["relative_residual"] < 1e-9
+        # true residual of the direct solve (cond ~ 1e11: LAPACK dpbsv reaches 2.3e-8 and
+        # SuperLU 1.8e-7 on the same matrix, tests/golden/gen_cfg3_golden.py)
+        assert spline.lastSolve["relative_residual"] < 1e-7
         errs[nel] = math.sqrt(assemble((lap(uh - soln) ** 2) * spline.dx))
         if nel == 512:
             gap = rel(U.get_local(), U_lu)

@@ -58,6 +58,7 @@ SIGNATURES = {
     "tg_win_spmv": [PW, c_vp, c_vp, c_vp, c_vp],
     "tg_win_spmv_dot": [PW, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp],
     "tg_win_zero_rows_cols": [PW, c_vp, c_vp, c_vp, c_dbl, c_i32, c_vp],
+    "tg_win_zero_rows_cols_hp": [PW, c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp],
     "tg_win_diag_inv": [PW, c_vp, c_i32, c_vp, c_vp],
     "tg_win_solve_cg": [PW, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_i32, c_i32, c_vp, PI32,
                         C.POINTER(c_dbl), c_vp],
@@ -112,7 +113,7 @@ SIGNATURES = {
     "tg_dgemm_batched": [c_i32, c_i32, c_i32, c_i32, c_i32, c_dbl, c_vp, c_i32, c_i64,
                          c_vp, c_i32, c_i64, c_dbl, c_vp, c_i32, c_i64, c_i32, c_vp],
     "tg_fp64_peak": [c_vp, C.POINTER(c_dbl), c_vp],
-    "tg_fd_scale": [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_dbl, c_i32, c_vp],
+    "tg_fd_scale": [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_i64, c_dbl, c_i32, c_vp],
     "tg_masked_copy": [c_vp, c_vp, c_vp, c_i64, c_vp],
     "tg_masked_fix": [c_vp, c_vp, c_vp, c_dbl, c_i64, c_vp],
     "tg_fd_fit": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32,

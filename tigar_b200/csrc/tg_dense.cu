@@ -195,17 +195,20 @@ extern "C" int tg_fp64_peak(double* scratch1, double* h_tflops, void* stream) {
 }
 
 // ---- fast diagonalisation ---------------------------------------------------------------
-// t[i0,i1,i2] *= 1 / (sigma + l0[i0] + l1[i1] + l2[i2])^pw ; non-finite or non-positive sums
-// (constrained hyperplanes carry +inf) give 0.
+// t[pl, i2] /= (sigma + l0[i0] + l1[i1] + l2[i2])^pw for the chunk of mq plane entries starting
+// at global plane index q0 (pl = q0 + local, i0 = pl % n0, i1 = pl / n0); the whole tensor is
+// q0 = 0, mq = n0*n1.  Non-finite or non-positive sums (constrained hyperplanes carry +inf)
+// give 0.
 __global__ void k_fd_scale(double* __restrict__ t, const double* __restrict__ l0,
                            const double* __restrict__ l1, const double* __restrict__ l2, int n0,
-                           int n1, int n2, double sigma, int pw) {
-  const int64_t n = (int64_t)n0 * n1 * n2;
+                           int n2, int64_t q0, int64_t mq, double sigma, int pw) {
+  const int64_t n = mq * n2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int i0 = (int)(i % n0);
-    const int64_t r = i / n0;
-    const int i1 = (int)(r % n1), i2 = (int)(r / n1);
+    const int64_t i2 = i / mq;
+    const int64_t pl = q0 + (i - i2 * mq);
+    const int64_t i1 = pl / n0;
+    const int i0 = (int)(pl - i1 * n0);
     double s = sigma + l0[i0] + (l1 ? l1[i1] : 0.0) + (l2 ? l2[i2] : 0.0);
     if (pw == 2) s = s * s;
     t[i] = (isfinite(s) && s > 0.0) ? t[i] / s : 0.0;
@@ -213,13 +216,14 @@ __global__ void k_fd_scale(double* __restrict__ t, const double* __restrict__ l0
 }
 
 extern "C" int tg_fd_scale(double* t, const double* l0, const double* l1, const double* l2,
-                           int32_t n0, int32_t n1, int32_t n2, double sigma, int32_t pw,
-                           void* stream) {
-  const int64_t n = (int64_t)n0 * n1 * n2;
-  if (n == 0) return 0;
+                           int32_t n0, int32_t n1, int32_t n2, int64_t q0, int64_t mq,
+                           double sigma, int32_t pw, void* stream) {
+  (void)n1;
+  const int64_t n = mq * n2;
+  if (n <= 0) return 0;
   int g = (int)((n + 255) / 256);
   if (g > 148 * 16) g = 148 * 16;
-  k_fd_scale<<<g, 256, 0, tg_stream(stream)>>>(t, l0, l1, l2, n0, n1, n2, sigma, pw);
+  k_fd_scale<<<g, 256, 0, tg_stream(stream)>>>(t, l0, l1, l2, n0, n2, q0, mq, sigma, pw);
   TG_LAUNCH_CHECK();
   return 0;
 }

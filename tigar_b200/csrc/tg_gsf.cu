@@ -62,7 +62,7 @@ struct GsfAcc {
 };
 
 template <int NL, int NQ, bool PAIR, bool LAST>
-__global__ void __launch_bounds__(GSF_THREADS)
+__global__ void __launch_bounds__(GSF_THREADS, (PAIR && NL >= 5) ? 2 : 3)
 k_gsf(const __grid_constant__ GsfArgs A) {
   constexpr int NLP = (NL + 1) & ~1;
   __shared__ __align__(16) double stab[GSF_CB * NQ * 3 * NLP];   // [c][q][k][a]
@@ -76,7 +76,7 @@ k_gsf(const __grid_constant__ GsfArgs A) {
   // ---- what this thread owns -------------------------------------------------------
   bool active;
   long long inner = 0, uoff = 0;
-  long long rowoff = 0, inrow = 0, len01 = 1;        // LAST && PAIR
+  int rowoff = 0, inrow = 0, len01 = 1;              // LAST && PAIR
   if (!LAST) {
     active = t < A.ninner;
     if (active) {
@@ -116,12 +116,12 @@ k_gsf(const __grid_constant__ GsfArgs A) {
       const long long dj1 = rem2 / l0, dj0 = rem2 - dj1 * l0;
       f1 = (A.dim == 3) ? A.S1[i1] + dj1 : 0;
       inner = f1 * A.F0 + A.S0[i0] + dj0;
-      rowoff = (long long)i1 * A.n0 + i0;
-      inrow = rem2;
-      len01 = l0 * l1;
+      rowoff = i1 * A.n0 + i0;
+      inrow = (int)rem2;
+      len01 = (int)(l0 * l1);
     }
   }
-  const long long nplane = (long long)A.n0 * A.n1;
+  const int nplane = A.n0 * A.n1;
 
   GsfAcc<NL, PAIR> acc;
 #pragma unroll
@@ -147,12 +147,36 @@ k_gsf(const __grid_constant__ GsfArgs A) {
       if (r < 0 || r >= A.nrL) return;
       double* p;
       if (PAIR)
-        p = A.out + A.rowptr[r * nplane + rowoff] + (long long)(j - A.col0L - A.loL[r]) * len01 + inrow;
+        p = A.out + A.rowptr[(long long)r * nplane + rowoff] +
+            (long long)((j - A.col0L - A.loL[r]) * len01 + inrow);
       else
-        p = A.out + r * nplane + inner;
+        p = A.out + (long long)r * nplane + inner;
       *p = add ? *p + val : val;
     }
   };
+
+  // one-ahead software prefetch over the flattened (cell, input) items: the next item's Gauss
+  // point values are in flight while the current one is contracted
+  auto load_item = [&](int e, int in, double* x) {
+    const int kin = plan[1 + 3 * in];
+    const double* xp = A.X + kin * A.skin + (long long)(e - A.cbase) * A.scell + inner * NQ;
+    if constexpr (NQ % 2 == 0) {
+#pragma unroll
+      for (int q = 0; q < NQ; q += 2) {
+        const double2 v = __ldcs(reinterpret_cast<const double2*>(xp + q));
+        x[q] = v.x;
+        x[q + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < NQ; q++) x[q] = __ldcs(xp + q);
+    }
+  };
+  double xn[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; q++) xn[q] = 0.0;
+  int en = A.c0, inn = 0;
+  if (active && nin > 0 && en < A.c1) load_item(en, inn, xn);
 
   for (int cb = A.c0; cb < A.c1; cb += GSF_CB) {
     const int ncb = min(GSF_CB, A.c1 - cb);
@@ -174,20 +198,15 @@ k_gsf(const __grid_constant__ GsfArgs A) {
       const int e = cb + c;
       if (active) {
         for (int in = 0; in < nin; in++) {
-          const int kin = plan[1 + 3 * in], al = plan[2 + 3 * in], be = plan[3 + 3 * in];
-          const double* xp = A.X + kin * A.skin + (long long)(e - A.cbase) * A.scell + inner * NQ;
+          const int al = plan[2 + 3 * in], be = plan[3 + 3 * in];
           double x[NQ];
-          if constexpr (NQ % 2 == 0) {
 #pragma unroll
-            for (int q = 0; q < NQ; q += 2) {
-              const double2 v = __ldcs(reinterpret_cast<const double2*>(xp + q));
-              x[q] = v.x;
-              x[q + 1] = v.y;
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < NQ; q++) x[q] = __ldcs(xp + q);
+          for (int q = 0; q < NQ; q++) x[q] = xn[q];
+          if (++inn == nin) {
+            inn = 0;
+            en++;
           }
+          if (en < A.c1) load_item(en, inn, xn);
 #pragma unroll
           for (int q = 0; q < NQ; q++) {
             const double* ta = &stab[((c * NQ + q) * 3 + al) * NLP];

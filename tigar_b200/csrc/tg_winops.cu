@@ -971,6 +971,60 @@ extern "C" int tg_win_zero_rows_cols(const tg_win* h_w, double* vals, const uint
   return 0;
 }
 
+// Same operation when the constrained set is a union of whole hyperplanes (side DoFs of
+// getSideDofs, BSplines.py:599-649, the usual case): hp[d][c] != 0 marks a constrained
+// hyperplane c of direction d (GLOBAL coordinates).  A row is touched only if it is constrained
+// itself or its window reaches a constrained hyperplane in some direction, so interior rows
+// leave after a handful of 1-byte loads instead of testing every column against the mask.
+__global__ void k_win_zero_rows_cols_hp(TgWin w, double* __restrict__ vals, int64_t nrows,
+                                        const uint8_t* __restrict__ hp0,
+                                        const uint8_t* __restrict__ hp1,
+                                        const uint8_t* __restrict__ hp2, double diag) {
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= nrows) return;
+  int rc[3];
+  tg_decode(r, w.nr, w.dim, rc);
+  const TgRowWin rw = tg_row_window(w, rc);
+  const uint8_t* hp[3] = {hp0, hp1, hp2};
+  bool mr = false, touch = false;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    if (d >= w.dim) continue;
+    mr = mr || hp[d][rc[d] + w.row0[d]] != 0;
+    for (int c = 0; c < rw.len[d]; c++) touch = touch || hp[d][rw.lo[d] + c + w.col0[d]] != 0;
+  }
+  if (!mr && !touch) return;
+  const TgRowAddr ra = tg_row_addr(w, rc, rw);
+  const int tot = rw.len[0] * rw.len[1] * rw.len[2];
+  for (int pos = lane; pos < tot; pos += 32) {
+    const int c0 = pos % rw.len[0];
+    const int t = pos / rw.len[0];
+    const int c1 = t % rw.len[1], c2 = t / rw.len[1];
+    int cc[3] = {rw.lo[0] + c0 + w.col0[0], rw.lo[1] + c1 + w.col0[1], rw.lo[2] + c2 + w.col0[2]};
+    bool mc = false, own = true;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      if (d >= w.dim) continue;
+      mc = mc || hp[d][cc[d]] != 0;
+      own = own && cc[d] == rc[d] + w.row0[d];
+    }
+    if (mr || mc) vals[ra.base + pos] = (mr && own) ? diag : 0.0;
+  }
+}
+
+extern "C" int tg_win_zero_rows_cols_hp(const tg_win* h_w, double* vals, const uint8_t* hp0,
+                                        const uint8_t* hp1, const uint8_t* hp2, double diag,
+                                        void* stream) {
+  TG_REQUIRE(h_w->layout == 0, "hyperplane BC kernel needs the row-major window layout");
+  int64_t nrows = tg_win_nrows(h_w);
+  if (nrows == 0) return 0;
+  k_win_zero_rows_cols_hp<<<(unsigned)tg_cdiv(nrows * 32, 256), 256, 0, tg_stream(stream)>>>(
+      tg_win_dev(h_w), vals, nrows, hp0, hp1, hp2, diag);
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void k_win_diag_inv(TgWin w, const double* __restrict__ vals, int64_t nrows,
                                int col_shift, double* __restrict__ dinv) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;

@@ -1222,8 +1222,35 @@ class TensorPatch(object):
             check(lib.tg_mask_set(dev.ptr(m), dev.ptr(dz), z.size, self.n_iga, dev.stream()))
         return m
 
+    def mask_planes(self, mask):
+        """(hp, exact): hp[d] = device uint8 flags of the hyperplanes of direction d that are
+        constrained as a whole; exact = the mask is exactly their union (side DoFs).  Cached
+        per mask tensor."""
+        hit = getattr(self, "_hp_cache", None)
+        if hit is not None and hit[0] is mask:
+            return hit[1], hit[2]
+        shape = tuple(reversed(self.ncp))
+        m = mask.view(shape) != 0
+        hp, nfree = [], 1
+        for d in range(self.dim):
+            ax = self.dim - 1 - d
+            other = tuple(a for a in range(self.dim) if a != ax)
+            full = (m.all(dim=other) if other else m).to(dev.U8).contiguous()
+            hp.append(full)
+            nfree *= self.ncp[d] - int(full.sum().item())
+        exact = int(m.sum().item()) == self.n_iga - nfree
+        self._hp_cache = (mask, hp, exact)
+        return hp, exact
+
     def apply_bcs_matrix(self, Cm, mask, diag=1.0):
         Cm.bc_mask, Cm.bc_diag = mask, float(diag)      # read by the preconditioned solvers
+        if Cm.window.layout == 0 and os.environ.get("TIGAR_B200_BC_HP", "1") == "1":
+            hp, exact = self.mask_planes(mask)
+            if exact:
+                P = [dev.ptr(hp[d]) if d < self.dim else None for d in range(3)]
+                check(lib.tg_win_zero_rows_cols_hp(Cm.window.ref(), dev.ptr(Cm.vals), P[0], P[1],
+                                                   P[2], float(diag), dev.stream()))
+                return Cm
         if self.part is not None:
             pp, pl = self.pp, self.plane
             rowmask = mask[pp["k0"] * pl:pp["k1"] * pl]

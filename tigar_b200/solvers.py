@@ -186,7 +186,7 @@ class FastDiag(object):
             self._gemm(0, 0, n0 * n1, n2, n2, a, n0 * n1, 0, U[2], n2, 0, b, n0 * n1, 0, 1)
             a, b = b, a
         L = [dev.ptr(l) for l in self.lam] + [None] * (3 - dim)
-        check(lib.tg_fd_scale(a, L[0], L[1], L[2], n0, n1, n2, self.sigma, 1, st))
+        check(lib.tg_fd_scale(a, L[0], L[1], L[2], n0, n1, n2, 0, n0 * n1, self.sigma, 1, st))
         # backward: U_d
         if dim > 2:
             self._gemm(0, 1, n0 * n1, n2, n2, a, n0 * n1, 0, U[2], n2, 0, b, n0 * n1, 0, 1)

@@ -20,6 +20,8 @@ def main(path, only=None):
     seen = set()
     for r in rows[2:]:
         name = r[H.index('Kernel Name')].split('(')[0]
+        if 'launch__grid_size' in H:          # instantiations shared by several stages
+            name += " grid=" + r[H.index('launch__grid_size')]
         if name in seen or (only and only not in name):
             continue
         seen.add(name)
