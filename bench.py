@@ -6,16 +6,25 @@ BCs -> solve) on synthetic tensor-product B-spline patches.
   python bench.py --gpus N --steps K --warmup W            (our CUDA path)
   python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm)
 
-Metric (BASELINE.json): IGA DoF/s end to end.  One "step" = one complete pass
-of the hot path over the patch.  Workload at N=1: BASELINE configs[1], 3-D
-cubic B-spline Poisson on 256^3 cells (17.4 M IGA DoFs), element-fused path
-(global A_FE would be 682 GB).
+Metric (BASELINE.json): IGA DoF/s end to end.  One "step" = one complete pass of the hot path
+over the patch, starting from the knot vectors: generators and Greville control net (made on
+the device inside the step), 1-D tables, Gauss-point kernel, global sum-factorised assembly of
+C = M^T A M and M^T b, homogeneous BCs, solve, solution vector.  Workload at N=1: BASELINE
+configs[1], 3-D cubic B-spline Poisson on 256^3 cells (17.4 M IGA DoFs), element-fused path
+(global A_FE would be 682 GB).  N>1: the same patch, slabs of IGA planes per
+rank (strong scaling), launched by torchrun.
 
-  value     device-timed throughput, control net / knots already resident in HBM
-  e2e       same pass through the tIGAr API from HOST buffers (pinned control
-            net H2D, solution vector D2H inside the timed region)
-  roofline  the dominant kernel (windowed SpMV inside CG, HBM-bound), timed
-            live with CUDA events on the solver stream
+  value      device-timed throughput (max over ranks)
+  e2e        same pass through the tIGAr API with the host->device copies of its inputs
+             (knot vectors, zero-DoF lists) and the device->host read of the solution vector
+             inside the timed region
+  roofline   the kernel class with the largest share of the step, timed live with CUDA events
+             on the launching stream inside the timed region; `rooflines` lists every class
+             (HBM fraction on algorithmic bytes, FP64 fraction on algorithmic flops against
+             the DFMA peak measured by tg_fp64_peak)
+  parity     checks of the LAST timed step printed in the line: true residual |b - C U|/|b|
+             recomputed with an independent SpMV, checksums of U, L2 error against the
+             manufactured solution -- identical across N up to round-off
   cpu_baseline  the numpy/scipy oracle ("port") on a bounded sample, host cores
 """
 import argparse
@@ -62,7 +71,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -103,45 +112,53 @@ class ClockSampler(object):
 
 # ------------------------------------------------------------------ problem
 def build_inputs(nel, net=True):
-    """Host-side inputs of one step: knot vectors (and, for callers that want the host
-    array, the Greville control net -- the timed step generates it on the device)."""
-    import numpy as np
+    """Host-side inputs of one step: knot vectors and the control-mesh object (and, for
+    callers that want the host array, the Greville control net -- the timed step generates it
+    on the device)."""
     import torch
     from tIGAr.BSplines import ExplicitBSplineControlMesh, uniformKnots
     kv = [uniformKnots(P, 0.0, 1.0, nel) for _ in range(3)]
     cm = ExplicitBSplineControlMesh([P] * 3, kv)
     if not net:
         return kv, cm, None
-    net = cm.controlNet()
-    pinned = torch.from_numpy(net)
+    pinned = torch.from_numpy(cm.controlNet())
     if torch.cuda.is_available():
         pinned = pinned.pin_memory()
     return kv, cm, pinned
 
 
-def one_step(kv, cm, control_net, mode, rtol, to_host):
-    """One pass of the hot path through the tIGAr API.  Returns
-    (n_dofs, cg_iterations, stage event list, result)."""
+def bench_pc():
+    return os.environ.get("TIGAR_B200_BENCH_PC", "fd")
+
+
+def one_step(kv, cm, control_net, mode, rtol, to_host, keep=False):
+    """One pass of the hot path through the tIGAr API.  ``control_net`` None: the generator
+    makes the Greville net on the device (the default of the product); ``cm`` None: the
+    control-mesh object is built inside the step as well.  Returns
+    (n_dofs, cg_iterations, stage event list, result, MTAM[, extras])."""
     import torch
     from tIGAr import (EqualOrderSpline, ExtractedSpline, TrialFunction, TestFunction,
                        Function, KrylovSolver, inner, sin, pi)
+    from tIGAr.BSplines import ExplicitBSplineControlMesh
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     ev[0].record()
+    if cm is None:
+        cm = ExplicitBSplineControlMesh([P] * 3, kv)
     gen = EqualOrderSpline(1, cm)
     sp = gen.getScalarSpline(0)
     for d in range(3):
         for side in (0, 1):
             gen.addZeroDofs(0, sp.getSideDofs(d, side))
     spline = ExtractedSpline(gen, 2 * P, mode=mode, controlNet=control_net)
-    ks = KrylovSolver("cg", os.environ.get("TIGAR_B200_BENCH_PC", "fd"))
+    ks = KrylovSolver("cg", bench_pc())
     ks.parameters["relative_tolerance"] = rtol
     spline.setSolverOptions(linearSolver=ks)
     ev[1].record()                                              # extract done
     u, v = TrialFunction(spline.V), TestFunction(spline.V)
     x = spline.spatialCoordinates()
-    f = 3 * pi ** 2 * sin(pi * x[0]) * sin(pi * x[1]) * sin(pi * x[2])
+    soln = sin(pi * x[0]) * sin(pi * x[1]) * sin(pi * x[2])
     a = inner(spline.grad(u), spline.grad(v)) * spline.dx
-    L = inner(f, v) * spline.dx
+    L = inner(3 * pi ** 2 * soln, v) * spline.dx
     MTAM, MTb = spline.assembleLinearSystem(a, L)
     ev[2].record()                                              # assemble + PtAP + BCs done
     uh = Function(spline.V)
@@ -149,7 +166,10 @@ def one_step(kv, cm, control_net, mode, rtol, to_host):
     ev[3].record()                                              # solve done
     res = U.get_local() if to_host else U.t
     ev[4].record()
-    return spline._patch.n_iga, spline.lastSolve["iterations"], ev, res, MTAM
+    out = (spline._patch.n_iga, spline.lastSolve["iterations"], ev, res, MTAM)
+    if keep:
+        out = out + (dict(spline=spline, MTb=MTb, U=U, uh=uh, soln=soln),)
+    return out
 
 
 def spmv_bytes(W):
@@ -159,11 +179,43 @@ def spmv_bytes(W):
     return 8 * W.nnz + (16 if W.layout == 1 else 24) * W.nrows
 
 
+def parity_checks(ex, MTAM, world):
+    """Driver-visible parity of the last timed step (outside the timed region): the true
+    residual with an independent SpMV on this rank's rows, checksums of the (replicated) IGA
+    DoF vector and the L2 error against the manufactured solution."""
+    import torch
+    from tIGAr import assemble
+    spline, U, b = ex["spline"], ex["U"].t, ex["MTb"].t
+    W = getattr(MTAM, "window", None)
+    out = {}
+    if W is not None:
+        p = spline._patch
+        if p.part is not None:
+            pp, pl = p.pp, p.plane
+            xe = U[pp["c0"] * pl:pp["c1"] * pl].contiguous()
+        else:
+            xe = U
+        r = MTAM.matvec(xe)
+        r.sub_(b)
+        s = torch.stack([(r * r).sum(), (b * b).sum()])
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(s)
+        out["true_relative_residual"] = math.sqrt(float(s[0]) / max(float(s[1]), 1e-300))
+    out["sum_U"] = float(U.sum())
+    out["norm_U"] = float(U.norm())
+    out["l2_error_vs_manufactured"] = math.sqrt(abs(assemble(((ex["uh"] - ex["soln"]) ** 2)
+                                                             * spline.dx)))
+    out["solver"] = spline.lastSolve.get("method")
+    out["solver_relative_residual"] = spline.lastSolve.get("relative_residual")
+    return out
+
+
 # ------------------------------------------------------------------ CPU arm
 _CPU_THREADS_USED = 1
 
 
-def cpu_port_step(nel):
+def cpu_port_step(nel, stages=None):
     import numpy as np
     from oracle import pipeline as OP
     from oracle import bsplines as OB
@@ -178,6 +230,8 @@ def cpu_port_step(nel):
     dt = time.perf_counter() - t
     global _CPU_THREADS_USED          # process CPU time / wall time of the last CPU step
     _CPU_THREADS_USED = max(1, int(round((time.process_time() - c) / max(dt, 1e-9))))
+    if stages is not None:
+        stages.update({k: round(v, 3) for k, v in pr.times.items()})
     return pr.ts.ncp, dt, pr.iters
 
 
@@ -223,7 +277,7 @@ def run_reference(args):
     nd = res[0][0]
     val = n / dt
     sample = ("%d concurrent independent copies (one per host core) of: 3-D cubic B-spline "
-              "Poisson, %d^3 cells (%d DoFs), CG rtol %g, single-copy time %.2f s"
+              "Poisson, %d^3 cells (%d DoFs), Jacobi-CG rtol %g, single-copy time %.2f s"
               % (procs, nel, nd, CG_RTOL, res[0][1]))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT,
@@ -231,7 +285,10 @@ def run_reference(args):
         "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "3D cubic B-spline Poisson %d^3 cells" % args.nel,
-                   "note": "CPU arm runs a bounded sample of the workload: " + sample},
+                   "note": "CPU arm runs a bounded sample of the workload: " + sample
+                           + ".  The per-DoF cost of the port grows with size (732 DoF/s per "
+                             "core at 32^3 vs 790 at 16^3, DESIGN.md 5), so the small sample "
+                             "flatters the CPU arm"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port",
                          "sample": sample + "; numpy/scipy oracle (FEniCS/PETSc absent)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -239,7 +296,28 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------ GPU arm
+def rooflines_from(prof, steps, ms_total, hbm_peak, fp64_peak):
+    rows = []
+    for name, d in prof.items():
+        if d["launches"] == 0 or d["ms"] <= 0:
+            continue
+        avg_ms = d["ms"] / d["launches"]
+        bpl = d["bytes"] / d["launches"]
+        fpl = d["flops"] / d["launches"]
+        gbs = bpl / (avg_ms * 1e-3) / 1e9
+        tfs = fpl / (avg_ms * 1e-3) / 1e12
+        rows.append({"kernel": name, "launches_per_step": d["launches"] / max(steps, 1),
+                     "ms_per_step": d["ms"] / max(steps, 1), "avg_launch_ms": avg_ms,
+                     "bytes_per_launch": bpl, "achieved_gbs": gbs, "hbm_frac": gbs / hbm_peak,
+                     "flops_per_launch": fpl, "achieved_tflops": tfs,
+                     "fp64_frac": (tfs / fp64_peak) if fp64_peak else None,
+                     "share_of_step": d["ms"] / ms_total if ms_total > 0 else None})
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    return rows
+
+
 def run_ours(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -249,131 +327,184 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from tigar_b200._lib import lib
-    import ctypes as C
+    from tigar_b200._lib import lib, check
+    from tigar_b200 import dev
 
-    if world > 1:
-        from tigar_b200 import multigpu
-        return multigpu.bench(args, METRIC, UNIT, CG_RTOL)
-
-    nel = args.nel
-    mode = args.mode
-    kv, cm, pinned = build_inputs(nel, net=False)
+    nel, mode = args.nel, args.mode
+    if world > 1 and mode != "fused":
+        raise SystemExit("multi-GPU runs use the element-fused path")
+    kv, cm, _ = build_inputs(nel, net=False)
 
     def barrier():
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
+
+    def maxr(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    fp64 = C.c_double(0.0)
+    check(lib.tg_fp64_peak(dev.ptr(dev.zeros(1)), C.byref(fp64), dev.stream()))
+    fp64_peak = fp64.value
+    hbm_peak, which = measured_peaks()
 
     for _ in range(args.warmup):
         one_step(kv, cm, None, mode, CG_RTOL, False)
     barrier()
 
-    # ---- device-resident timing (value) + live SpMV timing --------------------
+    # ---- device timing (value) with live per-kernel event timing ------------------------
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     lib.tg_prof_enable(1)
+    dev.PROF.start()
     l0 = lib.tg_launch_count()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     barrier()
     t0.record()
     stages = []
-    for _ in range(args.steps):
-        n_dofs, iters, ev, _, MTAM = one_step(kv, cm, None, mode, CG_RTOL, False)
+    r = MTAM = None
+    for k in range(args.steps):
+        del r, MTAM
+        r = one_step(kv, cm, None, mode, CG_RTOL, False, keep=(k == args.steps - 1))
+        n_dofs, iters, ev, _, MTAM = r[:5]
         stages.append(ev)
     t1.record()
     barrier()
-    ms = t0.elapsed_time(t1)
+    ms = maxr(t0.elapsed_time(t1))
     launches = lib.tg_launch_count() - l0
+    prof = dev.PROF.stop()
     spmv_ms, spmv_n = C.c_double(0), C.c_int64(0)
     lib.tg_prof_get(C.byref(spmv_ms), C.byref(spmv_n))
     lib.tg_prof_enable(0)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
+    extras = r[5]
     W = getattr(MTAM, "window", None)          # None: matrix-free operator (--mode matfree)
-    stage_ms = {"extract": 0.0, "assemble_ptap_bcs": 0.0, "solve": 0.0}
+    if spmv_n.value > 0 and W is not None:     # Jacobi-CG inside the C driver
+        prof["k_win_spmv (CG matvec + p.Ap)"] = dict(launches=int(spmv_n.value),
+                                                      ms=spmv_ms.value,
+                                                      bytes=spmv_bytes(W) * spmv_n.value,
+                                                      flops=2.0 * W.nnz * spmv_n.value)
+    stage_ms = [0.0, 0.0, 0.0]
     for ev in stages:
-        stage_ms["extract"] += ev[0].elapsed_time(ev[1])
-        stage_ms["assemble_ptap_bcs"] += ev[1].elapsed_time(ev[2])
-        stage_ms["solve"] += ev[2].elapsed_time(ev[3])
-    for k in stage_ms:
-        stage_ms[k] /= max(args.steps, 1)
-    del MTAM, stages
+        for i in range(3):
+            stage_ms[i] += ev[i].elapsed_time(ev[i + 1]) / max(args.steps, 1)
+    stage_ms = [maxr(v) for v in stage_ms]
+    parity = parity_checks(extras, MTAM, world)
+    nz = len(extras["spline"]._zeroDofsRaw)
+    local_nnz = W.nnz if W is not None else 0
+    del MTAM, stages, extras, r
     value = n_dofs * args.steps / (ms * 1e-3)
 
-    # ---- end to end from host buffers -----------------------------------------
-    for _ in range(1):
-        one_step(kv, cm, None, mode, CG_RTOL, True)
+    # ---- end to end: host inputs in, host solution out ------------------------------------
+    one_step(kv, None, None, mode, CG_RTOL, rank == 0)
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     wall0 = time.perf_counter()
     for _ in range(args.steps):
-        _, _, _, res, MT = one_step(kv, cm, None, mode, CG_RTOL, True)
-        del MT
+        rr = one_step(kv, None, None, mode, CG_RTOL, rank == 0)
+        del rr
     e1.record()
     barrier()
-    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - wall0))
+    e2e_ms = maxr(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - wall0)))
     e2e = {"value": n_dofs * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-           "h2d_bytes_per_step": int(sum(len(k) for k in kv) * 8),
-           "d2h_bytes_per_step": int(n_dofs * 8)}
+           "h2d_bytes_per_step": int((sum(len(k) for k in kv) * 8 + nz * 8) * world),
+           "d2h_bytes_per_step": int(n_dofs * 8),
+           "note": "inputs = knot vectors + zero-DoF lists (every rank uploads its copy); the "
+                   "Greville control net is generated on the device inside the step; output = "
+                   "the IGA DoF vector read back by rank 0"}
+    if rank != 0:
+        dist.barrier()
+        dist.destroy_process_group()
+        return
 
-    peak, which = measured_peaks()
-    bytes_per_launch = spmv_bytes(W) if W is not None else 0
-    avg_ms = spmv_ms.value / max(spmv_n.value, 1)
-    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    kname = {0: "k_win_spmv<true>", 1: "k_win_spmv_tma<true>", 2: "k_sell_spmv<7,true>", 3: "k_win_spmv_pf<true>"}[
-        int(lib.tg_last_spmv_kind())]
-    if W is None:
-        kname = "none timed (matrix-free: tigar_qp + k_assemble_vector per CG iteration)"
-    roofline = {"bound": "hbm", "kernel": kname + " (CG matvec + p.Ap partials)",
-                "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
-                "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
-                "launches_timed": int(spmv_n.value),
-                "share_of_step": spmv_ms.value / ms if ms > 0 else None}
-    tfile = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    rows = rooflines_from(prof, args.steps, ms, hbm_peak, fp64_peak)
+    traffic = {}
+    tfile = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
     if os.path.exists(tfile):
         try:
             with open(tfile) as f:
-                roofline["traffic"] = json.load(f).get(str(nel))
+                traffic = json.load(f).get("%d_n%d" % (nel, world), {})
         except Exception:
-            pass
+            traffic = {}
+    for r_ in rows:
+        r_["traffic"] = traffic.get(r_["kernel"])
+    if rows:
+        top = rows[0]
+        hbm_bound = top["hbm_frac"] >= (top["fp64_frac"] or 0.0)
+        roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"],
+                    "peak": hbm_peak, "peak_source": which, "unit": "GB/s",
+                    "frac": top["hbm_frac"], "traffic": top["traffic"],
+                    "traffic_source": ("ncu --set full dram__bytes per launch, profiles/"
+                                       "r2_ncu_traffic.json") if top["traffic"] else None,
+                    "bytes_per_launch": top["bytes_per_launch"],
+                    "avg_launch_ms": top["avg_launch_ms"],
+                    "launches_timed": int(round(top["launches_per_step"] * args.steps)),
+                    "share_of_step": top["share_of_step"],
+                    "fp64_frac": top["fp64_frac"], "fp64_peak_tflops": fp64_peak,
+                    "limiter": "hbm" if hbm_bound else "fp64 pipe (no FP64 tensor path on B200)"}
+    else:
+        roofline = {"bound": "hbm", "kernel": "none timed", "achieved": 0.0, "peak": hbm_peak,
+                    "peak_source": which, "unit": "GB/s", "frac": 0.0, "traffic": None}
 
+    wl = "3D cubic B-spline Poisson %d^3 cells" % nel
+    if nel == 256:
+        wl += ", %d GPU%s (BASELINE configs[1])" % (world, "" if world == 1 else "s")
+    pc = bench_pc()
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D cubic B-spline Poisson %d^3 cells, 1 GPU (BASELINE configs[1])"
-                               % nel if nel == 256 else
-                               "3D cubic B-spline Poisson %d^3 cells" % nel,
-                   "degree": P, "cells": nel ** 3, "iga_dofs": n_dofs, "path": mode,
-                   "quad_degree": 2 * P, "cg_rtol": CG_RTOL, "cg_iterations": iters,
-                   "preconditioner": os.environ.get("TIGAR_B200_BENCH_PC", "fd"),
-                   "l2": ("inputs larger than L2 (matrix %.1f GB streamed every CG iteration)"
-                          % (8e-9 * W.nnz)) if W is not None else
+        "config": {"workload": wl, "degree": P, "cells": nel ** 3, "iga_dofs": n_dofs,
+                   "path": mode, "quad_degree": 2 * P, "cg_rtol": CG_RTOL,
+                   "cg_iterations": iters,
+                   "preconditioner": {"fd": "fast diagonalisation (tensor-product eigenbasis)",
+                                      "jacobi": "jacobi"}.get(pc, pc),
+                   "partition": None if world == 1 else
+                   "slabs of IGA planes (last direction), p halo cell layers recomputed, "
+                   "row-distributed CG over NCCL (halo send/recv, all-reduced scalars, "
+                   "all-to-all transposes inside the FD preconditioner)",
+                   "l2": ("inputs larger than L2 (local matrix %.1f GB, intermediates of the "
+                          "assembly streamed once)" % (8e-9 * local_nnz)) if W is not None else
                          "inputs larger than L2 (matrix-free: control net, operand and "
                          "coefficient chunks streamed every CG iteration)"},
-        "stage_ms": stage_ms, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline}
+        "stage_ms": {"extract": stage_ms[0], "assemble_ptap_bcs": stage_ms[1],
+                     "solve": stage_ms[2]},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "parity": parity,
+        "roofline": roofline, "rooflines": rows,
+        "fp64_peak_tflops_measured": fp64_peak}
 
-    if not args.no_ptap:
+    if world == 1 and not args.no_ptap:
+        torch.cuda.empty_cache()
         try:
-            out["ptap"] = ptap_roofline(args.ptap_nel, peak)
+            out["ptap"] = ptap_roofline(args.ptap_nel, hbm_peak)
         except Exception as e:                  # keep the headline line if the extra fails
             out["ptap"] = {"error": "%s: %s" % (type(e).__name__, e)}
-    if not args.no_cpu:
-        nd, dt, its = cpu_port_step(args.cpu_nel)
+    if world == 1 and not args.no_cpu:
+        st = {}
+        nd, dt, its = cpu_port_step(args.cpu_nel, st)
         out["cpu_baseline"] = {
             "value": nd / dt, "unit": UNIT, "cores": _CPU_THREADS_USED, "kind": "port",
-            "sample": "same problem at %d^3 cells (%d DoFs), one pass, %.1f s, CG its %d; "
+            "stage_s": st,
+            "sample": "same problem at %d^3 cells (%d DoFs), one pass, %.1f s, Jacobi-CG its %d; "
                       "numpy/scipy oracle; cores = process CPU time / wall time (%d host "
                       "cores available)" % (args.cpu_nel, nd, dt, its, os.cpu_count() or 1)}
     print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def ptap_roofline(nel, peak):
     """The global-CSR M^T A M (MatPtAP, common.py:1194-1195) at a 3-D cubic size
-    whose operands are cheap to hold -- BASELINE.json's second metric.
+    whose operands fit one GPU -- BASELINE.json's second metric.
     ``achieved`` uses BASELINE.md's algorithmic bytes (CSR(A) + CSR(M) + CSR(C)
     with 8 B value + 4 B column per nnz + 4 B row pointer per row, each operand
     once); ``streamed`` is what the three march passes move by design (8 B/value,
@@ -384,8 +515,11 @@ def ptap_roofline(nel, peak):
     from tIGAr.BSplines import uniformKnots
     kv = [uniformKnots(P, 0.0, 1.0, nel)] * 3
     patch = TensorPatch([P] * 3, kv)
-    A = WinMatrix(patch.window("A"))
-    A.vals.copy_(torch.rand(A.window.nnz, dtype=torch.float64, device="cuda"))
+    wA = patch.window("A")
+    A = WinMatrix(wA, torch.empty(wA.nnz, dtype=torch.float64, device="cuda"))
+    chunk = 1 << 28
+    for o in range(0, wA.nnz, chunk):             # random fill without a second 57 GB tensor
+        A.vals[o:o + chunk].uniform_(0.0, 1.0)
     ts = []
     for rep in range(6):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -423,15 +557,15 @@ def ptap_roofline(nel, peak):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nel", type=int, default=256)
     ap.add_argument("--mode", default="fused", choices=["fused", "csr", "matfree"])
-    ap.add_argument("--cpu-nel", type=int, default=20)
+    ap.add_argument("--cpu-nel", type=int, default=24)
     ap.add_argument("--ref-nel", type=int, default=16)
     ap.add_argument("--ref-procs", type=int, default=0, help="CPU arm: concurrent copies (0 = all cores)")
-    ap.add_argument("--ptap-nel", type=int, default=64)
+    ap.add_argument("--ptap-nel", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ptap", action="store_true")
     args = ap.parse_args()

@@ -20,7 +20,10 @@ def main():
     from gpu_util import make_pair, uk, rel
     from tIGAr import TrialFunction, TestFunction, Function, inner, sin, pi, assemble, mpirank
     PI = math.pi
-    for deg, nels in [([3, 3, 3], [6, 5, 9]), ([2, 2, 2], [5, 5, 4]), ([2, 2], [9, 11])]:
+    cases = [(s, d, n) for s in ("fd", "jacobi")
+             for d, n in [([3, 3, 3], [6, 5, 9]), ([2, 2, 2], [5, 5, 4]), ([2, 2], [9, 11])]]
+    for solver, deg, nels in cases:
+        os.environ["TIGAR_B200_SOLVER"] = solver      # row-distributed FD-CG / Jacobi-CG
         kv = [uk(p, n) for p, n in zip(deg, nels)]
         gen, spline, pr = make_pair(deg, kv, mode=None)
         assert spline.mode == "fused" and spline.patch().part is not None
@@ -38,11 +41,27 @@ def main():
         l2 = math.sqrt(assemble(((uh - soln) ** 2) * spline.dx))
         l2o = pr.error(Uo, "l2", lambda X: np.prod(np.sin(PI * X[..., :len(deg)]), axis=-1))
         ok = err < 1e-10 and abs(l2 - l2o) / l2o < 1e-6
-        print("rank %d deg %s: rel diff vs oracle %.2e, its %d, L2 %.6e vs %.6e -> %s"
-              % (dist.get_rank(), deg, err, spline.lastSolve["iterations"], l2, l2o,
+        ok = ok and spline.lastSolve["method"] == solver
+        if solver == "fd":                            # exact preconditioner on this geometry
+            ok = ok and spline.lastSolve["iterations"] <= 2
+        print("rank %d %s deg %s: rel diff vs oracle %.2e, its %d, L2 %.6e vs %.6e -> %s"
+              % (dist.get_rank(), solver, deg, err, spline.lastSolve["iterations"], l2, l2o,
                  "OK" if ok else "FAIL"), flush=True)
         if not ok:
             sys.exit(1)
+    # curved rational geometry (configs[3] in small): FD-CG across ranks against the oracle
+    os.environ["TIGAR_B200_SOLVER"] = "fd"
+    from test_gpu_nurbs import build, forms
+    spline, pr = build(3, [5, 6, 7], 3, None)
+    a, L = forms(spline, 3)
+    uh = Function(spline.V)
+    U = spline.solveLinearVariationalProblem(a == L, uh)
+    Uo = pr.run(lambda X: np.sin(PI * X[..., 0]) * X[..., 1] + 1.0)
+    err = rel(U.get_local(), Uo)
+    print("rank %d annulus: rel diff vs oracle %.2e, FD-CG its %d" % (
+        dist.get_rank(), err, spline.lastSolve["iterations"]), flush=True)
+    if not (err < 1e-10 and spline.lastSolve["iterations"] < 60):
+        sys.exit(1)
     dist.barrier()
     dist.destroy_process_group()
     print("MGPU_PARITY_OK", flush=True)

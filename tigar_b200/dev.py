@@ -56,3 +56,53 @@ def stream():
 
 def sync():
     torch.cuda.current_stream().synchronize()
+
+
+class _Prof(object):
+    """Live per-kernel timing for bench.py's rooflines: CUDA events on the stream the kernels
+    are launched on (torch's current stream), recorded around every launch of a named kernel
+    class together with its algorithmic bytes / flops.  Off unless ``start()`` was called."""
+
+    def __init__(self):
+        self.on = False
+        self.rec = {}
+
+    def start(self):
+        self.on = True
+        self.rec = {}
+
+    class _Range(object):
+        def __init__(self, prof, name, nbytes, flops):
+            self.p, self.name, self.nbytes, self.flops = prof, name, nbytes, flops
+
+        def __enter__(self):
+            if self.p.on:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e1 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+            return self
+
+        def __exit__(self, *exc):
+            if self.p.on:
+                self.e1.record()
+                self.p.rec.setdefault(self.name, []).append((self.e0, self.e1, self.nbytes,
+                                                             self.flops))
+            return False
+
+    def range(self, name, nbytes=0, flops=0):
+        return self._Range(self, name, nbytes, flops)
+
+    def stop(self):
+        """-> {name: dict(launches, ms, bytes, flops)} (synchronises)."""
+        self.on = False
+        torch.cuda.synchronize()
+        out = {}
+        for name, lst in self.rec.items():
+            ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in lst)
+            out[name] = dict(launches=len(lst), ms=ms, bytes=sum(x[2] for x in lst),
+                             flops=sum(x[3] for x in lst))
+        self.rec = {}
+        return out
+
+
+PROF = _Prof()

@@ -667,7 +667,8 @@ class TensorPatch(object):
             lc = min(lc_max, self.slab_hi - k)
             ncells = lc * plane_cells
             X0 = buf("X0", nslots * ncells * nqp)
-            self._qp_eval(B, P, k * plane_cells, ncells, X0, gsf=(ncells * nqp, lc, k))
+            with dev.PROF.range("tigar_qp (generated Gauss-point kernel)", 8 * nslots * ncells * nqp):
+                self._qp_eval(B, P, k * plane_cells, ncells, X0, gsf=(ncells * nqp, lc, k))
             for pair, st, G, out in ((1, mst, F, A), (0, vst, n, b)):
                 if st is None:
                     continue
@@ -680,7 +681,11 @@ class TensorPatch(object):
                     n1o, mi1, t1 = st[0]
                     Y1 = buf(tag + "Y1", n1o * nel[1] * G[0] * nq2c * nq[1])
                     ninner = nel[1] * nq2c * nq[1]
-                    check(lib.tg_gsf_stage(
+                    nin_tot = int(t1[:, 0].sum())
+                    with dev.PROF.range("k_gsf %s stage 1" % ("matrix" if pair else "vector"),
+                                        8 * (nin_tot * ncells * nqp + n1o * nel[1] * G[0] * nq2c * nq[1]),
+                                        2.0 * nin_tot * ncells * nqp * nl[0] * (nl[0] if pair else 1)):
+                      check(lib.tg_gsf_stage(
                         dev.ptr(X0), ncells * nqp, ninner * nq[0], 0, 0, nel[0], nel[0], nl[0],
                         nq[0], nd, tabs[0][0], tabs[0][1], dev.ptr(rbs[0]),
                         dev.ptr(dplan((tag, 0), t1)), n1o, mi1, pair, ninner, nq2c, nq[1],
@@ -690,7 +695,12 @@ class TensorPatch(object):
                     n2o, mi2, t2 = st[1]
                     Y2 = buf(tag + "Y2", n2o * lc * G[1] * G[0] * nq[2])
                     ninner = G[0] * nq2c
-                    check(lib.tg_gsf_stage(
+                    nin_tot = int(t2[:, 0].sum())
+                    y1sz = nel[1] * G[0] * nq2c * nq[1]
+                    with dev.PROF.range("k_gsf %s stage 2" % ("matrix" if pair else "vector"),
+                                        8 * (nin_tot * y1sz + n2o * lc * G[1] * G[0] * nq[2]),
+                                        2.0 * nin_tot * y1sz * nl[1] * (nl[1] if pair else 1)):
+                      check(lib.tg_gsf_stage(
                         dev.ptr(Y1), nel[1] * G[0] * nq2c * nq[1], ninner * nq[1], 0, 0, nel[1],
                         nel[1], nl[1], nq[1], nd, tabs[1][0], tabs[1][1], dev.ptr(rbs[1]),
                         dev.ptr(dplan((tag, 1), t2)), n2o, mi2, pair, ninner, lc, nq[2],
@@ -702,7 +712,11 @@ class TensorPatch(object):
                     n1o, mi1, t1 = st[0]
                     Y1 = buf(tag + "Y1", n1o * lc * G[0] * nq[1])
                     ninner = lc * nq[1]
-                    check(lib.tg_gsf_stage(
+                    nin_tot = int(t1[:, 0].sum())
+                    with dev.PROF.range("k_gsf %s stage 1" % ("matrix" if pair else "vector"),
+                                        8 * (nin_tot * ncells * nqp + n1o * lc * G[0] * nq[1]),
+                                        2.0 * nin_tot * ncells * nqp * nl[0] * (nl[0] if pair else 1)):
+                      check(lib.tg_gsf_stage(
                         dev.ptr(X0), ncells * nqp, ninner * nq[0], 0, 0, nel[0], nel[0], nl[0],
                         nq[0], nd, tabs[0][0], tabs[0][1], dev.ptr(rbs[0]),
                         dev.ptr(dplan((tag, 0), t1)), n1o, mi1, pair, ninner, 1, nq[1],
@@ -710,7 +724,16 @@ class TensorPatch(object):
                         None, dev.stream()))
                     Xl, skl, scl, ninl = Y1, lc * G[0] * nq[1], G[0] * nq[1], G[0]
                 nlo, mil, tl = st[L]
-                check(lib.tg_gsf_stage(
+                nin_tot = int(tl[:, 0].sum())
+                if pair:       # bytes: the stage input once + the rows of C these layers finish
+                    outb = 8.0 * W.nnz * lc / max(1, self.slab_hi - self.slab_lo)
+                else:
+                    outb = 8.0 * ninl * lc
+                with dev.PROF.range("k_gsf %s stage %d (writes %s)" % (
+                        "matrix" if pair else "vector", dim, "C" if pair else "b"),
+                        8 * nin_tot * skl + outb,
+                        2.0 * nin_tot * skl * nl[L] * (nl[L] if pair else 1)):
+                  check(lib.tg_gsf_stage(
                     dev.ptr(Xl), skl, scl, k, k, k + lc, nel[L], nl[L], nq[L], nd, tabs[L][0],
                     tabs[L][1], dev.ptr(rbs[L]), dev.ptr(dplan((tag, L), tl)), nlo, mil, pair,
                     ninl, 1, 1, None, 0, 0, 0, 0, 1, W.ref() if pair else None, G[0],
@@ -1278,8 +1301,8 @@ class TensorPatch(object):
         Returns (x, iterations, relative residual, method used)."""
         from . import solvers
         method = os.environ.get("TIGAR_B200_SOLVER", method)
-        if self.part is not None:
-            method = "jacobi" if method in ("auto", "direct") else method
+        if self.part is not None and method in ("auto", "direct"):
+            method = "fd"           # row-distributed system: FD-preconditioned CG over NCCL
         if method == "auto":
             import torch
             free, _ = torch.cuda.mem_get_info()
@@ -1287,11 +1310,24 @@ class TensorPatch(object):
         if method == "direct":
             bc = solvers.BandCholesky(Cm).factor()
             xs = bc.solve(b)
-            # true relative residual of the direct solution (one SpMV)
-            r = Cm.matvec(xs)
-            r.sub_(b)
+            # iterative refinement with the true residual (one SpMV + one pair of band solves
+            # per pass): removes the round-off the factorisation accumulates over a wide band,
+            # which is what limits the answer when cond ~ h^-4 (biharmonic, configs[2])
             bb = float(b.norm())
+            r = Cm.matvec(xs)
+            r.neg_().add_(b)
             rel = float(r.norm()) / bb if bb > 0 else 0.0
+            for _ in range(3):
+                if rel < 1e-15:
+                    break
+                dx = bc.solve(r)
+                check(lib.tg_axpy(dev.ptr(dx), 1.0, dev.ptr(xs), dx.numel(), dev.stream()))
+                r2 = Cm.matvec(dx)
+                r2.neg_().add_(b)
+                rel2 = float(r2.norm()) / bb if bb > 0 else 0.0
+                if not rel2 < rel:
+                    break
+                xs, r, rel = dx, r2, rel2
             return xs, 1, rel, "direct"
         if method == "fd":
             if self.part is not None:

@@ -23,11 +23,7 @@ tensor-product structure gives that alignment for free:
 logic is exercised on CPU with the gloo backend (tests/test_multigpu_cpu.py)
 while the product always runs it with ``DeviceOps`` (the C-ABI kernels).
 """
-import ctypes as C
-import json
 import math
-import os
-import time
 
 import numpy as np
 
@@ -216,6 +212,201 @@ class DeviceOps(object):
         return self.x
 
 
+
+# ----------------------------------------------------------------------------
+class FastDiagDist(object):
+    """Fast-diagonalisation preconditioner (tigar_b200/solvers.py) on a slab-distributed
+    vector.  The mode products of the first directions are local to a slab; the one along the
+    LAST (partitioned) direction needs whole fibres, so the vector is re-partitioned by an
+    all-to-all over NVLink into chunks of the (i0, i1) plane index, transformed, scaled in
+    the eigenbasis, transformed back and returned by the reverse all-to-all: two exchanges
+    of the local vector (17 MB per rank at 256^3 on 8 GPUs) per application -- the path's
+    one genuine exchange step besides the halo of the matvec."""
+
+    def __init__(self, patch, mask, diag, dinv_local):
+        import torch
+        import torch.distributed as dist
+        from . import dev, solvers
+        from ._lib import lib, check
+        self.torch, self.dist, self.dev, self.lib, self.check = torch, dist, dev, lib, check
+        self.patch = patch
+        self.rank, self.size = patch.part
+        pp = patch.pp
+        self.dim = patch.dim
+        L = self.dim - 1
+        self.k0, self.k1 = pp["k0"], pp["k1"]
+        self.nl = self.k1 - self.k0
+        self.plane = patch.plane
+        self.nloc = patch.n_loc
+        self.nd = list(patch.ncp) + [1] * (3 - self.dim)
+        self.nL = patch.ncp[L]
+        bounds = pp["bounds"]
+        self.bounds = bounds
+        # plane chunks of the transposed partition
+        self.q = [(self.plane * r) // self.size for r in range(self.size + 1)]
+        self.mq = self.q[self.rank + 1] - self.q[self.rank]
+        self.gmask = mask
+        self.lmask = None if mask is None else mask[self.k0 * self.plane:self.k1 * self.plane]
+        self.cinv = 1.0 / float(diag) if diag else 1.0
+        # 1-D eigen data: every rank computes the (tiny) decompositions itself
+        helper = solvers.FastDiag.__new__(solvers.FastDiag)
+        helper.patch, helper.dim = patch, self.dim
+        free = solvers.FastDiag._free_planes(helper, mask)
+        eig = [solvers._gen_eig(D, free[d]) for d, D in enumerate(patch.dirs)]
+        c, sigma = self._fit(eig, free, dinv_local)
+        self.weights, self.sigma = c, sigma
+        self.lam = [dev.from_np(c[d] * eig[d][0]) for d in range(self.dim)]
+        self.U = [dev.from_np(np.ascontiguousarray(eig[d][1].T)) for d in range(self.dim)]
+        self.t1 = dev.empty(max(self.nloc, self.mq * self.nL))
+        self.t2 = dev.empty(max(self.nloc, self.mq * self.nL))
+        self.send_splits = [(self.q[s + 1] - self.q[s]) * self.nl for s in range(self.size)]
+        self.recv_splits = [self.mq * (bounds[s + 1] - bounds[s]) for s in range(self.size)]
+
+    def _fit(self, eig, free, dinv_local):
+        """Least-squares fit of the direction weights to diag(C) (solvers.FastDiag._fit) with
+        the right-hand side summed over the ranks."""
+        torch, dist, dev, lib, check = self.torch, self.dist, self.dev, self.lib, self.check
+        dim, L = self.dim, self.dim - 1
+        md = [eig[d][2] for d in range(dim)]
+        kd = [eig[d][3] for d in range(dim)]
+        d_md = [dev.from_np(a) for a in md]
+        d_kd = [dev.from_np(a) for a in kd]
+        scratch = dev.empty(256)
+        out4 = dev.zeros(4)
+
+        def P(Lst, d):
+            if d >= dim:
+                return None
+            return dev.ptr(Lst[d]) + (8 * self.k0 if d == L else 0)
+        nloc3 = list(self.nd)
+        nloc3[L] = self.nl
+        dC = dinv_local.reciprocal()
+        check(lib.tg_fd_fit(dev.ptr(dC), dev.ptr(self.lmask) if self.lmask is not None else None,
+                            P(d_kd, 0), P(d_kd, 1), P(d_kd, 2), P(d_md, 0), P(d_md, 1),
+                            P(d_md, 2), nloc3[0], nloc3[1], nloc3[2], dev.ptr(scratch),
+                            dev.ptr(out4), dev.stream()))
+        dist.all_reduce(out4)
+        rhs = dev.to_np(out4)
+        nb = dim + 1
+
+        def f(a, dd):
+            v = kd[dd] if a == dd else md[dd]
+            return np.where(free[dd], v, 0.0)
+        G = np.ones((nb, nb))
+        for a in range(nb):
+            for b in range(nb):
+                for dd in range(dim):
+                    G[a, b] *= float(np.dot(f(a, dd), f(b, dd)))
+        r = np.concatenate([rhs[:dim], rhs[3:4]])
+        try:
+            sol = np.linalg.solve(G, r)
+        except np.linalg.LinAlgError:
+            return [1.0] * dim, 0.0
+        c, sigma = list(sol[:dim]), float(sol[dim])
+        if not all(np.isfinite(sol)) or min(c) <= 0.0:
+            return [1.0] * dim, 0.0
+        return [float(x) for x in c], max(sigma, 0.0) if sigma > -1e-10 * max(c) else 0.0
+
+    def _gemm(self, ta, tb, M, N, K, A, lda, sA, B, ldb, sB, Cc, ldc, sC, batch):
+        self.check(self.lib.tg_dgemm_batched(ta, tb, M, N, K, 1.0, A, lda, sA, B, ldb, sB, 0.0,
+                                             Cc, ldc, sC, batch, self.dev.stream()))
+
+    def _to_fibres(self, src, dst):
+        """slab layout [i_L local][plane]  ->  [i_L (all)][my plane chunk]"""
+        torch, dist = self.torch, self.dist
+        v = src[:self.nloc].view(self.nl, self.plane)
+        pack = torch.cat([v[:, self.q[s]:self.q[s + 1]].reshape(-1) for s in range(self.size)])
+        dist.all_to_all_single(dst[:self.mq * self.nL], pack, self.recv_splits, self.send_splits)
+
+    def _to_slabs(self, src, dst):
+        torch, dist = self.torch, self.dist
+        recv = torch.empty(self.nloc, dtype=src.dtype, device=src.device)
+        dist.all_to_all_single(recv, src[:self.mq * self.nL], self.send_splits, self.recv_splits)
+        out = dst[:self.nloc].view(self.nl, self.plane)
+        off = 0
+        for s in range(self.size):
+            w = self.q[s + 1] - self.q[s]
+            out[:, self.q[s]:self.q[s + 1]].copy_(recv[off:off + w * self.nl].view(self.nl, w))
+            off += w * self.nl
+
+    def apply(self, r, z):
+        dev, lib, check = self.dev, self.lib, self.check
+        dim, L = self.dim, self.dim - 1
+        n0, n1, _ = self.nd
+        nl, nL, mq = self.nl, self.nL, self.mq
+        st = dev.stream()
+        U = [dev.ptr(u) for u in self.U]
+        a, b = self.t1, self.t2
+        check(lib.tg_masked_copy(dev.ptr(a), dev.ptr(r), dev.ptr(self.lmask) if self.lmask
+                                 is not None else None, self.nloc, st))
+        # local mode products (directions before the partitioned one)
+        if dim == 3:
+            self._gemm(1, 0, n0, n1 * nl, n0, U[0], n0, 0, dev.ptr(a), n0, 0, dev.ptr(b), n0, 0, 1)
+            a, b = b, a
+            self._gemm(0, 0, n0, n1, n1, dev.ptr(a), n0, n0 * n1, U[1], n1, 0, dev.ptr(b), n0,
+                       n0 * n1, nl)
+            a, b = b, a
+        else:
+            self._gemm(1, 0, n0, nl, n0, U[0], n0, 0, dev.ptr(a), n0, 0, dev.ptr(b), n0, 0, 1)
+            a, b = b, a
+        # whole fibres of the last direction on every rank
+        self._to_fibres(a, b)
+        a, b = b, a
+        self._gemm(0, 0, mq, nL, nL, dev.ptr(a), mq, 0, U[L], nL, 0, dev.ptr(b), mq, 0, 1)
+        a, b = b, a
+        lam = [dev.ptr(l) for l in self.lam] + [None] * (3 - dim)
+        if dim == 3:
+            check(lib.tg_fd_scale(dev.ptr(a), lam[0], lam[1], lam[2], n0, n1, nL,
+                                  self.q[self.rank], mq, self.sigma, 1, st))
+        else:
+            # 2-D: the "plane" is the first direction, the fibre direction is the second
+            check(lib.tg_fd_scale(dev.ptr(a), lam[0], None, lam[1], n0, 1, nL,
+                                  self.q[self.rank], mq, self.sigma, 1, st))
+        self._gemm(0, 1, mq, nL, nL, dev.ptr(a), mq, 0, U[L], nL, 0, dev.ptr(b), mq, 0, 1)
+        a, b = b, a
+        self._to_slabs(a, b)
+        a, b = b, a
+        if dim == 3:
+            self._gemm(0, 1, n0, n1, n1, dev.ptr(a), n0, n0 * n1, U[1], n1, 0, dev.ptr(b), n0,
+                       n0 * n1, nl)
+            a, b = b, a
+            self._gemm(0, 0, n0, n1 * nl, n0, U[0], n0, 0, dev.ptr(a), n0, 0, dev.ptr(z), n0, 0, 1)
+        else:
+            self._gemm(0, 0, n0, nl, n0, U[0], n0, 0, dev.ptr(a), n0, 0, dev.ptr(z), n0, 0, 1)
+        if self.lmask is not None:
+            check(lib.tg_masked_fix(dev.ptr(z), dev.ptr(r), dev.ptr(self.lmask), self.cinv,
+                                    self.nloc, st))
+        return z
+
+
+def solve_fd_pcg_dist(patch, Cm, b, mask, diag, rtol, atol, maxit):
+    """CG preconditioned by fast diagonalisation on the slab-distributed system: the halo
+    exchange + local SpMV of ``DeviceOps``, the preconditioner above, scalars all-reduced."""
+    import torch
+    import torch.distributed as dist
+    from . import dev, solvers
+    from ._lib import lib, check
+    ops = DeviceOps(patch, Cm)
+    ops.begin(b)                    # allocates p_ext / dinv (Jacobi diagonal: used for the fit)
+    fd = FastDiagDist(patch, mask, diag, ops.dinv)
+    s = dev.zeros(2)
+
+    def allsum(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev.device())
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def spmv_dot(p, q):
+        assert p.data_ptr() == ops.p.data_ptr()
+        ops.exchange_halo()
+        check(lib.tg_win_spmv_dot(Cm.window.ref(), dev.ptr(Cm.vals), dev.ptr(ops.p_ext), ops.xoff,
+                                  dev.ptr(q), dev.ptr(ops.scratch), dev.ptr(s), dev.stream()))
+        return allsum(float(s[0].item()))
+    x, its, rel = solvers.pcg(spmv_dot, fd.apply, b, None, rtol, atol, maxit, reduce=allsum,
+                              p_buf=ops.p)
+    return x, its, rel
+
+
 def gather_planes(local, patch):
     """All-gather a slab-distributed IGA vector into the full vector (every
     rank gets it): the FE/IGA functions the forms evaluate are replicated."""
@@ -235,101 +426,3 @@ def gather_planes(local, patch):
         n = (bounds[r + 1] - bounds[r]) * pl
         full[bounds[r] * pl:bounds[r] * pl + n].copy_(out[r * mx:r * mx + n])
     return full
-
-
-# ----------------------------------------------------------------------------
-def bench(args, METRIC, UNIT, CG_RTOL):
-    """bench.py leg for N > 1 (launched by torchrun, one rank per GPU): the same
-    256^3 workload, strong scaling; max-over-ranks device time."""
-    import torch
-    import torch.distributed as dist
-    import bench as B
-    from ._lib import lib
-    rank, world = dist.get_rank(), dist.get_world_size()
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    nel = args.nel
-    kv, cm, pinned = B.build_inputs(nel)
-    dev_cols = [pinned[:, i].contiguous().cuda() for i in range(4)]
-
-    def barrier():
-        dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        B.one_step(kv, cm, dev_cols, "fused", CG_RTOL, False)
-    barrier()
-    sampler = B.ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    lib.tg_prof_enable(0)
-    l0 = lib.tg_launch_count()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0.record()
-    stages = []
-    for _ in range(args.steps):
-        n_dofs, iters, ev, _, MTAM = B.one_step(kv, cm, dev_cols, "fused", CG_RTOL, False)
-        stages.append(ev)
-    t1.record()
-    barrier()
-    ms = torch.tensor([t0.elapsed_time(t1)], device="cuda")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-    launches = lib.tg_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
-    W = MTAM.window
-    stage_ms = [0.0, 0.0, 0.0]
-    for ev in stages:
-        for i in range(3):
-            stage_ms[i] += ev[i].elapsed_time(ev[i + 1]) / max(args.steps, 1)
-    st = torch.tensor(stage_ms, device="cuda")
-    dist.all_reduce(st, op=dist.ReduceOp.MAX)
-    local_nnz, local_rows = W.nnz, W.nrows
-    del MTAM, stages
-    # live timing of the local SpMV (device events around the kernel only)
-    # end to end from host buffers: rank 0 holds the host control net and
-    # broadcasts it; every rank returns its slab, gathered to the host of rank 0
-    B.one_step(kv, cm, pinned, "fused", CG_RTOL, True)
-    barrier()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        _, _, _, res, MT = B.one_step(kv, cm, pinned, "fused", CG_RTOL, True)
-        del MT
-    e1.record()
-    barrier()
-    e2e_ms = torch.tensor([max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - wall0))],
-                          device="cuda")
-    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_ms.item())
-    if rank == 0:
-        peak, which = B.measured_peaks()
-        out = {
-            "metric": METRIC, "value": n_dofs * args.steps / (ms * 1e-3), "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "3D cubic B-spline Poisson %d^3 cells, %d GPUs" % (nel, world),
-                       "degree": B.P, "cells": nel ** 3, "iga_dofs": n_dofs, "path": "fused",
-                       "partition": "slabs of IGA planes (last direction), p halo cell layers "
-                                    "recomputed, row-distributed Jacobi-CG over NCCL",
-                       "quad_degree": 2 * B.P, "cg_rtol": CG_RTOL, "cg_iterations": iters,
-                       "l2": "inputs larger than L2 (local matrix %.1f GB per rank)"
-                             % (8e-9 * local_nnz)},
-            "stage_ms": {"extract": float(st[0]), "assemble_ptap_bcs": float(st[1]),
-                         "solve": float(st[2])},
-            "clocks": clocks,
-            "e2e": {"value": n_dofs * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(pinned.numel() * 8 * world),
-                    "d2h_bytes_per_step": int(n_dofs * 8)},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_win_spmv<true> (rank-local rows)",
-                         "achieved": None, "peak": peak, "peak_source": which, "unit": "GB/s",
-                         "frac": None, "traffic": None,
-                         "note": "per-kernel roofline is reported by the N=1 run"}}
-        print(json.dumps(out))
-    dist.barrier()
-    dist.destroy_process_group()

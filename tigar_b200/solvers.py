@@ -226,10 +226,12 @@ class _Vec(object):
 
 
 def pcg(spmv_dot, precond, b, x0=None, rtol=1e-12, atol=0.0, maxit=10000, reduce=None,
-        exchange=None):
+        p_buf=None):
     """Preconditioned CG.  ``spmv_dot(p, q) -> p.q`` computes q = A p and returns the (global)
-    dot product; ``precond(r, z)`` writes z = B^-1 r; ``reduce`` sums a host scalar over ranks.
-    Returns (x, iterations, relative residual).  Raises SolverBreakdown when p.Ap <= 0."""
+    dot product; ``precond(r, z)`` writes z = B^-1 r; ``reduce`` sums a host scalar over ranks;
+    ``p_buf``: where the search direction lives (a view into the halo-extended vector of a
+    row-distributed matrix).  Returns (x, iterations, relative residual).  Raises
+    SolverBreakdown when p.Ap <= 0."""
     n = b.numel()
     V = _Vec(n)
     if reduce is not None:
@@ -249,7 +251,11 @@ def pcg(spmv_dot, precond, b, x0=None, rtol=1e-12, atol=0.0, maxit=10000, reduce
     if rr <= tol2:
         return x, 0, (math.sqrt(rr / bb) if bb > 0 else 0.0)
     precond(r, z)
-    p = z.clone()
+    if p_buf is None:
+        p = z.clone()
+    else:
+        p = p_buf
+        p.copy_(z)
     rz = V.dot(r, z)
     out1 = V.s[1:2]
     while rr > tol2 and it < maxit:
@@ -285,11 +291,20 @@ def solve_fd_pcg(patch, Cm, b, mask=None, diag=1.0, x0=None, rtol=1e-12, atol=0.
     scratch = dev.empty(lib.tg_cg_scratch_len())
     s = dev.zeros(2)
 
+    W = Cm.window
+    spmv_bytes = 8 * W.nnz + 24 * W.nrows
+
     def spmv_dot(p, q):
-        check(lib.tg_win_spmv_dot(Cm.window.ref(), dev.ptr(Cm.vals), dev.ptr(p), 0, dev.ptr(q),
-                                  dev.ptr(scratch), dev.ptr(s), dev.stream()))
+        with dev.PROF.range("k_win_spmv (CG matvec + p.Ap)", spmv_bytes, 2.0 * W.nnz):
+            check(lib.tg_win_spmv_dot(W.ref(), dev.ptr(Cm.vals), dev.ptr(p), 0, dev.ptr(q),
+                                      dev.ptr(scratch), dev.ptr(s), dev.stream()))
         return float(s[0].item())
-    x, its, rel = pcg(spmv_dot, fd.apply, b, x0, rtol, atol, maxit)
+
+    def precond(r, z):
+        with dev.PROF.range("k_dgemm x6 + k_fd_scale (FD preconditioner)", 16 * 8 * n,
+                            fd.flops_per_apply):
+            return fd.apply(r, z)
+    x, its, rel = pcg(spmv_dot, precond, b, x0, rtol, atol, maxit)
     return x, its, rel, fd
 
 
