@@ -99,7 +99,34 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
     w('extern "C" __global__ void __launch_bounds__(NTH) %s(const QpArgs A) {'
       % ("tigar_qp" if op is None else "tigar_op"))
     w("  __shared__ double tb0[Q0*N0*ND], tb1[Q1*N1*ND], tb2[Q2*N2*ND];")
-    w("  __shared__ double cf[NEN], s1[Q0*N1*N2], s2[Q0*Q1*N2];")
+    # jets: all functions of a group go through the three contraction stages TOGETHER (one
+    # barrier per stage and group instead of one per function and derivative order: the
+    # per-function version spent its time in ~40 barriers of 4 FMAs each)
+    byf = {}
+    for k, (f, comp, al) in enumerate(jets):
+        byf.setdefault((f, comp), []).append((k, al))
+    S1, S2 = q0 * n1 * n2, q0 * q1 * n2
+    groups, cur, cost = [], [], 0
+    for key, lst in byf.items():
+        c1 = len(set(al[0] for _, al in lst))
+        c2 = len(set((al[0], al[1]) for _, al in lst))
+        mine = 8 * (nen + c1 * S1 + c2 * S2)
+        if cur and cost + mine > 28 * 1024:
+            groups.append(cur)
+            cur, cost = [], 0
+        cur.append(key)
+        cost += mine
+    if cur:
+        groups.append(cur)
+
+    def gsizes(grp):
+        c1 = sum(len(set(al[0] for _, al in byf[key])) for key in grp)
+        c2 = sum(len(set((al[0], al[1]) for _, al in byf[key])) for key in grp)
+        return len(grp), c1, c2
+    mg = max([gsizes(g)[0] for g in groups] + [1])
+    m1 = max([gsizes(g)[1] for g in groups] + [1])
+    m2 = max([gsizes(g)[2] for g in groups] + [1])
+    w("  __shared__ double cf[%d*NEN], s1[%d], s2[%d];" % (mg, m1 * S1, m2 * S2))
     w("  const int tid = threadIdx.x;")
     w("  const long long cl = blockIdx.x;")
     if op is None:
@@ -126,12 +153,9 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
         w("  for (int i = tid; i < Q2*N2*ND; i += NTH) tb2[i] = 1.0;")
     w("  const bool active = tid < NQP;")
     w("  const int qa = tid %% Q0, qb = (tid / Q0) %% Q1, qc = tid / (Q0*Q1);" .replace("%%", "%"))
-    # jets, grouped by function, then by a0, then by (a0,a1)
     w("  double %s;" % ", ".join("j%d = 0.0" % k for k in range(max(len(jets), 1))))
-    byf = {}
-    for k, (f, comp, al) in enumerate(jets):
-        byf.setdefault((f, comp), []).append((k, al))
-    for (f, comp), lst in byf.items():
+    for grp in groups:
+        # stage 0: coefficients of the cell's functions
         w("  __syncthreads();")
         w("  for (int a = tid; a < NEN; a += NTH) {")
         w("    int l0 = a %% N0, t = a / N0, l1 = t %% N1, l2 = t / N1;".replace("%%", "%"))
@@ -140,29 +164,42 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
             w("    g += (long long)A.n[0] * A.idx[1][e1*N1 + l1];")
         if dim > 2:
             w("    g += (long long)A.n[0] * A.n[1] * A.idx[2][e2*N2 + l2];")
-        w("    cf[a] = A.coef[%d][g];" % f)
+        for gi, (f, comp) in enumerate(grp):
+            w("    cf[%d*NEN + a] = A.coef[%d][g];" % (gi, f))
         w("  }")
-        a0s = sorted(set(al[0] for _, al in lst))
-        for a0 in a0s:
-            w("  __syncthreads();")
-            w("  for (int o = tid; o < Q0*N1*N2; o += NTH) {")
-            w("    int qq = o %% Q0, r = o / Q0; double acc = 0.0;".replace("%%", "%"))
-            w("    #pragma unroll\n    for (int l = 0; l < N0; l++) acc += cf[r*N0 + l] * tb0[(qq*N0 + l)*ND + %d];" % a0)
-            w("    s1[o] = acc;\n  }")
-            a1s = sorted(set(al[1] for _, al in lst if al[0] == a0))
-            for a1 in a1s:
-                w("  __syncthreads();")
-                w("  for (int o = tid; o < Q0*Q1*N2; o += NTH) {")
-                w("    int x0 = o %% Q0, t = o / Q0, x1 = t %% Q1, l2 = t / Q1; double acc = 0.0;"
-                  .replace("%%", "%"))
-                w("    #pragma unroll\n    for (int l = 0; l < N1; l++) acc += s1[(l2*N1 + l)*Q0 + x0] * tb1[(x1*N1 + l)*ND + %d];" % a1)
-                w("    s2[o] = acc;\n  }")
-                w("  __syncthreads();")
-                for k, al in lst:
-                    if al[0] == a0 and al[1] == a1:
-                        w("  if (active) { double acc = 0.0;")
-                        w("    #pragma unroll\n    for (int l = 0; l < N2; l++) acc += s2[(l*Q1 + qb)*Q0 + qa] * tb2[(qc*N2 + l)*ND + %d];" % al[2])
-                        w("    j%d = acc; }" % k)
+        # stage 1: contract direction 0 for every (function, a0)
+        slot1, slot2 = {}, {}
+        for gi, key in enumerate(grp):
+            for a0 in sorted(set(al[0] for _, al in byf[key])):
+                slot1[(gi, a0)] = len(slot1)
+            for a01 in sorted(set((al[0], al[1]) for _, al in byf[key])):
+                slot2[(gi,) + a01] = len(slot2)
+        w("  __syncthreads();")
+        w("  for (int o = tid; o < Q0*N1*N2; o += NTH) {")
+        w("    const int qq = o %% Q0, r = o / Q0;".replace("%%", "%"))
+        for (gi, a0), sl in slot1.items():
+            w("    { double acc = 0.0;")
+            w("      #pragma unroll\n      for (int l = 0; l < N0; l++) acc += cf[%d*NEN + r*N0 + l] * tb0[(qq*N0 + l)*ND + %d];" % (gi, a0))
+            w("      s1[%d + o] = acc; }" % (sl * S1))
+        w("  }")
+        # stage 2: contract direction 1 for every (function, a0, a1)
+        w("  __syncthreads();")
+        w("  for (int o = tid; o < Q0*Q1*N2; o += NTH) {")
+        w("    const int x0 = o %% Q0, t = o / Q0, x1 = t %% Q1, l2 = t / Q1;".replace("%%", "%"))
+        for (gi, a0, a1), sl in slot2.items():
+            w("    { double acc = 0.0;")
+            w("      #pragma unroll\n      for (int l = 0; l < N1; l++) acc += s1[%d + (l2*N1 + l)*Q0 + x0] * tb1[(x1*N1 + l)*ND + %d];" % (slot1[(gi, a0)] * S1, a1))
+            w("      s2[%d + o] = acc; }" % (sl * S2))
+        w("  }")
+        # stage 3: the jets at this thread's Gauss point
+        w("  __syncthreads();")
+        w("  if (active) {")
+        for gi, key in enumerate(grp):
+            for k, al in byf[key]:
+                w("    { double acc = 0.0;")
+                w("      #pragma unroll\n      for (int l = 0; l < N2; l++) acc += s2[%d + (l*Q1 + qb)*Q0 + qa] * tb2[(qc*N2 + l)*ND + %d];" % (slot2[(gi, al[0], al[1])] * S2, al[2]))
+                w("      j%d = acc; }" % k)
+        w("  }")
     if op is None:
         w("  if (!active) return;")
     else:

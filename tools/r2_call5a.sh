@@ -3,7 +3,7 @@ mkdir -p gpurun_out
 set -x
 timeout 900 python -m pytest tests/test_gpu_solvers.py -q -k "config2" > gpurun_out/r2c5_cfg3.log 2>&1
 tail -12 gpurun_out/r2c5_cfg3.log
-timeout 900 python bench.py > gpurun_out/r2c5_bench_256.json 2> gpurun_out/r2c5_bench_256.err
+timeout 900 python bench.py --no-ptap --no-cpu > gpurun_out/r2c5_bench_256.json 2> gpurun_out/r2c5_bench_256.err
 tail -3 gpurun_out/r2c5_bench_256.err
 python - <<'P'
 import json
