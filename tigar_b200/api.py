@@ -99,10 +99,13 @@ class SubDomain(object):
 
 # ---------------------------------------------------------------- vectors
 class DeviceVector(object):
-    """Minimal stand-in for a DOLFIN PETScVector living in HBM."""
+    """Minimal stand-in for a DOLFIN PETScVector living in HBM.  ``distributed=True`` marks a
+    slab of a row-distributed vector: its norm is reduced over the ranks (a PETSc Vec's norm
+    is global), so every rank of a Newton loop takes the same branch."""
 
-    def __init__(self, t):
+    def __init__(self, t, distributed=False):
         self.t = t
+        self.distributed = distributed
 
     def get_local(self):
         return dev.to_np(self.t).copy()
@@ -131,6 +134,10 @@ class DeviceVector(object):
         scratch = dev.empty(lib.tg_cg_scratch_len())
         check(lib.tg_dot(dev.ptr(self.t), dev.ptr(self.t), self.t.numel(), dev.ptr(scratch),
                          dev.ptr(out), dev.stream()))
+        if self.distributed:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(out)
         return math.sqrt(float(out.item()))
 
     def vec(self):
@@ -1071,7 +1078,7 @@ class ExtractedSpline(object):
         MTb = self._assemble_kind(form, "iga")
         if applyBCs:
             self._patch.apply_bcs_vector(MTb, self._bc_mask())
-        return DeviceVector(MTb)
+        return DeviceVector(MTb, distributed=self._patch.part is not None)
 
     def extractMatrix(self, A, applyBCs=True, diag=1):
         """M^T A M then zeroRowsColumns, common.py:1176-1204."""
@@ -1119,7 +1126,7 @@ class ExtractedSpline(object):
         if applyBCs:
             self._patch.apply_bcs_matrix(A, self._bc_mask(), 1)
             self._patch.apply_bcs_vector(b, self._bc_mask())
-        return A, DeviceVector(b)
+        return A, DeviceVector(b, distributed=self._patch.part is not None)
 
     def solveLinearSystem(self, MTAM, MTb, u):
         """common.py:1236-1263: returns the IGA DoF vector, updates ``u``."""
@@ -1130,15 +1137,22 @@ class ExtractedSpline(object):
         maxit = prm.get("maximum_iterations", 200000)
         from .matfree import FormOperator
         if isinstance(MTAM, FormOperator):
-            from .matfree import solve_matfree_cg
-            x, its, rel = solve_matfree_cg(MTAM, MTb.t, rtol, atol, maxit)
-            self.lastSolve = dict(iterations=its, relative_residual=rel)
+            from .matfree import solve_matfree_cg, solve_matfree_fd
+            method = os.environ.get("TIGAR_B200_SOLVER", self._solver_method(ls))
+            if method == "jacobi":
+                x, its, rel = solve_matfree_cg(MTAM, MTb.t, rtol, atol, maxit)
+            else:
+                x, its, rel = solve_matfree_fd(MTAM, MTb.t, rtol, atol, maxit)
+                method = "fd"
+            self.lastSolve = dict(iterations=its, relative_residual=rel, method=method)
+            self._check_converged(ls, its, rel, maxit, rtol, atol)
             u.set_iga(x)
             return DeviceVector(x)
         if self.nFields > 1:
             from . import multifield as MF
             x, its, rel = MF.solve_block_cg(MTAM, MTb.t, rtol, atol, maxit)
-            self.lastSolve = dict(iterations=its, relative_residual=rel)
+            self.lastSolve = dict(iterations=its, relative_residual=rel, method="jacobi")
+            self._check_converged(ls, its, rel, maxit, rtol, atol)
             u.set_iga(x)
             return DeviceVector(x)
         x0 = None if u.iga is None else u.iga.clone()

@@ -369,13 +369,20 @@ static int tg_cg_driver(SPMV spmv, DIAG diag, const double* b, double* x, int64_
       if ((rc = tg_cg_xpby(p, r, dinv, n, nxt, cur, stream))) return rc;
     }
     double* last = (it & 1) ? s + 3 : s + 0;
+    double hpap = 0.0;
     TG_CHECK(cudaMemcpyAsync(hs, last, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TG_CHECK(cudaMemcpyAsync(&hpap, s + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
     TG_CHECK(cudaStreamSynchronize(st));
     if (prof) tg_prof_collect(nstep);
     rr = hs[1];
     if (!(rr == rr)) {
       tg_set_error("CG produced NaN at iteration %d", it);
       return 3;
+    }
+    if (rr > tol2 && !(hpap > 0.0)) {
+      tg_set_error("CG breakdown at iteration %d: p.Ap = %g (matrix not symmetric positive "
+                   "definite)", it, hpap);
+      return 4;
     }
   }
   if (h_iters) *h_iters = it;

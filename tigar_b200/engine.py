@@ -586,6 +586,19 @@ class TensorPatch(object):
         return all(lib.tg_gsf_supported(B.nloc[d], int(B.c.nq[d])) for d in range(self.dim))
 
     @staticmethod
+    def _dedupe(nodes):
+        """(unique nodes, slot of every input node): hash-consed nodes are identical objects
+        when two terms carry the same coefficient."""
+        uniq, slot, seen = [], [], {}
+        for n in nodes:
+            k = seen.get(n.uid)
+            if k is None:
+                k = seen[n.uid] = len(uniq)
+                uniq.append(n)
+            slot.append(k)
+        return uniq, slot
+
+    @staticmethod
     def _gsf_plan(entries, dim, pair):
         """entries: [(input kind, ((al, be),)*dim)] -> per stage (nout, maxin, host plan).
         Terms whose derivative orders agree in all REMAINING directions share an output kind."""
@@ -756,12 +769,15 @@ class TensorPatch(object):
         stride = i32arr([2] * self.dim if kind == "fe" else B.nloc)
         if out is None and self.dim in (2, 3):
             keys = sorted(terms, key=self._sf_key)
-            P = self._setup_cached(cache, lambda: [terms[k] for k in keys], funcs)
+            # terms with the same coefficient (symmetric forms: (a,b) and (b,a)) share a slot
+            uniq, slot = self._dedupe([terms[k] for k in keys])
+            gcache = None if cache is None else cache.setdefault("gsf", {})
+            P = self._setup_cached(gcache, lambda: uniq, funcs)
             if self._gsf_ok(B, W, P):
-                ent = [(i, tuple((pad3(k[0])[d], pad3(k[1])[d]) for d in range(self.dim)))
+                ent = [(slot[i], tuple((pad3(k[0])[d], pad3(k[1])[d]) for d in range(self.dim)))
                        for i, k in enumerate(keys)]
                 A = WinMatrix(W, dev.empty(W.storage()))
-                self._gsf_run(B, kind, P, len(keys), ent, None, A, None, 0, 0)
+                self._gsf_run(B, kind, P, len(uniq), ent, None, A, None, 0, 0)
                 return A
         if lib.tg_assemble_sf_supported(B.ref()):
             # sum-factorised kernel: one coefficient slot per non-zero term
@@ -813,13 +829,15 @@ class TensorPatch(object):
         W = self.window("A" if kind == "fe" else "C")
         P = None
         if self.dim in (2, 3) and (self.part is None or kind == "iga"):
-            P = self._qp_setup(nodes, funcs)
-            if self._gsf_ok(B, W, P):
+            uniq, slot = self._dedupe(nodes)      # symmetric terms share a coefficient slot
+            Pg = self._qp_setup(uniq, funcs)
+            if self._gsf_ok(B, W, Pg):
                 dim = self.dim
                 nm = len(mk)
-                ment = [(i, tuple((pad3(k[0])[d], pad3(k[1])[d]) for d in range(dim)))
+                ment = [(slot[i], tuple((pad3(k[0])[d], pad3(k[1])[d]) for d in range(dim)))
                         for i, k in enumerate(mk)]
-                vent = [(nm + i, tuple((a[d], 0) for d in range(dim))) for i, a in enumerate(alS)]
+                vent = [(slot[nm + i], tuple((a[d], 0) for d in range(dim)))
+                        for i, a in enumerate(alS)]
                 A = WinMatrix(W, dev.empty(W.storage()))
                 if self.part is not None:
                     b = dev.empty(self.n_loc)
@@ -827,7 +845,7 @@ class TensorPatch(object):
                 else:
                     b = dev.empty(B.ntot)
                     r0, nr = 0, int(B.c.n[dim - 1])
-                self._gsf_run(B, kind, P, nm + len(alS), ment, vent, A, b, r0, nr)
+                self._gsf_run(B, kind, Pg, len(uniq), ment, vent, A, b, r0, nr)
                 return A, b
         if not lib.tg_assemble_sf_supported(B.ref()):
             return (self.assemble_matrix(mterms, funcs, kind),

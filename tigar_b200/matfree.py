@@ -171,6 +171,7 @@ class FormOperator(object):
                                  diag=True)
         d = dev.zeros(self.n)
         jit.launch_op(kern, B, [dev.ptr(self._funcs[f]) for f in fids], d, list(B.nloc))
+        d[d == 0.0] = 1.0                      # as tg_win_diag_inv: a zero diagonal acts as 1
         return d.reciprocal_()                 # one-time element-wise reciprocal
 
 
@@ -206,6 +207,36 @@ class MatFreeOps(BlockOps):
         if self.mask is not None:
             self.check(self.lib.tg_zero_entries(self.dev.ptr(y), self.dev.ptr(self.mask), self.n,
                                                 self.dev.stream()))
+
+
+def solve_matfree_fd(op, b, rtol=1e-12, atol=0.0, maxit=10000):
+    """CG on the matrix-free operator, preconditioned by fast diagonalisation
+    (tigar_b200/solvers.py): exact for an affine geometry, a few dozen operator applications
+    otherwise -- what makes the 512^3 patch on one GPU practical (Jacobi-CG needs 175)."""
+    from . import dev, solvers
+    from ._lib import lib, check
+    mask = op.spline._bc_mask() if op.applyBCs else None
+    fd = solvers.FastDiag(op.patch, mask, op.diag, op.jacobi_dinv())
+    n = op.n
+    scratch = dev.empty(lib.tg_cg_scratch_len())
+    s = dev.zeros(2)
+
+    def spmv_dot(p, q):
+        # y = P C P p + diag (I - P) p ; inside CG every iterate is zero on the constrained
+        # DoFs, so this is C p with those entries zeroed
+        with dev.PROF.range("tigar_op (matrix-free operator, one launch per colour)", 0, 0):
+            if p.data_ptr() != op.xvec.data_ptr():
+                op.xvec.copy_(p)
+            if mask is not None:
+                check(lib.tg_zero_entries(dev.ptr(op.xvec), dev.ptr(mask), n, dev.stream()))
+            op.apply(q)
+            if mask is not None:
+                check(lib.tg_zero_entries(dev.ptr(q), dev.ptr(mask), n, dev.stream()))
+        check(lib.tg_dot(dev.ptr(op.xvec), dev.ptr(q), n, dev.ptr(scratch), dev.ptr(s),
+                         dev.stream()))
+        return float(s[0].item())
+    x, its, rel = solvers.pcg(spmv_dot, fd.apply, b, None, rtol, atol, maxit, p_buf=op.xvec)
+    return x, its, rel
 
 
 def solve_matfree_cg(op, b, rtol=1e-12, atol=0.0, maxit=100000, check_every=5, jacobi=True):
