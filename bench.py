@@ -131,6 +131,17 @@ def bench_pc():
     return os.environ.get("TIGAR_B200_BENCH_PC", "fd")
 
 
+WORKLOAD = ["explicit"]        # "annulus": BASELINE configs[3], cubic NURBS quarter annulus
+
+
+def build_annulus(nel):
+    """configs[3]: the igakit-like NURBS object of the quarter annulus (the workload's INPUT;
+    built once on the host, its homogeneous control net is uploaded inside the timed e2e step)
+    wrapped in the reference's NURBSControlMesh."""
+    from tIGAr.NURBS import NURBSControlMesh, quarter_annulus
+    return NURBSControlMesh(quarter_annulus(P, [nel] * 3, 3))
+
+
 def one_step(kv, cm, control_net, mode, rtol, to_host, keep=False):
     """One pass of the hot path through the tIGAr API.  ``control_net`` None: the generator
     makes the Greville net on the device (the default of the product); ``cm`` None: the
@@ -142,6 +153,7 @@ def one_step(kv, cm, control_net, mode, rtol, to_host, keep=False):
     from tIGAr.BSplines import ExplicitBSplineControlMesh
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     ev[0].record()
+    annulus = WORKLOAD[0] == "annulus"
     if cm is None:
         cm = ExplicitBSplineControlMesh([P] * 3, kv)
     gen = EqualOrderSpline(1, cm)
@@ -156,9 +168,19 @@ def one_step(kv, cm, control_net, mode, rtol, to_host, keep=False):
     ev[1].record()                                              # extract done
     u, v = TrialFunction(spline.V), TestFunction(spline.V)
     x = spline.spatialCoordinates()
-    soln = sin(pi * x[0]) * sin(pi * x[1]) * sin(pi * x[2])
-    a = inner(spline.grad(u), spline.grad(v)) * spline.dx
-    L = inner(3 * pi ** 2 * soln, v) * spline.dx
+    if annulus:
+        # u = (r-1)(2-r) sin(2 theta) sin(pi z): zero on the whole boundary of the patch;
+        # f = -div grad u built symbolically as poisson-nurbs.py:127-133 does
+        from tIGAr import sqrt
+        u, v = spline.rationalize(u), spline.rationalize(v)
+        r = sqrt(x[0] * x[0] + x[1] * x[1])
+        soln = (r - 1.0) * (2.0 - r) * (2.0 * x[0] * x[1] / (r * r)) * sin(pi * x[2])
+        a = inner(spline.grad(u), spline.grad(v)) * spline.dx
+        L = inner(-spline.div(spline.grad(soln)), v) * spline.dx
+    else:
+        soln = sin(pi * x[0]) * sin(pi * x[1]) * sin(pi * x[2])
+        a = inner(spline.grad(u), spline.grad(v)) * spline.dx
+        L = inner(3 * pi ** 2 * soln, v) * spline.dx
     MTAM, MTb = spline.assembleLinearSystem(a, L)
     ev[2].record()                                              # assemble + PtAP + BCs done
     uh = Function(spline.V)
@@ -168,7 +190,8 @@ def one_step(kv, cm, control_net, mode, rtol, to_host, keep=False):
     ev[4].record()
     out = (spline._patch.n_iga, spline.lastSolve["iterations"], ev, res, MTAM)
     if keep:
-        out = out + (dict(spline=spline, MTb=MTb, U=U, uh=uh, soln=soln),)
+        out = out + (dict(spline=spline, MTb=MTb, U=U, soln=soln,
+                          uh=spline.rationalize(uh) if annulus else uh),)
     return out
 
 
@@ -334,6 +357,11 @@ def run_ours(args):
     if world > 1 and mode != "fused":
         raise SystemExit("multi-GPU runs use the element-fused path")
     kv, cm, _ = build_inputs(nel, net=False)
+    WORKLOAD[0] = args.workload
+    net_bytes = 0
+    if args.workload == "annulus":
+        cm = build_annulus(nel)
+        net_bytes = int(cm.bnet.size * 8)
 
     def barrier():
         if world > 1:
@@ -402,24 +430,28 @@ def run_ours(args):
     value = n_dofs * args.steps / (ms * 1e-3)
 
     # ---- end to end: host inputs in, host solution out ------------------------------------
-    one_step(kv, None, None, mode, CG_RTOL, rank == 0)
+    cm_e2e = cm if args.workload == "annulus" else None     # explicit: rebuilt from the knots
+    one_step(kv, cm_e2e, None, mode, CG_RTOL, rank == 0)
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     wall0 = time.perf_counter()
     for _ in range(args.steps):
-        rr = one_step(kv, None, None, mode, CG_RTOL, rank == 0)
+        rr = one_step(kv, cm_e2e, None, mode, CG_RTOL, rank == 0)
         del rr
     e1.record()
     barrier()
     e2e_ms = maxr(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - wall0)))
     e2e = {"value": n_dofs * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-           "h2d_bytes_per_step": int((sum(len(k) for k in kv) * 8 + nz * 8) * world),
+           "h2d_bytes_per_step": int((sum(len(k) for k in kv) * 8 + nz * 8 + net_bytes) * world),
            "d2h_bytes_per_step": int(n_dofs * 8),
-           "note": "inputs = knot vectors + zero-DoF lists (every rank uploads its copy); the "
-                   "Greville control net is generated on the device inside the step; output = "
-                   "the IGA DoF vector read back by rank 0"}
+           "note": ("inputs = knot vectors + zero-DoF lists (every rank uploads its copy); the "
+                    "Greville control net is generated on the device inside the step; output = "
+                    "the IGA DoF vector read back by rank 0") if not net_bytes else
+                   ("inputs = the NURBS object's homogeneous control net (uploaded by every "
+                    "rank, it is replicated), knot vectors, zero-DoF lists; output = the IGA "
+                    "DoF vector read back by rank 0")}
     if rank != 0:
         dist.barrier()
         dist.destroy_process_group()
@@ -454,9 +486,14 @@ def run_ours(args):
         roofline = {"bound": "hbm", "kernel": "none timed", "achieved": 0.0, "peak": hbm_peak,
                     "peak_source": which, "unit": "GB/s", "frac": 0.0, "traffic": None}
 
-    wl = "3D cubic B-spline Poisson %d^3 cells" % nel
-    if nel == 256:
-        wl += ", %d GPU%s (BASELINE configs[1])" % (world, "" if world == 1 else "s")
+    if args.workload == "annulus":
+        wl = ("3D cubic NURBS Poisson on the quarter annulus, %d^3 cells, %d GPU%s (BASELINE "
+              "configs[3]%s)" % (nel, world, "" if world == 1 else "s",
+                                 "" if nel == 512 else " geometry at reduced size"))
+    else:
+        wl = "3D cubic B-spline Poisson %d^3 cells" % nel
+        if nel == 256:
+            wl += ", %d GPU%s (BASELINE configs[1])" % (world, "" if world == 1 else "s")
     pc = bench_pc()
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -562,6 +599,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nel", type=int, default=256)
     ap.add_argument("--mode", default="fused", choices=["fused", "csr", "matfree"])
+    ap.add_argument("--workload", default="explicit", choices=["explicit", "annulus"],
+                    help="explicit: BASELINE configs[1] (default); annulus: configs[3]")
     ap.add_argument("--cpu-nel", type=int, default=24)
     ap.add_argument("--ref-nel", type=int, default=16)
     ap.add_argument("--ref-procs", type=int, default=0, help="CPU arm: concurrent copies (0 = all cores)")

@@ -462,10 +462,13 @@ int tg_pcg_update(double* x, double* r, const double* p, const double* q, double
 /* The reference's default solve() is a sparse direct LU (common.py:1255-1256).  In the
  * reference's own DoF numbering the IGA matrix of a 2-D (or small 3-D) patch is banded;
  * LAPACK lower band storage AB[(i-j) + j*ldab], ldab >= bw + 32, zero-initialised.
+ * Equal-order multi-field systems (field blocks of common.py:337-351): block (fr, fc) of the
+ * nf x nf grid is written in the node-major interleaved numbering row' = nf*row + fr (band
+ * nf*bw + nf - 1); nf = 1, fr = fc = 0 for a scalar system.
  * info: device int32, zero-initialised; from_win sets -1 if a non-zero lies outside the band,
  * cholesky sets k+1 if the pivot block at column k is not positive definite.                  */
 int tg_band_from_win(const tg_win* h_w, const double* vals, int32_t bw, int32_t ldab,
-                     double* AB, int32_t* info, void* stream);
+                     double* AB, int32_t* info, int32_t nf, int32_t fr, int32_t fc, void* stream);
 int tg_band_cholesky(int64_t n, int32_t bw, int32_t ldab, double* AB, int32_t* info,
                      void* stream);
 /* L L^T x = b ; b is overwritten (work), work: n doubles, x must not alias b.                 */

@@ -73,6 +73,32 @@ def build(force=False):
     return compile_cxx(reference_cxx_string())
 
 
+REFERENCE_DEMOS = {"poisson.py": "/root/reference/demos/poisson/poisson.py",
+                   "biharmonic.py": "/root/reference/demos/biharmonic/biharmonic.py"}
+DEMO_DIR = os.path.join(REF_DIR, "demos")
+
+
+def stage_demos():
+    """The north_star's acceptance scripts (demos/poisson/poisson.py, demos/biharmonic/
+    biharmonic.py) must run UNMODIFIED on the device, but /root/reference does not exist on the
+    GPU box.  Like the compiled reference routine above, byte-identical copies are staged under
+    ``oracle/_ref/demos/`` (git-ignored: never in the history; not gpurun-ignored: they travel
+    with the snapshot).  tests/test_gpu_reference_demos.py runs them there and checks their
+    sha256 against the digests recorded here when the reference tree is present."""
+    import hashlib
+    import shutil
+    out = {}
+    for name, src in REFERENCE_DEMOS.items():
+        if not os.path.exists(src):
+            continue
+        os.makedirs(DEMO_DIR, exist_ok=True)
+        dst = os.path.join(DEMO_DIR, name)
+        shutil.copyfile(src, dst)
+        with open(dst, "rb") as f:
+            out[name] = hashlib.sha256(f.read()).hexdigest()
+    return out
+
+
 def load():
     """Import the compiled reference routine, or None if it was never built."""
     p = so_path()
@@ -87,3 +113,4 @@ def load():
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    print(stage_demos())

@@ -232,7 +232,7 @@ def test_reference_demos_run_unmodified_on_the_api_layer(demo, rate, tmp_path):
     ("biharmonic.py", ["3", "4", "2"], r"rate ([0-9.]+)\)", lambda r: abs(r[-1] - 2.0) < 0.5),
     ("poisson_annulus.py", ["2", "4", "2"], r"rate ([0-9.]+)\)", lambda r: r[-1] > 2.5),
     ("elasticity.py", ["2", "4", "3"], r"rate ([0-9.]+)\)", lambda r: abs(r[-1] - 3.0) < 0.2),
-    ("scordelis_lo.py", ["6", "0.001"], r"Relative norm: ([0-9.eE+-]+)", lambda r: r[-1] < 1e-6),
+    ("scordelis_lo.py", ["6", "0.001", "jacobi"], r"Relative norm: ([0-9.eE+-]+)", lambda r: r[-1] < 1e-6),
 ])
 def test_examples_run_on_the_api_layer(script, args, pattern, check, tmp_path):
     """examples/*.py through tests/run_emulated.py at tiny sizes: the scripts stay in step

@@ -93,6 +93,13 @@ def test_elasticity_2d_matches_oracle(mode):
     U = spline.solveLinearSystem(MTAM, MTb, uh)
     assert rel(U.get_local(), Uo) < 1e-10
     assert rel(uh.comps[1].iga.cpu().numpy(), Uo[n:]) < 1e-10
+    # no linearSolver = the reference's direct LU (common.py:1255-1256): band Cholesky on the
+    # node-major interleaved block system
+    spline.setSolverOptions()
+    ud = Function(spline.V)
+    Ud = spline.solveLinearSystem(MTAM, MTb, ud)
+    assert spline.lastSolve["method"] == "direct"
+    assert rel(Ud.get_local(), Uo) < 1e-11
 
 
 def test_elasticity_3d_three_fields_fused_and_newton():
@@ -116,7 +123,8 @@ def test_elasticity_3d_three_fields_fused_and_newton():
     assert rel(un.iga.cpu().numpy(), Uo) < 1e-8
 
 
-def test_kl_shell_scordelis_lo_roof_on_the_device():
+@pytest.mark.parametrize("solver", ["jacobi", "direct"])
+def test_kl_shell_scordelis_lo_roof_on_the_device(solver):
     """BASELINE configs[4] in small: the SVK Kirchhoff-Love shell residual of the
     reference's kl-shell-svk demo (tests/test_kl_shell_cpu.shell_forms, CPU-checked) on the
     cubic NURBS Scordelis-Lo roof, three fields, Newton with J = derivative(R, y) through
@@ -145,8 +153,10 @@ def test_kl_shell_scordelis_lo_roof_on_the_device():
     assert relm(K.to_scipy(), Kh) < 1e-10
     ks = KrylovSolver("cg", "jacobi")
     ks.parameters["relative_tolerance"] = 1e-11
-    spline.setSolverOptions(maxIters=6, relativeTolerance=1e-6, linearSolver=ks)
+    spline.setSolverOptions(maxIters=6, relativeTolerance=1e-6,
+                            linearSolver=ks if solver == "jacobi" else None)
     spline.solveNonlinearVariationalProblem(res, dres, y)
+    assert spline.lastSolve["method"] == solver
     Uv = y.iga.cpu().numpy()
     s1 = host.ts.splines[1]
     span = int(s1.getKnotSpan(0.5))

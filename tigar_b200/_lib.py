@@ -120,7 +120,7 @@ SIGNATURES = {
                   c_vp, c_vp, c_vp],
     "tg_xpby": [c_vp, c_dbl, c_vp, c_i64, c_vp],
     "tg_pcg_update": [c_vp, c_vp, c_vp, c_vp, c_dbl, c_i64, c_vp, c_vp, c_vp],
-    "tg_band_from_win": [PW, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp],
+    "tg_band_from_win": [PW, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp],
     "tg_band_cholesky": [c_i64, c_i32, c_i32, c_vp, c_vp, c_vp],
     "tg_band_solve": [c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp],
     "tg_win_asym": [PW, c_vp, c_vp, c_vp],

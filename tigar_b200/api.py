@@ -572,23 +572,50 @@ class AbstractCoordinateChartSpline(AbstractExtractionGenerator):
     Python loop of generateM (:1497-1509) is replaced by the Kronecker-window
     kernel ``tg_m_fill``."""
 
+    def isTensorProduct(self):
+        """True when every field is a tensor-product ``BSpline`` (the structured fast path);
+        False for a user ``AbstractScalarBasis`` (generic CSR path, tigar_b200/generic.py)."""
+        return all(isinstance(self.getScalarSpline(i), BSpline)
+                   for i in range(-1, self.getNFields()))
+
     def _tensor_spline(self, field):
         sp = self.getScalarSpline(field)
         if not isinstance(sp, BSpline):
-            raise NotImplementedError(
-                "only tensor-product BSpline bases are on the CUDA path "
-                "(generic AbstractScalarBasis: next row n4)")
+            raise NotImplementedError("this operation needs a tensor-product BSpline basis")
         return sp
 
     def patch(self):
         if self._patch is None:
-            sp = self._tensor_spline(-1)
-            self._patch = TensorPatch([s.p for s in sp.splines], None, splines=sp.splines,
-                                      eps=self.getIgnoreEps())
+            if self.isTensorProduct():
+                sp = self._tensor_spline(-1)
+                self._patch = TensorPatch([s.p for s in sp.splines], None, splines=sp.splines,
+                                          eps=self.getIgnoreEps())
+            else:
+                # generic basis: carrier B-splines bring its tensor-product extraction mesh
+                # and the Q_p Lagrange tables; the IGA side is the basis' own M (CSR)
+                from .bsplines import TensorMesh
+                from .generic import carrier_splines
+                if not isinstance(self.mesh, TensorMesh):
+                    raise NotImplementedError(
+                        "generic AbstractScalarBasis: generateMesh() must return a "
+                        "tensor-product TensorMesh (element soups are out of scope)")
+                if self.getNFields() != 1:
+                    raise NotImplementedError("generic bases: one field")
+                sp = carrier_splines(self.mesh, int(self.getDegree(-1)))
+                self._patch = TensorPatch([s.p for s in sp], None, splines=sp,
+                                          eps=self.getIgnoreEps())
+                self._patch.generic = True
+                self._patch.n_iga = int(self.getNcp(-1))
         return self._patch
 
     def generateM_control(self):
-        return self.patch().build_M()
+        if self.isTensorProduct():
+            return self.patch().build_M()
+        # the reference's loop (common.py:1497-1509): the user's basis evaluated at every FE node
+        from .generic import CsrMatrix
+        x = self.patch().fe_node_coords()
+        rows = [self.getNodesAndEvals(x[I], -1) for I in range(x.shape[0])]
+        return CsrMatrix.from_rows(rows, int(self.getNcp(-1)), self.getIgnoreEps())
 
     def equalOrder(self):
         """True if every field uses the control mesh's scalar spline (same degrees and
@@ -730,6 +757,11 @@ class ExtractedSpline(object):
             if mode not in (None, "fused"):
                 raise NotImplementedError("multi-GPU runs use the element-fused path")
             mode = "fused"
+        if getattr(self, "_generic", False):
+            if mode not in (None, "csr"):
+                raise NotImplementedError("a generic AbstractScalarBasis uses the csr path "
+                                          "(FE assembly + M^T A M with its own M)")
+            mode = "csr"
         self.mode = mode or os.environ.get("TIGAR_B200_MODE") or self._auto_mode()
         if self.mode not in ("csr", "fused", "matfree"):
             raise ValueError("mode must be 'csr', 'fused' or 'matfree'")
@@ -748,15 +780,26 @@ class ExtractedSpline(object):
         self.p = [generator.getDegree(i) for i in range(self.nFields)]
         self.mesh = generator.mesh
         self.comm = generator.getComm()
-        sp = generator._tensor_spline(-1)
-        if self.nFields > 1 and not generator.equalOrder():
-            raise NotImplementedError("multi-field splines are built for equal-order "
-                                      "fields (every field on the control mesh's spline)")
+        self._generic = not generator.isTensorProduct()
         part = (self.comm.rank, self.comm.size) if self.comm.size > 1 else None
-        if self.nFields > 1 and part is not None:
-            raise NotImplementedError("multi-field systems run on one GPU")
-        self._patch = TensorPatch([s.p for s in sp.splines], None, quadDeg=quadDeg,
-                                  splines=sp.splines, eps=generator.getIgnoreEps(), part=part)
+        if self._generic:
+            if part is not None:
+                raise NotImplementedError("generic bases run on one GPU")
+            base = generator.patch()                  # carrier of the FE side
+            self._patch = TensorPatch(base.degrees, None, quadDeg=quadDeg, splines=base.splines,
+                                      eps=generator.getIgnoreEps())
+            self._patch.generic = True
+            self._patch.n_iga = base.n_iga
+        else:
+            sp = generator._tensor_spline(-1)
+            if self.nFields > 1 and not generator.equalOrder():
+                raise NotImplementedError("multi-field splines are built for equal-order "
+                                          "fields (every field on the control mesh's spline)")
+            if self.nFields > 1 and part is not None:
+                raise NotImplementedError("multi-field systems run on one GPU")
+            self._patch = TensorPatch([s.p for s in sp.splines], None, quadDeg=quadDeg,
+                                      splines=sp.splines, eps=generator.getIgnoreEps(),
+                                      part=part)
         self.V = FunctionSpace(self, self.nFields)
         self.V_control = FunctionSpace(self, 1, control=True)
         self.VE, self.VE_control = generator.VE, generator.VE_control
@@ -855,7 +898,9 @@ class ExtractedSpline(object):
 
     def M_matrix(self):
         if self._M is None:
-            if self.generator is not None and self.generator._M is not None:
+            if getattr(self, "_generic", False):
+                self._M = self.generator.M            # the basis' own rows (CSR)
+            elif self.generator is not None and self.generator._M is not None:
                 self._M = self.generator._M
             else:
                 self._M = self._patch.build_M()
@@ -1136,6 +1181,14 @@ class ExtractedSpline(object):
         atol = prm.get("absolute_tolerance", 0.0)
         maxit = prm.get("maximum_iterations", 200000)
         from .matfree import FormOperator
+        from .generic import GenericPtAP
+        if isinstance(MTAM, GenericPtAP):
+            x0 = None if u.iga is None else u.iga.clone()
+            x, its, rel = MTAM.solve(MTb.t, x0, rtol, atol, maxit)
+            self.lastSolve = dict(iterations=its, relative_residual=rel, method="cg")
+            self._check_converged(ls, its, rel, maxit, rtol, atol)
+            u.set_iga(x)
+            return DeviceVector(x)
         if isinstance(MTAM, FormOperator):
             from .matfree import solve_matfree_cg, solve_matfree_fd
             method = os.environ.get("TIGAR_B200_SOLVER", self._solver_method(ls))
@@ -1150,8 +1203,9 @@ class ExtractedSpline(object):
             return DeviceVector(x)
         if self.nFields > 1:
             from . import multifield as MF
-            x, its, rel = MF.solve_block_cg(MTAM, MTb.t, rtol, atol, maxit)
-            self.lastSolve = dict(iterations=its, relative_residual=rel, method="jacobi")
+            x, its, rel, used = MF.solve_block(MTAM, MTb.t, rtol, atol, maxit,
+                                               self._solver_method(ls))
+            self.lastSolve = dict(iterations=its, relative_residual=rel, method=used)
             self._check_converged(ls, its, rel, maxit, rtol, atol)
             u.set_iga(x)
             return DeviceVector(x)

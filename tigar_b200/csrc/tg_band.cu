@@ -26,8 +26,11 @@ int tg_dgemm_lower_nt(int M, int K, double alpha, const double* A, int lda, doub
                       double* C, int ldc, cudaStream_t st);
 
 // ---- windowed CSR -> lower band -----------------------------------------------------------
+// Block (fr, fc) of an nf x nf equal-order multi-field system goes to the node-major
+// interleaved numbering  row' = nf*row + fr, col' = nf*col + fc  (band = nf*bw + nf - 1).
 __global__ void k_band_from_win(TgWin w, const double* __restrict__ vals, int bw, int ldab,
-                                double* __restrict__ AB, int* __restrict__ info) {
+                                double* __restrict__ AB, int* __restrict__ info, int nf, int fr,
+                                int fc) {
   const int64_t nrows = (int64_t)w.nr[0] * w.nr[1] * w.nr[2];
   const int lane = threadIdx.x & 31;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -44,15 +47,16 @@ __global__ void k_band_from_win(TgWin w, const double* __restrict__ vals, int bw
       const int d1 = t % rw.len[1], d2 = t / rw.len[1];
       const int64_t col = (rw.lo[0] + d0) +
                           (int64_t)w.nc[0] * ((rw.lo[1] + d1) + (int64_t)w.nc[1] * (rw.lo[2] + d2));
-      if (col > row) continue;
-      const int64_t off = row - col;
+      const int64_t brow = (int64_t)nf * row + fr, bcol = (int64_t)nf * col + fc;
+      if (bcol > brow) continue;
+      const int64_t off = brow - bcol;
       const double v = vals[ra.base + ((long long)(d2 * rw.len[1] + d1) * ra.len0 +
                                        (rw.lo[0] + d0 - ra.lo0)) * ra.stride];
       if (off > bw) {
         if (v != 0.0) atomicExch(info, -1);
         continue;
       }
-      AB[off + col * (int64_t)ldab] = v;
+      AB[off + bcol * (int64_t)ldab] = v;
     }
   }
 }
@@ -60,14 +64,16 @@ __global__ void k_band_from_win(TgWin w, const double* __restrict__ vals, int bw
 // AB must be zero-initialised by the caller.  info (device int, zero-initialised): -1 if an
 // entry outside the band was non-zero.
 extern "C" int tg_band_from_win(const tg_win* h_w, const double* vals, int32_t bw, int32_t ldab,
-                                double* AB, int32_t* info, void* stream) {
+                                double* AB, int32_t* info, int32_t nf, int32_t fr, int32_t fc,
+                                void* stream) {
+  TG_REQUIRE(nf >= 1 && fr >= 0 && fr < nf && fc >= 0 && fc < nf, "field indices");
   TG_REQUIRE(h_w->layout == 0, "band conversion needs the row-major window layout");
   const int64_t n = tg_win_nrows(h_w);
   if (n == 0) return 0;
   int64_t g = tg_cdiv(n * 32, 256);
   if (g > 148 * 32) g = 148 * 32;
   k_band_from_win<<<(unsigned)g, 256, 0, tg_stream(stream)>>>(tg_win_dev(h_w), vals, bw, ldab, AB,
-                                                             info);
+                                                             info, nf, fr, fc);
   TG_LAUNCH_CHECK();
   return 0;
 }

@@ -465,6 +465,9 @@ class TensorPatch(object):
 
     def mt_vec(self, M, b):
         """M^T b (multTranspose, common.py:97-109)."""
+        from .generic import CsrMatrix
+        if isinstance(M, CsrMatrix):
+            return M.transpose().matvec(b)
         out = dev.empty(self.n_iga)
         check(lib.tg_mt_vec(self.window("M").ref(), self.window("MT").ref(), dev.ptr(M.vals),
                             dev.ptr(b), dev.ptr(out), dev.stream()))
@@ -1231,6 +1234,9 @@ class TensorPatch(object):
 
     def ptap(self, A, M=None, keep_AP=False):
         """C = M^T A M on windowed operands (MatPtAP, common.py:1194-1195)."""
+        from .generic import CsrMatrix, GenericPtAP
+        if isinstance(M, CsrMatrix):
+            return GenericPtAP(A, M)
         if not keep_AP and not os.environ.get("TIGAR_B200_PTAP_GENERIC"):
             if os.environ.get("TIGAR_B200_PTAP", "march") == "march" \
                     and self._march_setup() is not None:
@@ -1285,6 +1291,8 @@ class TensorPatch(object):
 
     def apply_bcs_matrix(self, Cm, mask, diag=1.0):
         Cm.bc_mask, Cm.bc_diag = mask, float(diag)      # read by the preconditioned solvers
+        if Cm.window is None:                           # operator form (generic basis)
+            return Cm
         if Cm.window.layout == 0 and os.environ.get("TIGAR_B200_BC_HP", "1") == "1":
             hp, exact = self.mask_planes(mask)
             if exact:

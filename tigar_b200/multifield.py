@@ -224,3 +224,42 @@ def solve_block_cg(Cm, b, rtol=1e-12, atol=0.0, maxit=100000, check_every=5):
     """Jacobi-CG on a BlockMatrix (same driver as the row-distributed solver)."""
     from .multigpu import dist_cg
     return dist_cg(BlockOps(Cm), b, rtol, atol, maxit, check_every)
+
+
+def solve_block(Cm, b, rtol=1e-12, atol=0.0, maxit=100000, method="auto"):
+    """solve() of common.py:1255-1258 for an equal-order multi-field system.  "auto": the
+    reference's default is a direct LU -> band Cholesky on the node-major interleaved system
+    while it is affordable (with iterative refinement), Jacobi-CG beyond.
+    Returns (x, iterations, relative residual, method)."""
+    import os
+    import torch
+    from . import dev, solvers
+    method = os.environ.get("TIGAR_B200_SOLVER", method)
+    if method in ("auto", "fd"):
+        free, _ = torch.cuda.mem_get_info()
+        nbytes, flops = solvers.BlockBandCholesky.cost(Cm)
+        method = "direct" if solvers._affordable(nbytes, flops, free) else "jacobi"
+    if method == "jacobi":
+        x, its, rel = solve_block_cg(Cm, b, rtol, atol, maxit)
+        return x, its, rel, "jacobi"
+    ops = BlockOps(Cm)
+    ops.tmp = dev.empty(Cm.n)
+    bc = solvers.BlockBandCholesky(Cm).factor(matvec=ops.matvec)
+    x = bc.solve(b)
+    bb = float(b.norm())
+    r = dev.empty(b.numel())
+    ops.matvec(x, r)
+    r.neg_().add_(b)
+    rel = float(r.norm()) / bb if bb > 0 else 0.0
+    for _ in range(3):                       # iterative refinement (see TensorPatch.solve)
+        if rel < 1e-15:
+            break
+        x2 = bc.solve(r).add_(x)
+        r2 = dev.empty(b.numel())
+        ops.matvec(x2, r2)
+        r2.neg_().add_(b)
+        rel2 = float(r2.norm()) / bb if bb > 0 else 0.0
+        if not rel2 < rel:
+            break
+        x, r, rel = x2, r2, rel2
+    return x, 1, rel, "direct"

@@ -352,7 +352,7 @@ class BandCholesky(object):
         self.AB = dev.zeros(self.ldab * self.n)
         info = dev.zeros(1, dev.I32)
         check(lib.tg_band_from_win(w.ref(), dev.ptr(Cm.vals), self.bw, self.ldab, dev.ptr(self.AB),
-                                   dev.ptr(info), dev.stream()))
+                                   dev.ptr(info), 1, 0, 0, dev.stream()))
         check(lib.tg_band_cholesky(self.n, self.bw, self.ldab, dev.ptr(self.AB), dev.ptr(info),
                                    dev.stream()))
         code = int(info.item())
@@ -374,11 +374,77 @@ class BandCholesky(object):
         return x
 
 
-def direct_affordable(w, free_bytes=None):
-    """Policy: use the band solver when its storage and work are small next to the device."""
+class BlockBandCholesky(object):
+    """Direct solve of an equal-order multi-field system (BlockMatrix of windowed blocks on one
+    pattern): the blocks are interleaved node-major (row' = nf*row + field), which keeps the
+    band at nf*bw + nf - 1, and factored by the same band Cholesky.  This is what makes the
+    Newton steps of the Kirchhoff-Love shell (4th order, cond ~ h^-4) solvable: the reference
+    uses a direct LU there as well (common.py:1255-1256)."""
+
+    def __init__(self, Bm):
+        self.Bm = Bm
+        self.nf, self.nb = Bm.nf, Bm.n
+        any_block = next(iter(Bm.blocks.values()))
+        self.w = any_block.window
+        self.n = self.nf * self.nb
+        self.bw = self.nf * BandCholesky.bandwidth(self.w) + self.nf - 1
+        self.ldab = self.bw + BandCholesky.NB + ((self.bw + BandCholesky.NB) & 1)
+        self.AB = None
+
+    @classmethod
+    def cost(cls, Bm):
+        w = next(iter(Bm.blocks.values())).window
+        n = Bm.nf * Bm.n
+        bw = Bm.nf * BandCholesky.bandwidth(w) + Bm.nf - 1
+        return 8.0 * n * (bw + BandCholesky.NB + 1), float(n) * (bw + BandCholesky.NB) ** 2
+
+    def factor(self, matvec=None, sym_tol=1e-9):
+        import torch
+        if matvec is not None:                  # symmetry test: x.Ay = y.Ax for random x, y
+            g = torch.Generator(device=dev.device()).manual_seed(1)
+            x = torch.rand(self.n, dtype=torch.float64, device=dev.device(), generator=g)
+            y = torch.rand(self.n, dtype=torch.float64, device=dev.device(), generator=g)
+            ax, ay = dev.empty(self.n), dev.empty(self.n)
+            matvec(x, ax)
+            matvec(y, ay)
+            s1, s2 = float(torch.dot(y, ax)), float(torch.dot(x, ay))
+            if abs(s1 - s2) > sym_tol * max(abs(s1), abs(s2), 1e-300):
+                raise SolverBreakdown("block matrix is not symmetric (y.Ax = %.12e, x.Ay = %.12e)"
+                                      % (s1, s2))
+        self.AB = dev.zeros(self.ldab * self.n)
+        info = dev.zeros(1, dev.I32)
+        for (f, g_), B in sorted(self.Bm.blocks.items()):
+            check(lib.tg_band_from_win(B.window.ref(), dev.ptr(B.vals), self.bw, self.ldab,
+                                       dev.ptr(self.AB), dev.ptr(info), self.nf, f, g_,
+                                       dev.stream()))
+        check(lib.tg_band_cholesky(self.n, self.bw, self.ldab, dev.ptr(self.AB), dev.ptr(info),
+                                   dev.stream()))
+        code = int(info.item())
+        if code != 0:
+            self.AB = None
+            raise SolverBreakdown("band Cholesky (block system): %s" % (
+                "non-zero outside the computed band" if code < 0 else
+                "pivot block at row %d is not positive definite" % (code - 1)))
+        return self
+
+    def solve(self, b):
+        """b, result: field-major (globalDof numbering, common.py:254-262)."""
+        rhs = b.view(self.nf, self.nb).t().contiguous().view(-1)        # -> node-major
+        work, x = dev.empty(self.n), dev.empty(self.n)
+        check(lib.tg_band_solve(self.n, self.bw, self.ldab, dev.ptr(self.AB), dev.ptr(rhs),
+                                dev.ptr(work), dev.ptr(x), dev.stream()))
+        return x.view(self.nb, self.nf).t().contiguous().view(-1)
+
+
+def _affordable(nbytes, flops, free_bytes):
     lim_gb = float(os.environ.get("TIGAR_B200_DIRECT_GB", "12"))
     lim_flops = float(os.environ.get("TIGAR_B200_DIRECT_FLOPS", "3e13"))
-    nbytes, flops = BandCholesky.cost(w)
     if free_bytes is not None and nbytes > 0.5 * free_bytes:
         return False
     return nbytes <= lim_gb * 2 ** 30 and flops <= lim_flops
+
+
+def direct_affordable(w, free_bytes=None):
+    """Policy: use the band solver when its storage and work are small next to the device."""
+    nbytes, flops = BandCholesky.cost(w)
+    return _affordable(nbytes, flops, free_bytes)
