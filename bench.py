@@ -190,7 +190,8 @@ def one_step(kv, cm, control_net, mode, rtol, to_host, keep=False):
     ev[4].record()
     out = (spline._patch.n_iga, spline.lastSolve["iterations"], ev, res, MTAM)
     if keep:
-        out = out + (dict(spline=spline, MTb=MTb, U=U, soln=soln,
+        # (the Function object itself must stay alive: forms refer to it by id)
+        out = out + (dict(spline=spline, MTb=MTb, U=U, soln=soln, uh_function=uh,
                           uh=spline.rationalize(uh) if annulus else uh),)
     return out
 
