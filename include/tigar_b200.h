@@ -80,6 +80,10 @@ typedef struct {
 
 const char* tg_last_error(void);
 int tg_version(void);
+/* sizeof(tg_win) / sizeof(tg_basis) as compiled into the library: lets a binding (ctypes, cgo,
+ * ...) verify its own struct definition before it passes a pointer                         */
+int64_t tg_sizeof_win(void);
+int64_t tg_sizeof_basis(void);
 /* kernels launched by this library so far (bench.py's gpu_launches claim) */
 int64_t tg_launch_count(void);
 /* number of SMs of the current device (grid sizing) */

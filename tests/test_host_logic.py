@@ -153,6 +153,33 @@ def test_cabi_exports_every_declared_symbol():
     assert lib.tg_version() >= 100
 
 
+def test_integration_stub_matches_header_and_library():
+    """INTEGRATION.md's ctypes structs are generated from the header (tools/gen_ctypes_stub.py);
+    executing the documented stub against the built library must give the header's field
+    lists and the library's own sizeof (VERDICT r1 #11: a stale stub passed a short struct)."""
+    import ctypes as C
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "gen_ctypes_stub", os.path.join(ROOT, "tools", "gen_ctypes_stub.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    hdr = open(os.path.join(ROOT, "include", "tigar_b200.h")).read()
+    structs = gen.parse_structs(hdr)
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = md[md.index(gen.BEGIN) + len(gen.BEGIN):md.index(gen.END)]
+    code = re.search(r"```python\n(.*?)```", block, re.S).group(1)
+    assert code.strip() == gen.stub(structs).strip(), "run tools/gen_ctypes_stub.py --write"
+    lib = C.CDLL(os.path.join(ROOT, "tigar_b200", "libtigar_b200.so"))
+    lib.tg_sizeof_win.restype = lib.tg_sizeof_basis.restype = C.c_int64
+    ns = {"C": C, "lib": lib}
+    exec(code, ns)                                    # includes the sizeof assertions
+    from tigar_b200 import _lib
+    for name in ("tg_win", "tg_basis"):
+        assert [f[0] for f in ns[name]._fields_] == [f[0] for f in structs[name]]
+        assert [f[0] for f in getattr(_lib, name)._fields_] == [f[0] for f in structs[name]]
+        assert C.sizeof(ns[name]) == C.sizeof(getattr(_lib, name))
+
+
 def test_product_does_not_import_oracle():
     import subprocess
     import sys

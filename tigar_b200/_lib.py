@@ -45,6 +45,8 @@ SIGNATURES = {
     "tg_last_error": [],
     "tg_version": [],
     "tg_device_sm_count": [],
+    "tg_sizeof_win": [],
+    "tg_sizeof_basis": [],
     "tg_launch_count": [],
     "tg_last_spmv_kind": [],
     "tg_bspline_eval_batch": [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32,
@@ -130,12 +132,19 @@ SIGNATURES = {
                      c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_vp, c_i64,
                      c_i64, c_i64, c_i64, c_i32, PW, c_i64, c_i32, c_i32, c_vp, c_vp],
 }
-_RESTYPES = {"tg_last_error": C.c_char_p, "tg_prof_enable": None, "tg_prof_get": None, "tg_launch_count": c_i64, "tg_win_storage": c_i64}
+_RESTYPES = {"tg_sizeof_win": c_i64, "tg_sizeof_basis": c_i64, "tg_last_error": C.c_char_p, "tg_prof_enable": None, "tg_prof_get": None, "tg_launch_count": c_i64, "tg_win_storage": c_i64}
 
 for _name, _args in SIGNATURES.items():
     _f = getattr(lib, _name)          # AttributeError if a symbol is missing
     _f.argtypes = _args
     _f.restype = _RESTYPES.get(_name, C.c_int)
+
+
+if lib.tg_sizeof_win() != C.sizeof(tg_win) or lib.tg_sizeof_basis() != C.sizeof(tg_basis):
+    raise ImportError("tigar_b200: descriptor structs of the ctypes binding (%d, %d bytes) do not "
+                      "match libtigar_b200.so (%d, %d): rebuild the library"
+                      % (C.sizeof(tg_win), C.sizeof(tg_basis), lib.tg_sizeof_win(),
+                         lib.tg_sizeof_basis()))
 
 
 class TigarError(RuntimeError):

@@ -12,7 +12,11 @@ void tg_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* tg_last_error(void) { return g_err; }
-extern "C" int tg_version(void) { return 100; }
+extern "C" int tg_version(void) { return 200; }
+// sizeof of the descriptor structs as THIS library was compiled: a binding whose struct
+// definition is stale (too short / differently padded) can detect it before passing a pointer
+extern "C" int64_t tg_sizeof_win(void) { return (int64_t)sizeof(tg_win); }
+extern "C" int64_t tg_sizeof_basis(void) { return (int64_t)sizeof(tg_basis); }
 
 extern "C" int tg_device_sm_count(void) {
   int dev = 0, sms = 0;

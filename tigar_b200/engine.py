@@ -114,13 +114,22 @@ class Window(object):
     def transpose(self):
         lo, hi = [], []
         for d in range(self.dim):
-            l = np.full(self.nc[d], np.iinfo(np.int32).max, dtype=np.int64)
-            h = np.full(self.nc[d], -1, dtype=np.int64)
-            # a column c is covered by every row r with lo[r] <= c <= hi[r]
-            for rr in range(self.nr[d]):
-                a, b = self.lo[d][rr], self.hi[d][rr]
-                l[a:b + 1] = np.minimum(l[a:b + 1], rr)
-                h[a:b + 1] = np.maximum(h[a:b + 1], rr)
+            a, b = self.lo[d].astype(np.int64), self.hi[d].astype(np.int64)
+            if np.all(np.diff(a) >= 0) and np.all(np.diff(b) >= 0):
+                # monotone windows (every spline / FE pattern): column c is covered by the
+                # rows from the first one with hi >= c to the last one with lo <= c
+                c = np.arange(self.nc[d], dtype=np.int64)
+                l = np.searchsorted(b, c, side="left")
+                h = np.searchsorted(a, c, side="right") - 1
+                empty = l > h
+                l[empty] = np.iinfo(np.int32).max
+                h[empty] = -1
+            else:
+                l = np.full(self.nc[d], np.iinfo(np.int32).max, dtype=np.int64)
+                h = np.full(self.nc[d], -1, dtype=np.int64)
+                for rr in range(self.nr[d]):
+                    l[a[rr]:b[rr] + 1] = np.minimum(l[a[rr]:b[rr] + 1], rr)
+                    h[a[rr]:b[rr] + 1] = np.maximum(h[a[rr]:b[rr] + 1], rr)
             lo.append(l)
             hi.append(h)
         return Window(self.nc, self.nr, lo, hi)
@@ -130,8 +139,12 @@ class Window(object):
         lo, hi = [], []
         for d in range(self.dim):
             assert self.nc[d] == other.nr[d]
-            l = np.array([other.lo[d][a:b + 1].min() for a, b in zip(self.lo[d], self.hi[d])])
-            h = np.array([other.hi[d][a:b + 1].max() for a, b in zip(self.lo[d], self.hi[d])])
+            ol, oh = other.lo[d], other.hi[d]
+            if np.all(np.diff(ol) >= 0) and np.all(np.diff(oh) >= 0):
+                l, h = ol[self.lo[d]], oh[self.hi[d]]          # monotone: ends of the range
+            else:
+                l = np.array([ol[a:b + 1].min() for a, b in zip(self.lo[d], self.hi[d])])
+                h = np.array([oh[a:b + 1].max() for a, b in zip(self.lo[d], self.hi[d])])
             lo.append(l)
             hi.append(h)
         return Window(self.nr, other.nc, lo, hi)
@@ -359,7 +372,11 @@ class TensorPatch(object):
         self.quadDeg = 2 * self.pf if quadDeg is None else int(quadDeg)
         self.nq = self.quadDeg // 2 + 1                 # Gauss-Legendre points / direction
         self.eps = eps
-        self.dirs = [Dir1D(s, self.pf, self.nq, eps) for s in self.splines]
+        self.dirs = []
+        for s in self.splines:          # directions with the same knot vector share their tables
+            twin = next((D for D in self.dirs if D.s.p == s.p and len(D.s.knots) == len(s.knots)
+                         and np.array_equal(D.s.knots, s.knots)), None)
+            self.dirs.append(twin if twin is not None else Dir1D(s, self.pf, self.nq, eps))
         self.nel = [D.nel for D in self.dirs]
         self.ncp = [D.ncp for D in self.dirs]
         self.nfe = [D.nfe for D in self.dirs]
