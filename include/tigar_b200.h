@@ -500,6 +500,12 @@ int tg_win_asym(const tg_win* h_w, const double* vals, double* out2, void* strea
  *                          pair = 0, the vector slab [vec_row0, vec_row0+vec_nr) of the last
  *                          direction; ninner = F0*F1 (pair) or the plane size; h_F0 = total 1-D
  *                          window length of the first direction.
+ *   perm, h_Wperm          3-D matrices: the stage before the last (perm = 1, last = 0) writes the
+ *                          pair index (f1, f0) in the thread order of the last stage
+ *                          (u = S1[i1]*F0 + S0[i0]*len1 + dj1*len0 + dj0, windows of h_Wperm,
+ *                          h_F0 = F0) and the last stage (perm = 1) reads it so: every (cell,
+ *                          input) item of a CTA is then one contiguous run, staged by 1-D bulk
+ *                          async copies (TMA) through a shared-memory ring (even nq).
  * tg_gsf_supported(nloc, nq): instantiated for 2 <= nloc <= 5, nq in {nloc, nloc+1}.           */
 int tg_gsf_supported(int32_t nloc, int32_t nq);
 int tg_gsf_stage(const double* X, int64_t skin, int64_t scell, int32_t cbase,
@@ -509,7 +515,8 @@ int tg_gsf_stage(const double* X, int64_t skin, int64_t scell, int32_t cbase,
                  int32_t maxin, int32_t pair, int64_t ninner, int32_t nv, int32_t nw,
                  double* Y, int64_t skout, int64_t so_f, int64_t so_u, int64_t so_v,
                  int32_t last, const tg_win* h_W, int64_t h_F0, int32_t vec_row0,
-                 int32_t vec_nr, double* out, void* stream);
+                 int32_t vec_nr, double* out, int32_t perm, const tg_win* h_Wperm,
+                 void* stream);
 
 #ifdef __cplusplus
 }

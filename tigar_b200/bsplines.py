@@ -54,63 +54,116 @@ def dof2ijk(dof, M, N):
 
 
 class DofList(list):
-    """A plain Python list of DoF ids (what the reference's ``getSideDofs`` returns,
-    BSplines.py:599-649) that also remembers the numpy arrays it was concatenated from, so
-    that a 4e5-entry zero-DoF list does not have to be converted back element by element
-    (30 ms per step at 256^3).  Any in-place edit other than ``+=`` drops the arrays."""
+    """A Python list of DoF ids (what the reference's ``getSideDofs`` returns,
+    BSplines.py:599-649) that is backed by the numpy arrays it was concatenated from and only
+    becomes a real list of Python ints when list semantics are asked for: the 4e5 side DoFs of a
+    256^3 patch cost 10 ms per step to box and 30 ms to unbox again.  ``len``, iteration, ``+``,
+    ``+=`` and numpy conversion (``__array__``) work on the arrays; every other list method
+    materialises first.  Any in-place edit other than ``+=`` drops the arrays."""
 
     MAX_CHUNKS = 64          # many tiny pieces: converting the list itself is cheaper
 
-    def __init__(self, items=(), chunks=None):
-        list.__init__(self, items)
-        self._chunks = chunks if chunks is not None else ([] if len(self) == 0 else None)
+    def __init__(self, items=(), chunks=None, lazy=False):
+        if lazy:
+            list.__init__(self)
+            self._chunks = list(chunks)
+            self._mat = False
+        else:
+            list.__init__(self, items)
+            self._chunks = chunks if chunks is not None else ([] if list.__len__(self) == 0
+                                                              else None)
+            self._mat = True
         self._n = sum(c.size for c in self._chunks) if self._chunks is not None else 0
 
     @staticmethod
     def from_array(a):
         a = np.ascontiguousarray(a, dtype=np.int64).ravel()
-        return DofList(a.tolist(), [a])
+        return DofList(chunks=[a], lazy=True)
+
+    def _materialise(self):
+        if not self._mat:
+            items = self.asarray().tolist()
+            self._mat = True
+            list.extend(self, items)
+        return self
 
     def _valid(self):
-        return self._chunks is not None and self._n == len(self)
+        return self._chunks is not None and (not self._mat or self._n == list.__len__(self))
 
     def asarray(self):
         """int64 array of the entries (duplicates and order kept)."""
-        if self._valid() and self._chunks:
+        if self._valid():
             ch = self._chunks
+            if not ch:
+                return np.zeros(0, dtype=np.int64)
             return ch[0] if len(ch) == 1 else np.concatenate(ch)
-        return np.array(self, dtype=np.int64)
+        return np.array(list(list.__iter__(self)), dtype=np.int64)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.asarray()
+        return a if dtype is None else a.astype(dtype)
+
+    def __len__(self):
+        return list.__len__(self) if self._mat else self._n
+
+    def __bool__(self):
+        return len(self) > 0
+
+    def __iter__(self):
+        if self._mat:
+            return list.__iter__(self)
+        return iter(self.asarray().tolist())
 
     def __iadd__(self, other):
+        lazy_other = isinstance(other, DofList) and other._valid()
+        if not self._mat and self._valid() and len(self._chunks) < self.MAX_CHUNKS:
+            new = other._chunks if lazy_other else [np.array(list(other), dtype=np.int64).ravel()]
+            self._chunks = self._chunks + list(new)
+            self._n += sum(c.size for c in new)
+            return self
         ok = self._valid() and len(self._chunks) < self.MAX_CHUNKS
+        self._materialise()
         list.__iadd__(self, other)
         if ok:
-            if isinstance(other, DofList) and other._valid():
-                new = other._chunks
-            else:
-                new = [np.array(other, dtype=np.int64).ravel()]
-            self._chunks = self._chunks + new
+            new = other._chunks if lazy_other else [np.array(list(other), dtype=np.int64).ravel()]
+            self._chunks = self._chunks + list(new)
             self._n += sum(c.size for c in new)
         else:
             self._chunks = None
         return self
 
     def __add__(self, other):
-        out = DofList(self, None if self._chunks is None else list(self._chunks))
+        if not self._mat and self._valid():
+            out = DofList(chunks=self._chunks, lazy=True)
+        else:
+            out = DofList(list(self), None if self._chunks is None else list(self._chunks))
         out += other
         return out
 
+    def _read(name):                                  # noqa: N805
+        def f(self, *a, **k):
+            self._materialise()
+            return getattr(list, name)(self, *a, **k)
+        f.__name__ = name
+        return f
+
     def _edit(name):                                  # noqa: N805
         def f(self, *a, **k):
+            self._materialise()
             self._chunks = None
             return getattr(list, name)(self, *a, **k)
         f.__name__ = name
         return f
 
+    for _n in ("__getitem__", "__contains__", "__eq__", "__ne__", "__repr__", "__str__", "index",
+               "count", "copy", "__reversed__", "__mul__", "__rmul__", "__lt__", "__le__",
+               "__gt__", "__ge__"):
+        locals()[_n] = _read(_n)
     for _n in ("append", "extend", "insert", "pop", "remove", "sort", "reverse", "clear",
                "__setitem__", "__delitem__", "__imul__"):
         locals()[_n] = _edit(_n)
-    del _n, _edit
+    del _n, _edit, _read
+    __hash__ = None
 
 
 class BSpline1(object):

@@ -22,8 +22,18 @@
 // chunks of cell layers (bounded intermediates); partial sums that cross a chunk boundary are
 // added to C by the next chunk (flag per pair, uniform over the CTA).
 // The load vector takes the same route with (p+1) sums per thread.
+//
+// Input staging: a CTA's 256 inner indices x NQ values of one (cell, input) item are ONE
+// contiguous 8 KB run, so (NQ even, 16-byte aligned strides) thread 0 streams the items through a
+// 4-slot shared-memory ring with 1-D bulk async copies (TMA, cp.async.bulk + mbarrier
+// full/empty pairs), three items ahead of the contraction: memory latency is covered by bytes in
+// flight in shared memory (96 KB per SM) instead of by registers (the march holds (p+1)^2 FP64
+// sums per thread and runs at 24 warps/SM).  For the last stage to see contiguous items too, the
+// stage before it writes its output already in the order of the rows of C (perm_* arguments).
+// Fallback (odd NQ or unaligned): one-ahead register prefetch.
 #include "tg_common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 #define GSF_CB 8
 #define GSF_THREADS 256
@@ -54,6 +64,14 @@ struct GsfArgs {
   const int* loL;          // [nrL] window start of the last direction (local columns)
   int row0L, nrL, col0L;   // owned rows of the last direction / column shift
   double* out;             // C values or the load vector
+  // permuted output of the stage before the last (3-D pairs): position of (f1, f0) in the
+  // thread order of the last stage, u = S1[i1]*F0 + S0[i0]*len1 + dj1*len0 + dj0
+  int perm_out, perm_in;
+  const int64_t* pS0;      // [n0+1] (also used by perm_out)
+  const int64_t* pS1;      // [n1+1]
+  const int32_t* pLo1;     // [n1]
+  int pn0;
+  long long pF0;
 };
 
 template <int NL, bool PAIR>
@@ -61,10 +79,13 @@ struct GsfAcc {
   double v[PAIR ? NL * NL : NL];
 };
 
-template <int NL, int NQ, bool PAIR, bool LAST>
-__global__ void __launch_bounds__(GSF_THREADS, (PAIR && NL >= 5) ? 2 : 3)
+template <int NL, int NQ, bool PAIR, bool LAST, int MINB, bool TMA>
+__global__ void __launch_bounds__(GSF_THREADS, (PAIR && NL >= 5) ? 2 : MINB)
 k_gsf(const __grid_constant__ GsfArgs A) {
   constexpr int NLP = (NL + 1) & ~1;
+  constexpr int NS = TMA ? ((NQ <= 4) ? 4 : 3) : 1;               // ring slots
+  __shared__ __align__(128) double ring[TMA ? NS * GSF_THREADS * NQ : 2];
+  __shared__ __align__(8) uint64_t fullb[NS], emptyb[NS];
   __shared__ __align__(16) double stab[GSF_CB * NQ * 3 * NLP];   // [c][q][k][a]
   __shared__ int sfirst[GSF_CB + 1];
   const int tid = threadIdx.x;
@@ -77,6 +98,7 @@ k_gsf(const __grid_constant__ GsfArgs A) {
   bool active;
   long long inner = 0, uoff = 0;
   int rowoff = 0, inrow = 0, len01 = 1;              // LAST && PAIR
+  int pS0i0 = 0, pl0 = 1, pdj0 = 0;                   // perm_out: this thread's (i0, dj0)
   if (!LAST) {
     active = t < A.ninner;
     if (active) {
@@ -84,6 +106,18 @@ k_gsf(const __grid_constant__ GsfArgs A) {
       const long long w = t % A.nw, r = t / A.nw;
       const long long v = r % A.nv, u = r / A.nv;
       uoff = u * A.so_u + v * A.so_v + w;
+      if (PAIR && A.perm_out) {
+        // u = f0 = S0[i0] + dj0 : find i0
+        int lo = 0, hi = A.pn0;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (A.pS0[mid] <= u) lo = mid; else hi = mid;
+        }
+        pS0i0 = (int)A.pS0[lo];
+        pl0 = (int)A.pS0[lo + 1] - pS0i0;
+        pdj0 = (int)u - pS0i0;
+        uoff = v * A.so_v + w;                         // the f-dependent part is added per store
+      }
     }
   } else if (!PAIR) {
     active = t < A.ninner;
@@ -115,7 +149,7 @@ k_gsf(const __grid_constant__ GsfArgs A) {
       const long long l0 = A.S0[i0 + 1] - A.S0[i0];
       const long long dj1 = rem2 / l0, dj0 = rem2 - dj1 * l0;
       f1 = (A.dim == 3) ? A.S1[i1] + dj1 : 0;
-      inner = f1 * A.F0 + A.S0[i0] + dj0;
+      inner = A.perm_in ? t : f1 * A.F0 + A.S0[i0] + dj0;
       rowoff = i1 * A.n0 + i0;
       inrow = (int)rem2;
       len01 = (int)(l0 * l1);
@@ -140,8 +174,14 @@ k_gsf(const __grid_constant__ GsfArgs A) {
 
   auto store = [&](double val, int i, int j, bool add) {
     if (!LAST) {
-      const long long f = PAIR ? A.rowbase[i] + j : i;
-      A.Y[ko * A.skout + f * A.so_f + uoff] = val;
+      if (PAIR && A.perm_out) {
+        const long long s1 = A.pS1[i], l1 = A.pS1[i + 1] - s1;
+        const long long u = s1 * A.pF0 + (long long)pS0i0 * l1 + (j - A.pLo1[i]) * pl0 + pdj0;
+        A.Y[ko * A.skout + u * A.so_f + uoff] = val;
+      } else {
+        const long long f = PAIR ? A.rowbase[i] + j : i;
+        A.Y[ko * A.skout + f * A.so_f + uoff] = val;
+      }
     } else {
       const int r = i - A.row0L;
       if (r < 0 || r >= A.nrL) return;
@@ -155,8 +195,21 @@ k_gsf(const __grid_constant__ GsfArgs A) {
     }
   };
 
-  // one-ahead software prefetch over the flattened (cell, input) items: the next item's Gauss
-  // point values are in flight while the current one is contracted
+  // ---- input staging ---------------------------------------------------------------------
+  // TMA: items (cell, input) stream through the ring, thread 0 issues NS-1 items ahead.
+  // otherwise: one-ahead software prefetch into registers.
+  const long long inner0 = blockIdx.x * (long long)GSF_THREADS;
+  const int nvalid = (int)min((long long)GSF_THREADS, A.ninner - inner0);
+  const int nitems = (A.c1 - A.c0) * nin;
+  auto issue = [&](int it) {                // thread 0 only
+    const int slot = it % NS;
+    const int e = A.c0 + it / nin, in = it % nin;
+    const int kin = plan[1 + 3 * in];
+    const double* src = A.X + kin * A.skin + (long long)(e - A.cbase) * A.scell + inner0 * NQ;
+    const uint32_t bytes = (uint32_t)nvalid * NQ * 8u;
+    tg_mbar_expect_tx(&fullb[slot], bytes);
+    tg_bulk_g2s(&ring[slot * GSF_THREADS * NQ], src, bytes, &fullb[slot]);
+  };
   auto load_item = [&](int e, int in, double* x) {
     const int kin = plan[1 + 3 * in];
     const double* xp = A.X + kin * A.skin + (long long)(e - A.cbase) * A.scell + inner * NQ;
@@ -176,7 +229,22 @@ k_gsf(const __grid_constant__ GsfArgs A) {
 #pragma unroll
   for (int q = 0; q < NQ; q++) xn[q] = 0.0;
   int en = A.c0, inn = 0;
-  if (active && nin > 0 && en < A.c1) load_item(en, inn, xn);
+  int item = 0;
+  if (TMA) {
+    if (tid == 0) {
+#pragma unroll
+      for (int k = 0; k < NS; k++) {
+        tg_mbar_init(&fullb[k], 1);
+        tg_mbar_init(&emptyb[k], GSF_THREADS);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+      for (int it = 0; it < NS - 1 && it < nitems; it++) issue(it);
+  } else {
+    if (active && nin > 0 && en < A.c1) load_item(en, inn, xn);
+  }
 
   for (int cb = A.c0; cb < A.c1; cb += GSF_CB) {
     const int ncb = min(GSF_CB, A.c1 - cb);
@@ -196,10 +264,11 @@ k_gsf(const __grid_constant__ GsfArgs A) {
     __syncthreads();
     for (int c = 0; c < ncb; c++) {
       const int e = cb + c;
-      if (active) {
-        for (int in = 0; in < nin; in++) {
-          const int al = plan[2 + 3 * in], be = plan[3 + 3 * in];
-          double x[NQ];
+      for (int in = 0; in < nin; in++) {
+        const int al = plan[2 + 3 * in], be = plan[3 + 3 * in];
+        double x[NQ];
+        if (!TMA) {
+          if (!active) continue;
 #pragma unroll
           for (int q = 0; q < NQ; q++) x[q] = xn[q];
           if (++inn == nin) {
@@ -207,24 +276,45 @@ k_gsf(const __grid_constant__ GsfArgs A) {
             en++;
           }
           if (en < A.c1) load_item(en, inn, xn);
-#pragma unroll
-          for (int q = 0; q < NQ; q++) {
-            const double* ta = &stab[((c * NQ + q) * 3 + al) * NLP];
-            if (PAIR) {
-              const double* tb = &stab[((c * NQ + q) * 3 + be) * NLP];
-              double y[NL];
-#pragma unroll
-              for (int b = 0; b < NL; b++) y[b] = tb[b] * x[q];
-#pragma unroll
-              for (int a = 0; a < NL; a++) {
-                const double ta_a = ta[a];
-#pragma unroll
-                for (int b = 0; b < NL; b++) acc.v[a * NL + b] = fma(ta_a, y[b], acc.v[a * NL + b]);
-              }
-            } else {
-#pragma unroll
-              for (int a = 0; a < NL; a++) acc.v[a] = fma(ta[a], x[q], acc.v[a]);
+        } else {
+          // every thread of the CTA takes part in the ring protocol, active or not
+          const int slot = item % NS;
+          if (tid == 0) {
+            const int nx = item + NS - 1;                   // refill the slot freed by item-1
+            if (nx < nitems) {
+              if (nx >= NS) tg_mbar_wait(&emptyb[nx % NS], (uint32_t)((nx / NS - 1) & 1));
+              issue(nx);
             }
+          }
+          tg_mbar_wait(&fullb[slot], (uint32_t)((item / NS) & 1));
+#pragma unroll
+          for (int q = 0; q < NQ; q += 2) {
+            const double2 v =
+                *reinterpret_cast<const double2*>(&ring[(slot * GSF_THREADS + tid) * NQ + q]);
+            x[q] = v.x;
+            x[q + 1] = v.y;
+          }
+          tg_mbar_arrive(&emptyb[slot]);
+          item++;
+          if (!active) continue;
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+          const double* ta = &stab[((c * NQ + q) * 3 + al) * NLP];
+          if (PAIR) {
+            const double* tb = &stab[((c * NQ + q) * 3 + be) * NLP];
+            double y[NL];
+#pragma unroll
+            for (int b = 0; b < NL; b++) y[b] = tb[b] * x[q];
+#pragma unroll
+            for (int a = 0; a < NL; a++) {
+              const double ta_a = ta[a];
+#pragma unroll
+              for (int b = 0; b < NL; b++) acc.v[a * NL + b] = fma(ta_a, y[b], acc.v[a * NL + b]);
+            }
+          } else {
+#pragma unroll
+            for (int a = 0; a < NL; a++) acc.v[a] = fma(ta[a], x[q], acc.v[a]);
           }
         }
       }
@@ -263,13 +353,28 @@ k_gsf(const __grid_constant__ GsfArgs A) {
 }
 
 template <int NL, int NQ>
-static int gsf_launch2(const GsfArgs& A, int pair, int last, long long nthreads, int nout,
+static int gsf_launch2(const GsfArgs& A, int pair, int last, int tma, long long nthreads, int nout,
                        cudaStream_t st) {
   dim3 grid((unsigned)tg_cdiv(nthreads, GSF_THREADS), (unsigned)nout);
-  if (pair && last) k_gsf<NL, NQ, true, true><<<grid, GSF_THREADS, 0, st>>>(A);
-  else if (pair) k_gsf<NL, NQ, true, false><<<grid, GSF_THREADS, 0, st>>>(A);
-  else if (last) k_gsf<NL, NQ, false, true><<<grid, GSF_THREADS, 0, st>>>(A);
-  else k_gsf<NL, NQ, false, false><<<grid, GSF_THREADS, 0, st>>>(A);
+  // experiment switch: 4 resident CTAs per SM (64 registers, small spills) instead of 3
+  static const int minb4 = getenv("TIGAR_B200_GSF_MINB4") ? atoi(getenv("TIGAR_B200_GSF_MINB4")) : 0;
+  if constexpr (NQ % 2 == 0) {
+    if (tma) {
+      if (pair && last) k_gsf<NL, NQ, true, true, 3, true><<<grid, GSF_THREADS, 0, st>>>(A);
+      else if (pair) k_gsf<NL, NQ, true, false, 3, true><<<grid, GSF_THREADS, 0, st>>>(A);
+      else if (last) k_gsf<NL, NQ, false, true, 3, true><<<grid, GSF_THREADS, 0, st>>>(A);
+      else k_gsf<NL, NQ, false, false, 3, true><<<grid, GSF_THREADS, 0, st>>>(A);
+      TG_LAUNCH_CHECK();
+      return 0;
+    }
+  }
+  if (minb4 && pair && NL == 4 && NQ == 4) {
+    if (last) k_gsf<NL, NQ, true, true, 4, false><<<grid, GSF_THREADS, 0, st>>>(A);
+    else k_gsf<NL, NQ, true, false, 4, false><<<grid, GSF_THREADS, 0, st>>>(A);
+  } else if (pair && last) k_gsf<NL, NQ, true, true, 3, false><<<grid, GSF_THREADS, 0, st>>>(A);
+  else if (pair) k_gsf<NL, NQ, true, false, 3, false><<<grid, GSF_THREADS, 0, st>>>(A);
+  else if (last) k_gsf<NL, NQ, false, true, 3, false><<<grid, GSF_THREADS, 0, st>>>(A);
+  else k_gsf<NL, NQ, false, false, 3, false><<<grid, GSF_THREADS, 0, st>>>(A);
   TG_LAUNCH_CHECK();
   return 0;
 }
@@ -294,7 +399,8 @@ extern "C" int tg_gsf_stage(const double* X, int64_t skin, int64_t scell, int32_
                             int32_t maxin, int32_t pair, int64_t ninner, int32_t nv, int32_t nw,
                             double* Y, int64_t skout, int64_t so_f, int64_t so_u, int64_t so_v,
                             int32_t last, const tg_win* h_W, int64_t h_F0, int32_t vec_row0,
-                            int32_t vec_nr, double* out, void* stream) {
+                            int32_t vec_nr, double* out, int32_t perm, const tg_win* h_Wperm,
+                            void* stream) {
   TG_REQUIRE(tg_gsf_supported(nloc, nq), "gsf: unsupported (nloc, nq)");
   TG_REQUIRE(nd >= 1 && nd <= 3, "gsf: tables hold derivative orders 0..2");
   GsfArgs A;
@@ -326,10 +432,23 @@ extern "C" int tg_gsf_stage(const double* X, int64_t skin, int64_t scell, int32_
       A.n0 = (int)ninner;      // plane size as n0*n1 with n1 = 1
     }
   }
+  // perm: this stage writes (perm, not last) / reads (perm, last) the pair index (f1, f0) in the
+  // thread order of the last stage, which makes the last stage's items contiguous
+  if (perm && pair) {
+    TG_REQUIRE(h_Wperm && h_Wperm->dim == 3, "gsf: perm layout is for 3-D windows");
+    A.pS0 = h_Wperm->S[0]; A.pS1 = h_Wperm->S[1]; A.pLo1 = h_Wperm->lo[1];
+    A.pn0 = h_Wperm->nr[0]; A.pF0 = h_F0;
+    if (last) A.perm_in = 1; else A.perm_out = 1;
+  }
   if (nthreads <= 0 || c1 <= c0) return 0;
+  // bulk-copy ring: even NQ, 16-byte aligned strides, contiguous items per CTA
+  int tma = (nq % 2 == 0) && ((uintptr_t)X % 16 == 0) && (skin % 2 == 0) && (scell % 2 == 0) &&
+            (!last || !pair || h_W->dim == 2 || A.perm_in);
+  static const int no_tma = getenv("TIGAR_B200_GSF_TMA") ? !atoi(getenv("TIGAR_B200_GSF_TMA")) : 0;
+  if (no_tma) tma = 0;
   cudaStream_t st = tg_stream(stream);
 #define GSF_CASE(NL_, NQ_) \
-  if (nloc == NL_ && nq == NQ_) return gsf_launch2<NL_, NQ_>(A, pair, last, nthreads, nout, st);
+  if (nloc == NL_ && nq == NQ_) return gsf_launch2<NL_, NQ_>(A, pair, last, tma, nthreads, nout, st);
   GSF_CASE(2, 2) GSF_CASE(2, 3) GSF_CASE(3, 3) GSF_CASE(3, 4) GSF_CASE(4, 4) GSF_CASE(4, 5)
   GSF_CASE(5, 5) GSF_CASE(5, 6)
 #undef GSF_CASE

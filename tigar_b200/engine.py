@@ -706,6 +706,7 @@ class TensorPatch(object):
                 if st is None:
                     continue
                 tag = "m" if pair else "v"
+                perm = 0
                 rbs = [self._gsf_dir(B, Wg, d, bool(pair))[0] for d in range(dim)]
                 outp = dev.ptr(out.vals) if pair else dev.ptr(out)
                 if dim == 3:
@@ -723,8 +724,11 @@ class TensorPatch(object):
                         nq[0], nd, tabs[0][0], tabs[0][1], dev.ptr(rbs[0]),
                         dev.ptr(dplan((tag, 0), t1)), n1o, mi1, pair, ninner, nq2c, nq[1],
                         dev.ptr(Y1), nel[1] * G[0] * nq2c * nq[1], nq2c * nq[1],
-                        G[0] * nq2c * nq[1], nq[1], 0, None, 0, 0, 0, None, dev.stream()))
-                    # stage 2: march e1; inner = (f0, e2l, q2l)
+                        G[0] * nq2c * nq[1], nq[1], 0, None, 0, 0, 0, None, 0, None,
+                        dev.stream()))
+                    # stage 2: march e1; inner = (f0, e2l, q2l).  Matrices: the pair index
+                    # (f1, f0) is written in the thread order of the last stage (perm)
+                    perm = 1 if pair and os.environ.get("TIGAR_B200_GSF_PERM", "1") == "1" else 0
                     n2o, mi2, t2 = st[1]
                     Y2 = buf(tag + "Y2", n2o * lc * G[1] * G[0] * nq[2])
                     ninner = G[0] * nq2c
@@ -737,8 +741,10 @@ class TensorPatch(object):
                         dev.ptr(Y1), nel[1] * G[0] * nq2c * nq[1], ninner * nq[1], 0, 0, nel[1],
                         nel[1], nl[1], nq[1], nd, tabs[1][0], tabs[1][1], dev.ptr(rbs[1]),
                         dev.ptr(dplan((tag, 1), t2)), n2o, mi2, pair, ninner, lc, nq[2],
-                        dev.ptr(Y2), lc * G[1] * G[0] * nq[2], G[0] * nq[2], nq[2],
-                        G[1] * G[0] * nq[2], 0, None, 0, 0, 0, None, dev.stream()))
+                        dev.ptr(Y2), lc * G[1] * G[0] * nq[2],
+                        nq[2] if perm else G[0] * nq[2], nq[2],
+                        G[1] * G[0] * nq[2], 0, None, G[0] if perm else 0, 0, 0, None, perm,
+                        W.ref() if perm else None, dev.stream()))
                     Xl, skl, scl, ninl = Y2, lc * G[1] * G[0] * nq[2], G[1] * G[0] * nq[2], G[1] * G[0]
                 else:
                     # stage 1: march e0; inner = (e1c, q1l)
@@ -754,7 +760,7 @@ class TensorPatch(object):
                         nq[0], nd, tabs[0][0], tabs[0][1], dev.ptr(rbs[0]),
                         dev.ptr(dplan((tag, 0), t1)), n1o, mi1, pair, ninner, 1, nq[1],
                         dev.ptr(Y1), lc * G[0] * nq[1], nq[1], G[0] * nq[1], 0, 0, None, 0, 0, 0,
-                        None, dev.stream()))
+                        None, 0, None, dev.stream()))
                     Xl, skl, scl, ninl = Y1, lc * G[0] * nq[1], G[0] * nq[1], G[0]
                 nlo, mil, tl = st[L]
                 nin_tot = int(tl[:, 0].sum())
@@ -770,7 +776,8 @@ class TensorPatch(object):
                     dev.ptr(Xl), skl, scl, k, k, k + lc, nel[L], nl[L], nq[L], nd, tabs[L][0],
                     tabs[L][1], dev.ptr(rbs[L]), dev.ptr(dplan((tag, L), tl)), nlo, mil, pair,
                     ninl, 1, 1, None, 0, 0, 0, 0, 1, W.ref() if pair else None, G[0],
-                    vrow0, vnr, outp, dev.stream()))
+                    vrow0, vnr, outp, perm if (pair and dim == 3) else 0,
+                    W.ref() if (pair and dim == 3 and perm) else None, dev.stream()))
             k += lc
         self.launches += 1
 
