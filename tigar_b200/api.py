@@ -781,7 +781,8 @@ class ExtractedSpline(object):
         self.mesh = generator.mesh
         self.comm = generator.getComm()
         self._generic = not generator.isTensorProduct()
-        part = (self.comm.rank, self.comm.size) if self.comm.size > 1 else None
+        csize = self.comm.size
+        part = (self.comm.rank, csize) if csize > 1 else None
         if self._generic:
             if part is not None:
                 raise NotImplementedError("generic bases run on one GPU")

@@ -72,7 +72,8 @@ class DofList(list):
             list.__init__(self, items)
             self._chunks = chunks if chunks is not None else ([] if list.__len__(self) == 0
                                                               else None)
-            self._mat = True
+            # an empty list is trivially "not yet materialised": += of arrays stays lazy
+            self._mat = list.__len__(self) > 0
         self._n = sum(c.size for c in self._chunks) if self._chunks is not None else 0
 
     @staticmethod

@@ -172,27 +172,35 @@ k_gsf(const __grid_constant__ GsfArgs A) {
         if (a + s < NL && (!PAIR || b + s < NL)) carried |= 1u << (a * NL + b);
   }
 
-  auto store = [&](double val, int i, int j, bool add) {
+  // Output addressing, hoisted per row i of the marched direction: every finished sum of row i
+  // goes to  rowp(i) + j * jstride  (jstride is a per-thread constant), so a flush costs one
+  // address computation per row, not one per entry.
+  int jstride;
+  double* ybase = nullptr;
+  if (!LAST) {
+    ybase = A.Y + ko * A.skout + uoff;
+    jstride = (int)((PAIR && A.perm_out) ? pl0 * A.so_f : A.so_f);
+  } else {
+    jstride = PAIR ? len01 : 0;
+  }
+  auto rowp = [&](int i, bool& ok) -> double* {
+    ok = true;
     if (!LAST) {
-      if (PAIR && A.perm_out) {
+      if (!PAIR) return ybase + (long long)i * A.so_f;            // + 0 * jstride (j unused)
+      if (A.perm_out) {
         const long long s1 = A.pS1[i], l1 = A.pS1[i + 1] - s1;
-        const long long u = s1 * A.pF0 + (long long)pS0i0 * l1 + (j - A.pLo1[i]) * pl0 + pdj0;
-        A.Y[ko * A.skout + u * A.so_f + uoff] = val;
-      } else {
-        const long long f = PAIR ? A.rowbase[i] + j : i;
-        A.Y[ko * A.skout + f * A.so_f + uoff] = val;
+        return ybase + (s1 * A.pF0 + (long long)pS0i0 * l1 + pdj0 -
+                        (long long)A.pLo1[i] * pl0) * A.so_f;
       }
-    } else {
-      const int r = i - A.row0L;
-      if (r < 0 || r >= A.nrL) return;
-      double* p;
-      if (PAIR)
-        p = A.out + A.rowptr[(long long)r * nplane + rowoff] +
-            (long long)((j - A.col0L - A.loL[r]) * len01 + inrow);
-      else
-        p = A.out + (long long)r * nplane + inner;
-      *p = add ? *p + val : val;
+      return ybase + A.rowbase[i] * A.so_f;
     }
+    const int r = i - A.row0L;
+    ok = (r >= 0 && r < A.nrL);
+    if (!ok) return nullptr;
+    if (PAIR)
+      return A.out + A.rowptr[(long long)r * nplane + rowoff] + inrow -
+             (long long)(A.col0L + A.loL[r]) * len01;
+    return A.out + (long long)r * nplane + inner;
   };
 
   // ---- input staging ---------------------------------------------------------------------
@@ -318,24 +326,33 @@ k_gsf(const __grid_constant__ GsfArgs A) {
           }
         }
       }
-      // pairs / functions whose support ends with this cell are complete
+      // pairs / functions whose support ends with this cell are complete.  The shift s is
+      // uniform over the CTA: one static code path per value (no per-entry predicates)
       const int first = sfirst[c];
       int s = sfirst[c + 1] - first;
       if (s > NL || e + 1 == A.c1) s = NL;      // end of the direction or of the chunk: flush all
-      if (active) {
-#pragma unroll
-        for (int a = 0; a < NL; a++)
-#pragma unroll
-          for (int b = 0; b < (PAIR ? NL : 1); b++)
-            if (a < s || (PAIR && b < s))
-              store(acc.v[PAIR ? a * NL + b : a], first + a, first + b,
-                    (carried >> (a * NL + b)) & 1u);
-      }
-      // shift the window of partial sums by s functions (s is uniform over the CTA)
       unsigned nc = 0;
 #pragma unroll
       for (int ss = 1; ss <= NL; ss++) {
         if (s != ss) continue;
+        if (active) {
+#pragma unroll
+          for (int a = 0; a < NL; a++) {
+            if (!(a < ss || PAIR)) continue;          // vector: only the leaving functions
+            bool ok;
+            double* rp = rowp(first + a, ok);
+            if (!ok) continue;
+#pragma unroll
+            for (int b = 0; b < (PAIR ? NL : 1); b++) {
+              if (!(a < ss || (PAIR && b < ss))) continue;
+              double* q = PAIR ? rp + (long long)(first + b) * jstride : rp;
+              const double val = acc.v[PAIR ? a * NL + b : a];
+              if (LAST && ((carried >> (a * NL + b)) & 1u)) *q += val;
+              else *q = val;
+            }
+          }
+        }
+        // shift the window of partial sums by ss functions
 #pragma unroll
         for (int a = 0; a < NL; a++)
 #pragma unroll
@@ -356,11 +373,15 @@ template <int NL, int NQ>
 static int gsf_launch2(const GsfArgs& A, int pair, int last, int tma, long long nthreads, int nout,
                        cudaStream_t st) {
   dim3 grid((unsigned)tg_cdiv(nthreads, GSF_THREADS), (unsigned)nout);
-  // experiment switch: 4 resident CTAs per SM (64 registers, small spills) instead of 3
-  static const int minb4 = getenv("TIGAR_B200_GSF_MINB4") ? atoi(getenv("TIGAR_B200_GSF_MINB4")) : 0;
+  // TIGAR_B200_GSF_MINB=2: two resident CTAs per SM (up to 128 registers, no spills) for the
+  // TMA-staged matrix kernels, whose memory latency is covered by the ring, not by occupancy
+  static const int minb2 = getenv("TIGAR_B200_GSF_MINB") ? atoi(getenv("TIGAR_B200_GSF_MINB")) == 2 : 0;
   if constexpr (NQ % 2 == 0) {
     if (tma) {
-      if (pair && last) k_gsf<NL, NQ, true, true, 3, true><<<grid, GSF_THREADS, 0, st>>>(A);
+      if (pair && minb2) {
+        if (last) k_gsf<NL, NQ, true, true, 2, true><<<grid, GSF_THREADS, 0, st>>>(A);
+        else k_gsf<NL, NQ, true, false, 2, true><<<grid, GSF_THREADS, 0, st>>>(A);
+      } else if (pair && last) k_gsf<NL, NQ, true, true, 3, true><<<grid, GSF_THREADS, 0, st>>>(A);
       else if (pair) k_gsf<NL, NQ, true, false, 3, true><<<grid, GSF_THREADS, 0, st>>>(A);
       else if (last) k_gsf<NL, NQ, false, true, 3, true><<<grid, GSF_THREADS, 0, st>>>(A);
       else k_gsf<NL, NQ, false, false, 3, true><<<grid, GSF_THREADS, 0, st>>>(A);
@@ -368,10 +389,7 @@ static int gsf_launch2(const GsfArgs& A, int pair, int last, int tma, long long 
       return 0;
     }
   }
-  if (minb4 && pair && NL == 4 && NQ == 4) {
-    if (last) k_gsf<NL, NQ, true, true, 4, false><<<grid, GSF_THREADS, 0, st>>>(A);
-    else k_gsf<NL, NQ, true, false, 4, false><<<grid, GSF_THREADS, 0, st>>>(A);
-  } else if (pair && last) k_gsf<NL, NQ, true, true, 3, false><<<grid, GSF_THREADS, 0, st>>>(A);
+  if (pair && last) k_gsf<NL, NQ, true, true, 3, false><<<grid, GSF_THREADS, 0, st>>>(A);
   else if (pair) k_gsf<NL, NQ, true, false, 3, false><<<grid, GSF_THREADS, 0, st>>>(A);
   else if (last) k_gsf<NL, NQ, false, true, 3, false><<<grid, GSF_THREADS, 0, st>>>(A);
   else k_gsf<NL, NQ, false, false, 3, false><<<grid, GSF_THREADS, 0, st>>>(A);

@@ -121,11 +121,13 @@ class DeviceOps(object):
         self.n = patch.n_loc
         self.xoff = patch.xoff
         self.rank, self.size = patch.part
-        # every rank's extended range (tiny all-gather of two ints)
-        mine = torch.tensor([pp["c0"], pp["c1"]], dtype=torch.int64, device=dev.device())
-        allr = [torch.zeros_like(mine) for _ in range(self.size)]
-        dist.all_gather(allr, mine)
-        ext = [(int(t[0]), int(t[1])) for t in allr]
+        # every rank's extended range: a pure function of the partition bounds and the global
+        # window of the last direction, so each rank computes all of them (no all-gather)
+        lo, hi = patch.window_global_C_last()
+        b = pp["bounds"]
+        ext = [(int(np.min(lo[b[r]:b[r + 1]])), int(np.max(hi[b[r]:b[r + 1]])) + 1)
+               for r in range(self.size)]
+        assert ext[self.rank] == (pp["c0"], pp["c1"])
         self.recvs, self.sends = all_halo_plans(pp["bounds"], ext)[self.rank]
 
     def begin(self, b):
@@ -390,20 +392,22 @@ def solve_fd_pcg_dist(patch, Cm, b, mask, diag, rtol, atol, maxit):
     ops.begin(b)                    # allocates p_ext / dinv (Jacobi diagonal: used for the fit)
     fd = FastDiagDist(patch, mask, diag, ops.dinv)
     s = dev.zeros(2)
+    red = dev.zeros(1)
 
     def allsum(v):
-        t = torch.tensor([v], dtype=torch.float64, device=dev.device())
-        dist.all_reduce(t)
-        return float(t.item())
+        red.fill_(v)
+        dist.all_reduce(red)
+        return float(red.item())
 
     def spmv_dot(p, q):
         assert p.data_ptr() == ops.p.data_ptr()
         ops.exchange_halo()
         check(lib.tg_win_spmv_dot(Cm.window.ref(), dev.ptr(Cm.vals), dev.ptr(ops.p_ext), ops.xoff,
                                   dev.ptr(q), dev.ptr(ops.scratch), dev.ptr(s), dev.stream()))
-        return allsum(float(s[0].item()))
+        dist.all_reduce(s[0:1])              # reduced on the device: one host read, not two
+        return float(s[0].item())
     x, its, rel = solvers.pcg(spmv_dot, fd.apply, b, None, rtol, atol, maxit, reduce=allsum,
-                              p_buf=ops.p)
+                              p_buf=ops.p, reduce_dev=dist.all_reduce)
     return x, its, rel
 
 

@@ -215,10 +215,14 @@ class _Vec(object):
         self.n = n
         self.scratch = dev.empty(lib.tg_cg_scratch_len())
         self.s = dev.zeros(4)
+        self.reduce_dev = None
 
     def dot(self, a, b):
         check(lib.tg_dot(dev.ptr(a), dev.ptr(b), self.n, dev.ptr(self.scratch), dev.ptr(self.s),
                          dev.stream()))
+        if self.reduce_dev is not None:          # all-reduce on the device, one host read
+            self.reduce_dev(self.s[0:1])
+            return float(self.s[0].item())
         return self.reduce(float(self.s[0].item()))
 
     def reduce(self, v):
@@ -226,7 +230,7 @@ class _Vec(object):
 
 
 def pcg(spmv_dot, precond, b, x0=None, rtol=1e-12, atol=0.0, maxit=10000, reduce=None,
-        p_buf=None):
+        p_buf=None, reduce_dev=None):
     """Preconditioned CG.  ``spmv_dot(p, q) -> p.q`` computes q = A p and returns the (global)
     dot product; ``precond(r, z)`` writes z = B^-1 r; ``reduce`` sums a host scalar over ranks;
     ``p_buf``: where the search direction lives (a view into the halo-extended vector of a
@@ -236,6 +240,7 @@ def pcg(spmv_dot, precond, b, x0=None, rtol=1e-12, atol=0.0, maxit=10000, reduce
     V = _Vec(n)
     if reduce is not None:
         V.reduce = reduce
+    V.reduce_dev = reduce_dev
     st = dev.stream
     x = dev.zeros(n) if x0 is None else x0
     r = b.clone()
@@ -268,7 +273,11 @@ def pcg(spmv_dot, precond, b, x0=None, rtol=1e-12, atol=0.0, maxit=10000, reduce
         alpha = rz / pAp
         check(lib.tg_pcg_update(dev.ptr(x), dev.ptr(r), dev.ptr(p), dev.ptr(q), alpha, n,
                                 dev.ptr(V.scratch), dev.ptr(out1), st()))
-        rr = V.reduce(float(out1[0].item()))
+        if reduce_dev is not None:
+            reduce_dev(out1)
+            rr = float(out1[0].item())
+        else:
+            rr = V.reduce(float(out1[0].item()))
         it += 1
         if not (rr == rr):
             raise FloatingPointError("CG produced NaN at iteration %d" % it)
