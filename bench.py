@@ -519,6 +519,15 @@ def run_ours(args):
         "roofline": roofline, "rooflines": rows,
         "fp64_peak_tflops_measured": fp64_peak}
 
+    gs = [r_ for r_ in rows if r_["kernel"].startswith("k_gsf matrix")]
+    if gs:
+        t = sum(r_["ms_per_step"] for r_ in gs)
+        byts = sum(r_["bytes_per_launch"] * r_["launches_per_step"] for r_ in gs)
+        out["ptap_fused"] = {
+            "what": "M^T A M of the production (element-fused) path = the march stages: "
+                    "algorithmic bytes of all stages / their summed device time",
+            "ms": t, "bytes": byts, "achieved": byts / (t * 1e-3) / 1e9, "unit": "GB/s",
+            "frac": byts / (t * 1e-3) / 1e9 / hbm_peak, "peak": hbm_peak}
     if world == 1 and not args.no_ptap:
         torch.cuda.empty_cache()
         try:

@@ -414,3 +414,29 @@ def test_nonzero_bc_via_newton_and_projection():
         errs.append(math.sqrt(assemble(((u - soln) ** 2) * spline.dx)))
     rate = math.log(errs[0] / errs[1]) / math.log(2.0)
     assert errs[1] < 2e-4 and 2.6 < rate < 3.6, (errs, rate)
+
+
+def test_fe_vector_write_refreshes_the_iga_dofs():
+    """ADVICE r1: ``u.vector().set_local(...)`` (the reference idiom) writes FE coefficients;
+    the element-fused path reads IGA DoFs -- they are re-derived (FEtoIGA) instead of being read
+    stale."""
+    from tIGAr import Function, TestFunction, inner
+    deg, nels = [2, 2], [6, 5]
+    kv = [uk(p, n) for p, n in zip(deg, nels)]
+    gen, spline, pr = make_pair(deg, kv, mode="fused")
+    rng = np.random.RandomState(7)
+    Uv = rng.rand(spline.patch().n_iga)
+    ref = Function(spline.V)
+    ref.set_iga(dev_from(Uv))
+    v = TestFunction(spline.V)
+    b_ref = spline.assembleVector(inner(ref, v) * spline.dx, applyBCs=False).get_local()
+    w = Function(spline.V)
+    w.set_iga(dev_from(np.zeros_like(Uv)))            # stale IGA data ...
+    w.vector().set_local(ref.vector().get_local())    # ... overwritten through the FE vector
+    b = spline.assembleVector(inner(w, v) * spline.dx, applyBCs=False).get_local()
+    assert rel(b, b_ref) < 1e-9
+
+
+def dev_from(a):
+    from tigar_b200 import dev
+    return dev.from_np(np.asarray(a, dtype=np.float64))

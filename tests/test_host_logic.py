@@ -64,7 +64,7 @@ def run_program(prog, xi, wq, jetvals):
               cosh=math.cosh, atan=math.atan, mov=lambda a: a)
     f2 = dict(add=lambda a, b: a + b, sub=lambda a, b: a - b, mul=lambda a, b: a * b,
               div=lambda a, b: a / b, pow=lambda a, b: a ** b, max=max, min=min,
-              gt=lambda a, b: float(a > b))
+              gt=lambda a, b: float(a > b), selz=lambda a, b: b if a != 0 else 0.0)
     names = {v: k for k, v in S.OPCODES.items()}
     for op, dst, a, b in prog.prog:
         n = names[op]
@@ -808,3 +808,26 @@ def test_dof_list_is_a_list_that_remembers_its_arrays():
     gen.addZeroDofs(1, [3, 4])
     assert list(gen.zeroDofs) == list(a) + [d + 36 for d in a] + [39, 40]
     assert gen.zeroDofs.asarray().tolist() == list(gen.zeroDofs)
+
+
+def test_conditional_is_a_true_select():
+    """UFL's conditional selects; an inf/NaN in the unselected branch (the usual
+    use guards a singularity: conditional(gt(r, eps), 1/r, 0)) must not reach the result, and
+    the derivative of a selected branch is the selected derivative."""
+    x = S.xi(0)
+    c = S.binary("gt", x, S.const(0.5))
+    e = S.select(c, S.div(S.ONE, S.sub(x, S.const(0.25))), S.const(7.0))     # singular at 0.25
+    prog = S.compile_program([e, S.diff(e, 0)], 1)
+    v = run_program(prog, [0.25], 1.0, {})
+    assert v[0] == 7.0 and v[1] == 0.0                       # no NaN from 0 * inf
+    v = run_program(prog, [0.75], 1.0, {})
+    assert abs(v[0] - 2.0) < 1e-15 and abs(v[1] + 4.0) < 1e-14
+    # the form language uses it term by term
+    r = U.Tensor(U.Scalar.coef(x))
+    t = U.conditional(U.gt(r, 0.5), 1.0 / (r - 0.25), 0.0)
+    p2 = S.compile_program([t.a[()].node() if hasattr(t.a[()], "node") else t.a.item().node()], 1)
+    assert run_program(p2, [0.25], 1.0, {})[0] == 0.0
+    # generated CUDA carries the ternary
+    from tigar_b200 import jit
+    src, _ = jit.generate(prog, 1, [3, 1, 1], [3, 1, 1], 1, [], 0)
+    assert "!= 0.0) ?" in src

@@ -35,7 +35,8 @@ def vec_run_program(prog, xi, wq, jetvals):
               abs=np.abs, tan=np.tan, tanh=np.tanh, sinh=np.sinh, cosh=np.cosh,
               atan=np.arctan, mov=lambda a: a)
     f2 = dict(add=np.add, sub=np.subtract, mul=np.multiply, div=np.divide, pow=np.power,
-              max=np.maximum, min=np.minimum, gt=lambda a, b: (a > b).astype(float))
+              max=np.maximum, min=np.minimum, gt=lambda a, b: (a > b).astype(float),
+              selz=lambda a, b: np.where(np.asarray(a) != 0, b, 0.0))
     names = {v: k for k, v in S.OPCODES.items()}
     for op, dst, a, b in prog.prog:
         nm = names[op]

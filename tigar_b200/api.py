@@ -103,15 +103,18 @@ class DeviceVector(object):
     slab of a row-distributed vector: its norm is reduced over the ranks (a PETSc Vec's norm
     is global), so every rank of a Newton loop takes the same branch."""
 
-    def __init__(self, t, distributed=False):
+    def __init__(self, t, distributed=False, owner=None):
         self.t = t
         self.distributed = distributed
+        self.owner = owner            # the Function whose FE coefficients this vector is
 
     def get_local(self):
         return dev.to_np(self.t).copy()
 
     def set_local(self, a):
         self.t.copy_(dev.from_np(np.asarray(a, dtype=np.float64)))
+        if self.owner is not None:    # u.vector().set_local(...): the FE data is now the truth
+            self.owner._fe_written()
 
     def size(self):
         return self.t.numel()
@@ -213,7 +216,13 @@ class Function(U.Tensor):
         self._fe = None
 
     def vector(self):
-        return DeviceVector(self.fe_tensor())
+        return DeviceVector(self.fe_tensor(), owner=self)
+
+    def _fe_written(self):
+        """The FE coefficients were written through ``u.vector()`` (the reference idiom): the
+        IGA DoFs are stale and are re-derived on demand (FEtoIGA, common.py:968-993) instead of
+        being read silently by the element-fused / matrix-free paths."""
+        self.iga = None
 
     def assign(self, other):
         """``u.assign(v)`` or ``u.assign(c1*v1 + c2*v2 + ...)`` (dolfin accepts linear
@@ -1000,6 +1009,8 @@ class ExtractedSpline(object):
                     out[fid] = f.iga
                 elif f._fe is None and not f.V.control:
                     out[fid] = _LazyZero(f, self._patch.n_iga)   # never assigned: zero (dolfin)
+                elif f._fe is not None and self.nFields == 1:
+                    out[fid] = _LazyIGA(f, self)     # only FE data: derive the IGA DoFs
             else:
                 out[fid] = _LazyFE(f)
         return _FuncTable(out)
@@ -1352,6 +1363,21 @@ class _LazyFE(object):
         return self.f.fe_tensor()
 
 
+class _LazyIGA(object):
+    """A Function that only has FE coefficients (written through ``u.vector()``): its IGA DoFs
+    are the pseudo-inverse problem of FEtoIGA (common.py:968-993), solved when first needed."""
+
+    def __init__(self, f, spline):
+        self.f, self.spline = f, spline
+
+    def resolve(self):
+        if self.f.iga is None:
+            fe = self.f._fe
+            self.f.iga = self.spline.FEtoIGA(self.f).t
+            self.f._fe = fe
+        return self.f.iga
+
+
 class _LazyZero(object):
     """A Function that was never assigned reads as zero; its IGA data is created the first
     time a kernel needs it."""
@@ -1368,7 +1394,7 @@ class _LazyZero(object):
 class _FuncTable(dict):
     def __getitem__(self, k):
         v = dict.__getitem__(self, k)
-        if isinstance(v, (_LazyFE, _LazyZero)):
+        if isinstance(v, (_LazyFE, _LazyZero, _LazyIGA)):
             v = v.resolve()
             dict.__setitem__(self, k, v)
         return v

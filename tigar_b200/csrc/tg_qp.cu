@@ -145,6 +145,7 @@ __global__ void k_qp_eval(TgBasis B, TgJetSpec J, const int4* __restrict__ prog,
       case OP_COSH: r = cosh(a); break;
       case OP_ATAN: r = atan(a); break;
       case OP_GT: r = (a > b) ? 1.0 : 0.0; break;
+      case OP_SEL: r = (a != 0.0) ? b : 0.0; break;
       default: r = 0.0; break;
     }
     R[in.y] = r;

@@ -23,7 +23,7 @@ _UN = {"neg": "-(%s)", "sin": "sin(%s)", "cos": "cos(%s)", "exp": "exp(%s)", "lo
        "sinh": "sinh(%s)", "cosh": "cosh(%s)", "atan": "atan(%s)", "mov": "(%s)"}
 _BIN = {"add": "(%s + %s)", "sub": "(%s - %s)", "mul": "(%s * %s)", "div": "(%s / %s)",
         "pow": "pow(%s, %s)", "max": "fmax(%s, %s)", "min": "fmin(%s, %s)",
-        "gt": "((%s > %s) ? 1.0 : 0.0)"}
+        "gt": "((%s > %s) ? 1.0 : 0.0)", "selz": "((%s != 0.0) ? %s : 0.0)"}
 _NAMES = {v: k for k, v in S.OPCODES.items()}
 
 MAXFUN = 16

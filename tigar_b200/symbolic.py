@@ -16,10 +16,10 @@ import math
 # opcodes: keep in sync with tigar_b200/csrc/tg_qp.cu
 OPCODES = dict(nop=0, const=1, mov=2, add=3, sub=4, mul=5, div=6, neg=7, sin=8, cos=9,
                exp=10, log=11, sqrt=12, pow=13, abs=14, tan=15, tanh=16, max=17, min=18,
-               sinh=19, cosh=20, atan=21, gt=22)
+               sinh=19, cosh=20, atan=21, gt=22, selz=23)
 _UNARY = ("neg", "sin", "cos", "exp", "log", "sqrt", "abs", "tan", "tanh", "sinh", "cosh",
           "atan")
-_BINARY = ("add", "sub", "mul", "div", "pow", "max", "min", "gt")
+_BINARY = ("add", "sub", "mul", "div", "pow", "max", "min", "gt", "selz")
 
 _table = {}
 _counter = [0]
@@ -264,12 +264,24 @@ def binary(name, a, b):
     return _mk(name, a, b)
 
 
+def selz(cond, a):
+    """(cond != 0) ? a : 0 -- a TRUE select: an inf/NaN in an unselected ``a`` does not reach
+    the result (cond * a would give 0 * inf = NaN)."""
+    cond, a = as_node(cond), as_node(a)
+    if a is ZERO or cond is ZERO:
+        return ZERO
+    if cond.is_const():
+        return a if _c(cond) != 0.0 else ZERO
+    return _mk("selz", cond, a)
+
+
 def select(cond, a, b):
-    """cond in {0,1}: cond*a + (1-cond)*b."""
+    """cond in {0,1}: a where cond != 0, b elsewhere (UFL ``conditional`` is a select, not an
+    arithmetic blend: the usual use guards a singularity in the other branch)."""
     cond, a, b = as_node(cond), as_node(a), as_node(b)
     if a is b:
         return a
-    return add(mul(cond, a), mul(sub(ONE, cond), b))
+    return add(selz(cond, a), selz(sub(ONE, cond), b))
 
 
 # ------------------------------------------------------------ differentiation
@@ -324,6 +336,8 @@ def _diff_rule(n, d):
     da = d(a)
     if op == "neg":
         return neg(da)
+    if op == "selz":                     # the condition is piecewise constant
+        return selz(a, d(n.args[1]))
     if op in ("add", "sub", "mul", "div", "pow", "max", "min", "gt"):
         b = n.args[1]
         db = d(b)

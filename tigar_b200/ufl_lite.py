@@ -376,8 +376,16 @@ def conditional(cond, a, b):
     branches may contain test/trial functions."""
     c = _as_scalar(cond)
     a, b = as_tensor(a), as_tensor(b)
-    one_minus = Scalar.coef(S.ONE).add(c, -1.0)
-    return a._zip(b, lambda x, y: c.mul(x).add(one_minus.mul(y)))
+    cn = c.terms.get((None, None), S.ZERO) if set(c.terms) <= {(None, None)} else None
+    if cn is None:
+        raise ValueError("conditional: the condition must not contain test/trial functions")
+    ncn = S.sub(S.ONE, cn)
+
+    def sel(x, y):
+        # a true select on every coefficient: term-wise (cond ? x : 0) + (!cond ? y : 0)
+        out = Scalar({k: S.selz(cn, v) for k, v in x.terms.items()})
+        return out.add(Scalar({k: S.selz(ncn, v) for k, v in y.terms.items()}))
+    return a._zip(b, sel)
 
 
 def tr(a):
