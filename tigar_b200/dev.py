@@ -12,10 +12,16 @@ I64 = torch.int64
 U8 = torch.uint8
 
 
+_cuda_ok = [False]
+
+
 def require_cuda():
+    if _cuda_ok[0]:                     # torch.cuda.is_available() costs up to 1 ms per call
+        return
     if not torch.cuda.is_available():
         raise RuntimeError("tigar_b200 needs a CUDA device (B200, sm_100a); "
                            "there is no CPU fallback")
+    _cuda_ok[0] = True
 
 
 def device():

@@ -320,7 +320,17 @@ def enabled():
     return not os.environ.get("TIGAR_B200_NO_JIT")
 
 
+def _signature(prog, *rest):
+    """Cheap identity of a kernel request: the register program itself (not the generated
+    source: emitting 4 000 lines per Newton step costs more than the launch)."""
+    return hash((tuple(map(tuple, prog.prog)), tuple(prog.consts), tuple(prog.outregs), rest))
+
+
 def get_kernel(prog, dim, nloc, nq, nd, jets, nfun, layout="cell"):
+    sig = ("qp", _signature(prog, dim, tuple(nloc), tuple(nq), nd, tuple(jets), nfun, layout))
+    k = _cache.get(sig)
+    if k is not None:
+        return k
     src, nth = generate(prog, dim, nloc, nq, nd, jets, nfun, layout=layout)
     key = hashlib.sha1(src.encode()).hexdigest()
     k = _cache.get(key)
@@ -329,6 +339,7 @@ def get_kernel(prog, dim, nloc, nq, nd, jets, nfun, layout="cell"):
         check(lib.tg_jit_compile(src.encode(), b"tigar_qp", C.byref(h)))
         k = (h, nth)
         _cache[key] = k
+    _cache[sig] = k
     return k
 
 
@@ -358,6 +369,12 @@ def launch(kernel, B, coef_ptrs, cell0, ncells, out, gsf=None):
 
 # ---- fused matrix-free operator kernel (generate(..., op=...)) -------------------------------
 def get_op_kernel(prog, dim, nloc, nq, nd, jets, nfun, op, diag=False):
+    sig = ("op", _signature(prog, dim, tuple(nloc), tuple(nq), nd, tuple(jets), nfun,
+                            tuple(map(tuple, op)) if op and not isinstance(op[0], int)
+                            else tuple(op), diag))
+    k = _cache.get(sig)
+    if k is not None:
+        return k
     src, nth = generate(prog, dim, nloc, nq, nd, jets, nfun, op=op, diag=diag)
     key = hashlib.sha1(src.encode()).hexdigest()
     k = _cache.get(key)
@@ -366,6 +383,7 @@ def get_op_kernel(prog, dim, nloc, nq, nd, jets, nfun, op, diag=False):
         check(lib.tg_jit_compile(src.encode(), b"tigar_op", C.byref(h)))
         k = (h, nth)
         _cache[key] = k
+    _cache[sig] = k
     return k
 
 
