@@ -216,6 +216,45 @@ class DeviceOps(object):
 
 
 # ----------------------------------------------------------------------------
+class SlabTranspose(object):
+    """Re-partition of a slab-distributed tensor-product vector (slabs of planes of the LAST
+    direction, layout [i_L local][plane]) into chunks of the plane index holding whole fibres
+    of the last direction (layout [i_L (all)][plane chunk] = column-major (chunk x n_L)), and
+    back: one ``all_to_all_single`` each way.  Pure torch.distributed (NCCL on the device, gloo
+    in tests/test_multigpu_cpu.py)."""
+
+    def __init__(self, bounds, plane, rank, size):
+        self.rank, self.size, self.plane = rank, size, plane
+        self.bounds = list(bounds)
+        self.nl = bounds[rank + 1] - bounds[rank]
+        self.nL = bounds[-1]
+        self.q = [(plane * r) // size for r in range(size + 1)]
+        self.mq = self.q[rank + 1] - self.q[rank]
+        self.nloc = self.nl * plane
+        self.send_splits = [(self.q[s + 1] - self.q[s]) * self.nl for s in range(size)]
+        self.recv_splits = [self.mq * (bounds[s + 1] - bounds[s]) for s in range(size)]
+
+    def to_fibres(self, src, dst):
+        import torch
+        import torch.distributed as dist
+        v = src[:self.nloc].view(self.nl, self.plane)
+        pack = torch.cat([v[:, self.q[s]:self.q[s + 1]].reshape(-1) for s in range(self.size)])
+        dist.all_to_all_single(dst[:self.mq * self.nL], pack, self.recv_splits, self.send_splits)
+
+    def to_slabs(self, src, dst):
+        import torch
+        import torch.distributed as dist
+        recv = torch.empty(self.nloc, dtype=src.dtype, device=src.device)
+        dist.all_to_all_single(recv, src[:self.mq * self.nL].contiguous(), self.send_splits,
+                               self.recv_splits)
+        out = dst[:self.nloc].view(self.nl, self.plane)
+        off = 0
+        for s in range(self.size):
+            w = self.q[s + 1] - self.q[s]
+            out[:, self.q[s]:self.q[s + 1]].copy_(recv[off:off + w * self.nl].view(self.nl, w))
+            off += w * self.nl
+
+
 class FastDiagDist(object):
     """Fast-diagonalisation preconditioner (tigar_b200/solvers.py) on a slab-distributed
     vector.  The mode products of the first directions are local to a slab; the one along the
@@ -245,8 +284,8 @@ class FastDiagDist(object):
         bounds = pp["bounds"]
         self.bounds = bounds
         # plane chunks of the transposed partition
-        self.q = [(self.plane * r) // self.size for r in range(self.size + 1)]
-        self.mq = self.q[self.rank + 1] - self.q[self.rank]
+        self.tr = SlabTranspose(bounds, self.plane, self.rank, self.size)
+        self.q, self.mq = self.tr.q, self.tr.mq
         self.gmask = mask
         self.lmask = None if mask is None else mask[self.k0 * self.plane:self.k1 * self.plane]
         self.cinv = 1.0 / float(diag) if diag else 1.0
@@ -261,8 +300,6 @@ class FastDiagDist(object):
         self.U = [dev.from_np(np.ascontiguousarray(eig[d][1].T)) for d in range(self.dim)]
         self.t1 = dev.empty(max(self.nloc, self.mq * self.nL))
         self.t2 = dev.empty(max(self.nloc, self.mq * self.nL))
-        self.send_splits = [(self.q[s + 1] - self.q[s]) * self.nl for s in range(self.size)]
-        self.recv_splits = [self.mq * (bounds[s + 1] - bounds[s]) for s in range(self.size)]
 
     def _fit(self, eig, free, dinv_local):
         """Least-squares fit of the direction weights to diag(C) (solvers.FastDiag._fit) with
@@ -314,22 +351,10 @@ class FastDiagDist(object):
                                              Cc, ldc, sC, batch, self.dev.stream()))
 
     def _to_fibres(self, src, dst):
-        """slab layout [i_L local][plane]  ->  [i_L (all)][my plane chunk]"""
-        torch, dist = self.torch, self.dist
-        v = src[:self.nloc].view(self.nl, self.plane)
-        pack = torch.cat([v[:, self.q[s]:self.q[s + 1]].reshape(-1) for s in range(self.size)])
-        dist.all_to_all_single(dst[:self.mq * self.nL], pack, self.recv_splits, self.send_splits)
+        self.tr.to_fibres(src, dst)
 
     def _to_slabs(self, src, dst):
-        torch, dist = self.torch, self.dist
-        recv = torch.empty(self.nloc, dtype=src.dtype, device=src.device)
-        dist.all_to_all_single(recv, src[:self.mq * self.nL], self.send_splits, self.recv_splits)
-        out = dst[:self.nloc].view(self.nl, self.plane)
-        off = 0
-        for s in range(self.size):
-            w = self.q[s + 1] - self.q[s]
-            out[:, self.q[s]:self.q[s + 1]].copy_(recv[off:off + w * self.nl].view(self.nl, w))
-            off += w * self.nl
+        self.tr.to_slabs(src, dst)
 
     def apply(self, r, z):
         dev, lib, check = self.dev, self.lib, self.check
