@@ -98,5 +98,9 @@ def test_unsupported_inputs_fail_loudly():
     from tigar_b200.engine import TensorPatch
     with pytest.raises(NotImplementedError):
         TensorPatch([2], [OB.uniform_knots(2, 0.0, 1.0, 6, True)])            # periodic
+    # a C^-1 knot: the spline is supported on the element-fused path (no FE space), but the
+    # csr path's operands (A_FE, M on a DG space) are not built
+    tp = TensorPatch([2], [[0, 0, 0, 0.5, 0.5, 0.5, 1, 1, 1]])
+    assert tp.window("C").nnz == 2 * 9
     with pytest.raises(NotImplementedError):
-        TensorPatch([2], [[0, 0, 0, 0.5, 0.5, 0.5, 1, 1, 1]])                  # C^-1 knot
+        tp.window("A")

@@ -95,3 +95,33 @@ def test_gsf_matches_the_oracle_and_uses_the_march_kernels():
     pr.ptap()
     assert relm(C.to_scipy(), pr.C) < 1e-12
     assert rel(b.get_local(), pr.b) < 1e-12
+
+
+def test_discontinuous_spline_on_the_fused_path():
+    """A spline with an interior knot of multiplicity p+1 is discontinuous there; the reference
+    extracts it to a DG space (BSplines.py:419-427, common.py:332-351).  The element-fused path
+    needs no FE space: system and solution against the oracle's direct IGA Galerkin assembly."""
+    import scipy.sparse.linalg as spla
+    from tIGAr import Function
+    from oracle import pipeline as OP
+    deg = [2, 2]
+    kv = [[0, 0, 0, .25, .5, .5, .5, .75, 1, 1, 1], uk(2, 5)]
+    gen, spline, pr = make_pair(deg, kv, mode=None)
+    assert spline.mode == "fused" and gen.extractionElement() == "DG"
+    a, L = _forms(spline, "poisson")
+    C, b = spline.assembleLinearSystem(a, L)
+    f = lambda X: (np.sin(PI * X[..., 0]) + 0.3 * np.cos(X[..., 0])) * np.sin(PI * X[..., 1]) \
+        + 0.3 * np.cos(X[..., 1])
+    Co, bo = pr.direct_iga(f)
+    # the oracle's Poisson form has no mass term: assemble that variant for the matrix check
+    from tIGAr import TrialFunction, TestFunction, inner
+    u, v = TrialFunction(spline.V), TestFunction(spline.V)
+    C1 = spline.assembleMatrix(inner(spline.grad(u), spline.grad(v)) * spline.dx, applyBCs=False)
+    assert relm(C1.to_scipy(), Co.tocsr()) < 1e-12
+    assert rel(spline.assembleVector(L, applyBCs=False).get_local(), bo) < 1e-12
+    uh = Function(spline.V)
+    U = spline.solveLinearSystem(C, b, uh)
+    Uo = spla.spsolve(C.to_scipy().tocsc(), b.get_local())
+    assert rel(U.get_local(), Uo) < 1e-10
+    with pytest.raises(NotImplementedError):
+        make_pair(deg, kv, mode="csr")

@@ -505,11 +505,10 @@ class AbstractExtractionGenerator(object):
         are never needed by the element-fused path)."""
         self.mesh = self.generateMesh()
         self.nsd = self.getNsd()
-        if self.useDG():
-            raise NotImplementedError("DG extraction (discontinuous splines) is not built")
-        self.VE_control = ("Lagrange", self.getDegree(-1))
-        self.VE = ("Lagrange", self.getDegree(0)) if self.getNFields() == 1 else \
-            tuple(("Lagrange", self.getDegree(i)) for i in range(self.getNFields()))
+        fam = self.extractionElement()          # "DG" for discontinuous splines: the FE space is
+        self.VE_control = (fam, self.getDegree(-1))   # then only a label (fused / matfree paths)
+        self.VE = (fam, self.getDegree(0)) if self.getNFields() == 1 else \
+            tuple((fam, self.getDegree(i)) for i in range(self.getNFields()))
         self.V_control = FunctionSpace(self, 1, control=True)
         self.V = FunctionSpace(self, self.getNFields())
         self._patch = None
@@ -766,6 +765,13 @@ class ExtractedSpline(object):
             if mode not in (None, "fused"):
                 raise NotImplementedError("multi-GPU runs use the element-fused path")
             mode = "fused"
+        if any(getattr(D, "discontinuous", False) for D in getattr(self._patch, "dirs", [])):
+            # discontinuous splines (interior knot of multiplicity p+1): the reference extracts
+            # to a DG space (BSplines.py:419-427); here only the paths that never form A_FE / M
+            if mode == "csr":
+                raise NotImplementedError("discontinuous B-splines: use mode='fused' or 'matfree' "
+                                          "(the csr path would need a DG extraction space)")
+            mode = mode or "fused"
         if getattr(self, "_generic", False):
             if mode not in (None, "csr"):
                 raise NotImplementedError("a generic AbstractScalarBasis uses the csr path "

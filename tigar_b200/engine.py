@@ -266,11 +266,25 @@ class Dir1D(object):
         if s.multiplicities[0] != s.p + 1 or s.multiplicities[-1] != s.p + 1:
             raise NotImplementedError(
                 "tigar_b200 tensor-product fast path needs open (non-periodic) knot vectors")
-        if s.isDiscontinuous():
-            raise NotImplementedError("discontinuous B-splines need DG extraction (not built)")
         self.d_uk = dev.from_np(s.uniqueKnots)
         self.d_espan = dev.from_np(s.elementSpans())
         self.tables = {}
+        # cell -> first basis function, and the 1-D window of the IGA system matrix (pairs of
+        # functions that share a cell): needs no FE space
+        self.first = s.elementSpans().astype(np.int64) - s.p
+        lo = np.full(self.ncp, np.iinfo(np.int64).max, dtype=np.int64)
+        hi = np.full(self.ncp, -1, dtype=np.int64)
+        for a in range(s.p + 1):
+            np.minimum.at(lo, self.first + a, self.first)
+            np.maximum.at(hi, self.first + a, self.first + s.p)
+        self.c_lo, self.c_hi = lo, hi
+        self.discontinuous = bool(s.isDiscontinuous())
+        if self.discontinuous:
+            # a discontinuous spline needs a DG extraction space (BSplines.py:419-427); the
+            # element-fused and matrix-free paths never form M or A_FE, so they work as they are
+            self.m_first = self.m_vals = self.x_fe = None
+            self.m_lo = self.m_hi = None
+            return
         # 1-D extraction rows at the FE nodes (reference per-node evaluation)
         x = dev.empty(self.nfe)
         check(lib.tg_fe_nodes_1d(dev.ptr(self.d_uk), self.nel, self.pf, dev.ptr(x), dev.stream()))
@@ -444,6 +458,10 @@ class TensorPatch(object):
 
     def _global_window(self, name):
         if name not in self._win:
+            if name != "C" and any(D.discontinuous for D in self.dirs):
+                raise NotImplementedError(
+                    "discontinuous B-splines need DG extraction for the csr path (A_FE, M); "
+                    "use mode='fused' or 'matfree'")
             if name == "M":
                 w = Window(self.nfe, self.ncp, [D.m_lo for D in self.dirs],
                            [D.m_hi for D in self.dirs])
@@ -463,7 +481,9 @@ class TensorPatch(object):
             elif name == "PT":
                 w = self._global_window("P").transpose()
             elif name == "C":
-                w = self._global_window("MT").compose(self._global_window("P"))
+                # pairs of functions sharing a cell (= MT o A o M composed, without FE windows)
+                w = Window(self.ncp, self.ncp, [D.c_lo for D in self.dirs],
+                           [D.c_hi for D in self.dirs])
             else:
                 raise KeyError(name)
             self._win[name] = w
