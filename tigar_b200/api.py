@@ -109,7 +109,9 @@ class DeviceVector(object):
         self.owner = owner            # the Function whose FE coefficients this vector is
 
     def get_local(self):
-        return dev.to_np(self.t).copy()
+        a = dev.to_np(self.t)
+        # an independent host array (to_np of a large vector already is a fresh pinned block)
+        return a if self.t.numel() * 8 >= (1 << 20) and self.t.is_cuda else a.copy()
 
     def set_local(self, a):
         self.t.copy_(dev.from_np(np.asarray(a, dtype=np.float64)))

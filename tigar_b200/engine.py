@@ -715,13 +715,56 @@ class TensorPatch(object):
                 plans[tag] = dev.from_np(tab.ravel())
             return plans[tag]
         tabs = [(B.c.tab[d], B.c.idx[d]) for d in range(dim)]
+        # Opt-in (TIGAR_B200_GSF_OVERLAP=1): the Gauss-point kernel of chunk k+1 on a second
+        # stream while the march stages of chunk k run on the caller's (two coefficient buffers,
+        # an event per chunk each way).  Measured on B200 at 256^3: no gain (250.8 vs 252.6 ms per
+        # step -- the kernels time-slice, both are bound by instruction issue), so the default
+        # keeps one stream and clean per-kernel timings.
+        import torch
+        chunks = []
         k = self.slab_lo
         while k < self.slab_hi:
             lc = min(lc_max, self.slab_hi - k)
+            chunks.append((k, lc))
+            k += lc
+        overlap = len(chunks) > 1 and os.environ.get("TIGAR_B200_GSF_OVERLAP", "0") == "1"
+        main = torch.cuda.current_stream()
+        side = main
+        if overlap:
+            if getattr(self, "_side_stream", None) is None:
+                self._side_stream = torch.cuda.Stream()
+            side = self._side_stream
+            side.wait_stream(main)           # the coefficient functions were produced on main
+        xsize = nslots * max(c[1] for c in chunks) * plane_cells * nqp
+        xbufs = [buf("X0a", xsize), buf("X0b", xsize) if overlap else None]
+        qp_done = [None] * len(chunks)
+        readers_done = [None] * len(chunks)
+
+        def launch_qp(ci):
+            kk, ll = chunks[ci]
+            nc_ = ll * plane_cells
+            Xc = xbufs[ci % 2] if overlap else xbufs[0]
+            with torch.cuda.stream(side):
+                if overlap and ci >= 2:      # the buffer is free once chunk ci-2 has been read
+                    side.wait_event(readers_done[ci - 2])
+                with dev.PROF.range("tigar_qp (generated Gauss-point kernel)",
+                                    8 * nslots * nc_ * nqp):
+                    self._qp_eval(B, P, kk * plane_cells, nc_, Xc, gsf=(nc_ * nqp, ll, kk))
+                if overlap:
+                    qp_done[ci] = torch.cuda.Event()
+                    qp_done[ci].record(side)
+            return Xc
+
+        Xnext = launch_qp(0)
+        for ci, (k, lc) in enumerate(chunks):
             ncells = lc * plane_cells
-            X0 = buf("X0", nslots * ncells * nqp)
-            with dev.PROF.range("tigar_qp (generated Gauss-point kernel)", 8 * nslots * ncells * nqp):
-                self._qp_eval(B, P, k * plane_cells, ncells, X0, gsf=(ncells * nqp, lc, k))
+            X0 = Xnext
+            if overlap:
+                main.wait_event(qp_done[ci])
+                if ci + 1 < len(chunks):
+                    Xnext = launch_qp(ci + 1)
+            elif ci + 1 < len(chunks):
+                pass                          # launched after this chunk's stages (same buffer)
             for pair, st, G, out in ((1, mst, F, A), (0, vst, n, b)):
                 if st is None:
                     continue
@@ -798,7 +841,13 @@ class TensorPatch(object):
                     ninl, 1, 1, None, 0, 0, 0, 0, 1, W.ref() if pair else None, G[0],
                     vrow0, vnr, outp, perm if (pair and dim == 3) else 0,
                     W.ref() if (pair and dim == 3 and perm) else None, dev.stream()))
-            k += lc
+            if overlap:
+                readers_done[ci] = torch.cuda.Event()
+                readers_done[ci].record(main)
+            elif ci + 1 < len(chunks):
+                Xnext = launch_qp(ci + 1)
+        if overlap:
+            main.wait_stream(side)
         self.launches += 1
 
     def assemble_matrix(self, terms, funcs, kind="fe", out=None, cache=None):
