@@ -423,10 +423,12 @@ class File(object):
             f.write('<?xml version="1.0"?>\n<VTKFile type="StructuredGrid" version="0.1">\n')
             f.write('<StructuredGrid WholeExtent="%s"><Piece Extent="%s">\n' % (ext, ext))
             f.write('<PointData Scalars="u"><DataArray type="Float64" Name="u" format="ascii">\n')
-            f.write(" ".join(repr(float(v)) for v in vals))
+            f.flush()          # ndarray.tofile writes through the descriptor, not Python's buffer
+            np.asarray(vals, dtype=np.float64).tofile(f, sep=" ", format="%.17g")
             f.write('\n</DataArray></PointData>\n<Points><DataArray type="Float64" '
                     'NumberOfComponents="3" format="ascii">\n')
-            f.write(" ".join(repr(float(v)) for v in pts.ravel()))
+            f.flush()
+            pts.ravel().tofile(f, sep=" ", format="%.17g")
             f.write('\n</DataArray></Points>\n</Piece></StructuredGrid>\n</VTKFile>\n')
         with open(self.name, "w") as f:
             f.write('<?xml version="1.0"?>\n<VTKFile type="Collection" version="0.1">\n'
