@@ -727,6 +727,18 @@ class TensorPatch(object):
             lc = min(lc_max, self.slab_hi - k)
             chunks.append((k, lc))
             k += lc
+        # algorithmic flops of the Gauss-point kernel per point: the straight-line program (one
+        # flop per operation; transcendentals counted once) + the three contraction stages of
+        # every jet (one FMA chain of length nloc per stage and distinct derivative prefix)
+        byf = {}
+        for (f_, comp, al) in P["prog"].jets:
+            byf.setdefault((f_, comp), []).append(pad3(al))
+        jfma = 0
+        for lst in byf.values():
+            jfma += (len(set(a[0] for a in lst)) * nl[0]
+                     + len(set((a[0], a[1]) for a in lst)) * (nl[1] if dim > 1 else 0)
+                     + len(lst) * (nl[2] if dim > 2 else 0))
+        qp_flops = float(len(P["prog"].prog) + 2 * jfma)
         overlap = len(chunks) > 1 and os.environ.get("TIGAR_B200_GSF_OVERLAP", "0") == "1"
         main = torch.cuda.current_stream()
         side = main
@@ -748,7 +760,7 @@ class TensorPatch(object):
                 if overlap and ci >= 2:      # the buffer is free once chunk ci-2 has been read
                     side.wait_event(readers_done[ci - 2])
                 with dev.PROF.range("tigar_qp (generated Gauss-point kernel)",
-                                    8 * nslots * nc_ * nqp):
+                                    8 * nslots * nc_ * nqp, qp_flops * nc_ * nqp):
                     self._qp_eval(B, P, kk * plane_cells, nc_, Xc, gsf=(nc_ * nqp, ll, kk))
                 if overlap:
                     qp_done[ci] = torch.cuda.Event()
