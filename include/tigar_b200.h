@@ -91,6 +91,14 @@ int tg_device_sm_count(void);
 
 /* ---- (i) extraction ---------------------------------------------------- */
 
+/* The reference's one native routine, basisFuncsInner(ghostKnots,nGhost,u,pl,i,ndu,left,right,
+ * ders) (BSplines.py:73-120, bound at :135-145): Piegl-Tiller A2.2 with the caller's index
+ * i = span+1, batched over n points.  ghostKnots/u/i/ders are device pointers;
+ * ders[n*(p+1)].  Same operation order, no FMA contraction: bit-exact.              */
+int tg_basis_funcs_inner(const double* ghostKnots, int32_t nGhost, int32_t p,
+                         const double* u, const int32_t* i, int64_t n, double* ders,
+                         void* stream);
+
 /* Batched span search + Cox-de Boor: BSpline1.getKnotSpan / getNodes /
  * basisFuncs -> basisFuncsInner (BSplines.py:285-351, 73-120).  Bit-exact
  * with the reference recurrence (no FMA contraction).
@@ -347,9 +355,13 @@ int tg_win_zero_rows_cols(const tg_win* h_w, double* vals, const uint8_t* rowmas
 /* same, for a constrained set that is a union of whole hyperplanes (the side DoFs of
  * getSideDofs, BSplines.py:599-649): hp_d[c] != 0 marks hyperplane c of direction d (global
  * coordinates; h_w's row0/col0 place a slab-local block).  Rows whose window reaches no
- * constrained hyperplane are skipped after a few byte loads.  Row-major layout only.        */
+ * constrained hyperplane are skipped after a few byte loads.  h_sel[d] (device) / h_nsel[d]:
+ * the LOCAL row coordinates of direction d that can be affected (window reaches a constrained
+ * hyperplane): only those sub-grids are visited, one launch per direction (NULL: all rows).
+ * Row-major layout only.                                                                     */
 int tg_win_zero_rows_cols_hp(const tg_win* h_w, double* vals, const uint8_t* hp0,
-                             const uint8_t* hp1, const uint8_t* hp2, double diag, void* stream);
+                             const uint8_t* hp1, const uint8_t* hp2, double diag,
+                             const int32_t* const* h_sel, const int32_t* h_nsel, void* stream);
 int tg_win_diag_inv(const tg_win* h_w, const double* vals, int32_t col_shift, double* dinv,
                     void* stream);
 /* Jacobi-CG on a windowed matrix; same contract as tg_solve_cg.             */

@@ -104,3 +104,24 @@ def test_unsupported_inputs_fail_loudly():
     assert tp.window("C").nnz == 2 * 9
     with pytest.raises(NotImplementedError):
         tp.window("A")
+
+
+@pytest.mark.gpu
+def test_basis_funcs_inner_is_the_reference_native_routine():
+    """tIGAr.BSplines.basisFuncsInner(ghostKnots,nGhost,u,pl,i,ndu,left,right,ders)
+    (BSplines.py:73-120, 135-145): the caller's index i = span+1, result in ``ders`` --
+    bit-exact with the oracle recurrence, also for a span the point does not lie in."""
+    from tIGAr.BSplines import basisFuncsInner, BSpline1, uniformKnots
+    from oracle import bsplines as OB
+    for p in (1, 2, 3, 5):
+        kv = uniformKnots(p, -1.0, 2.0, 7)
+        ours, ref = BSpline1(p, kv), OB.BSpline1(p, kv)
+        rng = np.random.default_rng(p)
+        for u in list(rng.uniform(-1.0, 2.0, 6)) + [-1.0, 2.0, ref.uniqueKnots[3]]:
+            span = ref.getKnotSpan(u)
+            for sp in (span, min(span + 1, ref.getKnotSpan(2.0))):
+                ders = np.zeros(p + 1)
+                basisFuncsInner(ref.ghostKnots, ref.nGhost, u, p, sp + 1, np.zeros((p + 1, p + 1)),
+                                np.zeros(p + 1), np.zeros(p + 1), ders)
+                assert np.array_equal(ders, ref.basisFuncs(sp, u))
+                assert np.array_equal(ours.basisFuncs(sp, u), ders)

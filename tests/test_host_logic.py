@@ -97,6 +97,26 @@ def test_symbolic_compile_and_diff():
     assert prog.nreg < 40
 
 
+def test_shared_denominators_are_inverted_once():
+    """compile_program: a/w, b/w, c/w share ONE reciprocal (the geometry divides 9-12
+    numerators by the weight / determinant); a denominator used once keeps its division, and
+    a guarded division by zero still selects the other branch."""
+    a, b, c = (S.jet(1, i, (0, 0, 0)) for i in range(3))
+    w, d = S.jet(2, 0, (0, 0, 0)), S.xi(0) + 2.0
+    outs = [a / w + b / w, c / w, a / d, S.selz(S.binary("gt", w, S.ZERO), a / w)]
+    prog = S.compile_program(outs, 1)
+    names = {v: k for k, v in S.OPCODES.items()}
+    assert sum(names[op] == "div" for op, _, _, _ in prog.prog) == 2        # 1/w and a/d
+    jv = {(1, 0, (0, 0, 0)): 0.7, (1, 1, (0, 0, 0)): -1.3, (1, 2, (0, 0, 0)): 2.9,
+          (2, 0, (0, 0, 0)): 1.7}
+    got = run_program(prog, [0.25], 1.0, jv)
+    ref = [0.7 / 1.7 - 1.3 / 1.7, 2.9 / 1.7, 0.7 / 2.25, 0.7 / 1.7]
+    assert np.allclose(got, ref, rtol=4e-16, atol=0)
+    jv[(2, 0, (0, 0, 0))] = 0.0
+    with np.errstate(all="ignore"):
+        assert run_program(prog, [0.25], 1.0, jv)[3] == 0.0
+
+
 def test_hash_consing_and_folding():
     a = S.xi(0) + S.xi(1)
     b = S.xi(1) + S.xi(0)

@@ -49,6 +49,7 @@ SIGNATURES = {
     "tg_sizeof_basis": [],
     "tg_launch_count": [],
     "tg_last_spmv_kind": [],
+    "tg_basis_funcs_inner": [c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp],
     "tg_bspline_eval_batch": [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32,
                               c_vp, c_i64, c_vp, c_vp, c_vp, c_vp],
     "tg_fe_nodes_1d": [c_vp, c_i32, c_i32, c_vp, c_vp],
@@ -60,7 +61,7 @@ SIGNATURES = {
     "tg_win_spmv": [PW, c_vp, c_vp, c_vp, c_vp],
     "tg_win_spmv_dot": [PW, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp],
     "tg_win_zero_rows_cols": [PW, c_vp, c_vp, c_vp, c_dbl, c_i32, c_vp],
-    "tg_win_zero_rows_cols_hp": [PW, c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp],
+    "tg_win_zero_rows_cols_hp": [PW, c_vp, c_vp, c_vp, c_vp, c_dbl, PVP, PI32, c_vp],
     "tg_win_diag_inv": [PW, c_vp, c_i32, c_vp, c_vp],
     "tg_win_solve_cg": [PW, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_i32, c_i32, c_vp, PI32,
                         C.POINTER(c_dbl), c_vp],

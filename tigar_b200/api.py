@@ -753,6 +753,7 @@ def _sorted_unique(z):
 
 class ExtractedSpline(object):
     """common.py:667-1433."""
+    _unit_weights = False        # all control weights exactly 1 (set by _set_control_net)
 
     def __init__(self, sourceArg, quadDeg, mesh=None, doPermutation=DEFAULT_DO_PERMUTATION,
                  comm=worldcomm, mode=None, controlNet=None):
@@ -885,6 +886,7 @@ class ExtractedSpline(object):
         nsd+1 device tensors (already resident)."""
         import torch
         self.cpFuncs = []
+        unit = getattr(P, "unit_weights", None)
         if isinstance(P, (list, tuple)):
             cols = list(P)
             self.controlNet = None
@@ -894,6 +896,10 @@ class ExtractedSpline(object):
             self.controlNet = t
             d = t.to(dev.device(), non_blocking=True)            # one H2D copy
             cols = [d[:, i].contiguous() for i in range(self.nsd + 1)]
+        if unit is None:
+            unit = os.environ.get("TIGAR_B200_UNIT_WEIGHTS", "1") == "1" and \
+                bool((cols[self.nsd] == 1.0).all().item())
+        self._unit_weights = bool(unit)
         for i in range(self.nsd + 1):
             f = Function(self.V_control)
             f.set_iga(cols[i])
@@ -939,7 +945,12 @@ class ExtractedSpline(object):
         dim = self._patch.dim
         U.DEFAULT_DIM[0] = dim
         self.boundaryMarkers = None
-        comps = [self.cpFuncs[i] / self.cpFuncs[self.nsd] for i in range(self.nsd)]
+        if self._unit_weights:
+            # all weights are exactly 1 (explicit B-spline meshes, BSplines.py:935-960): the
+            # weight function is the partition of unity, F = P/w = P up to one rounding
+            comps = [self.cpFuncs[i] for i in range(self.nsd)]
+        else:
+            comps = [self.cpFuncs[i] / self.cpFuncs[self.nsd] for i in range(self.nsd)]
         self.F = U.as_vector(comps)
         self.DF = U.parametric_grad(self.F, dim)                    # [nsd, dim]
         self.g = U.dot(self.DF.T, self.DF)                          # getMetric
@@ -1006,6 +1017,8 @@ class ExtractedSpline(object):
         return self.F
 
     def rationalize(self, u):
+        if self._unit_weights:
+            return u
         return u / self.cpFuncs[self.nsd]
 
     # -- assembly ------------------------------------------------------------

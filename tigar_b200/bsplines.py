@@ -167,6 +167,28 @@ class DofList(list):
     __hash__ = None
 
 
+def basisFuncsInner(ghostKnots, nGhost, u, pl, i, ndu, left, right, ders):
+    """The reference's native routine (BSplines.py:73-120, 135-145) on the device: the ``pl+1``
+    non-zero basis functions at ``u`` for index ``i = span+1`` are written into ``ders``
+    (a numpy array, as in the reference).  ``ghostKnots``: numpy array or device tensor.
+    ``ndu/left/right`` are the reference's scratch arrays; they are not touched (the reference
+    passes ``ndu.flatten()``, a copy, so callers never see them filled either).  ``u`` and ``i``
+    may be arrays of equal length (batched; ``ders`` then has shape (n, pl+1))."""
+    g = ghostKnots if hasattr(ghostKnots, "data_ptr") else \
+        dev.from_np(np.ascontiguousarray(ghostKnots, dtype=np.float64))
+    uu = np.atleast_1d(np.asarray(u, dtype=np.float64)).ravel()
+    ii = np.atleast_1d(np.asarray(i, dtype=np.int32)).ravel()
+    if len(uu) != len(ii):
+        raise ValueError("basisFuncsInner: u and i differ in length")
+    if len(ii) and (ii.min() - pl + nGhost < 0 or ii.max() + pl - 1 + nGhost >= g.numel()):
+        raise IndexError("basisFuncsInner: index i reaches outside the ghost knots")
+    out = dev.empty(len(uu) * (pl + 1))
+    du, di = dev.from_np(uu), dev.from_np(ii)      # (named: both must outlive the launch)
+    check(lib.tg_basis_funcs_inner(dev.ptr(g), int(nGhost), int(pl), dev.ptr(du), dev.ptr(di),
+                                   len(uu), dev.ptr(out), dev.stream()))
+    np.asarray(ders).reshape(-1)[:] = dev.to_np(out)
+
+
 class BSpline1(object):
     """Univariate B-spline (BSplines.py:164-351)."""
 
@@ -264,10 +286,11 @@ class BSpline1(object):
         return [int(i) for i in dev.to_np(self.evalBatch([u])[1][0])]
 
     def basisFuncs(self, knotSpan, u):
-        span, _, vals = self.evalBatch([u])
-        if int(span[0].item()) != int(knotSpan):
-            raise ValueError("basisFuncs: knotSpan %d does not contain u=%r" % (knotSpan, u))
-        return dev.to_np(vals[0]).copy()
+        """BSplines.py:321-351: the caller's span is used as given (not searched again)."""
+        ders = np.zeros(self.p + 1)
+        basisFuncsInner(self.deviceKnots()[1], self.nGhost, u, self.p, int(knotSpan) + 1,
+                        None, None, None, ders)
+        return ders
 
 
 class AbstractScalarBasis(object):
@@ -434,6 +457,11 @@ class BSpline(AbstractScalarBasis):
         return DofList.from_array(out[0] if len(out) == 1 else np.concatenate(out))
 
 
+class _UnitWeightColumns(list):
+    """Device columns of a control net whose weights are all exactly 1."""
+    unit_weights = True
+
+
 class ExplicitBSplineControlMesh(AbstractControlMesh):
     """Physical == parametric space: Greville control points, unit weights
     (BSplines.py:910-963)."""
@@ -473,7 +501,7 @@ class ExplicitBSplineControlMesh(AbstractControlMesh):
         sp = self.scalarSpline.splines
         n = [s.getNcp() for s in sp] + [1] * (3 - len(sp))
         ncp = int(np.prod(n))
-        cols = []
+        cols = _UnitWeightColumns()
         for d in range(self.nsd + 1):
             out = dev.empty(ncp)
             if d < self.nvar:

@@ -83,6 +83,28 @@ extern "C" int tg_bspline_eval_batch(const double* knots, int32_t nk, const doub
   return 0;
 }
 
+// basisFuncsInner itself (BSplines.py:73-120): caller-supplied index i (= span + 1) per point
+__global__ void k_basis_funcs_inner(const double* __restrict__ ghost, int nG, int p,
+                                    const double* __restrict__ u, const int32_t* __restrict__ i,
+                                    int64_t n, double* __restrict__ ders) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double d[TG_MAXP + 1];
+  tg_basis_funcs(ghost, nG, u[t], p, i[t], d);
+  for (int j = 0; j <= p; j++) ders[t * (p + 1) + j] = d[j];
+}
+
+extern "C" int tg_basis_funcs_inner(const double* ghostKnots, int32_t nGhost, int32_t p,
+                                    const double* u, const int32_t* i, int64_t n, double* ders,
+                                    void* stream) {
+  TG_REQUIRE(p >= 1 && p <= TG_MAXP, "degree out of range");
+  if (n == 0) return 0;
+  k_basis_funcs_inner<<<(unsigned)tg_cdiv(n, 128), 128, 0, tg_stream(stream)>>>(
+      ghostKnots, nGhost, p, u, i, n, ders);
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
 // node e*pf+a ; a=0/pf exactly on the unique knots; interior uk[e]+(a*h)/pf
 __device__ inline double tg_fe_node(const double* __restrict__ uk, int e, int a, int pf) {
   if (a == 0) return uk[e];

@@ -979,12 +979,23 @@ extern "C" int tg_win_zero_rows_cols(const tg_win* h_w, double* vals, const uint
 __global__ void k_win_zero_rows_cols_hp(TgWin w, double* __restrict__ vals, int64_t nrows,
                                         const uint8_t* __restrict__ hp0,
                                         const uint8_t* __restrict__ hp1,
-                                        const uint8_t* __restrict__ hp2, double diag) {
-  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+                                        const uint8_t* __restrict__ hp2, double diag, int dsel,
+                                        const int32_t* __restrict__ sel, int nsel) {
+  // dsel >= 0: only the rows whose coordinate in direction dsel is one of sel[0..nsel) (local
+  // row coordinates) are visited: warp k handles the k-th row of that sub-grid
+  const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (r >= nrows) return;
   int rc[3];
-  tg_decode(r, w.nr, w.dim, rc);
+  if (dsel < 0) {
+    if (wid >= nrows) return;
+    tg_decode(wid, w.nr, w.dim, rc);
+  } else {
+    int n[3] = {w.nr[0], w.nr[1], w.nr[2]};
+    n[dsel] = nsel;
+    if (wid >= (int64_t)n[0] * n[1] * n[2]) return;
+    tg_decode(wid, n, w.dim, rc);
+    rc[dsel] = sel[rc[dsel]];
+  }
   const TgRowWin rw = tg_row_window(w, rc);
   const uint8_t* hp[3] = {hp0, hp1, hp2};
   bool mr = false, touch = false;
@@ -1013,15 +1024,32 @@ __global__ void k_win_zero_rows_cols_hp(TgWin w, double* __restrict__ vals, int6
   }
 }
 
+// h_sel[d] / h_nsel[d]: device list of the LOCAL row coordinates of direction d whose window
+// reaches a constrained hyperplane (or that are constrained themselves); the union over d of
+// these sub-grids contains every row the operation touches (it is idempotent, overlaps are
+// harmless).  h_sel == NULL: scan all rows.
 extern "C" int tg_win_zero_rows_cols_hp(const tg_win* h_w, double* vals, const uint8_t* hp0,
                                         const uint8_t* hp1, const uint8_t* hp2, double diag,
+                                        const int32_t* const* h_sel, const int32_t* h_nsel,
                                         void* stream) {
   TG_REQUIRE(h_w->layout == 0, "hyperplane BC kernel needs the row-major window layout");
   int64_t nrows = tg_win_nrows(h_w);
   if (nrows == 0) return 0;
-  k_win_zero_rows_cols_hp<<<(unsigned)tg_cdiv(nrows * 32, 256), 256, 0, tg_stream(stream)>>>(
-      tg_win_dev(h_w), vals, nrows, hp0, hp1, hp2, diag);
-  TG_LAUNCH_CHECK();
+  if (!h_sel) {
+    k_win_zero_rows_cols_hp<<<(unsigned)tg_cdiv(nrows * 32, 256), 256, 0, tg_stream(stream)>>>(
+        tg_win_dev(h_w), vals, nrows, hp0, hp1, hp2, diag, -1, nullptr, 0);
+    TG_LAUNCH_CHECK();
+    return 0;
+  }
+  for (int d = 0; d < h_w->dim; d++) {
+    if (h_nsel[d] <= 0) continue;
+    int64_t n = h_nsel[d];
+    for (int e = 0; e < h_w->dim; e++)
+      if (e != d) n *= h_w->nr[e];
+    k_win_zero_rows_cols_hp<<<(unsigned)tg_cdiv(n * 32, 256), 256, 0, tg_stream(stream)>>>(
+        tg_win_dev(h_w), vals, nrows, hp0, hp1, hp2, diag, d, h_sel[d], h_nsel[d]);
+    TG_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -1402,8 +1402,21 @@ class TensorPatch(object):
             hp, exact = self.mask_planes(mask)
             if exact:
                 P = [dev.ptr(hp[d]) if d < self.dim else None for d in range(3)]
-                check(lib.tg_win_zero_rows_cols_hp(Cm.window.ref(), dev.ptr(Cm.vals), P[0], P[1],
-                                                   P[2], float(diag), dev.stream()))
+                # local row coordinates per direction whose window reaches a constrained plane
+                W = Cm.window
+                sels = []
+                for d in range(self.dim):
+                    hflag = dev.to_np(hp[d]).astype(bool)
+                    cs = np.concatenate([[0], np.cumsum(hflag)])
+                    lo = W.lo[d].astype(np.int64) + W.col0[d]
+                    hi = W.hi[d].astype(np.int64) + W.col0[d]
+                    rows = np.arange(W.nr[d]) + W.row0[d]
+                    need = (cs[hi + 1] - cs[lo] > 0) | hflag[rows]
+                    sels.append(dev.from_np(np.flatnonzero(need).astype(np.int32)))
+                check(lib.tg_win_zero_rows_cols_hp(
+                    W.ref(), dev.ptr(Cm.vals), P[0], P[1], P[2], float(diag),
+                    vparr([dev.ptr(t) or 0 for t in sels] + [0] * (3 - self.dim)),
+                    i32arr([t.numel() for t in sels] + [0] * (3 - self.dim)), dev.stream()))
                 return Cm
         if self.part is not None:
             pp, pl = self.pp, self.plane

@@ -130,11 +130,13 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
     w("  const int tid = threadIdx.x;")
     w("  const long long cl = blockIdx.x;")
     if op is None:
-        w("  long long c = A.cell0 + cl;")
-        w("  int e0 = (int)(c % A.nel[0]), e1 = 0, e2 = 0;")
+        # 32-bit cell arithmetic (launch() checks the range): a 64-bit division is ~100
+        # instructions, and every thread of the block decodes the cell
+        w("  const unsigned c = (unsigned)(A.cell0 + cl);")
+        w("  int e0 = (int)(c % (unsigned)A.nel[0]), e1 = 0, e2 = 0;")
         if dim > 1:
-            w("  { long long r = c / A.nel[0]; e1 = (int)(r % A.nel[1]); " +
-              ("e2 = (int)(r / A.nel[1]);" if dim > 2 else "") + " }")
+            w("  { const unsigned r = c / (unsigned)A.nel[0]; e1 = (int)(r % (unsigned)A.nel[1]); " +
+              ("e2 = (int)(r / (unsigned)A.nel[1]);" if dim > 2 else "") + " }")
     else:
         w("  __shared__ double cq[NQP], u1[N0*Q1*Q2], u2[N0*N1*Q2], accs[NEN];")
         w("  int e0 = A.co[0] + A.cs[0] * (int)(cl % A.cn[0]), e1 = 0, e2 = 0;")
@@ -360,6 +362,8 @@ def launch(kernel, B, coef_ptrs, cell0, ncells, out, gsf=None):
         a.n[d], a.nel[d] = b.n[d], b.nel[d]
     for i, p in enumerate(coef_ptrs):
         a.coef[i] = p
+    if cell0 + ncells >= 2 ** 32:
+        raise ValueError("more than 2^32 cells in one patch")
     a.cell0 = cell0
     a.out = dev.ptr(out)
     if gsf is not None:

@@ -258,6 +258,8 @@ def binary(name, a, b):
         return div(a, b)
     if name == "pow":
         return power(a, b)
+    if name == "selz":
+        return selz(a, b)
     if a.is_const() and b.is_const():
         x, y = _c(a), _c(b)
         return const(dict(max=max(x, y), min=min(x, y), gt=1.0 if x > y else 0.0)[name])
@@ -448,9 +450,49 @@ class Program(object):
         self.outregs = outregs
 
 
+def share_reciprocals(outputs):
+    """The DAGs with every denominator that divides two or more numerators inverted ONCE
+    (``a/b -> a*(1/b)``): an FP64 division is ~15 instructions with a slow-path branch, and the
+    geometry (P/w, g^-1) divides 9-12 numerators by the same weight / determinant.  Changes the
+    rounding of those quotients by <= 1 ulp; the host interpreter runs the same program."""
+    nodes, seen, stack = [], set(), list(outputs)
+    while stack:
+        n = stack.pop()
+        if n.uid in seen:
+            continue
+        seen.add(n.uid)
+        nodes.append(n)
+        if n.op not in ("const", "xi", "wq", "jet", "param"):
+            stack.extend(n.args)
+    uses = {}
+    for n in nodes:
+        if n.op == "div" and not n.args[1].is_const():
+            uses[n.args[1].uid] = uses.get(n.args[1].uid, 0) + 1
+    shared = set(u for u, c in uses.items() if c >= 2)
+    if not shared:
+        return outputs
+    memo = {}
+    # children were created before their parents (hash-consing), so uid order is topological
+    for n in sorted(nodes, key=lambda m: m.uid):
+        if n.op in ("const", "xi", "wq", "jet", "param"):
+            memo[n.uid] = n
+            continue
+        args = [memo[a.uid] for a in n.args]
+        if n.op == "div" and n.args[1].uid in shared:
+            r = mul(args[0], _mk("div", ONE, args[1]))
+        elif all(a is b for a, b in zip(args, n.args)):
+            r = n
+        elif n.op in _UNARY:
+            r = func(n.op, args[0])
+        else:
+            r = binary(n.op, args[0], args[1])
+        memo[n.uid] = r
+    return [memo[o.uid] for o in outputs]
+
+
 def compile_program(outputs, dim):
     """Topologically order the DAG under ``outputs`` and allocate registers."""
-    outputs = [as_node(o) for o in outputs]
+    outputs = share_reciprocals([as_node(o) for o in outputs])
     order, seen = [], set()
     # iterative post-order
     for root in outputs:
