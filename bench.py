@@ -426,6 +426,15 @@ def run_ours(args):
     stage_ms = [maxr(v) for v in stage_ms]
     parity = parity_checks(extras, MTAM, world)
     nz = len(extras["spline"]._zeroDofsRaw)
+    if net_bytes:      # bytes of the control net each rank actually uploads (its slab + halo)
+        mine = float(getattr(extras["spline"], "_h2d_bytes", net_bytes))
+        if world > 1:
+            t = torch.tensor([mine], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t)
+            mine = float(t.item())
+        net_bytes_all = int(mine)
+    else:
+        net_bytes_all = 0
     local_nnz = W.nnz if W is not None else 0
     del MTAM, stages, extras, r
     value = n_dofs * args.steps / (ms * 1e-3)
@@ -445,14 +454,15 @@ def run_ours(args):
     barrier()
     e2e_ms = maxr(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - wall0)))
     e2e = {"value": n_dofs * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-           "h2d_bytes_per_step": int((sum(len(k) for k in kv) * 8 + nz * 8 + net_bytes) * world),
+           "h2d_bytes_per_step": int((sum(len(k) for k in kv) * 8 + nz * 8) * world
+                                     + net_bytes_all),
            "d2h_bytes_per_step": int(n_dofs * 8),
            "note": ("inputs = knot vectors + zero-DoF lists (every rank uploads its copy); the "
                     "Greville control net is generated on the device inside the step; output = "
                     "the IGA DoF vector read back by rank 0") if not net_bytes else
-                   ("inputs = the NURBS object's homogeneous control net (uploaded by every "
-                    "rank, it is replicated), knot vectors, zero-DoF lists; output = the IGA "
-                    "DoF vector read back by rank 0")}
+                   ("inputs = the NURBS object's homogeneous control net (every rank uploads "
+                    "the planes its cell layers read: its slab + halo), knot vectors, zero-DoF "
+                    "lists; output = the IGA DoF vector read back by rank 0")}
     if rank != 0:
         dist.barrier()
         dist.destroy_process_group()

@@ -115,7 +115,7 @@ def test_basis_funcs_inner_is_the_reference_native_routine():
     from oracle import bsplines as OB
     for p in (1, 2, 3, 5):
         kv = uniformKnots(p, -1.0, 2.0, 7)
-        ours, ref = BSpline1(p, kv), OB.BSpline1(p, kv)
+        ours, ref = BSpline1(p, kv), OB.Spline1(p, kv)
         rng = np.random.default_rng(p)
         for u in list(rng.uniform(-1.0, 2.0, 6)) + [-1.0, 2.0, ref.uniqueKnots[3]]:
             span = ref.getKnotSpan(u)

@@ -372,6 +372,27 @@ def pad3(alpha):
     return a + (0,) * (3 - len(a))
 
 
+class SlabVector(object):
+    """Planes [p0, p1) of the last direction of an IGA vector whose other planes this rank never
+    reads (a coefficient function on a slab partition: the control net of a NURBS patch).  The
+    Gauss-point kernels index coefficient vectors GLOBALLY, so they are given the virtual base
+    ``ptr - 8*p0*plane``; only the rank's own cell layers are launched and their basis
+    functions lie inside the stored planes (``TensorPatch.coef_planes``)."""
+
+    def __init__(self, t, p0, p1, plane):
+        assert t.numel() == (p1 - p0) * plane
+        self.t, self.p0, self.p1, self.plane = t, int(p0), int(p1), int(plane)
+
+    def numel(self):
+        return self.t.numel()
+
+
+def coef_ptr(x):
+    if isinstance(x, SlabVector):
+        return dev.ptr(x.t) - 8 * x.p0 * x.plane
+    return dev.ptr(x)
+
+
 class TensorPatch(object):
     """A tensor-product B-spline patch and its Q_pf Lagrange background mesh."""
 
@@ -416,6 +437,18 @@ class TensorPatch(object):
             self.xoff = plane * (self.pp["k0"] - self.pp["c0"])
         else:
             self.part = None
+
+    def coef_planes(self):
+        """Planes of the last direction that the rank's cell layers (halo layers included)
+        read from a coefficient function: [first function of the first cell, last function of
+        the last cell], widened to the column range of the rank's matrix rows."""
+        if self.part is None:
+            return 0, self.ncp[-1]
+        D = self.dirs[-1]
+        first = D.s.elementSpans().astype(np.int64) - D.p
+        lo = min(int(first[self.slab_lo]), self.pp["c0"])
+        hi = max(int(first[self.slab_hi - 1]) + D.p + 1, self.pp["c1"])
+        return lo, hi
 
     def window_global_C_last(self):
         """(lo, hi) of the global C window in the last direction."""
@@ -541,7 +574,7 @@ class TensorPatch(object):
             jets += [fpos[f], comp] + list(pad3(al))
         nder = max([max(al) for (_, _, al) in prog.jets] + [0])
         P = dict(prog=prog, fids=fids, njets=len(prog.jets), jets=i32arr(jets),
-                 coefs=vparr([dev.ptr(funcs[f]) for f in fids]),
+                 coefs=vparr([coef_ptr(funcs[f]) for f in fids]),
                  keep=[funcs[f] for f in fids],
                  ncomp=i32arr([1] * len(fids)),
                  d_prog=dev.from_np(np.array(prog.prog, dtype=np.int32).reshape(-1, 4))
@@ -563,7 +596,7 @@ class TensorPatch(object):
             cache["P"] = P
         else:
             P["keep"] = [funcs[f] for f in P["fids"]]
-            P["coefs"] = vparr([dev.ptr(t) for t in P["keep"]])
+            P["coefs"] = vparr([coef_ptr(t) for t in P["keep"]])
         return P
 
     def _qp_eval(self, B, P, cell0, ncells, out, gsf=None):
@@ -581,7 +614,7 @@ class TensorPatch(object):
                 k = jit.get_kernel(P["prog"], self.dim, nloc, nq, B.nder + 1, jets,
                                    len(P["fids"]), layout="gsf")
                 P["jit"][key] = k
-            jit.launch(k, B, [dev.ptr(t) for t in P["keep"]], cell0, ncells, out, gsf=gsf)
+            jit.launch(k, B, [coef_ptr(t) for t in P["keep"]], cell0, ncells, out, gsf=gsf)
             return
         if jit.enabled() and len(P["fids"]) <= jit.MAXFUN:
             k = P.setdefault("jit", {}).get(B.nder)
@@ -593,7 +626,7 @@ class TensorPatch(object):
                 k = jit.get_kernel(P["prog"], self.dim, nloc, nq, B.nder + 1, jets,
                                    len(P["fids"]))
                 P["jit"][B.nder] = k
-            jit.launch(k, B, [dev.ptr(t) for t in P["keep"]], cell0, ncells, out)
+            jit.launch(k, B, [coef_ptr(t) for t in P["keep"]], cell0, ncells, out)
             return
         check(lib.tg_qp_eval(B.ref(), len(P["fids"]), P["coefs"], P["ncomp"], P["njets"],
                              P["jets"], dev.ptr(P["d_prog"]), len(P["prog"].prog),
