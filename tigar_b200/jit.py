@@ -259,47 +259,41 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
     for s, r in enumerate(prog.outregs):
         w("  ov%d = %s;" % (s, names[r]))
     w("  }")
-    if diag:
-        for s, (aS, aT) in enumerate(op):
-            aS = tuple(aS) + (0,) * (3 - len(aS))
-            aT = tuple(aT) + (0,) * (3 - len(aT))
-            w("  __syncthreads();")
-            w("  if (active) cq[tid] = ov%d;" % s)
-            w("  __syncthreads();")
-            w("  for (int a = tid; a < NEN; a += NTH) {")
-            w("    int l0 = a %% N0, t = a / N0, l1 = t %% N1, l2 = t / N1; double acc = 0.0;"
-              .replace("%%", "%"))
-            w("    for (int q2 = 0; q2 < Q2; q2++) {")
-            w("      const double w2 = tb2[(q2*N2 + l2)*ND + %d] * tb2[(q2*N2 + l2)*ND + %d];"
-              % (aS[2], aT[2]))
-            w("      for (int q1 = 0; q1 < Q1; q1++) {")
-            w("        const double w1 = w2 * tb1[(q1*N1 + l1)*ND + %d] * tb1[(q1*N1 + l1)*ND + %d];"
-              % (aS[1], aT[1]))
-            w("        #pragma unroll\n        for (int q0 = 0; q0 < Q0; q0++)")
-            w("          acc += w1 * tb0[(q0*N0 + l0)*ND + %d] * tb0[(q0*N0 + l0)*ND + %d] * cq[(q2*Q1 + q1)*Q0 + q0];"
-              % (aS[0], aT[0]))
-            w("      }\n    }")
-            w("    accs[a] += acc;\n  }")
-    # test-function contraction, one output slot at a time (u1, u2 as in k_assemble_vector)
-    for s, al in enumerate([] if diag else op):
-        al = tuple(al) + (0,) * (3 - len(al))
+    # test-function contraction, one output slot at a time (u1, u2 as in k_assemble_vector);
+    # diag: the same three sum-factorised stages with the PRODUCT of the test and trial tables
+    # (N_a is a tensor product, so sum_q c(q) D^s N_a(q) D^t N_a(q) factorises too: 3*(p+1)^4
+    # FMAs per slot and cell instead of (p+1)^6)
+    def tabx(d, q, a, al):
+        T, N = "tb%d" % d, "N%d" % d
+        if diag:
+            return "%s[(%s*%s + %s)*ND + %d] * %s[(%s*%s + %s)*ND + %d]" % (
+                T, q, N, a, al[0][d], T, q, N, a, al[1][d])
+        return "%s[(%s*%s + %s)*ND + %d]" % (T, q, N, a, al[d])
+    for s, al in enumerate(op):
+        if diag:
+            al = (tuple(al[0]) + (0,) * (3 - len(al[0])), tuple(al[1]) + (0,) * (3 - len(al[1])))
+        else:
+            al = tuple(al) + (0,) * (3 - len(al))
         w("  __syncthreads();")
         w("  if (active) cq[tid] = ov%d;" % s)
         w("  __syncthreads();")
         w("  for (int o = tid; o < N0*Q1*Q2; o += NTH) {")
         w("    int a0 = o %% N0, r = o / N0; double acc = 0.0;".replace("%%", "%"))
-        w("    #pragma unroll\n    for (int q = 0; q < Q0; q++) acc += tb0[(q*N0 + a0)*ND + %d] * cq[r*Q0 + q];" % al[0])
+        w("    #pragma unroll\n    for (int q = 0; q < Q0; q++) acc += %s * cq[r*Q0 + q];"
+          % tabx(0, "q", "a0", al))
         w("    u1[o] = acc;\n  }")
         w("  __syncthreads();")
         w("  for (int o = tid; o < N0*N1*Q2; o += NTH) {")
         w("    int a0 = o %% N0, t = o / N0, a1 = t %% N1, q2 = t / N1; double acc = 0.0;"
           .replace("%%", "%"))
-        w("    #pragma unroll\n    for (int q = 0; q < Q1; q++) acc += tb1[(q*N1 + a1)*ND + %d] * u1[(q2*Q1 + q)*N0 + a0];" % al[1])
+        w("    #pragma unroll\n    for (int q = 0; q < Q1; q++) acc += %s * u1[(q2*Q1 + q)*N0 + a0];"
+          % tabx(1, "q", "a1", al))
         w("    u2[o] = acc;\n  }")
         w("  __syncthreads();")
         w("  for (int a = tid; a < NEN; a += NTH) {")
         w("    int a01 = a %% (N0*N1), a2 = a / (N0*N1); double acc = 0.0;".replace("%%", "%"))
-        w("    #pragma unroll\n    for (int q = 0; q < Q2; q++) acc += tb2[(q*N2 + a2)*ND + %d] * u2[q*N0*N1 + a01];" % al[2])
+        w("    #pragma unroll\n    for (int q = 0; q < Q2; q++) acc += %s * u2[q*N0*N1 + a01];"
+          % tabx(2, "q", "a2", al))
         w("    accs[a] += acc;\n  }")
     w("  __syncthreads();")
     w("  for (int a = tid; a < NEN; a += NTH) {")

@@ -158,7 +158,17 @@ class FormOperator(object):
         from . import dev, jit
         p = self.patch
         keys = sorted(self.mterms)
-        prog = S.compile_program([self.mterms[k] for k in keys], p.dim)
+        # (s, t) and (t, s) with the same coefficient contribute the same diagonal: one slot
+        groups = {}
+        for k in keys:
+            a, b = tuple(k[0][:3]), tuple(k[1][:3])
+            groups.setdefault((min(a, b), max(a, b), self.mterms[k].uid), []).append(k)
+        outs, pairs = [], []
+        for (a, b, _), ks in sorted(groups.items()):
+            node = self.mterms[ks[0]]
+            outs.append(node if len(ks) == 1 else S.mul(S.const(float(len(ks))), node))
+            pairs.append((a, b))
+        prog = S.compile_program(outs, p.dim)
         fids = sorted(set(j[0] for j in prog.jets))
         jets = [(fids.index(f), c, tuple(al) + (0,) * (3 - len(al))) for (f, c, al) in prog.jets]
         nder = max([max(al) for (_, _, al) in prog.jets]
@@ -166,11 +176,11 @@ class FormOperator(object):
         B = p.basis("iga", nder)
         nloc = list(B.nloc) + [1] * (3 - p.dim)
         nq = [int(B.c.nq[d]) for d in range(3)]
-        pairs = [(tuple(k[0][:3]), tuple(k[1][:3])) for k in keys]
         kern = jit.get_op_kernel(prog, p.dim, nloc, nq, B.nder + 1, jets, len(fids), pairs,
                                  diag=True)
         d = dev.zeros(self.n)
-        jit.launch_op(kern, B, [dev.ptr(self._funcs[f]) for f in fids], d, list(B.nloc))
+        with dev.PROF.range("tigar_op diag=1 (generated Jacobi-diagonal kernel, per colour)", 0, 0):
+            jit.launch_op(kern, B, [dev.ptr(self._funcs[f]) for f in fids], d, list(B.nloc))
         d[d == 0.0] = 1.0                      # as tg_win_diag_inv: a zero diagonal acts as 1
         return d.reciprocal_()                 # one-time element-wise reciprocal
 
@@ -235,7 +245,11 @@ def solve_matfree_fd(op, b, rtol=1e-12, atol=0.0, maxit=10000):
         check(lib.tg_dot(dev.ptr(op.xvec), dev.ptr(q), n, dev.ptr(scratch), dev.ptr(s),
                          dev.stream()))
         return float(s[0].item())
-    x, its, rel = solvers.pcg(spmv_dot, fd.apply, b, None, rtol, atol, maxit, p_buf=op.xvec)
+    def precond(r, z):
+        with dev.PROF.range("k_dgemm x6 + k_fd_scale (FD preconditioner)", 16 * 8 * n,
+                            fd.flops_per_apply):
+            return fd.apply(r, z)
+    x, its, rel = solvers.pcg(spmv_dot, precond, b, None, rtol, atol, maxit, p_buf=op.xvec)
     return x, its, rel
 
 
