@@ -164,6 +164,13 @@ def test_newton_projection_and_extraction_round_trip(scalar_backend, tmp_path):
     w.set_iga(g.iga.clone())
     from tIGAr import assemble
     assert assemble(((w - (x[0] * x[1] + 0.5)) ** 2) * spline.dx) < 1e-20
+    # lumped-mass projection (common.py:1416-1430): U = (M^T b) / (M^T m); exact for a constant
+    gl = spline.project(0.0 * x[0] + 2.5, rationalize=False, lumpMass=True)
+    assert np.allclose(gl.iga.numpy(), 2.5, rtol=1e-13)
+    gq = spline.project(x[0] * x[1] + 0.5, rationalize=False, lumpMass=True)
+    m = spline.assembleVector(1.0 * v * spline.dx, applyBCs=False).get_local()
+    b = spline.assembleVector((x[0] * x[1] + 0.5) * v * spline.dx, applyBCs=False).get_local()
+    assert np.allclose(gq.iga.numpy(), b / m, rtol=1e-13)
     # on-disk round trip
     d = str(tmp_path / "extraction")
     gen.writeExtraction(d)

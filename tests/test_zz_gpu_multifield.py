@@ -225,6 +225,12 @@ def test_matrix_free_mode_on_the_device(deg, nels):
     op0._dinv = None
     d3 = dev.to_np(op0.jacobi_dinv())                     # default: generated diagonal kernel
     assert rel(d3, d1) < 1e-12
+    # assembleLinearSystem: load vector and diagonal from ONE Gauss-point pass (the march's
+    # second vector job on product tables, engine.assemble_vector_and_diag)
+    opS, bS = mf.assembleLinearSystem(a2, L2, applyBCs=False)
+    assert opS._dinv is not None, "the shared pass did not run"
+    assert rel(dev.to_np(opS._dinv), d1) < 1e-12
+    assert rel(bS.get_local(), mf.assembleVector(L2, applyBCs=False).get_local()) < 1e-13
     ks = KrylovSolver("cg", "jacobi")
     ks.parameters["relative_tolerance"] = 1e-13
     mf.setSolverOptions(linearSolver=ks)

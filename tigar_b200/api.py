@@ -1216,6 +1216,20 @@ class ExtractedSpline(object):
         """common.py:1223-1234.  Matrix and vector share one Gauss-point pass."""
         kind = "fe" if self.mode == "csr" else "iga"
         ms, vs = lhsForm.scalar(), rhsForm.scalar()
+        if (self.mode == "matfree" and self.nFields == 1 and ms.arity() == 2 and vs.arity() == 1
+                and not any(k[0] is None for k in vs.terms)
+                and os.environ.get("TIGAR_B200_MF_DIAG_PASS", "1") == "1"):
+            # load vector and Jacobi diagonal of the operator from one Gauss-point pass
+            op = self.assembleMatrix(lhsForm, applyBCs)
+            vt = {k[0]: n for k, n in self._weighted(vs).items()}
+            both = getattr(self._patch, "assemble_vector_and_diag", None)
+            r = both(vt, op.mterms, self._funcs("iga")) if both is not None else None
+            if r is not None:
+                op.set_diagonal(r[1])
+                if applyBCs:
+                    self._patch.apply_bcs_vector(r[0], self._bc_mask())
+                return op, DeviceVector(r[0])
+            return op, self.assembleVector(rhsForm, applyBCs)
         if (self.nFields > 1 or self.mode == "matfree" or ms.arity() != 2 or vs.arity() != 1
                 or any(k[0] is None for k in vs.terms)):
             return (self.assembleMatrix(lhsForm, applyBCs),
@@ -1367,13 +1381,18 @@ class ExtractedSpline(object):
 
     def project(self, toProject, applyBCs=False, rationalize=True, lumpMass=False):
         """L2 projection onto the spline space, common.py:1392-1433."""
-        if lumpMass:
-            raise NotImplementedError("lumped projection")
         u = self.rationalize(TrialFunction(self.V))
         v = self.rationalize(TestFunction(self.V))
         retval = Function(self.V)
-        self.solveLinearVariationalProblem(
-            U.inner(u, v) * self.dx == U.inner(toProject, v) * self.dx, retval, applyBCs)
+        if not lumpMass:
+            self.solveLinearVariationalProblem(
+                U.inner(u, v) * self.dx == U.inner(toProject, v) * self.dx, retval, applyBCs)
+        else:
+            # row-sum lumping (common.py:1416-1430): U = (M^T b) / (M^T m), m = int 1 . v
+            one = U.Constant(1.0) if self.nFields == 1 else U.Constant(self.nFields * (1.0,))
+            lhs = self.assembleVector(U.inner(one, v) * self.dx, applyBCs=False)
+            rhs = self.assembleVector(U.inner(toProject, v) * self.dx, applyBCs=applyBCs)
+            retval.set_iga(rhs.t / lhs.t)
         return self.rationalize(retval) if rationalize else retval
 
     def FEtoIGA(self, u):

@@ -705,10 +705,12 @@ class TensorPatch(object):
             self._bases[key] = hit
         return hit
 
-    def _gsf_run(self, B, kind, P, nslots, mentries, ventries, A, b, vrow0, vnr):
+    def _gsf_run(self, B, kind, P, nslots, mentries, ventries, A, b, vrow0, vnr, xvec=None):
         """One pass over the cell layers of this patch (or slab): Gauss-point kernel into the
         blocked coefficient layout, then the march stages of the matrix (``mentries``) and of
-        the load vector (``ventries``).  A / b may be None."""
+        the load vector (``ventries``).  A / b may be None.  ``xvec``: further vector jobs fed
+        by the same Gauss-point pass, [(entries, out, [(tab, idx)]*dim, nd)], each with its own
+        1-D tables (the matrix diagonal: ``assemble_vector_and_diag``)."""
         dim, L = self.dim, self.dim - 1
         nel = [int(B.c.nel[d]) for d in range(dim)]
         nq = [int(B.c.nq[d]) for d in range(dim)]
@@ -723,9 +725,15 @@ class TensorPatch(object):
         plane_cells = int(np.prod(nel[:L]))
         # bytes per layer of the last direction: coefficients + intermediates
         per = nslots * plane_cells * nqp
-        for st, G in ((mst, F), (vst, n)):
-            if st is None:
-                continue
+        tabs = [(B.c.tab[d], B.c.idx[d]) for d in range(dim)]
+        jobs = []
+        if mst is not None:
+            jobs.append((1, mst, F, A, tabs, nd, "m"))
+        if vst is not None:
+            jobs.append((0, vst, n, b, tabs, nd, "v"))
+        for i, (xe, xo, xt, xnd) in enumerate(xvec or []):
+            jobs.append((0, self._gsf_plan(xe, dim, False), n, xo, xt, xnd, "x%d" % i))
+        for _, st, G, _, _, _, _ in jobs:
             if dim == 3:
                 per += st[0][0] * nel[1] * G[0] * nq[2] * nq[1] + st[1][0] * G[1] * G[0] * nq[2]
             else:
@@ -747,7 +755,6 @@ class TensorPatch(object):
             if tag not in plans:
                 plans[tag] = dev.from_np(tab.ravel())
             return plans[tag]
-        tabs = [(B.c.tab[d], B.c.idx[d]) for d in range(dim)]
         # Opt-in (TIGAR_B200_GSF_OVERLAP=1): the Gauss-point kernel of chunk k+1 on a second
         # stream while the march stages of chunk k run on the caller's (two coefficient buffers,
         # an event per chunk each way).  Measured on B200 at 256^3: no gain (250.8 vs 252.6 ms per
@@ -810,10 +817,7 @@ class TensorPatch(object):
                     Xnext = launch_qp(ci + 1)
             elif ci + 1 < len(chunks):
                 pass                          # launched after this chunk's stages (same buffer)
-            for pair, st, G, out in ((1, mst, F, A), (0, vst, n, b)):
-                if st is None:
-                    continue
-                tag = "m" if pair else "v"
+            for pair, st, G, out, tabs, nd, tag in jobs:
                 perm = 0
                 rbs = [self._gsf_dir(B, Wg, d, bool(pair))[0] for d in range(dim)]
                 outp = dev.ptr(out.vals) if pair else dev.ptr(out)
@@ -894,6 +898,60 @@ class TensorPatch(object):
         if overlap:
             main.wait_stream(side)
         self.launches += 1
+
+    def assemble_vector_and_diag(self, vterms, mterms, funcs):
+        """(b, diag C) from ONE Gauss-point pass: the load vector of ``vterms`` and the diagonal
+        of the extracted matrix of ``mterms`` (its Jacobi preconditioner / the data the FD
+        preconditioner is fitted to) without the matrix.  N_i is a tensor product, so
+            C_ii = sum_q c(q) prod_d D^{a_d}N_{i_d}(q_d) D^{b_d}N_{i_d}(q_d)
+        is a load-vector assembly against 1-D tables of PRODUCTS D^s N D^t N: a second vector
+        job of the march, fed by the same coefficient buffer.  None if the march does not cover
+        the case (more than 3 product columns in a direction, slab partition, 1-D)."""
+        dim = self.dim
+        if dim not in (2, 3) or self.part is not None:
+            return None
+        vkeys = sorted(vterms)
+        groups = {}
+        for k in sorted(mterms):          # (s,t) and (t,s) with one coefficient: one slot
+            a, c = pad3(k[0])[:3], pad3(k[1])[:3]
+            groups.setdefault((min(a, c), max(a, c), mterms[k].uid), []).append(k)
+        dnodes, dpairs = [], []
+        for (a, c, _), ks in sorted(groups.items()):
+            node = mterms[ks[0]]
+            dnodes.append(node if len(ks) == 1 else S.mul(S.const(float(len(ks))), node))
+            dpairs.append((a, c))
+        cols = [sorted(set((min(a[d], c[d]), max(a[d], c[d])) for a, c in dpairs))
+                for d in range(dim)]
+        if any(len(cl) > 3 for cl in cols):
+            return None
+        uniq, slot = self._dedupe([vterms[k] for k in vkeys] + dnodes)
+        P = self._qp_setup(uniq, funcs)
+        nder = max([P["nder"]] + [max(pad3(k)[:3]) for k in vkeys]
+                   + [max(a + c) for a, c in dpairs])
+        B = self.basis("iga", nder)
+        if not self._gsf_ok(B, None, P):
+            return None
+        nd = B.nder + 1
+        key = ("ptab", nder, tuple(map(tuple, cols)))
+        ptabs = self._bases.get(key)
+        if ptabs is None:                  # 1-D tables (nel x nq x nloc x 3): host, once
+            ptabs = []
+            for d in range(dim):
+                t = dev.to_np(B.keep[d]["tabN"]).reshape(-1, nd)
+                pt = np.zeros((t.shape[0], 3))
+                for j, (s_, t_) in enumerate(cols[d]):
+                    pt[:, j] = t[:, s_] * t[:, t_]
+                ptabs.append(dev.from_np(pt.ravel()))
+            self._bases[key] = ptabs
+        vent = [(slot[i], tuple((pad3(k)[d], 0) for d in range(dim))) for i, k in enumerate(vkeys)]
+        dent = [(slot[len(vkeys) + j],
+                 tuple((cols[d].index((min(a[d], c[d]), max(a[d], c[d]))), 0) for d in range(dim)))
+                for j, (a, c) in enumerate(dpairs)]
+        b, dg = dev.empty(B.ntot), dev.empty(B.ntot)
+        xt = [(dev.ptr(ptabs[d]), B.c.idx[d]) for d in range(dim)]
+        self._gsf_run(B, "iga", P, len(uniq), None, vent, None, b, 0, int(B.c.n[dim - 1]),
+                      xvec=[(dent, dg, xt, 3)])
+        return b, dg
 
     def assemble_matrix(self, terms, funcs, kind="fe", out=None, cache=None):
         """terms: {(alphaTest, alphaTrial): Node} (coefficient already includes

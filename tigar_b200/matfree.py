@@ -58,6 +58,12 @@ class FormOperator(object):
     def shape(self):
         return (self.n, self.n)
 
+    def set_diagonal(self, d):
+        """diag(C) computed elsewhere (engine.assemble_vector_and_diag: same Gauss-point pass
+        as the load vector); a zero diagonal acts as 1 (as tg_win_diag_inv)."""
+        d[d == 0.0] = 1.0
+        self._dinv = d.reciprocal_()
+
     def apply(self, y):
         """y = C * self.xvec (no BCs)."""
         y.zero_()
