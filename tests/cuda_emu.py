@@ -25,6 +25,8 @@ using std::fmax; using std::fmin;
 #define __global__
 #define __shared__ static
 #define __launch_bounds__(x)
+#define __align__(n) __attribute__((aligned(n)))
+struct double2 { double x, y; };
 struct EmuIdx { int x; };
 static thread_local EmuIdx threadIdx, blockIdx;
 static std::barrier<>* emu_bar = nullptr;
