@@ -98,12 +98,7 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
       % (nd, nen, nqp, nth, dim))
     w('extern "C" __global__ void __launch_bounds__(NTH) %s(const QpArgs A) {'
       % ("tigar_qp" if op is None else "tigar_op"))
-    # tt*: the 1-D tables transposed to [q][derivative][local function] (the jets read the
-    # N local functions of a (q, derivative) pair as one or two 16-byte loads); tb*: the
-    # original [q][local function][derivative] order for the test-function contraction (op)
-    w("  __shared__ __align__(16) double tt0[Q0*N0*ND], tt1[Q1*N1*ND], tt2[Q2*N2*ND];")
-    if op is not None:
-        w("  __shared__ double tb0[Q0*N0*ND], tb1[Q1*N1*ND], tb2[Q2*N2*ND];")
+    w("  __shared__ double tb0[Q0*N0*ND], tb1[Q1*N1*ND], tb2[Q2*N2*ND];")
     # jets: all functions of a group go through the three contraction stages TOGETHER (one
     # barrier per stage and group instead of one per function and derivative order: the
     # per-function version spent its time in ~40 barriers of 4 FMAs each)
@@ -131,7 +126,7 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
     mg = max([gsizes(g)[0] for g in groups] + [1])
     m1 = max([gsizes(g)[1] for g in groups] + [1])
     m2 = max([gsizes(g)[2] for g in groups] + [1])
-    w("  __shared__ __align__(16) double cf[%d*NEN], s1[%d], s2[%d];" % (mg, m1 * S1, m2 * S2))
+    w("  __shared__ double cf[%d*NEN], s1[%d], s2[%d];" % (mg, m1 * S1, m2 * S2))
     w("  const int tid = threadIdx.x;")
     w("  const long long cl = blockIdx.x;")
     if op is None:
@@ -149,18 +144,15 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
             w("  { long long r = cl / A.cn[0]; e1 = A.co[1] + A.cs[1] * (int)(r % A.cn[1]); " +
               ("e2 = A.co[2] + A.cs[2] * (int)(r / A.cn[1]);" if dim > 2 else "") + " }")
         w("  for (int a = tid; a < NEN; a += NTH) accs[a] = 0.0;")
-    for d in range(3):
-        Q, N, e = "Q%d" % d, "N%d" % d, "e%d" % d
-        w("  for (int i = tid; i < %s*%s*ND; i += NTH) {" % (Q, N))
-        if d < dim:
-            w("    const double v = A.tab[%d][(long long)%s*%s*%s*ND + i];" % (d, e, Q, N))
-        else:
-            w("    const double v = 1.0;")
-        w("    const int a = i %% ND, r = i / ND, l = r %% %s, q = r / %s;" % (N, N))
-        w("    tt%d[(q*ND + a)*%s + l] = v;" % (d, N))
-        if op is not None:
-            w("    tb%d[i] = v;" % d)
-        w("  }")
+    w("  for (int i = tid; i < Q0*N0*ND; i += NTH) tb0[i] = A.tab[0][(long long)e0*Q0*N0*ND + i];")
+    if dim > 1:
+        w("  for (int i = tid; i < Q1*N1*ND; i += NTH) tb1[i] = A.tab[1][(long long)e1*Q1*N1*ND + i];")
+    else:
+        w("  for (int i = tid; i < Q1*N1*ND; i += NTH) tb1[i] = 1.0;")
+    if dim > 2:
+        w("  for (int i = tid; i < Q2*N2*ND; i += NTH) tb2[i] = A.tab[2][(long long)e2*Q2*N2*ND + i];")
+    else:
+        w("  for (int i = tid; i < Q2*N2*ND; i += NTH) tb2[i] = 1.0;")
     w("  const bool active = tid < NQP;")
     w("  const int qa = tid %% Q0, qb = (tid / Q0) %% Q1, qc = tid / (Q0*Q1);" .replace("%%", "%"))
     w("  double %s;" % ", ".join("j%d = 0.0" % k for k in range(max(len(jets), 1))))
@@ -184,66 +176,31 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
                 slot1[(gi, a0)] = len(slot1)
             for a01 in sorted(set((al[0], al[1]) for _, al in byf[key])):
                 slot2[(gi,) + a01] = len(slot2)
-        def vload(arr, base, n, name):
-            """n consecutive doubles of a shared array into registers (16-byte loads when n
-            is even: every base below is then a multiple of two doubles)."""
-            if n % 2 == 0:
-                for h in range(n // 2):
-                    w("      const double2 %s_%d = *reinterpret_cast<const double2*>(&%s[%s + %d]);"
-                      % (name, h, arr, base, 2 * h))
-                return ["%s_%d.%s" % (name, l // 2, "xy"[l % 2]) for l in range(n)]
-            for l in range(n):
-                w("      const double %s_%d = %s[%s + %d];" % (name, l, arr, base, l))
-            return ["%s_%d" % (name, l) for l in range(n)]
-
-        def dotp(cs, ts):
-            e = "0.0"
-            for c, t in zip(cs, ts):
-                e = "(%s + %s * %s)" % (e, c, t)
-            return e
-        # s1[slot][(l2*Q0 + q0)*N1 + l1], s2[slot][(q1*Q0 + q0)*N2 + l2]: the index the NEXT
-        # stage contracts is fastest
         w("  __syncthreads();")
         w("  for (int o = tid; o < Q0*N1*N2; o += NTH) {")
-        w("    const int qq = o %% Q0, r = o / Q0, l1 = r %% N1, l2 = r / N1;".replace("%%", "%"))
-        w("    const int so = (l2*Q0 + qq)*N1 + l1;")
-        w("    {")
-        T = {}
-        for a0 in sorted(set(a0 for (_, a0) in slot1)):
-            T[a0] = vload("tt0", "(qq*ND + %d)*N0" % a0, n0, "t%d" % a0)
-        for gi, key in enumerate(grp):
-            cs = vload("cf", "%d*NEN + r*N0" % gi, n0, "c%d" % gi)
-            for a0 in sorted(set(al[0] for _, al in byf[key])):
-                w("      s1[%d + so] = %s;" % (slot1[(gi, a0)] * S1, dotp(cs, T[a0])))
-        w("    }")
+        w("    const int qq = o %% Q0, r = o / Q0;".replace("%%", "%"))
+        for (gi, a0), sl in slot1.items():
+            w("    { double acc = 0.0;")
+            w("      #pragma unroll\n      for (int l = 0; l < N0; l++) acc += cf[%d*NEN + r*N0 + l] * tb0[(qq*N0 + l)*ND + %d];" % (gi, a0))
+            w("      s1[%d + o] = acc; }" % (sl * S1))
         w("  }")
         # stage 2: contract direction 1 for every (function, a0, a1)
         w("  __syncthreads();")
         w("  for (int o = tid; o < Q0*Q1*N2; o += NTH) {")
         w("    const int x0 = o %% Q0, t = o / Q0, x1 = t %% Q1, l2 = t / Q1;".replace("%%", "%"))
-        w("    const int so = (x1*Q0 + x0)*N2 + l2;")
-        w("    {")
-        T = {}
-        for a1 in sorted(set(a1 for (_, _, a1) in slot2)):
-            T[a1] = vload("tt1", "(x1*ND + %d)*N1" % a1, n1, "t%d" % a1)
-        for (gi, a0), sl in slot1.items():
-            cs = vload("s1", "%d + (l2*Q0 + x0)*N1" % (sl * S1), n1, "c%d_%d" % (gi, a0))
-            for (gj, b0, a1), sl2 in slot2.items():
-                if (gj, b0) == (gi, a0):
-                    w("      s2[%d + so] = %s;" % (sl2 * S2, dotp(cs, T[a1])))
-        w("    }")
+        for (gi, a0, a1), sl in slot2.items():
+            w("    { double acc = 0.0;")
+            w("      #pragma unroll\n      for (int l = 0; l < N1; l++) acc += s1[%d + (l2*N1 + l)*Q0 + x0] * tb1[(x1*N1 + l)*ND + %d];" % (slot1[(gi, a0)] * S1, a1))
+            w("      s2[%d + o] = acc; }" % (sl * S2))
         w("  }")
         # stage 3: the jets at this thread's Gauss point
         w("  __syncthreads();")
         w("  if (active) {")
-        T = {}
-        for a2 in sorted(set(al[2] for key in grp for _, al in byf[key])):
-            T[a2] = vload("tt2", "(qc*ND + %d)*N2" % a2, n2, "t%d" % a2)
-        for (gi, a0, a1), sl2 in slot2.items():
-            cs = vload("s2", "%d + (qb*Q0 + qa)*N2" % (sl2 * S2), n2, "c%d_%d_%d" % (gi, a0, a1))
-            for k, al in byf[grp[gi]]:
-                if (al[0], al[1]) == (a0, a1):
-                    w("    j%d = %s;" % (k, dotp(cs, T[al[2]])))
+        for gi, key in enumerate(grp):
+            for k, al in byf[key]:
+                w("    { double acc = 0.0;")
+                w("      #pragma unroll\n      for (int l = 0; l < N2; l++) acc += s2[%d + (l*Q1 + qb)*Q0 + qa] * tb2[(qc*N2 + l)*ND + %d];" % (slot2[(gi, al[0], al[1])] * S2, al[2]))
+                w("      j%d = acc; }" % k)
         w("  }")
     if op is None:
         w("  if (!active) return;")
