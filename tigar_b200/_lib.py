@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtigar_b200.so")
+LIB_PATH = os.environ.get("TIGAR_B200_LIB") or os.path.join(_HERE, "libtigar_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

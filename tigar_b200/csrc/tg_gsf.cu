@@ -37,6 +37,11 @@
 
 #define GSF_CB 8
 #define GSF_THREADS 256
+#ifndef GSF_NS
+#define GSF_NS 4
+#endif
+// slots of the bulk-copy ring (each GSF_THREADS * NQ doubles): GSF_NS for NQ <= 4
+__host__ __device__ constexpr int gsf_ring_slots(int nq) { return nq <= 4 ? GSF_NS : 3; }
 
 struct GsfArgs {
   const double* X;
@@ -83,8 +88,9 @@ template <int NL, int NQ, bool PAIR, bool LAST, int MINB, bool TMA>
 __global__ void __launch_bounds__(GSF_THREADS, (PAIR && NL >= 5) ? 2 : MINB)
 k_gsf(const __grid_constant__ GsfArgs A) {
   constexpr int NLP = (NL + 1) & ~1;
-  constexpr int NS = TMA ? ((NQ <= 4) ? 4 : 3) : 1;               // ring slots
-  __shared__ __align__(128) double ring[TMA ? NS * GSF_THREADS * NQ : 2];
+  constexpr int NS = TMA ? gsf_ring_slots(NQ) : 1;                 // ring slots
+  extern __shared__ __align__(128) unsigned char gsf_dyn[];        // TMA ring (dynamic)
+  double* const ring = reinterpret_cast<double*>(gsf_dyn);
   __shared__ __align__(8) uint64_t fullb[NS], emptyb[NS];
   __shared__ __align__(16) double stab[GSF_CB * NQ * 3 * NLP];   // [c][q][k][a]
   __shared__ int sfirst[GSF_CB + 1];
@@ -378,13 +384,22 @@ static int gsf_launch2(const GsfArgs& A, int pair, int last, int tma, long long 
   static const int minb2 = getenv("TIGAR_B200_GSF_MINB") ? atoi(getenv("TIGAR_B200_GSF_MINB")) == 2 : 0;
   if constexpr (NQ % 2 == 0) {
     if (tma) {
+      constexpr int ring_bytes = gsf_ring_slots(NQ) * GSF_THREADS * NQ * 8;
+#define GSF_GO(P_, L_, M_)                                                                      \
+  do {                                                                                          \
+    if (ring_bytes + 4096 > 48 * 1024)                                                              \
+      TG_CHECK(cudaFuncSetAttribute(k_gsf<NL, NQ, P_, L_, M_, true>,                            \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));  \
+    k_gsf<NL, NQ, P_, L_, M_, true><<<grid, GSF_THREADS, ring_bytes, st>>>(A);                  \
+  } while (0)
       if (pair && minb2) {
-        if (last) k_gsf<NL, NQ, true, true, 2, true><<<grid, GSF_THREADS, 0, st>>>(A);
-        else k_gsf<NL, NQ, true, false, 2, true><<<grid, GSF_THREADS, 0, st>>>(A);
-      } else if (pair && last) k_gsf<NL, NQ, true, true, 3, true><<<grid, GSF_THREADS, 0, st>>>(A);
-      else if (pair) k_gsf<NL, NQ, true, false, 3, true><<<grid, GSF_THREADS, 0, st>>>(A);
-      else if (last) k_gsf<NL, NQ, false, true, 3, true><<<grid, GSF_THREADS, 0, st>>>(A);
-      else k_gsf<NL, NQ, false, false, 3, true><<<grid, GSF_THREADS, 0, st>>>(A);
+        if (last) GSF_GO(true, true, 2);
+        else GSF_GO(true, false, 2);
+      } else if (pair && last) GSF_GO(true, true, 3);
+      else if (pair) GSF_GO(true, false, 3);
+      else if (last) GSF_GO(false, true, 3);
+      else GSF_GO(false, false, 3);
+#undef GSF_GO
       TG_LAUNCH_CHECK();
       return 0;
     }
