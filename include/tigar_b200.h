@@ -467,6 +467,24 @@ int tg_masked_fix(double* z, const double* r, const uint8_t* mask, double cinv, 
 int tg_fd_fit(const double* diagC, const uint8_t* mask, const double* kd0, const double* kd1,
               const double* kd2, const double* md0, const double* md1, const double* md2,
               int32_t n0, int32_t n1, int32_t n2, double* scratch, double* out4, void* stream);
+
+/* Relative-error variant: minimises sum_i (sum_a x_a col_a(i)/d_i - 1)^2 (robust on curved /
+ * rational geometry, where the absolute fit is dominated by the largest diagonal entries).
+ * scratch: 15*64 doubles; out15 (device): the 10 upper-triangular Gram sums (G00 G01 G02 G03
+ * G11 G12 G13 G22 G23 G33; index 3 = mass column), the 4 right-hand sides, the DoF count.    */
+int tg_fd_fit_rel(const double* diagC, const uint8_t* mask, const double* kd0, const double* kd1,
+                  const double* kd2, const double* md0, const double* md1, const double* md2,
+                  int32_t n0, int32_t n1, int32_t n2, double* scratch, double* out15,
+                  void* stream);
+
+/* s_i = sqrt(B_ii / C_ii), B_ii the diagonal of the FD surrogate with weights (c_d, sigma);
+ * 1 on constrained DoFs: the diagonal scaling of z = S B^-1 S r.                            */
+int tg_fd_diag_scale(const double* diagC, const uint8_t* mask, const double* kd0,
+                     const double* kd1, const double* kd2, const double* md0, const double* md1,
+                     const double* md2, double c0, double c1, double c2, double sigma,
+                     int32_t n0, int32_t n1, int32_t n2, double* out, void* stream);
+/* y = x * s element-wise (y may alias x) */
+int tg_vmul(double* y, const double* x, const double* s, int64_t n, void* stream);
 /* preconditioned CG, vector kernels (driver: tigar_b200/solvers.py):
  *   xpby       : p = z + beta p
  *   pcg_update : x += a p ; r -= a q ; out1[0] = r.r   (scratch: tg_cg_scratch_len())         */

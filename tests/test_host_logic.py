@@ -851,3 +851,32 @@ def test_conditional_is_a_true_select():
     from tigar_b200 import jit
     src, _ = jit.generate(prog, 1, [3, 1, 1], [3, 1, 1], 1, [], 0)
     assert "!= 0.0) ?" in src
+
+
+def test_fd_weight_model_selection():
+    """solvers.choose_fd_weights: stiffness-only / mass-only / both are recovered exactly from
+    the relative-error normal equations, and a stiffness operator seen through a smoothly
+    varying coefficient (curved geometry) keeps sigma = 0 instead of the spurious mass term the
+    full model would fit."""
+    torch = pytest.importorskip("torch")
+    try:
+        from tigar_b200.solvers import choose_fd_weights
+    except (ImportError, OSError) as e:
+        pytest.skip("library not built: %s" % e)
+    rng = np.random.default_rng(0)
+    n = 4000
+    cols = rng.uniform(0.5, 2.0, (n, 4))
+
+    def sums(d):
+        u = cols / d[:, None]
+        G, r = u.T @ u, u.sum(0)
+        return np.array([G[a, b] for a in range(4) for b in range(a, 4)] + list(r) + [n])
+    c, s = choose_fd_weights(sums(cols[:, :3] @ np.array([2.0, 0.3, 1.5])), 3)
+    assert np.allclose(c, [2.0, 0.3, 1.5], rtol=1e-10) and s == 0.0
+    c, s = choose_fd_weights(sums(0.7 * cols[:, 3]), 3)
+    assert c == [0.0, 0.0, 0.0] and abs(s - 0.7) < 1e-10
+    c, s = choose_fd_weights(sums(cols @ np.array([2.0, 0.3, 1.5, 5.0])), 3)
+    assert np.allclose(c + [s], [2.0, 0.3, 1.5, 5.0], rtol=1e-10)
+    d = (cols[:, :3] @ np.array([2.0, 0.3, 1.5])) * rng.uniform(0.8, 1.25, n)
+    c, s = choose_fd_weights(sums(d), 3)
+    assert s == 0.0 and np.allclose(c, [2.0, 0.3, 1.5], rtol=0.05)

@@ -121,6 +121,11 @@ SIGNATURES = {
     "tg_masked_fix": [c_vp, c_vp, c_vp, c_dbl, c_i64, c_vp],
     "tg_fd_fit": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32,
                   c_vp, c_vp, c_vp],
+    "tg_fd_fit_rel": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32,
+                  c_vp, c_vp, c_vp],
+    "tg_fd_diag_scale": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_dbl,
+                         c_dbl, c_i32, c_i32, c_i32, c_vp, c_vp],
+    "tg_vmul": [c_vp, c_vp, c_vp, c_i64, c_vp],
     "tg_xpby": [c_vp, c_dbl, c_vp, c_i64, c_vp],
     "tg_pcg_update": [c_vp, c_vp, c_vp, c_vp, c_dbl, c_i64, c_vp, c_vp, c_vp],
     "tg_band_from_win": [PW, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp],

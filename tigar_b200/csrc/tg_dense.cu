@@ -331,6 +331,142 @@ extern "C" int tg_fd_fit(const double* diagC, const uint8_t* mask, const double*
   return 0;
 }
 
+// Relative-error version of the fit: minimise sum_i (sum_a x_a col_a(i) / d_i - 1)^2 over the
+// unconstrained DoFs, col_a = Kronecker diagonals (a = 0..2: stiffness in direction a, a = 3:
+// mass).  The normal equations are not separable (d_i is not): 10 Gram sums + 4 right-hand
+// sides + the count, one pass over diag(C).  part: [15][gridDim.x].
+__global__ void __launch_bounds__(1024)
+k_fd_fit_rel(const double* __restrict__ d, const uint8_t* __restrict__ mask,
+             const double* __restrict__ kd0, const double* __restrict__ kd1,
+             const double* __restrict__ kd2, const double* __restrict__ md0,
+             const double* __restrict__ md1, const double* __restrict__ md2, int n0, int n1,
+             int n2, double* __restrict__ part) {
+  __shared__ double sh[15][32];
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  double s[15];
+#pragma unroll
+  for (int a = 0; a < 15; a++) s[a] = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (mask && mask[i]) continue;
+    const double di = d[i];
+    if (!(di > 0.0)) continue;
+    const int i0 = (int)(i % n0);
+    const int64_t r = i / n0;
+    const int i1 = (int)(r % n1), i2 = (int)(r / n1);
+    const double m0 = md0[i0], m1 = md1 ? md1[i1] : 1.0, m2 = md2 ? md2[i2] : 1.0;
+    const double inv = 1.0 / di;
+    double u[4];
+    u[0] = kd0[i0] * m1 * m2 * inv;
+    u[1] = md1 ? m0 * kd1[i1] * m2 * inv : 0.0;
+    u[2] = md2 ? m0 * m1 * kd2[i2] * inv : 0.0;
+    u[3] = m0 * m1 * m2 * inv;
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = a; b < 4; b++) s[k++] += u[a] * u[b];
+#pragma unroll
+    for (int a = 0; a < 4; a++) s[10 + a] += u[a];
+    s[14] += 1.0;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < 15; a++) {
+    double v = tg_warp_sum(s[a]);
+    if (lane == 0) sh[a][wid] = v;
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int a = 0; a < 15; a++) {
+      double v = (lane < (blockDim.x >> 5)) ? sh[a][lane] : 0.0;
+      v = tg_warp_sum(v);
+      if (lane == 0) part[a * gridDim.x + blockIdx.x] = v;
+    }
+  }
+}
+
+__global__ void k_fd_fit_rel_final(const double* __restrict__ part, int nb,
+                                   double* __restrict__ out) {
+  const int a = threadIdx.x;
+  if (a < 15) {
+    double v = 0.0;
+    for (int b = 0; b < nb; b++) v += part[a * nb + b];
+    out[a] = v;
+  }
+}
+
+// scratch: 15*64 doubles ; out15 (device): G00 G01 G02 G03 G11 G12 G13 G22 G23 G33, r0..r3, count
+extern "C" int tg_fd_fit_rel(const double* diagC, const uint8_t* mask, const double* kd0,
+                             const double* kd1, const double* kd2, const double* md0,
+                             const double* md1, const double* md2, int32_t n0, int32_t n1,
+                             int32_t n2, double* scratch, double* out15, void* stream) {
+  const int nb = 64;
+  k_fd_fit_rel<<<nb, 1024, 0, tg_stream(stream)>>>(diagC, mask, kd0, kd1, kd2, md0, md1, md2, n0,
+                                                  n1, n2, scratch);
+  TG_LAUNCH_CHECK();
+  k_fd_fit_rel_final<<<1, 32, 0, tg_stream(stream)>>>(scratch, nb, out15);
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// Diagonal scaling of the FD preconditioner, z = S B^-1 S r with S = diag sqrt(B_ii / C_ii):
+// B_ii = sigma m0 m1 m2 + sum_d c_d k_d m m is the diagonal of the surrogate.  It follows the
+// smooth pointwise variation of the coefficients (weights of rational basis functions,
+// Jacobian of a curved map) that the constant direction weights cannot; S = I where the fit
+// is exact.  Constrained DoFs get 1.
+__global__ void k_fd_diag_scale(const double* __restrict__ d, const uint8_t* __restrict__ mask,
+                                const double* __restrict__ kd0, const double* __restrict__ kd1,
+                                const double* __restrict__ kd2, const double* __restrict__ md0,
+                                const double* __restrict__ md1, const double* __restrict__ md2,
+                                double c0, double c1, double c2, double sigma, int n0, int n1,
+                                int n2, double* __restrict__ out) {
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double v = 1.0;
+    const double di = d[i];
+    if (!(mask && mask[i]) && di > 0.0) {
+      const int i0 = (int)(i % n0);
+      const int64_t r = i / n0;
+      const int i1 = (int)(r % n1), i2 = (int)(r / n1);
+      const double m0 = md0[i0], m1 = md1 ? md1[i1] : 1.0, m2 = md2 ? md2[i2] : 1.0;
+      double b = sigma * m0 * m1 * m2 + c0 * kd0[i0] * m1 * m2;
+      if (md1) b += c1 * m0 * kd1[i1] * m2;
+      if (md2) b += c2 * m0 * m1 * kd2[i2];
+      if (b > 0.0) v = sqrt(b / di);
+    }
+    out[i] = v;
+  }
+}
+extern "C" int tg_fd_diag_scale(const double* diagC, const uint8_t* mask, const double* kd0,
+                                const double* kd1, const double* kd2, const double* md0,
+                                const double* md1, const double* md2, double c0, double c1,
+                                double c2, double sigma, int32_t n0, int32_t n1, int32_t n2,
+                                double* out, void* stream) {
+  const int64_t n = (int64_t)n0 * n1 * n2;
+  if (n <= 0) return 0;
+  k_fd_diag_scale<<<tg_vec_grid(n), 256, 0, tg_stream(stream)>>>(
+      diagC, mask, kd0, kd1, kd2, md0, md1, md2, c0, c1, c2, sigma, n0, n1, n2, out);
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// y = x * s (element-wise; y may alias x)
+__global__ void k_vmul(double* __restrict__ y, const double* __restrict__ x,
+                       const double* __restrict__ s, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = x[i] * s[i];
+}
+extern "C" int tg_vmul(double* y, const double* x, const double* s, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  k_vmul<<<tg_vec_grid(n), 256, 0, tg_stream(stream)>>>(y, x, s, n);
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---- vector kernels of the preconditioned CG driver -------------------------------------
 // p = z + beta p
 __global__ void k_xpby(double* __restrict__ p, double beta, const double* __restrict__ z,

@@ -24,6 +24,7 @@ logic is exercised on CPU with the gloo backend (tests/test_multigpu_cpu.py)
 while the product always runs it with ``DeviceOps`` (the C-ABI kernels).
 """
 import math
+import os
 
 import numpy as np
 
@@ -296,6 +297,12 @@ class FastDiagDist(object):
         eig = [solvers._gen_eig(D, free[d]) for d, D in enumerate(patch.dirs)]
         c, sigma = self._fit(eig, free, dinv_local)
         self.weights, self.sigma = c, sigma
+        self.S = None
+        if os.environ.get("TIGAR_B200_FD_SCALE", "1") == "1":
+            nloc3 = list(self.nd)
+            nloc3[L] = self.nl
+            self.S = solvers.diag_scale(eig, dinv_local, self.lmask, c, sigma, nloc3, self.dim,
+                                        offset_last=self.k0)
         self.lam = [dev.from_np(c[d] * eig[d][0]) for d in range(self.dim)]
         self.U = [dev.from_np(np.ascontiguousarray(eig[d][1].T)) for d in range(self.dim)]
         self.t1 = dev.empty(max(self.nloc, self.mq * self.nL))
@@ -320,6 +327,16 @@ class FastDiagDist(object):
         nloc3 = list(self.nd)
         nloc3[L] = self.nl
         dC = dinv_local.reciprocal()
+        if os.environ.get("TIGAR_B200_FD_FIT", "rel") != "abs":
+            from .solvers import choose_fd_weights
+            scr = dev.empty(15 * 64)
+            out15 = dev.zeros(15)
+            check(lib.tg_fd_fit_rel(dev.ptr(dC), dev.ptr(self.lmask) if self.lmask is not None
+                                    else None, P(d_kd, 0), P(d_kd, 1), P(d_kd, 2), P(d_md, 0),
+                                    P(d_md, 1), P(d_md, 2), nloc3[0], nloc3[1], nloc3[2],
+                                    dev.ptr(scr), dev.ptr(out15), dev.stream()))
+            dist.all_reduce(out15)
+            return choose_fd_weights(dev.to_np(out15), dim)
         check(lib.tg_fd_fit(dev.ptr(dC), dev.ptr(self.lmask) if self.lmask is not None else None,
                             P(d_kd, 0), P(d_kd, 1), P(d_kd, 2), P(d_md, 0), P(d_md, 1),
                             P(d_md, 2), nloc3[0], nloc3[1], nloc3[2], dev.ptr(scratch),
@@ -366,6 +383,8 @@ class FastDiagDist(object):
         a, b = self.t1, self.t2
         check(lib.tg_masked_copy(dev.ptr(a), dev.ptr(r), dev.ptr(self.lmask) if self.lmask
                                  is not None else None, self.nloc, st))
+        if self.S is not None:
+            check(lib.tg_vmul(dev.ptr(a), dev.ptr(a), dev.ptr(self.S), self.nloc, st))
         # local mode products (directions before the partitioned one)
         if dim == 3:
             self._gemm(1, 0, n0, n1 * nl, n0, U[0], n0, 0, dev.ptr(a), n0, 0, dev.ptr(b), n0, 0, 1)
@@ -400,6 +419,8 @@ class FastDiagDist(object):
             self._gemm(0, 0, n0, n1 * nl, n0, U[0], n0, 0, dev.ptr(a), n0, 0, dev.ptr(z), n0, 0, 1)
         else:
             self._gemm(0, 0, n0, nl, n0, U[0], n0, 0, dev.ptr(a), n0, 0, dev.ptr(z), n0, 0, 1)
+        if self.S is not None:
+            check(lib.tg_vmul(dev.ptr(z), dev.ptr(z), dev.ptr(self.S), self.nloc, st))
         if self.lmask is not None:
             check(lib.tg_masked_fix(dev.ptr(z), dev.ptr(r), dev.ptr(self.lmask), self.cinv,
                                     self.nloc, st))

@@ -82,6 +82,81 @@ def _gen_eig(D, free):
     return out
 
 
+def choose_fd_weights(sums, dim):
+    """Direction weights (c_d, sigma) of the FD surrogate from the 15 sums of
+    ``tg_fd_fit_rel`` (relative-error least squares against diag(C)).  Three nested models are
+    fitted -- stiffness only, mass only, both -- and the simplest one whose residual is within
+    a factor 2 of the best admissible (non-negative) one wins: on curved or rational geometry
+    the full model buys a slightly smaller residual with a large spurious mass term that
+    doubles the iteration count (annulus: 52 iterations against 20), while a genuine
+    reaction term or a pure mass matrix leaves the stiffness-only model far behind."""
+    sums = np.asarray(sums, dtype=np.float64)
+    G = np.zeros((4, 4))
+    k = 0
+    for a in range(4):
+        for b in range(a, 4):
+            G[a, b] = G[b, a] = sums[k]
+            k += 1
+    r, N = sums[10:14], max(float(sums[14]), 1.0)
+
+    def fit(idx):
+        Gi = G[np.ix_(idx, idx)]
+        try:
+            x = np.linalg.solve(Gi, r[idx])
+        except np.linalg.LinAlgError:
+            return None
+        if not np.all(np.isfinite(x)):
+            return None
+        res2 = max(float(N - 2.0 * x @ r[idx] + x @ Gi @ x), 0.0) / N
+        full = np.zeros(4)
+        full[idx] = x
+        return full, res2
+    cands = []
+    for idx in (list(range(dim)), [3], list(range(dim)) + [3]):
+        f = fit(idx)
+        if f is None:
+            continue
+        x, res2 = f
+        scale = max(np.abs(x).max(), 1e-300)
+        if np.any(x < -1e-9 * scale) or not np.any(x > 0):
+            continue
+        if len(idx) == dim and np.any(x[:dim] <= 0):       # stiffness-only needs all directions
+            continue
+        cands.append((np.maximum(x, 0.0), res2))
+    if not cands:
+        return [1.0] * dim, 0.0
+    best = min(c[1] for c in cands)
+    for x, res2 in cands:                                    # simplest first
+        if res2 <= 4.0 * best + 1e-20:
+            return [float(v) for v in x[:dim]], float(x[3])
+    return [1.0] * dim, 0.0
+
+
+def diag_scale(eig, dinv, mask, c, sigma, nd, dim, offset_last=0):
+    """S = diag sqrt(B_ii / C_ii) (``tg_fd_diag_scale``) for the DoFs of ``dinv`` (all of them,
+    or a slab of the last direction starting at plane ``offset_last``); None when S = I to
+    round-off (affine geometry: the surrogate is exact)."""
+    d_md = [dev.from_np(eig[d][2]) for d in range(dim)]
+    d_kd = [dev.from_np(eig[d][3]) for d in range(dim)]
+    L = dim - 1
+
+    def P(Lst, d):
+        if d >= dim:
+            return None
+        return dev.ptr(Lst[d]) + (8 * offset_last if d == L else 0)
+    dC = dinv.reciprocal()
+    out = dev.empty(dC.numel())
+    cc = list(c) + [0.0] * (3 - dim)
+    check(lib.tg_fd_diag_scale(dev.ptr(dC), dev.ptr(mask) if mask is not None else None,
+                               P(d_kd, 0), P(d_kd, 1), P(d_kd, 2), P(d_md, 0), P(d_md, 1),
+                               P(d_md, 2), cc[0], cc[1], cc[2], float(sigma), nd[0], nd[1],
+                               nd[2], dev.ptr(out), dev.stream()))
+    # (the .item() below also keeps d_md / d_kd alive until the kernel has run)
+    if float((out - 1.0).abs().max().item()) < 1e-9:
+        return None
+    return out
+
+
 class FastDiag(object):
     """z = B^-1 r with B the tensor-product surrogate of the extracted operator."""
 
@@ -100,6 +175,10 @@ class FastDiag(object):
         eig = [_gen_eig(D, free[d]) for d, D in enumerate(patch.dirs)]
         c, sigma = (weights if weights is not None else self._fit(eig, dinv))
         self.weights, self.sigma = c, sigma
+        self.S = None
+        if dinv is not None and weights is None and \
+                os.environ.get("TIGAR_B200_FD_SCALE", "1") == "1":
+            self.S = diag_scale(eig, dinv, self.mask, c, sigma, self.nd, dim=self.dim)
         self.lam = [dev.from_np(c[d] * eig[d][0]) for d in range(self.dim)]
         self.U = [dev.from_np(np.asfortranarray(eig[d][1]).T.copy()) for d in range(self.dim)]
         # from_np stores C-order; U^T in C order == U in column-major order
@@ -128,11 +207,19 @@ class FastDiag(object):
         kd = [eig[d][3] for d in range(dim)]
         d_md = [dev.from_np(a) for a in md]
         d_kd = [dev.from_np(a) for a in kd]
-        scratch = dev.empty(256)
-        out4 = dev.zeros(4)
         P = lambda L, d: dev.ptr(L[d]) if d < dim else None
         # diag(C) = 1/dinv
         d = dinv.reciprocal()
+        if os.environ.get("TIGAR_B200_FD_FIT", "rel") != "abs":
+            scratch = dev.empty(15 * 64)
+            out15 = dev.zeros(15)
+            check(lib.tg_fd_fit_rel(dev.ptr(d), dev.ptr(self.mask) if self.mask is not None
+                                    else None, P(d_kd, 0), P(d_kd, 1), P(d_kd, 2), P(d_md, 0),
+                                    P(d_md, 1), P(d_md, 2), self.nd[0], self.nd[1], self.nd[2],
+                                    dev.ptr(scratch), dev.ptr(out15), dev.stream()))
+            return choose_fd_weights(dev.to_np(out15), dim)
+        scratch = dev.empty(256)
+        out4 = dev.zeros(4)
         check(lib.tg_fd_fit(dev.ptr(d), dev.ptr(self.mask) if self.mask is not None else None,
                             P(d_kd, 0), P(d_kd, 1), P(d_kd, 2), P(d_md, 0), P(d_md, 1),
                             P(d_md, 2), self.nd[0], self.nd[1], self.nd[2], dev.ptr(scratch),
@@ -175,6 +262,8 @@ class FastDiag(object):
         U = [dev.ptr(u) for u in self.U]
         check(lib.tg_masked_copy(t1, dev.ptr(r), dev.ptr(self.mask) if self.mask is not None
                                  else None, self.n, st))
+        if self.S is not None:
+            check(lib.tg_vmul(t1, t1, dev.ptr(self.S), self.n, st))
         a, b = t1, t2
         # forward: U_d^T along every direction
         self._gemm(1, 0, n0, n1 * n2, n0, U[0], n0, 0, a, n0, 0, b, n0, 0, 1)
@@ -195,6 +284,8 @@ class FastDiag(object):
             self._gemm(0, 1, n0, n1, n1, a, n0, n0 * n1, U[1], n1, 0, b, n0, n0 * n1, n2)
             a, b = b, a
         self._gemm(0, 0, n0, n1 * n2, n0, U[0], n0, 0, a, n0, 0, dev.ptr(z), n0, 0, 1)
+        if self.S is not None:
+            check(lib.tg_vmul(dev.ptr(z), dev.ptr(z), dev.ptr(self.S), self.n, st))
         if self.mask is not None:
             check(lib.tg_masked_fix(dev.ptr(z), dev.ptr(r), dev.ptr(self.mask), self.cinv,
                                     self.n, st))
