@@ -298,7 +298,7 @@ class FastDiagDist(object):
         c, sigma = self._fit(eig, free, dinv_local)
         self.weights, self.sigma = c, sigma
         self.S = None
-        if os.environ.get("TIGAR_B200_FD_SCALE", "1") == "1":
+        if os.environ.get("TIGAR_B200_FD_SCALE", "0") == "1":
             nloc3 = list(self.nd)
             nloc3[L] = self.nl
             self.S = solvers.diag_scale(eig, dinv_local, self.lmask, c, sigma, nloc3, self.dim,

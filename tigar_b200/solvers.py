@@ -177,7 +177,7 @@ class FastDiag(object):
         self.weights, self.sigma = c, sigma
         self.S = None
         if dinv is not None and weights is None and \
-                os.environ.get("TIGAR_B200_FD_SCALE", "1") == "1":
+                os.environ.get("TIGAR_B200_FD_SCALE", "0") == "1":
             self.S = diag_scale(eig, dinv, self.mask, c, sigma, self.nd, dim=self.dim)
         self.lam = [dev.from_np(c[d] * eig[d][0]) for d in range(self.dim)]
         self.U = [dev.from_np(np.asfortranarray(eig[d][1]).T.copy()) for d in range(self.dim)]
