@@ -98,7 +98,12 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
       % (nd, nen, nqp, nth, dim))
     w('extern "C" __global__ void __launch_bounds__(NTH) %s(const QpArgs A) {'
       % ("tigar_qp" if op is None else "tigar_op"))
-    w("  __shared__ double tb0[Q0*N0*ND], tb1[Q1*N1*ND], tb2[Q2*N2*ND];")
+    # padded strides (bank conflicts): a table row per Gauss point is N*ND+1 doubles, a row of
+    # coefficients N0+1, a plane of the first intermediate N1*Q0+S1PAD
+    s1pad = 4 if (n1 * q0) % 16 == 0 else 0
+    w("#define TS0 (N0*ND+1)\n#define TS1 (N1*ND+1)\n#define TS2 (N2*ND+1)")
+    w("#define CFS ((N0+1)*N1*N2)\n#define S1PL (N1*Q0+%d)\n#define S1P (N2*S1PL)" % s1pad)
+    w("  __shared__ double tb0[Q0*TS0], tb1[Q1*TS1], tb2[Q2*TS2];")
     # jets: all functions of a group go through the three contraction stages TOGETHER (one
     # barrier per stage and group instead of one per function and derivative order: the
     # per-function version spent its time in ~40 barriers of 4 FMAs each)
@@ -126,7 +131,7 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
     mg = max([gsizes(g)[0] for g in groups] + [1])
     m1 = max([gsizes(g)[1] for g in groups] + [1])
     m2 = max([gsizes(g)[2] for g in groups] + [1])
-    w("  __shared__ double cf[%d*NEN], s1[%d], s2[%d];" % (mg, m1 * S1, m2 * S2))
+    w("  __shared__ double cf[%d*CFS], s1[%d*S1P], s2[%d];" % (mg, m1, m2 * S2))
     w("  const int tid = threadIdx.x;")
     w("  const long long cl = blockIdx.x;")
     if op is None:
@@ -144,15 +149,11 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
             w("  { long long r = cl / A.cn[0]; e1 = A.co[1] + A.cs[1] * (int)(r % A.cn[1]); " +
               ("e2 = A.co[2] + A.cs[2] * (int)(r / A.cn[1]);" if dim > 2 else "") + " }")
         w("  for (int a = tid; a < NEN; a += NTH) accs[a] = 0.0;")
-    w("  for (int i = tid; i < Q0*N0*ND; i += NTH) tb0[i] = A.tab[0][(long long)e0*Q0*N0*ND + i];")
-    if dim > 1:
-        w("  for (int i = tid; i < Q1*N1*ND; i += NTH) tb1[i] = A.tab[1][(long long)e1*Q1*N1*ND + i];")
-    else:
-        w("  for (int i = tid; i < Q1*N1*ND; i += NTH) tb1[i] = 1.0;")
-    if dim > 2:
-        w("  for (int i = tid; i < Q2*N2*ND; i += NTH) tb2[i] = A.tab[2][(long long)e2*Q2*N2*ND + i];")
-    else:
-        w("  for (int i = tid; i < Q2*N2*ND; i += NTH) tb2[i] = 1.0;")
+    for d in range(3):
+        Q, N, e = "Q%d" % d, "N%d" % d, "e%d" % d
+        src = ("A.tab[%d][(long long)%s*%s*%s*ND + i]" % (d, e, Q, N)) if d < dim else "1.0"
+        w("  for (int i = tid; i < %s*%s*ND; i += NTH) tb%d[(i / (%s*ND))*TS%d + i %% (%s*ND)] = %s;"
+          % (Q, N, d, N, d, N, src))
     w("  const bool active = tid < NQP;")
     w("  const int qa = tid %% Q0, qb = (tid / Q0) %% Q1, qc = tid / (Q0*Q1);" .replace("%%", "%"))
     w("  double %s;" % ", ".join("j%d = 0.0" % k for k in range(max(len(jets), 1))))
@@ -167,7 +168,7 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
         if dim > 2:
             w("    g += (long long)A.n[0] * A.n[1] * A.idx[2][e2*N2 + l2];")
         for gi, (f, comp) in enumerate(grp):
-            w("    cf[%d*NEN + a] = A.coef[%d][g];" % (gi, f))
+            w("    cf[%d*CFS + a + a / N0] = A.coef[%d][g];" % (gi, f))
         w("  }")
         # stage 1: contract direction 0 for every (function, a0)
         slot1, slot2 = {}, {}
@@ -179,10 +180,11 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
         w("  __syncthreads();")
         w("  for (int o = tid; o < Q0*N1*N2; o += NTH) {")
         w("    const int qq = o %% Q0, r = o / Q0;".replace("%%", "%"))
+        w("    const int so = (r / N1)*S1PL + (r %% N1)*Q0 + qq;".replace("%%", "%"))
         for (gi, a0), sl in slot1.items():
             w("    { double acc = 0.0;")
-            w("      #pragma unroll\n      for (int l = 0; l < N0; l++) acc += cf[%d*NEN + r*N0 + l] * tb0[(qq*N0 + l)*ND + %d];" % (gi, a0))
-            w("      s1[%d + o] = acc; }" % (sl * S1))
+            w("      #pragma unroll\n      for (int l = 0; l < N0; l++) acc += cf[%d*CFS + r*(N0+1) + l] * tb0[qq*TS0 + l*ND + %d];" % (gi, a0))
+            w("      s1[%d*S1P + so] = acc; }" % sl)
         w("  }")
         # stage 2: contract direction 1 for every (function, a0, a1)
         w("  __syncthreads();")
@@ -190,7 +192,7 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
         w("    const int x0 = o %% Q0, t = o / Q0, x1 = t %% Q1, l2 = t / Q1;".replace("%%", "%"))
         for (gi, a0, a1), sl in slot2.items():
             w("    { double acc = 0.0;")
-            w("      #pragma unroll\n      for (int l = 0; l < N1; l++) acc += s1[%d + (l2*N1 + l)*Q0 + x0] * tb1[(x1*N1 + l)*ND + %d];" % (slot1[(gi, a0)] * S1, a1))
+            w("      #pragma unroll\n      for (int l = 0; l < N1; l++) acc += s1[%d*S1P + l2*S1PL + l*Q0 + x0] * tb1[x1*TS1 + l*ND + %d];" % (slot1[(gi, a0)], a1))
             w("      s2[%d + o] = acc; }" % (sl * S2))
         w("  }")
         # stage 3: the jets at this thread's Gauss point
@@ -199,7 +201,7 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
         for gi, key in enumerate(grp):
             for k, al in byf[key]:
                 w("    { double acc = 0.0;")
-                w("      #pragma unroll\n      for (int l = 0; l < N2; l++) acc += s2[%d + (l*Q1 + qb)*Q0 + qa] * tb2[(qc*N2 + l)*ND + %d];" % (slot2[(gi, al[0], al[1])] * S2, al[2]))
+                w("      #pragma unroll\n      for (int l = 0; l < N2; l++) acc += s2[%d + (l*Q1 + qb)*Q0 + qa] * tb2[qc*TS2 + l*ND + %d];" % (slot2[(gi, al[0], al[1])] * S2, al[2]))
                 w("      j%d = acc; }" % k)
         w("  }")
     if op is None:
@@ -264,11 +266,11 @@ def generate(prog, dim, nloc, nq, nd, jets, nfun, op=None, diag=False, layout="c
     # (N_a is a tensor product, so sum_q c(q) D^s N_a(q) D^t N_a(q) factorises too: 3*(p+1)^4
     # FMAs per slot and cell instead of (p+1)^6)
     def tabx(d, q, a, al):
-        T, N = "tb%d" % d, "N%d" % d
+        T, TS = "tb%d" % d, "TS%d" % d
         if diag:
-            return "%s[(%s*%s + %s)*ND + %d] * %s[(%s*%s + %s)*ND + %d]" % (
-                T, q, N, a, al[0][d], T, q, N, a, al[1][d])
-        return "%s[(%s*%s + %s)*ND + %d]" % (T, q, N, a, al[d])
+            return "%s[%s*%s + %s*ND + %d] * %s[%s*%s + %s*ND + %d]" % (
+                T, q, TS, a, al[0][d], T, q, TS, a, al[1][d])
+        return "%s[%s*%s + %s*ND + %d]" % (T, q, TS, a, al[d])
     for s, al in enumerate(op):
         if diag:
             al = (tuple(al[0]) + (0,) * (3 - len(al[0])), tuple(al[1]) + (0,) * (3 - len(al[1])))
