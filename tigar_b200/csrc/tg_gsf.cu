@@ -342,6 +342,7 @@ k_gsf(const __grid_constant__ GsfArgs A) {
       for (int ss = 1; ss <= NL; ss++) {
         if (s != ss) continue;
         if (active) {
+          const long long fj = PAIR ? (long long)first * jstride : 0;   // one wide multiply
 #pragma unroll
           for (int a = 0; a < NL; a++) {
             if (!(a < ss || PAIR)) continue;          // vector: only the leaving functions
@@ -351,7 +352,7 @@ k_gsf(const __grid_constant__ GsfArgs A) {
 #pragma unroll
             for (int b = 0; b < (PAIR ? NL : 1); b++) {
               if (!(a < ss || (PAIR && b < ss))) continue;
-              double* q = PAIR ? rp + (long long)(first + b) * jstride : rp;
+              double* q = PAIR ? rp + fj + (long long)b * jstride : rp;
               const double val = acc.v[PAIR ? a * NL + b : a];
               if (LAST && ((carried >> (a * NL + b)) & 1u)) *q += val;
               else *q = val;
