@@ -530,6 +530,9 @@ int tg_win_asym(const tg_win* h_w, const double* vals, double* out2, void* strea
  *                          pair = 0, the vector slab [vec_row0, vec_row0+vec_nr) of the last
  *                          direction; ninner = F0*F1 (pair) or the plane size; h_F0 = total 1-D
  *                          window length of the first direction.
+ *   perm_rows              optional (device, [nr1][2], 16-byte aligned): per row i1 of h_Wperm
+ *                          {S1[i1]*F0, len1[i1] | lo1[i1] << 32} -- the writer of the permuted
+ *                          layout then needs one load per row; NULL: computed from h_Wperm.
  *   perm, h_Wperm          3-D matrices: the stage before the last (perm = 1, last = 0) writes the
  *                          pair index (f1, f0) in the thread order of the last stage
  *                          (u = S1[i1]*F0 + S0[i0]*len1 + dj1*len0 + dj0, windows of h_Wperm,
@@ -546,7 +549,7 @@ int tg_gsf_stage(const double* X, int64_t skin, int64_t scell, int32_t cbase,
                  double* Y, int64_t skout, int64_t so_f, int64_t so_u, int64_t so_v,
                  int32_t last, const tg_win* h_W, int64_t h_F0, int32_t vec_row0,
                  int32_t vec_nr, double* out, int32_t perm, const tg_win* h_Wperm,
-                 void* stream);
+                 const int64_t* perm_rows, void* stream);
 
 #ifdef __cplusplus
 }

@@ -136,7 +136,8 @@ SIGNATURES = {
     "tg_gsf_supported": [c_i32, c_i32],
     "tg_gsf_stage": [c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp,
                      c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_vp, c_i64,
-                     c_i64, c_i64, c_i64, c_i32, PW, c_i64, c_i32, c_i32, c_vp, c_i32, PW, c_vp],
+                     c_i64, c_i64, c_i64, c_i32, PW, c_i64, c_i32, c_i32, c_vp, c_i32, PW, c_vp,
+                     c_vp],
 }
 _RESTYPES = {"tg_sizeof_win": c_i64, "tg_sizeof_basis": c_i64, "tg_last_error": C.c_char_p, "tg_prof_enable": None, "tg_prof_get": None, "tg_launch_count": c_i64, "tg_win_storage": c_i64}
 

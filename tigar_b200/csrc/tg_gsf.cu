@@ -75,6 +75,7 @@ struct GsfArgs {
   const int64_t* pS0;      // [n0+1] (also used by perm_out)
   const int64_t* pS1;      // [n1+1]
   const int32_t* pLo1;     // [n1]
+  const longlong2* prow;   // [n1] packed {S1[i]*F0, len1[i] | lo1[i] << 32} or NULL
   int pn0;
   long long pF0;
 };
@@ -194,6 +195,11 @@ k_gsf(const __grid_constant__ GsfArgs A) {
     if (!LAST) {
       if (!PAIR) return ybase + (long long)i * A.so_f;            // + 0 * jstride (j unused)
       if (A.perm_out) {
+        if (A.prow) {          // one 16-byte load and 32-bit products per row
+          const longlong2 rc = __ldg(A.prow + i);
+          const int l1 = (int)(rc.y & 0xffffffffll), lo1 = (int)(rc.y >> 32);
+          return ybase + (rc.x + (long long)(pS0i0 * l1 + pdj0 - lo1 * pl0)) * A.so_f;
+        }
         const long long s1 = A.pS1[i], l1 = A.pS1[i + 1] - s1;
         return ybase + (s1 * A.pF0 + (long long)pS0i0 * l1 + pdj0 -
                         (long long)A.pLo1[i] * pl0) * A.so_f;
@@ -434,7 +440,7 @@ extern "C" int tg_gsf_stage(const double* X, int64_t skin, int64_t scell, int32_
                             double* Y, int64_t skout, int64_t so_f, int64_t so_u, int64_t so_v,
                             int32_t last, const tg_win* h_W, int64_t h_F0, int32_t vec_row0,
                             int32_t vec_nr, double* out, int32_t perm, const tg_win* h_Wperm,
-                            void* stream) {
+                            const int64_t* perm_rows, void* stream) {
   TG_REQUIRE(tg_gsf_supported(nloc, nq), "gsf: unsupported (nloc, nq)");
   TG_REQUIRE(nd >= 1 && nd <= 3, "gsf: tables hold derivative orders 0..2");
   GsfArgs A;
@@ -472,6 +478,7 @@ extern "C" int tg_gsf_stage(const double* X, int64_t skin, int64_t scell, int32_
     TG_REQUIRE(h_Wperm && h_Wperm->dim == 3, "gsf: perm layout is for 3-D windows");
     A.pS0 = h_Wperm->S[0]; A.pS1 = h_Wperm->S[1]; A.pLo1 = h_Wperm->lo[1];
     A.pn0 = h_Wperm->nr[0]; A.pF0 = h_F0;
+    A.prow = (!last) ? reinterpret_cast<const longlong2*>(perm_rows) : nullptr;
     if (last) A.perm_in = 1; else A.perm_out = 1;
   }
   if (nthreads <= 0 || c1 <= c0) return 0;

@@ -705,6 +705,21 @@ class TensorPatch(object):
             self._bases[key] = hit
         return hit
 
+    def _gsf_perm_rows(self, W, F0):
+        """Packed per-row constants of the permuted pair layout (tg_gsf_stage ``perm_rows``):
+        for every row i1 of the second direction {S1[i1]*F0, len1[i1] | lo1[i1] << 32}."""
+        key = ("gsf_prow", id(W), int(F0))
+        hit = self._bases.get(key)
+        if hit is None:
+            ln = W.len[1].astype(np.int64)
+            S1 = np.concatenate([[0], np.cumsum(ln)])[:-1]
+            pk = np.empty((len(ln), 2), dtype=np.int64)
+            pk[:, 0] = S1 * int(F0)
+            pk[:, 1] = ln | (W.lo[1].astype(np.int64) << 32)
+            hit = (dev.from_np(pk.ravel()), W)          # (keeps W alive: id() is the key)
+            self._bases[key] = hit
+        return hit[0]
+
     def _gsf_run(self, B, kind, P, nslots, mentries, ventries, A, b, vrow0, vnr, xvec=None):
         """One pass over the cell layers of this patch (or slab): Gauss-point kernel into the
         blocked coefficient layout, then the march stages of the matrix (``mentries``) and of
@@ -836,7 +851,7 @@ class TensorPatch(object):
                         nq[0], nd, tabs[0][0], tabs[0][1], dev.ptr(rbs[0]),
                         dev.ptr(dplan((tag, 0), t1)), n1o, mi1, pair, ninner, nq2c, nq[1],
                         dev.ptr(Y1), nel[1] * G[0] * nq2c * nq[1], nq2c * nq[1],
-                        G[0] * nq2c * nq[1], nq[1], 0, None, 0, 0, 0, None, 0, None,
+                        G[0] * nq2c * nq[1], nq[1], 0, None, 0, 0, 0, None, 0, None, None,
                         dev.stream()))
                     # stage 2: march e1; inner = (f0, e2l, q2l).  Matrices: the pair index
                     # (f1, f0) is written in the thread order of the last stage (perm)
@@ -856,7 +871,10 @@ class TensorPatch(object):
                         dev.ptr(Y2), lc * G[1] * G[0] * nq[2],
                         nq[2] if perm else G[0] * nq[2], nq[2],
                         G[1] * G[0] * nq[2], 0, None, G[0] if perm else 0, 0, 0, None, perm,
-                        W.ref() if perm else None, dev.stream()))
+                        W.ref() if perm else None,
+                        dev.ptr(self._gsf_perm_rows(W, G[0]))
+                        if perm and os.environ.get("TIGAR_B200_GSF_PROW", "1") == "1" else None,
+                        dev.stream()))
                     Xl, skl, scl, ninl = Y2, lc * G[1] * G[0] * nq[2], G[1] * G[0] * nq[2], G[1] * G[0]
                 else:
                     # stage 1: march e0; inner = (e1c, q1l)
@@ -872,7 +890,7 @@ class TensorPatch(object):
                         nq[0], nd, tabs[0][0], tabs[0][1], dev.ptr(rbs[0]),
                         dev.ptr(dplan((tag, 0), t1)), n1o, mi1, pair, ninner, 1, nq[1],
                         dev.ptr(Y1), lc * G[0] * nq[1], nq[1], G[0] * nq[1], 0, 0, None, 0, 0, 0,
-                        None, 0, None, dev.stream()))
+                        None, 0, None, None, dev.stream()))
                     Xl, skl, scl, ninl = Y1, lc * G[0] * nq[1], G[0] * nq[1], G[0]
                 nlo, mil, tl = st[L]
                 nin_tot = int(tl[:, 0].sum())
@@ -889,7 +907,7 @@ class TensorPatch(object):
                     tabs[L][1], dev.ptr(rbs[L]), dev.ptr(dplan((tag, L), tl)), nlo, mil, pair,
                     ninl, 1, 1, None, 0, 0, 0, 0, 1, W.ref() if pair else None, G[0],
                     vrow0, vnr, outp, perm if (pair and dim == 3) else 0,
-                    W.ref() if (pair and dim == 3 and perm) else None, dev.stream()))
+                    W.ref() if (pair and dim == 3 and perm) else None, None, dev.stream()))
             if overlap:
                 readers_done[ci] = torch.cuda.Event()
                 readers_done[ci].record(main)
