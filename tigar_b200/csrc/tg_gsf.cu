@@ -37,6 +37,7 @@
 
 #define GSF_CB 8
 #define GSF_THREADS 256
+#define GSF_MAXIN 64        // inputs summed into one output kind (plan row length)
 #ifndef GSF_NS
 #define GSF_NS 4
 #endif
@@ -99,6 +100,11 @@ k_gsf(const __grid_constant__ GsfArgs A) {
   const int ko = blockIdx.y;
   const int* plan = A.plan + (long long)ko * (1 + 3 * A.maxin);
   const int nin = plan[0];
+  // the plan of this output kind, one packed word per input (kin | al << 16 | be << 20), in
+  // shared memory: the item loop reads it once per item instead of three global loads
+  __shared__ int splan[GSF_MAXIN];
+  if (tid < nin) splan[tid] = plan[1 + 3 * tid] | (plan[2 + 3 * tid] << 16) | (plan[3 + 3 * tid] << 20);
+  __syncthreads();
   const long long t = blockIdx.x * (long long)GSF_THREADS + tid;
 
   // ---- what this thread owns -------------------------------------------------------
@@ -224,14 +230,14 @@ k_gsf(const __grid_constant__ GsfArgs A) {
   auto issue = [&](int it) {                // thread 0 only
     const int slot = it % NS;
     const int e = A.c0 + it / nin, in = it % nin;
-    const int kin = plan[1 + 3 * in];
+    const int kin = splan[in] & 0xffff;
     const double* src = A.X + kin * A.skin + (long long)(e - A.cbase) * A.scell + inner0 * NQ;
     const uint32_t bytes = (uint32_t)nvalid * NQ * 8u;
     tg_mbar_expect_tx(&fullb[slot], bytes);
     tg_bulk_g2s(&ring[slot * GSF_THREADS * NQ], src, bytes, &fullb[slot]);
   };
   auto load_item = [&](int e, int in, double* x) {
-    const int kin = plan[1 + 3 * in];
+    const int kin = splan[in] & 0xffff;
     const double* xp = A.X + kin * A.skin + (long long)(e - A.cbase) * A.scell + inner * NQ;
     if constexpr (NQ % 2 == 0) {
 #pragma unroll
@@ -285,7 +291,8 @@ k_gsf(const __grid_constant__ GsfArgs A) {
     for (int c = 0; c < ncb; c++) {
       const int e = cb + c;
       for (int in = 0; in < nin; in++) {
-        const int al = plan[2 + 3 * in], be = plan[3 + 3 * in];
+        const int pk = splan[in];
+        const int al = (pk >> 16) & 15, be = (pk >> 20) & 15;
         double x[NQ];
         if (!TMA) {
           if (!active) continue;
@@ -443,6 +450,7 @@ extern "C" int tg_gsf_stage(const double* X, int64_t skin, int64_t scell, int32_
                             const int64_t* perm_rows, void* stream) {
   TG_REQUIRE(tg_gsf_supported(nloc, nq), "gsf: unsupported (nloc, nq)");
   TG_REQUIRE(nd >= 1 && nd <= 3, "gsf: tables hold derivative orders 0..2");
+  TG_REQUIRE(maxin >= 1 && maxin <= GSF_MAXIN, "gsf: too many inputs per output kind");
   GsfArgs A;
   memset(&A, 0, sizeof(A));
   A.X = X; A.skin = skin; A.scell = scell; A.cbase = cbase; A.c0 = c0; A.c1 = c1; A.nel = nel;
