@@ -35,7 +35,9 @@
 #include <string.h>
 #include <stdlib.h>
 
+#ifndef GSF_CB
 #define GSF_CB 8
+#endif
 #define GSF_THREADS 256
 #define GSF_MAXIN 64        // inputs summed into one output kind (plan row length)
 #ifndef GSF_NS
