@@ -38,7 +38,9 @@
 #ifndef GSF_CB
 #define GSF_CB 8
 #endif
+#ifndef GSF_THREADS
 #define GSF_THREADS 256
+#endif
 #define GSF_MAXIN 64        // inputs summed into one output kind (plan row length)
 #ifndef GSF_NS
 #define GSF_NS 4
@@ -89,7 +91,7 @@ struct GsfAcc {
 };
 
 template <int NL, int NQ, bool PAIR, bool LAST, int MINB, bool TMA>
-__global__ void __launch_bounds__(GSF_THREADS, (PAIR && NL >= 5) ? 2 : MINB)
+__global__ void __launch_bounds__(GSF_THREADS, ((PAIR && NL >= 5) ? 2 : MINB) * (256 / GSF_THREADS))
 k_gsf(const __grid_constant__ GsfArgs A) {
   constexpr int NLP = (NL + 1) & ~1;
   constexpr int NS = TMA ? gsf_ring_slots(NQ) : 1;                 // ring slots
