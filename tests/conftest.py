@@ -13,6 +13,14 @@ def pytest_configure(config):
 
 
 @pytest.fixture(scope="session")
+def golden_inner():
+    """basisFuncsInner with caller-chosen indices, from the reference's own compiled C++
+    (tests/golden/gen_basisfuncs_inner_golden.py)."""
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "basisfuncs_inner_reference.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "bspline_reference.npz"))

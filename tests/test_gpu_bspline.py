@@ -125,3 +125,21 @@ def test_basis_funcs_inner_is_the_reference_native_routine():
                                 np.zeros(p + 1), np.zeros(p + 1), ders)
                 assert np.array_equal(ders, ref.basisFuncs(sp, u))
                 assert np.array_equal(ours.basisFuncs(sp, u), ders)
+
+
+def test_basis_funcs_inner_equals_the_reference_native_code(golden_inner):
+    """tg_basis_funcs_inner (scalar wrapper and batched) against vectors produced by the
+    reference's OWN compiled C++ basisFuncsInner for caller-chosen indices: bit-exact."""
+    from tIGAr.BSplines import basisFuncsInner
+    g = golden_inner
+    for name in g["names"]:
+        pre = str(name) + "_"
+        p, nG = int(g[pre + "p"]), int(g[pre + "nGhost"])
+        gk, us, ii, ref = g[pre + "ghostKnots"], g[pre + "u"], g[pre + "i"], g[pre + "ders"]
+        out = np.zeros_like(ref)
+        basisFuncsInner(gk, nG, us, p, ii, None, None, None, out)          # batched
+        assert np.array_equal(out, ref), name
+        d1 = np.zeros(p + 1)
+        basisFuncsInner(gk, nG, float(us[0]), p, int(ii[0]), np.zeros((p + 1, p + 1)),
+                        np.zeros(p + 1), np.zeros(p + 1), d1)              # reference call form
+        assert np.array_equal(d1, ref[0]), name

@@ -72,3 +72,19 @@ def test_index_helpers(golden):
                                     for j in range(4) for k in range(3)]), golden["ijk2dof"])
     assert np.array_equal(np.array([B.dof2ijk(d, 5, 4) for d in range(60)]), golden["dof2ijk"])
     assert np.array_equal(np.array([B.dof2ij(d, 7) for d in range(21)]), golden["dof2ij"])
+
+
+def test_basis_funcs_inner_with_caller_chosen_index(golden_inner):
+    """The oracle's restatement of basisFuncsInner (BSplines.py:73-120) against the reference's
+    own compiled routine called with arbitrary i = span+1 (neighbouring spans included):
+    bit-exact."""
+    g = golden_inner
+    n = 0
+    for name in g["names"]:
+        pre = str(name) + "_"
+        p, nG = int(g[pre + "p"]), int(g[pre + "nGhost"])
+        for u, i, ders in zip(g[pre + "u"], g[pre + "i"], g[pre + "ders"]):
+            got = B.basis_funcs_inner(g[pre + "ghostKnots"], nG, float(u), p, int(i))
+            assert np.array_equal(got, ders), (name, u, i)
+            n += 1
+    assert n > 150
